@@ -1,0 +1,49 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+PKG = os.path.join(ROOT, "rna-mpnn_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+GOLDEN_DIR = os.path.join(ROOT, "tests", "golden")
+GOLDEN_CASES = ["toy_degenerate", "ragged_k8", "default_k25", "real_k25", "single_k48"]
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box with -m gpu)")
+
+
+def pytest_collection_modifyitems(config, items):
+    if torch.cuda.is_available():
+        return
+    skip = pytest.mark.skip(reason="no CUDA device")
+    for item in items:
+        if "gpu" in item.keywords:
+            item.add_marker(skip)
+
+
+def load_golden(name):
+    """Golden vectors produced by the unmodified reference (tests/golden/make_golden.py)."""
+    from oracle.weights import RDesignConfig, make_state_dict
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    g = {k: z[k] for k in z.files}
+    c = [int(v) for v in g["cfg"]]
+    cfg = RDesignConfig(hidden_dim=c[0], k_neighbors=c[1], num_message_layers=c[2], num_dense_layers=c[3],
+                        dim_dense_layers=c[4], num_mpnn_layers=c[5], readout_hidden_dim=c[6],
+                        num_readout_layers=c[7])
+    g["config"] = cfg
+    g["params"] = make_state_dict(cfg, int(g["seed"]))
+    for k in ("X", "S", "mask"):
+        g[k] = torch.from_numpy(g[k])
+    return g
+
+
+@pytest.fixture(params=GOLDEN_CASES)
+def golden(request):
+    return load_golden(request.param)
