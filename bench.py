@@ -1,0 +1,297 @@
+#!/usr/bin/env python
+"""bench.py -- RNA nucleotides/s of the structure-to-sequence forward path on B200.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--precision fp32|bf16] [--workload c2|c3]
+
+One "step" = one pass of the hot path (kNN + featurizer -> 9 message-passing layers ->
+readout head with softmax/argmax) over one synthetic padded batch.  The N=1 workload is
+BASELINE.json configs[1]: synthetic RNA backbones L=256, K=30, batch 64, default model.
+N>1 shards whole structures across ranks (no data-path collective), weak scaling.
+
+`--impl reference` times the CPU arm (the oracle port of the reference's own PyTorch-CPU
+path, oracle/rdesign_oracle.py) on the host cores, on a bounded sample of the workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for p in (ROOT, os.path.join(ROOT, "rna-mpnn_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+import torch  # noqa: E402
+
+WORKLOADS = {
+    # name: (B, L, K, seed)  -- SURVEY.md section 8d
+    "c2": (64, 256, 30, 1002),
+    "c3": (8, 4096, 48, 1003),
+}
+FLOP_PER_EDGE_LAYER = 163_840      # SURVEY.md 8d, reference formulation (3-layer message MLP)
+FLOP_PER_NODE_LAYER = 393_216
+METRIC = "RNA nucleotides/sec (enc+dec fwd)"
+UNIT = "nt/s"
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"hbm_gbs": p["hbm_gbs"], "bf16_tflops": p["bf16_tflops"],
+                "bf16_tflops_sustained": p["bf16_tflops_sustained"], "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.lines, self.proc = index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            self.thread.join(timeout=2)
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def model_and_inputs(workload, rank=0):
+    from oracle.weights import RDesignConfig, make_state_dict, synthetic_backbones
+    B, L, K, seed = WORKLOADS[workload]
+    cfg = RDesignConfig(k_neighbors=K)
+    params = make_state_dict(cfg, 42)
+    X, S, mask = synthetic_backbones(B, L, seed + rank)
+    return cfg, params, X, S, mask
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def cpu_forward_rate(workload, budget_s, min_reps=1, sample_B=None):
+    """Oracle port of the reference's CPU path on all host cores, bounded sample."""
+    from oracle import rdesign_oracle as O
+    cfg, params, X, S, mask = model_and_inputs(workload)
+    B, L, K, _ = WORKLOADS[workload]
+    sB = sample_B or max(1, min(B, 8 if L <= 512 else 1))
+    Xs, Ss, ms = X[:sB], S[:sB], mask[:sB]
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    O.forward(params, Xs[:1], Ss[:1], ms[:1], K, cfg.scale)       # warm-up
+    reps, t0 = 0, time.perf_counter()
+    while True:
+        O.forward(params, Xs, Ss, ms, K, cfg.scale)
+        reps += 1
+        el = time.perf_counter() - t0
+        if reps >= min_reps and el >= budget_s:
+            break
+    nt = float(ms.sum()) * reps
+    return {"value": nt / el, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{sB} of {B} structures (L={L}, K={K}), {reps} forward passes in {el:.1f} s"}, el / reps
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    B, L, K, _ = WORKLOADS[args.workload]
+    # one step = one forward over the bounded sample (budget 0 -> exactly one pass)
+    for _ in range(min(args.warmup, 2)):
+        cpu_forward_rate(args.workload, 0.0)
+    vals, ms = [], []
+    for _ in range(args.steps):
+        cb, sec = cpu_forward_rate(args.workload, 0.0)
+        vals.append(cb["value"]); ms.append(sec * 1e3)
+    cb["value"] = sum(vals) / len(vals)
+    line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": sum(ms) / len(ms), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"{args.workload}: synthetic RNA backbones B={B} L={L} K={K}, RNAModel default "
+                                   "(9 layers), encoder + readout forward; CPU arm runs a bounded sample per step"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def run_ours(args):
+    import torch.distributed as dist
+    from rmpnn_b200 import _lib
+    from rmpnn_b200.engine import RDesignEngine
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L_ = _lib.lib()
+    prec = _lib.PREC_BF16 if args.precision == "bf16" else _lib.PREC_FP32
+
+    cfg, params, X, S, mask = model_and_inputs(args.workload, rank)
+    B, L, K, _ = WORKLOADS[args.workload]
+    eng = RDesignEngine(params, K, cfg.scale, device=dev, precision=prec)
+    Nv = int(mask.sum().item())
+    lengths = mask.sum(1).long()
+    Ne = int((lengths * torch.clamp(lengths, max=min(K, L))).sum().item())
+    sizes = (Nv, Ne)
+
+    Xd, md = X.to(dev), mask.to(dev)
+    Xp, mp = X.pin_memory(), mask.pin_memory()
+    samples_host = torch.empty(Nv, dtype=torch.int64).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
+    stream = torch.cuda.current_stream()
+
+    def step_resident():
+        return eng.forward(Xd, md, sizes=sizes)
+
+    def step_e2e():
+        xd = Xp.to(dev, non_blocking=True)
+        mk = mp.to(dev, non_blocking=True)
+        out = eng.forward(xd, mk, sizes=sizes)
+        samples_host.copy_(out["samples"], non_blocking=True)
+        return out
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step_resident()
+        step_e2e()
+    barrier()
+
+    # ---- device-resident timing (value) + dominant-kernel timing (roofline) ----
+    eng.kernel_timer = []                # the engine records (start, end) events around the message kernel
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    launches0 = L_.rmp_launch_count()
+    with ClockSampler(local) as clocks:
+        barrier()
+        for s, e in ev:
+            flush.zero_()                 # L2 flush between timed iterations (not timed)
+            s.record(stream)
+            step_resident()
+            e.record(stream)
+        barrier()
+    launches = (L_.rmp_launch_count() - launches0) // args.steps
+    step_ms = [s.elapsed_time(e) for s, e in ev]
+    total_ms = sum(step_ms)
+    ktimes = [s.elapsed_time(e) for s, e in eng.kernel_timer]
+    eng.kernel_timer = None
+
+    # ---- end-to-end through the public API with host buffers (e2e) ----
+    ev2 = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    barrier()
+    for s, e in ev2:
+        flush.zero_()
+        s.record(stream)
+        step_e2e()
+        e.record(stream)
+    barrier()
+    e2e_ms = sum(s.elapsed_time(e) for s, e in ev2)
+
+    t = torch.tensor([total_ms, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms, e2e_ms = t.tolist()
+    nt_all = Nv * world * args.steps
+    value = nt_all / (total_ms * 1e-3)
+    e2e = nt_all / (e2e_ms * 1e-3)
+
+    if rank == 0:
+        pk = peaks()
+        k_ms = sum(ktimes) / max(1, len(ktimes))
+        flop_launch = Ne * FLOP_PER_EDGE_LAYER
+        peak_tf = pk["bf16_tflops_sustained"]
+        achieved = flop_launch / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
+        roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
+                    "frac": achieved / peak_tf, "traffic": None,
+                    "kernel": eng.dominant_kernel_name(), "kernel_ms": k_ms,
+                    "kernel_share_of_step": sum(ktimes) / total_ms if total_ms else None,
+                    "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
+                    "algorithmic_flop_per_launch": flop_launch}
+        cb = None
+        if world == 1 and not args.no_cpu_baseline:
+            cb, _ = cpu_forward_rate(args.workload, 12.0)
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": max(3, args.warmup), "ms_per_step": total_ms / args.steps, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "bf16" if prec == _lib.PREC_BF16 else "f32",
+                "data": "synthetic",
+                "config": {"workload": f"{args.workload}: synthetic RNA backbones B={B} L={L} K={K} per GPU, "
+                                       "RNAModel default (9 layers, H=128), kNN+featurizer+layers+readout/argmax",
+                           "sharding": "whole structures per rank, no data-path collective",
+                           "l2": "256 MiB flush buffer written between timed iterations",
+                           "precision": args.precision},
+                "roofline": roofline, "cpu_baseline": cb,
+                "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": Xp.numel() * 4 + mp.numel() * 4,
+                        "d2h_bytes_per_step": samples_host.numel() * 8},
+                "gpu_launches": int(launches), "clocks": clocks.summary()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default=os.environ.get("RMPNN_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

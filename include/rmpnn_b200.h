@@ -1,0 +1,190 @@
+/*
+ * rmpnn_b200.h -- C ABI of the B200-native RNA-MPNN structure-to-sequence forward path.
+ *
+ * The reference (givemeone1astkiss/RNA-MPNN) has no native layer: its hot path is a
+ * sequence of ATen calls inside Python nn.Modules.  Each entry point below replaces
+ * one such group of calls; the reference location is cited as file:line under the
+ * reference repository root.  INTEGRATION.md shows the ctypes binding a maintainer
+ * adds on the reference side.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (PyTorch allocates all
+ *     inputs, outputs and workspaces); the library never allocates or frees device
+ *     memory and keeps no pointer after return;
+ *   - all work is enqueued on `stream` (a cudaStream_t passed as void*), no hidden
+ *     synchronisation, so calls can be captured in a CUDA graph;
+ *   - return value: 0 = OK, negative = argument error (RMP_E_*), positive =
+ *     cudaError_t of the failed launch; rmp_last_error_string() describes it;
+ *   - fp32 tensors are row-major contiguous; indices are int32 inside the library
+ *     and int64 only where the reference API exposes them (E_idx);
+ *   - B structures, N padded length, K = min(top_k, N) neighbour slots, H = 128.
+ *
+ * Layout in HBM
+ *   nodes are the valid residues in (b, i) order ("valid-only flattening",
+ *   rdesign/model/feature.py:176-177,235-237): Nv = sum_b L_b rows.
+ *   edges are (centre node, slot k) in row-major order; every valid node of
+ *   structure b has deg_b = min(K, L_b) edges, so a node's edges are contiguous
+ *   (CSR row_ptr) and Ne = sum_b L_b * deg_b.
+ */
+#ifndef RMPNN_B200_H
+#define RMPNN_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RMP_OK            0
+#define RMP_E_ARG        -1   /* null pointer / non-positive size */
+#define RMP_E_SHAPE      -2   /* unsupported dimension (e.g. H != 128, K > 128) */
+#define RMP_E_ALIGN      -3   /* pointer not 16-byte aligned */
+#define RMP_E_WORKSPACE  -4   /* workspace too small */
+#define RMP_E_ARCH       -5   /* device is not sm_100 */
+
+#define RMP_HIDDEN      128   /* hidden width the kernels are specialised for */
+#define RMP_NODE_RAW    101   /* angle 12 | rbf 80 | direction 9   (rdesign/config/glob.py:8-13)  */
+#define RMP_EDGE_RAW    115   /* quat 4  | rbf 96 | direction 15  (rdesign/config/glob.py:14-18) */
+#define RMP_MAX_K       128   /* neighbour slots supported by the warp top-K */
+
+/* precision of the fused layer path */
+#define RMP_PREC_FP32     0   /* fp32 CUDA-core kernels: 1e-4 logit parity with the reference's CPU path */
+#define RMP_PREC_BF16     1   /* bf16 operands on tcgen05 tensor cores, fp32 accumulate: 2e-2 budget */
+
+const char* rmp_version(void);
+const char* rmp_last_error_string(void);
+/* compute capability major*10+minor of the current device, or negative error */
+int rmp_device_arch(void);
+/* sizeof(struct rmp_mlp_desc) as compiled -- lets a foreign-language binding verify its mirror */
+int rmp_abi_struct_size(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+uint64_t rmp_launch_count(void);
+
+/* ------------------------------------------------------------------ graph index
+ * Valid-only flattening bookkeeping from the mask alone.
+ * Replaces: masked_select / nonzero / cumsum bookkeeping in
+ *   rdesign/model/feature.py:173-177, 227-237.
+ *   node_map [B*N]  : dense (b,i) -> flat node id, -1 for masked residues
+ *   node_src [B*N]  : flat node id -> dense b*N+i          (first Nv entries)
+ *   sinfo    [B*4]  : per structure {L_b, deg_b, node_off_b, edge_off_b}
+ *   row_ptr  [B*N+1]: CSR edge offsets per flat node        (first Nv+1 entries)
+ *   counts   [2]    : {Nv, Ne}
+ */
+int rmp_graph_index(const float* mask, int B, int N, int K,
+                    int32_t* node_map, int32_t* node_src, int32_t* sinfo,
+                    int32_t* row_ptr, int32_t* counts, void* stream);
+
+/* ------------------------------------------------------------------ kNN (a-1)
+ * Brute-force tiled kNN over one backbone atom per residue.
+ * Replaces: RNAFeatures._dist, rdesign/model/feature.py:42-50.
+ *   X          [B,N,A,3] fp32, atom `atom` of each residue is used
+ *   mask       [B,N] fp32 0/1
+ *   E_idx      [B,N,K] int64, ascending adjusted distance, ties -> lower index
+ *   D_neighbors[B,N,K] fp32 (may be NULL)
+ * Distances follow the reference's rounding sequence exactly:
+ *   sqrt(((dx*dx + dy*dy) + dz*dz) + 1e-6f), no FMA contraction; pairs with a
+ *   masked end are 20001 (= 10000 + rowmax(10000) + 1).  Self is included.
+ */
+int rmp_knn(const float* X, const float* mask, int B, int N, int A, int atom, int K,
+            int64_t* E_idx, float* D_neighbors, void* stream);
+
+/* ------------------------------------------------------------------ edge list (a-2)
+ * Replaces: rdesign/model/feature.py:227-233 (shift + masked_select + cat).
+ *   ctr, nbr [Ne] int32 flat node ids;  E_flat [2,Ne] int64 (row 0 centre, row 1 neighbour;
+ *   may be NULL); ne_cap = capacity of the outputs in edges.
+ */
+int rmp_edge_list(const int64_t* E_idx, const int32_t* node_map, const int32_t* node_src,
+                  const int32_t* sinfo, const int32_t* row_ptr, const int32_t* counts,
+                  int B, int N, int K, int ne_cap,
+                  int32_t* ctr, int32_t* nbr, int64_t* E_flat, void* stream);
+
+/* ------------------------------------------------------------------ raw features (a-3, a-4, a-5)
+ * Replaces: _dihedrals, _rbf/_get_rbf, _orientations_coarse, _quaternions,
+ *   rdesign/model/feature.py:52-154, 179-220.
+ *   frames   [B*N,9]  workspace: per-residue local frame (rows b1, n0, b1 x n0)
+ *   rbf_mu   [16]     fp32 RBF centres (torch.linspace(0,20,16) bits)
+ *   node_raw [Nv,101] angle12 | rbf80 | dir9
+ *   edge_raw [Ne,115] quat4 | rbf96 | dir15
+ */
+int rmp_rdesign_raw_features(const float* X, int B, int N,
+                             const int32_t* node_src, const int32_t* ctr, const int32_t* nbr,
+                             const int32_t* counts, int nv_cap, int ne_cap,
+                             const float* rbf_mu, float* frames,
+                             float* node_raw, float* edge_raw, void* stream);
+
+/* ------------------------------------------------------------------ fused row MLP (a-6, a-8, a-9)
+ * One launch = up to RMP_MAX_STAGES chained Linear(+exact GELU) stages over row
+ * tiles, input optionally gathered/concatenated, with a fused epilogue.
+ * Weights are passed TRANSPOSED and zero padded: Wt[k_pad][n_out], k_pad =
+ * round_up(k_in, 32), n_out % 128 == 0 (see rmp_pack_rows()).
+ */
+#define RMP_MAX_STAGES 4
+#define RMP_MAX_SEGS   3
+
+#define RMP_EPI_STORE      0  /* out[r,:] = y                                                          */
+#define RMP_EPI_NORMALIZE  1  /* reference Normalize: gain*(y-mu)/(sqrt(var_unbiased+1e-6)+1e-6)+bias
+                                 (rdesign/model/functional.py:79-96)                                   */
+#define RMP_EPI_RESID_LN   2  /* out = LayerNorm(resid + y), eps 1e-5 (rdesign/model/mpnn.py:37)        */
+#define RMP_EPI_SEGSUM     3  /* out[seg[r],:] += y * alpha   (scatter_sum / scale, mpnn.py:34)         */
+
+typedef struct rmp_mlp_desc {
+    /* input = concat over segments of src[idx ? idx[r] : r, 0:width] */
+    const float*   seg_src[RMP_MAX_SEGS];
+    const int32_t* seg_idx[RMP_MAX_SEGS];
+    int32_t        seg_width[RMP_MAX_SEGS];
+    int32_t        num_segs;
+    /* stages */
+    const float*   Wt[RMP_MAX_STAGES];      /* [k_pad][n_out] */
+    const float*   bias[RMP_MAX_STAGES];    /* [n_out] */
+    int32_t        k_in[RMP_MAX_STAGES];
+    int32_t        n_out[RMP_MAX_STAGES];
+    int32_t        gelu[RMP_MAX_STAGES];
+    int32_t        num_stages;
+    /* epilogue */
+    int32_t        epilogue;
+    const float*   gain;                    /* NORMALIZE / RESID_LN weight [n] */
+    const float*   beta;                    /* NORMALIZE / RESID_LN bias   [n] */
+    const float*   resid;                   /* RESID_LN: [rows, n]               */
+    const int32_t* seg_id;                  /* SEGSUM: destination row per input row (non-decreasing) */
+    float          alpha;                   /* SEGSUM scale (1/30)               */
+    float*         out;
+    /* rows: device count (rows_dev[rows_slot]) bounded by rows_cap */
+    const int32_t* rows_dev;
+    int32_t        rows_slot;
+    int32_t        rows_cap;
+} rmp_mlp_desc;
+
+int rmp_row_mlp(const rmp_mlp_desc* desc, void* stream);
+
+/* out[r,:] = LayerNorm(a[r,:] + b[r,:]) over 128 channels (norm1, rdesign/model/mpnn.py:35);
+ * b may be NULL.  If zero_b != 0 the rows of b are zeroed after being read (re-arms the
+ * segmented-sum buffer for the next layer). */
+int rmp_add_layernorm(const float* a, float* b, const float* gamma, const float* beta, float eps,
+                      const int32_t* rows_dev, int rows_slot, int rows_cap, int zero_b,
+                      float* out, void* stream);
+
+/* ------------------------------------------------------------------ head (a-9)
+ * Final Linear(128 or hidden -> 4) + softmax + argmax / temperature sampling.
+ * Replaces: Readout's last Linear (rdesign/model/functional.py:121-127) and
+ *   softmax/argmax (rdesign/model/rdesign.py:112-115).
+ *   W [4,k_in] (nn.Linear layout), b [4]
+ *   temperature <= 0 -> samples = argmax(probs); > 0 -> one categorical draw per node from
+ *   softmax(logits / T) with a counter-based generator keyed by (seed, node id).
+ *   logits/probs [rows,4] fp32, samples [rows] int64 (each may be NULL)
+ */
+int rmp_readout_head(const float* h, int k_in, const float* W, const float* b,
+                     float temperature, uint64_t seed,
+                     const int32_t* rows_dev, int rows_slot, int rows_cap,
+                     float* logits, float* probs, int64_t* samples, void* stream);
+
+/* ------------------------------------------------------------------ bf16 tensor-core layer path
+ * (tcgen05 / TMEM / TMA).  Declared here, implemented in layer_tc.cu.
+ */
+
+/* fp32 -> bf16 row conversion (h_E storage for the bf16 path), n elements */
+int rmp_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RMPNN_B200_H */

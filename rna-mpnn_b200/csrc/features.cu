@@ -1,0 +1,246 @@
+// Raw geometric features of the rdesign featurizer (fp32 CUDA-core math).
+//
+// Reference semantics: rdesign/model/feature.py:52-154 (_rbf, _get_rbf,
+// _quaternions, _orientations_coarse, _dihedrals) and :179-220 (feature order).
+// Nothing [B,N,N]-shaped is ever materialised: every node / edge recomputes its
+// few distances from the 6x3 coordinates of its one or two residues.
+#include "common.cuh"
+
+namespace rmp {
+
+struct V3 {
+    float x, y, z;
+};
+__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+__device__ __forceinline__ V3 cross(V3 a, V3 b) {
+    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
+}
+__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+__device__ __forceinline__ V3 ld3(const float* p) { return {p[0], p[1], p[2]}; }
+
+// v / |v| with 0/0 -> 0  (rdesign/utils/data.py:164-171)
+__device__ __forceinline__ V3 unit_nan0(V3 v) {
+    const float n = sqrtf(dot(v, v));
+    V3 r = {v.x / n, v.y / n, v.z / n};
+    if (isnan(r.x)) r.x = 0.f;
+    if (isnan(r.y)) r.y = 0.f;
+    if (isnan(r.z)) r.z = 0.f;
+    return r;
+}
+// F.normalize: v / max(|v|, eps)
+__device__ __forceinline__ V3 unit_eps(V3 v, float eps) {
+    const float n = fmaxf(sqrtf(dot(v, v)), eps);
+    return {v.x / n, v.y / n, v.z / n};
+}
+__device__ __forceinline__ float sign_of(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
+
+// sqrt(|a-b|^2 + 1e-6)   (rdesign/model/feature.py:62,65)
+__device__ __forceinline__ float eps_dist(V3 a, V3 b) {
+    const V3 d = a - b;
+    return sqrtf(dot(d, d) + 1e-6f);
+}
+
+struct RbfMu {
+    float mu[16];
+};
+
+// 16 Gaussian bumps  exp(-((d - mu)/1.25)^2)   (rdesign/model/feature.py:52-58)
+template <typename Store>
+__device__ __forceinline__ void rbf16(float d, const RbfMu& c, Store&& st) {
+#pragma unroll
+    for (int r = 0; r < 16; ++r) {
+        const float z = __fdiv_rn(d - c.mu[r], 1.25f);
+        st(r, expf(-(z * z)));
+    }
+}
+
+// --------------------------------------------------------------------------------
+// local frames: one thread per dense residue  (feature.py:90-107)
+// --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) frames_kernel(const float* __restrict__ X, int B, int N,
+                                                    float* __restrict__ frames) {
+    const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= (size_t)B * N) return;
+    const int i = (int)(idx % N);
+    float* q = frames + idx * 9;
+    if (i == N - 1) {
+#pragma unroll
+        for (int c = 0; c < 9; ++c) q[c] = 0.f;
+        return;
+    }
+    const float* xi = X + idx * 18;
+    const V3 c3 = ld3(xi + 12), o3 = ld3(xi + 15), p1 = ld3(xi + 18);   // C3'_i, O3'_i, P_{i+1}
+    const V3 u0 = unit_nan0(o3 - c3), u1 = unit_nan0(p1 - o3);
+    const V3 n0 = unit_nan0(cross(u0, u1));
+    const V3 b1 = unit_nan0(u0 - u1);
+    const V3 t = cross(b1, n0);
+    q[0] = b1.x; q[1] = b1.y; q[2] = b1.z;
+    q[3] = n0.x; q[4] = n0.y; q[5] = n0.z;
+    q[6] = t.x;  q[7] = t.y;  q[8] = t.z;
+}
+
+__device__ __forceinline__ V3 rotate(const float* q, V3 d) {
+    return {q[0] * d.x + q[1] * d.y + q[2] * d.z, q[3] * d.x + q[4] * d.y + q[5] * d.z,
+            q[6] * d.x + q[7] * d.y + q[8] * d.z};
+}
+
+// --------------------------------------------------------------------------------
+// node features: 64 nodes per block, staged in smem, written coalesced
+// --------------------------------------------------------------------------------
+constexpr int kNodeTile = 64;
+
+// pseudo-dihedral of flat atom slot t (feature.py:134-154): stride-5 differences over
+// the flattened [6N,3] atom list of structure b, zero padded residues included.
+__device__ __forceinline__ float dihedral_angle(const float* __restrict__ Xb, int N, int t) {
+    if (t < 3 || t >= 6 * N - 4) return 0.f;
+    const int s = t - 3;
+    V3 u[3];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) u[q] = unit_eps(ld3(Xb + (size_t)(s + q + 5) * 3) - ld3(Xb + (size_t)(s + q) * 3), 1e-12f);
+    const V3 na = unit_eps(cross(u[0], u[1]), 1e-12f);
+    const V3 nb = unit_eps(cross(u[1], u[2]), 1e-12f);
+    const float lo = (float)(-1.0 + 1e-7), hi = (float)(1.0 - 1e-7);
+    const float c = fminf(fmaxf(dot(na, nb), lo), hi);
+    return sign_of(dot(u[0], nb)) * acosf(c);
+}
+
+__global__ void __launch_bounds__(kNodeTile) node_raw_kernel(const float* __restrict__ X, int N,
+                                                            const int32_t* __restrict__ node_src,
+                                                            const int32_t* __restrict__ counts, int nv_cap,
+                                                            RbfMu mu, const float* __restrict__ frames,
+                                                            float* __restrict__ node_raw) {
+    __shared__ float tile[kNodeTile * RMP_NODE_RAW];
+    const int nv = min(counts[0], nv_cap);
+    const int v0 = blockIdx.x * kNodeTile;
+    if (v0 >= nv) return;
+    const int t = threadIdx.x, v = v0 + t;
+    if (v < nv) {
+        float* f = tile + t * RMP_NODE_RAW;
+        const int src = node_src[v];
+        const int b = src / N, i = src - b * N;
+        const float* Xb = X + (size_t)b * N * 18;
+        const float* xi = Xb + (size_t)i * 18;
+        // angle: cos | sin of the six slots
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            const float ang = dihedral_angle(Xb, N, 6 * i + a);
+            f[a] = cosf(ang);
+            f[6 + a] = sinf(ang);
+        }
+        // distance: atoms O5',C5',C4',C3',O3' to own P
+        const V3 p = ld3(xi);
+#pragma unroll
+        for (int a = 1; a < 6; ++a) {
+            float* dst = f + 12 + (a - 1) * 16;
+            rbf16(eps_dist(ld3(xi + a * 3), p), mu, [&](int r, float val) { dst[r] = val; });
+        }
+        // direction: frame_i * (P, C5', C4' - C3')
+        const float* q = frames + (size_t)src * 9;
+        const V3 c3 = ld3(xi + 12);
+        const int atoms[3] = {0, 2, 3};
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const V3 d = unit_nan0(rotate(q, ld3(xi + atoms[a] * 3) - c3));
+            f[92 + a * 3 + 0] = d.x; f[92 + a * 3 + 1] = d.y; f[92 + a * 3 + 2] = d.z;
+        }
+    }
+    __syncthreads();
+    const int rows = min(kNodeTile, nv - v0);
+    float* out = node_raw + (size_t)v0 * RMP_NODE_RAW;
+    for (int o = t; o < rows * RMP_NODE_RAW; o += kNodeTile) out[o] = tile[o];
+}
+
+// --------------------------------------------------------------------------------
+// edge features: 128 edges per block (one thread each), staged in smem (58.9 KB),
+// written as one contiguous coalesced span.
+// --------------------------------------------------------------------------------
+constexpr int kEdgeTile = 128;
+
+__global__ void __launch_bounds__(kEdgeTile) edge_raw_kernel(const float* __restrict__ X, int N,
+                                                            const int32_t* __restrict__ node_src,
+                                                            const int32_t* __restrict__ ctr,
+                                                            const int32_t* __restrict__ nbr,
+                                                            const int32_t* __restrict__ counts, int ne_cap,
+                                                            RbfMu mu, const float* __restrict__ frames,
+                                                            float* __restrict__ edge_raw) {
+    extern __shared__ float etile[];                       // [kEdgeTile][115]
+    const int ne = min(counts[1], ne_cap);
+    const int e0 = blockIdx.x * kEdgeTile;
+    if (e0 >= ne) return;
+    const int t = threadIdx.x, e = e0 + t;
+    if (e < ne) {
+        float* f = etile + t * RMP_EDGE_RAW;
+        const int si = node_src[ctr[e]], sj = node_src[nbr[e]];
+        const float* xi = X + (size_t)si * 18;
+        const float* xj = X + (size_t)sj * 18;
+        const float* qi = frames + (size_t)si * 9;
+        const float* qj = frames + (size_t)sj * 9;
+        float Qi[9], Qj[9];
+#pragma unroll
+        for (int c = 0; c < 9; ++c) { Qi[c] = qi[c]; Qj[c] = qj[c]; }
+        // orientation quaternion of R = Qi^T Qj   (feature.py:70-88, :124)
+        float R[3][3];
+#pragma unroll
+        for (int r = 0; r < 3; ++r)
+#pragma unroll
+            for (int c = 0; c < 3; ++c) R[r][c] = Qi[0 + r] * Qj[0 + c] + Qi[3 + r] * Qj[3 + c] + Qi[6 + r] * Qj[6 + c];
+        const float Rxx = R[0][0], Ryy = R[1][1], Rzz = R[2][2];
+        float qx = sign_of(R[2][1] - R[1][2]) * (0.5f * sqrtf(fabsf(1.f + (Rxx - Ryy - Rzz))));
+        float qy = sign_of(R[0][2] - R[2][0]) * (0.5f * sqrtf(fabsf(1.f + (-Rxx + Ryy - Rzz))));
+        float qz = sign_of(R[1][0] - R[0][1]) * (0.5f * sqrtf(fabsf(1.f + (-Rxx - Ryy + Rzz))));
+        float qw = sqrtf(fmaxf(1.f + (Rxx + Ryy + Rzz), 0.f)) / 2.f;
+        const float qn = fmaxf(sqrtf(qx * qx + qy * qy + qz * qz + qw * qw), 1e-12f);
+        f[0] = qx / qn; f[1] = qy / qn; f[2] = qz / qn; f[3] = qw / qn;
+        // distance: atom a of the CENTRE to P of the NEIGHBOUR   (feature.py:200-206, :62-63)
+        const V3 pj = ld3(xj);
+#pragma unroll
+        for (int a = 0; a < 6; ++a) {
+            float* dst = f + 4 + a * 16;
+            rbf16(eps_dist(ld3(xi + a * 3), pj), mu, [&](int r, float val) { dst[r] = val; });
+        }
+        // direction: frame_i * (neighbour P,O5',C5',C4',O3' - centre C3')   (feature.py:116-122)
+        const V3 c3 = ld3(xi + 12);
+        const int atoms[5] = {0, 1, 2, 3, 5};
+#pragma unroll
+        for (int a = 0; a < 5; ++a) {
+            const V3 d = unit_nan0(rotate(Qi, ld3(xj + atoms[a] * 3) - c3));
+            f[100 + a * 3 + 0] = d.x; f[100 + a * 3 + 1] = d.y; f[100 + a * 3 + 2] = d.z;
+        }
+    }
+    __syncthreads();
+    const int rows = min(kEdgeTile, ne - e0);
+    float* out = edge_raw + (size_t)e0 * RMP_EDGE_RAW;
+    for (int o = t; o < rows * RMP_EDGE_RAW; o += kEdgeTile) out[o] = etile[o];
+}
+
+}  // namespace rmp
+
+using namespace rmp;
+
+extern "C" int rmp_rdesign_raw_features(const float* X, int B, int N, const int32_t* node_src, const int32_t* ctr,
+                                        const int32_t* nbr, const int32_t* counts, int nv_cap, int ne_cap,
+                                        const float* rbf_mu_host, float* frames, float* node_raw, float* edge_raw,
+                                        void* stream) {
+    RMP_REQUIRE(X && node_src && ctr && nbr && counts && rbf_mu_host && frames, RMP_E_ARG,
+                "rmp_rdesign_raw_features: null pointer");
+    RMP_REQUIRE(B > 0 && N > 0 && nv_cap >= 0 && ne_cap >= 0, RMP_E_ARG, "rmp_rdesign_raw_features: bad sizes");
+    cudaStream_t st = (cudaStream_t)stream;
+    RbfMu mu;
+    memcpy(mu.mu, rbf_mu_host, sizeof(mu.mu));
+    const size_t total = (size_t)B * N;
+    frames_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, B, N, frames);
+    if (node_raw && nv_cap > 0)
+        node_raw_kernel<<<ceil_div(nv_cap, kNodeTile), kNodeTile, 0, st>>>(X, N, node_src, counts, nv_cap, mu, frames,
+                                                                           node_raw);
+    if (edge_raw && ne_cap > 0) {
+        const int smem = kEdgeTile * RMP_EDGE_RAW * (int)sizeof(float);
+        static bool attr_done = false;
+        if (!attr_done) {
+            cudaFuncSetAttribute(edge_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+            attr_done = true;
+        }
+        edge_raw_kernel<<<ceil_div(ne_cap, kEdgeTile), kEdgeTile, smem, st>>>(X, N, node_src, ctr, nbr, counts, ne_cap,
+                                                                              mu, frames, edge_raw);
+    }
+    return check_launch("rmp_rdesign_raw_features", 1 + (node_raw && nv_cap > 0) + (edge_raw && ne_cap > 0));
+}

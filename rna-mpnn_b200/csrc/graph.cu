@@ -1,0 +1,319 @@
+// Graph construction for the rdesign path: valid-only flattening bookkeeping,
+// brute-force kNN with a warp-level top-K, and the flat edge list.
+//
+// Reference semantics: rdesign/model/feature.py:42-50 (_dist), :173-177 and
+// :227-237 (mask_attend, shift, masked_select).  HBM-bound integer/byte work.
+#include "common.cuh"
+
+#include <cstdarg>
+
+namespace rmp {
+
+static thread_local char g_err[512] = "";
+static unsigned long long g_launches = 0;
+
+void note_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+}
+
+// --------------------------------------------------------------------------------
+// graph index
+// --------------------------------------------------------------------------------
+
+// One block per structure: rank of every valid residue inside its structure, L_b, deg_b.
+__global__ void __launch_bounds__(256) struct_rank_kernel(const float* __restrict__ mask, int N, int K,
+                                                         int32_t* __restrict__ node_map,
+                                                         int32_t* __restrict__ sinfo) {
+    __shared__ int warp_tot[8];
+    __shared__ int carry;
+    const int b = blockIdx.x, t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < N; base += 256) {
+        const int i = base + t;
+        const bool ok = (i < N) && (mask[(size_t)b * N + i] == 1.0f);
+        const unsigned bal = __ballot_sync(0xffffffffu, ok);
+        const int in_warp = __popc(bal & ((1u << lane) - 1u));
+        if (lane == 0) warp_tot[w] = __popc(bal);
+        __syncthreads();
+        int before = carry;
+        for (int q = 0; q < w; ++q) before += warp_tot[q];
+        if (i < N) node_map[(size_t)b * N + i] = ok ? before + in_warp : -1;
+        __syncthreads();
+        if (t == 0) {
+            int s = 0;
+            for (int q = 0; q < 8; ++q) s += warp_tot[q];
+            carry += s;
+        }
+        __syncthreads();
+    }
+    if (t == 0) {
+        const int L = carry;
+        sinfo[b * 4 + 0] = L;
+        sinfo[b * 4 + 1] = L < K ? L : K;
+    }
+}
+
+// Single block: exclusive scans over structures -> node_off, edge_off, totals.
+__global__ void __launch_bounds__(1024) struct_scan_kernel(int B, int32_t* __restrict__ sinfo,
+                                                          int32_t* __restrict__ counts) {
+    __shared__ int wn[32], we[32];
+    __shared__ int carry_n, carry_e;
+    const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+    if (t == 0) { carry_n = 0; carry_e = 0; }
+    __syncthreads();
+    for (int base = 0; base < B; base += 1024) {
+        const int b = base + t;
+        int L = 0, E = 0;
+        if (b < B) { L = sinfo[b * 4 + 0]; E = L * sinfo[b * 4 + 1]; }
+        int sn = L, se = E;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int a = __shfl_up_sync(0xffffffffu, sn, o);
+            const int c = __shfl_up_sync(0xffffffffu, se, o);
+            if (lane >= o) { sn += a; se += c; }
+        }
+        if (lane == 31) { wn[w] = sn; we[w] = se; }
+        __syncthreads();
+        int pn = carry_n, pe = carry_e;
+        for (int q = 0; q < w; ++q) { pn += wn[q]; pe += we[q]; }
+        if (b < B) { sinfo[b * 4 + 2] = pn + sn - L; sinfo[b * 4 + 3] = pe + se - E; }
+        __syncthreads();
+        if (t == 1023) { carry_n = pn + sn; carry_e = pe + se; }
+        __syncthreads();
+    }
+    if (t == 0) { counts[0] = carry_n; counts[1] = carry_e; }
+}
+
+__global__ void __launch_bounds__(256) node_finalize_kernel(int B, int N, const int32_t* __restrict__ sinfo,
+                                                           const int32_t* __restrict__ counts,
+                                                           int32_t* __restrict__ node_map,
+                                                           int32_t* __restrict__ node_src,
+                                                           int32_t* __restrict__ row_ptr) {
+    const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (idx == 0) row_ptr[counts[0]] = counts[1];
+    if (idx >= (size_t)B * N) return;
+    const int b = (int)(idx / N);
+    const int rank = node_map[idx];
+    if (rank < 0) return;
+    const int v = sinfo[b * 4 + 2] + rank;
+    node_map[idx] = v;
+    node_src[v] = (int32_t)idx;
+    row_ptr[v] = sinfo[b * 4 + 3] + rank * sinfo[b * 4 + 1];
+}
+
+// --------------------------------------------------------------------------------
+// kNN: one warp per query row, keys = (distance bits << 32 | index), ascending.
+// The K best keys live in a warp-distributed sorted list: slot s is register s/32
+// of lane s%32.  A candidate that beats the current K-th key is inserted by a
+// shuffle-based shift.  Ordering (distance, then index) is total, so the result is
+// deterministic and equals a stable ascending sort truncated to K.
+// --------------------------------------------------------------------------------
+typedef unsigned long long u64;
+constexpr u64 kKeyMax = ~0ull;
+constexpr int kKnnRowsPerWarp = 8;
+constexpr int kKnnWarps = 8;
+constexpr int kKnnSmemPoints = 8192;      // structures up to this length are staged in smem
+
+template <int R>
+__device__ __forceinline__ void warp_sorted_insert(u64 (&slot)[R], u64 x, int lane) {
+    int p = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) p += __popc(__ballot_sync(0xffffffffu, slot[r] < x));
+#pragma unroll
+    for (int r = R - 1; r >= 0; --r) {
+        const u64 up = __shfl_up_sync(0xffffffffu, slot[r], 1);
+        u64 prev = up;
+        if (r > 0) {
+            const u64 carry = __shfl_sync(0xffffffffu, slot[r - 1], 31);
+            if (lane == 0) prev = carry;
+        }
+        const int s = r * 32 + lane;
+        slot[r] = (s < p) ? slot[r] : ((s == p) ? x : prev);
+    }
+}
+
+template <int R>
+__device__ __forceinline__ u64 warp_slot_read(const u64 (&slot)[R], int s) {
+    u64 out = 0;
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        const u64 v = __shfl_sync(0xffffffffu, slot[r], s & 31);
+        if (r == (s >> 5)) out = v;
+    }
+    return out;
+}
+
+// adjusted distance of the reference: exact rounding sequence, no contraction.
+__device__ __forceinline__ float ref_pair_distance(float4 a, float4 b) {
+    if (a.w == 0.0f || b.w == 0.0f) return 20001.0f;       // 10000 + (rowmax 10000 + 1)
+    const float dx = __fsub_rn(b.x, a.x), dy = __fsub_rn(b.y, a.y), dz = __fsub_rn(b.z, a.z);
+    const float s = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    return __fsqrt_rn(__fadd_rn(s, 1e-6f));
+}
+
+template <int R, bool SMEM>
+__global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(const float* __restrict__ X,
+                                                             const float* __restrict__ mask, int N, int A,
+                                                             int atom, int K, int64_t* __restrict__ E_idx,
+                                                             float* __restrict__ D_out) {
+    extern __shared__ float4 s_pts[];
+    const int b = blockIdx.y, t = threadIdx.x, lane = t & 31, w = t >> 5;
+    const float* Xb = X + (size_t)b * N * A * 3 + (size_t)atom * 3;
+    const float* mb = mask + (size_t)b * N;
+    auto load_point = [&](int j) -> float4 {
+        const float* p = Xb + (size_t)j * A * 3;
+        return make_float4(p[0], p[1], p[2], mb[j] == 1.0f ? 1.0f : 0.0f);
+    };
+    if (SMEM) {
+        for (int j = t; j < N; j += kKnnWarps * 32) s_pts[j] = load_point(j);
+        __syncthreads();
+    }
+    const int row0 = (blockIdx.x * kKnnWarps + w) * kKnnRowsPerWarp;
+    for (int rr = 0; rr < kKnnRowsPerWarp; ++rr) {
+        const int i = row0 + rr;
+        if (i >= N) break;                                   // warp-uniform
+        const float4 pi = SMEM ? s_pts[i] : load_point(i);
+        u64 slot[R];
+#pragma unroll
+        for (int r = 0; r < R; ++r) slot[r] = kKeyMax;
+        u64 thresh = kKeyMax;
+        for (int base = 0; base < N; base += 32) {
+            const int j = base + lane;
+            u64 key = kKeyMax;
+            if (j < N) {
+                const float4 pj = SMEM ? s_pts[j] : load_point(j);
+                const float d = ref_pair_distance(pi, pj);
+                key = ((u64)__float_as_uint(d) << 32) | (unsigned)j;
+            }
+            unsigned m = __ballot_sync(0xffffffffu, key < thresh);
+            while (m) {
+                const int src = __ffs(m) - 1;
+                m &= m - 1;
+                const u64 x = __shfl_sync(0xffffffffu, key, src);
+                if (x < thresh) {
+                    warp_sorted_insert<R>(slot, x, lane);
+                    thresh = warp_slot_read<R>(slot, K - 1);
+                }
+            }
+        }
+        const size_t o = ((size_t)b * N + i) * K;
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+            const int s = r * 32 + lane;
+            if (s < K) {
+                E_idx[o + s] = (int64_t)(slot[r] & 0xffffffffull);
+                if (D_out) D_out[o + s] = __uint_as_float((unsigned)(slot[r] >> 32));
+            }
+        }
+    }
+}
+
+template <int R>
+static int launch_knn(const float* X, const float* mask, int B, int N, int A, int atom, int K,
+                      int64_t* E_idx, float* D, cudaStream_t st) {
+    dim3 grid(ceil_div(N, kKnnWarps * kKnnRowsPerWarp), B);
+    if (N <= kKnnSmemPoints) {
+        const size_t smem = (size_t)N * sizeof(float4);
+        auto k = knn_kernel<R, true>;
+        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        k<<<grid, kKnnWarps * 32, smem, st>>>(X, mask, N, A, atom, K, E_idx, D);
+    } else {
+        knn_kernel<R, false><<<grid, kKnnWarps * 32, 0, st>>>(X, mask, N, A, atom, K, E_idx, D);
+    }
+    return check_launch("rmp_knn");
+}
+
+// --------------------------------------------------------------------------------
+// flat edge list
+// --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) edge_list_kernel(const int64_t* __restrict__ E_idx,
+                                                       const int32_t* __restrict__ node_map,
+                                                       const int32_t* __restrict__ sinfo,
+                                                       const int32_t* __restrict__ row_ptr, int B, int N, int K,
+                                                       int ne_cap, int32_t* __restrict__ ctr,
+                                                       int32_t* __restrict__ nbr, int64_t* __restrict__ E_flat) {
+    const size_t idx = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (idx >= (size_t)B * N * K) return;
+    const int k = (int)(idx % K);
+    const size_t bi = idx / K;
+    const int b = (int)(bi / N);
+    const int v = node_map[bi];
+    if (v < 0 || k >= sinfo[b * 4 + 1]) return;
+    const int e = row_ptr[v] + k;
+    if (e >= ne_cap) return;
+    const int j = (int)E_idx[idx];
+    const int u = node_map[(size_t)b * N + j];
+    ctr[e] = v;
+    nbr[e] = u;
+    if (E_flat) {
+        E_flat[e] = v;
+        E_flat[(size_t)ne_cap + e] = u;
+    }
+}
+
+}  // namespace rmp
+
+using namespace rmp;
+
+extern "C" const char* rmp_version(void) { return "rmpnn_b200 0.1 (sm_100a)"; }
+extern "C" const char* rmp_last_error_string(void) { return g_err; }
+extern "C" int rmp_abi_struct_size(void) { return (int)sizeof(rmp_mlp_desc); }
+extern "C" uint64_t rmp_launch_count(void) { return __atomic_load_n(&g_launches, __ATOMIC_RELAXED); }
+
+extern "C" int rmp_device_arch(void) {
+    int dev = 0, major = 0, minor = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev);
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&minor, cudaDevAttrComputeCapabilityMinor, dev);
+    if (e != cudaSuccess) {
+        set_error("rmp_device_arch: %s", cudaGetErrorString(e));
+        return -(int)e;
+    }
+    return major * 10 + minor;
+}
+
+extern "C" int rmp_graph_index(const float* mask, int B, int N, int K, int32_t* node_map, int32_t* node_src,
+                               int32_t* sinfo, int32_t* row_ptr, int32_t* counts, void* stream) {
+    RMP_REQUIRE(mask && node_map && node_src && sinfo && row_ptr && counts, RMP_E_ARG, "rmp_graph_index: null pointer");
+    RMP_REQUIRE(B > 0 && N > 0 && K > 0, RMP_E_ARG, "rmp_graph_index: B, N, K must be positive");
+    cudaStream_t st = (cudaStream_t)stream;
+    struct_rank_kernel<<<B, 256, 0, st>>>(mask, N, K, node_map, sinfo);
+    struct_scan_kernel<<<1, 1024, 0, st>>>(B, sinfo, counts);
+    const size_t total = (size_t)B * N;
+    node_finalize_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(B, N, sinfo, counts, node_map, node_src,
+                                                                           row_ptr);
+    return check_launch("rmp_graph_index", 3);
+}
+
+extern "C" int rmp_knn(const float* X, const float* mask, int B, int N, int A, int atom, int K, int64_t* E_idx,
+                       float* D_neighbors, void* stream) {
+    RMP_REQUIRE(X && mask && E_idx, RMP_E_ARG, "rmp_knn: null pointer");
+    RMP_REQUIRE(B > 0 && N > 0 && A > 0 && atom >= 0 && atom < A, RMP_E_ARG, "rmp_knn: bad sizes");
+    RMP_REQUIRE(K > 0 && K <= N, RMP_E_SHAPE, "rmp_knn: K must be in [1, N] (pass min(top_k, N)), got %d", K);
+    RMP_REQUIRE(K <= RMP_MAX_K, RMP_E_SHAPE, "rmp_knn: K=%d exceeds RMP_MAX_K=%d", K, RMP_MAX_K);
+    RMP_REQUIRE(B <= 65535, RMP_E_SHAPE, "rmp_knn: B=%d exceeds 65535 structures per call", B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (K <= 32) return launch_knn<1>(X, mask, B, N, A, atom, K, E_idx, D_neighbors, st);
+    if (K <= 64) return launch_knn<2>(X, mask, B, N, A, atom, K, E_idx, D_neighbors, st);
+    return launch_knn<4>(X, mask, B, N, A, atom, K, E_idx, D_neighbors, st);
+}
+
+extern "C" int rmp_edge_list(const int64_t* E_idx, const int32_t* node_map, const int32_t* node_src,
+                             const int32_t* sinfo, const int32_t* row_ptr, const int32_t* counts, int B, int N,
+                             int K, int ne_cap, int32_t* ctr, int32_t* nbr, int64_t* E_flat, void* stream) {
+    (void)node_src;
+    (void)counts;
+    RMP_REQUIRE(E_idx && node_map && sinfo && row_ptr && ctr && nbr, RMP_E_ARG, "rmp_edge_list: null pointer");
+    RMP_REQUIRE(B > 0 && N > 0 && K > 0 && ne_cap >= 0, RMP_E_ARG, "rmp_edge_list: bad sizes");
+    if (ne_cap == 0) return RMP_OK;
+    const size_t total = (size_t)B * N * K;
+    edge_list_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        E_idx, node_map, sinfo, row_ptr, B, N, K, ne_cap, ctr, nbr, E_flat);
+    return check_launch("rmp_edge_list");
+}

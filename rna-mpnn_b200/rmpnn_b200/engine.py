@@ -1,0 +1,142 @@
+"""Forward engine of the rdesign path: sequences the C-ABI kernels over a padded batch.
+
+``RDesignEngine`` is what both the drop-in ``rdesign.model.rdesign.RNAModel`` and
+``bench.py`` call.  It owns the packed (kernel-layout) copies of the parameters and
+nothing else; activations are torch-allocated per call.
+
+Reference call sites: ``RNAModel.forward`` rdesign/model/rdesign.py:82-88,
+``RNAFeatures.forward`` rdesign/model/feature.py:156-238, ``MPNNLayer.forward``
+rdesign/model/mpnn.py:31-38, ``Readout`` rdesign/model/functional.py:123-127.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Dict, List, Mapping, Optional
+
+import torch
+
+from . import ops
+from ._lib import PREC_BF16, PREC_FP32
+
+
+@dataclass
+class LayerWeights:
+    message: List[ops.PackedLinear]
+    dense: List[ops.PackedLinear]
+    norm1_w: torch.Tensor
+    norm1_b: torch.Tensor
+    norm2_w: torch.Tensor
+    norm2_b: torch.Tensor
+
+
+def _indexed(params: Mapping[str, torch.Tensor], prefix: str):
+    ids = sorted({int(k[len(prefix):].split(".")[0]) for k in params if k.startswith(prefix)})
+    return [(params[f"{prefix}{i}.weight"], params[f"{prefix}{i}.bias"]) for i in ids]
+
+
+class RDesignWeights:
+    """Kernel-layout copy of an ``RNAModel`` state_dict (same key names as the reference)."""
+
+    def __init__(self, params: Mapping[str, torch.Tensor], device):
+        p = {k: v.detach().to(device=device, dtype=torch.float32).contiguous() for k, v in params.items()
+             if torch.is_tensor(v)}
+        self.device = torch.device(device)
+        if p["features.node_embedding.weight"].shape[0] != ops.HIDDEN:
+            raise ValueError("rmpnn_b200 kernels are specialised for hidden_dim = 128")
+        self.node_emb = ops.pack_linear(p["features.node_embedding.weight"], p["features.node_embedding.bias"])
+        self.edge_emb = ops.pack_linear(p["features.edge_embedding.weight"], p["features.edge_embedding.bias"])
+        self.norm_nodes = (p["features.norm_nodes.gain"], p["features.norm_nodes.bias"])
+        self.norm_edges = (p["features.norm_edges.gain"], p["features.norm_edges.bias"])
+        n_layers = 1 + max(int(k.split(".")[1]) for k in p if k.startswith("mpnn_layers."))
+        self.layers: List[LayerWeights] = []
+        for l in range(n_layers):
+            pre = f"mpnn_layers.{l}."
+            msg = [ops.pack_linear(w, b) for w, b in _indexed(p, pre + "message_layers.")]
+            den = [ops.pack_linear(w, b) for w, b in _indexed(p, pre + "dense.")]
+            if len(msg) > 4 or len(den) > 4:
+                raise ValueError("rmpnn_b200 fuses at most 4 Linear stages per launch")
+            self.layers.append(LayerWeights(msg, den, p[pre + "norm1.weight"], p[pre + "norm1.bias"],
+                                            p[pre + "norm2.weight"], p[pre + "norm2.bias"]))
+        ro = _indexed(p, "readout.readout_layers.")
+        self.readout_hidden = [ops.pack_linear(w, b) for w, b in ro[:-1]]
+        self.readout_w, self.readout_b = ro[-1]
+
+
+class RDesignEngine:
+    """featurizer -> N message-passing layers -> readout head, all on the C-ABI kernels."""
+
+    def __init__(self, params: Mapping[str, torch.Tensor], top_k: int, scale: float = 30.0,
+                 device="cuda", precision: int = PREC_FP32):
+        if not torch.cuda.is_available():
+            raise RuntimeError("rmpnn_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.w = RDesignWeights(params, device)
+        self.top_k = int(top_k)
+        self.scale = float(scale)
+        self.precision = precision
+        self.kernel_timer = None      # bench.py: list collecting (start, end) events of the message kernel
+        if precision not in (PREC_FP32, PREC_BF16):
+            raise ValueError("precision must be RMP_PREC_FP32 or RMP_PREC_BF16")
+
+    def dominant_kernel_name(self) -> str:
+        return "row_mlp_kernel<64> (edge message MLP + segmented sum, fp32 CUDA cores)"
+
+    # ---- stages -----------------------------------------------------------------
+    def graph(self, X, mask, sizes=None) -> ops.Graph:
+        return ops.build_graph(X, mask, self.top_k, sizes)
+
+    def embed(self, X, g: ops.Graph):
+        """h_V [Nv,128], h_E [Ne,128]   (rdesign/model/feature.py:179-224)."""
+        node_raw, edge_raw = ops.raw_features(X, g)
+        dev = node_raw.device
+        h_V = torch.empty(g.Nv, ops.HIDDEN, dtype=torch.float32, device=dev)
+        h_E = torch.empty(g.Ne, ops.HIDDEN, dtype=torch.float32, device=dev)
+        ops.row_mlp([(node_raw, None)], [(self.w.node_emb, False)], ops.EPI_NORMALIZE, h_V, g.Nv,
+                    gain=self.w.norm_nodes[0], beta=self.w.norm_nodes[1])
+        ops.row_mlp([(edge_raw, None)], [(self.w.edge_emb, False)], ops.EPI_NORMALIZE, h_E, g.Ne,
+                    gain=self.w.norm_edges[0], beta=self.w.norm_edges[1])
+        return h_V, h_E
+
+    def layer(self, l: int, h_V, h_E, g: ops.Graph, agg: Optional[torch.Tensor] = None):
+        """One MPNN layer (rdesign/model/rdesign.py:85 + rdesign/model/mpnn.py:31-38)."""
+        lw = self.w.layers[l]
+        if agg is None:
+            agg = torch.zeros_like(h_V)
+        if self.kernel_timer is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record(torch.cuda.current_stream())
+        ops.row_mlp([(h_E, None), (h_V, g.ctr), (h_V, g.nbr)], [(m, True) for m in lw.message],
+                    ops.EPI_SEGSUM, agg, g.Ne, seg_id=g.ctr, alpha=1.0 / self.scale)
+        if self.kernel_timer is not None:
+            ev[1].record(torch.cuda.current_stream())
+            self.kernel_timer.append(ev)
+        x1 = ops.add_layernorm(h_V, agg, lw.norm1_w, lw.norm1_b, 1e-5, zero_b=True)
+        out = torch.empty_like(h_V)
+        stages = [(d, True) for d in lw.dense[:-1]] + [(lw.dense[-1], False)]
+        ops.row_mlp([(x1, None)], stages, ops.EPI_RESID_LN, out, g.Nv, gain=lw.norm2_w, beta=lw.norm2_b, resid=x1)
+        return out
+
+    def encode(self, X, mask, sizes=None, return_layers=False):
+        g = self.graph(X, mask, sizes)
+        h_V, h_E = self.embed(X, g)
+        agg = torch.zeros_like(h_V)
+        layers = []
+        for l in range(len(self.w.layers)):
+            h_V = self.layer(l, h_V, h_E, g, agg)
+            if return_layers:
+                layers.append(h_V)
+        return (h_V, h_E, g, layers) if return_layers else (h_V, h_E, g)
+
+    def readout(self, h_V, temperature: float = 0.0, seed: int = 0):
+        """logits, probs, samples   (rdesign/model/functional.py:123-127, rdesign.py:112-115)."""
+        x = h_V
+        for pl in self.w.readout_hidden:
+            y = torch.empty(x.shape[0], pl.n_out, dtype=torch.float32, device=x.device)
+            ops.row_mlp([(x, None)], [(pl, True)], ops.EPI_STORE, y, x.shape[0])
+            x = y
+        return ops.readout_head(x, self.w.readout_w, self.w.readout_b, temperature, seed)
+
+    @torch.no_grad()
+    def forward(self, X, mask, sizes=None, temperature: float = 0.0, seed: int = 0) -> Dict[str, torch.Tensor]:
+        h_V, h_E, g = self.encode(X, mask, sizes)
+        logits, probs, samples = self.readout(h_V, temperature, seed)
+        return {"h_V": h_V, "logits": logits, "probs": probs, "samples": samples, "graph": g, "h_E": h_E}

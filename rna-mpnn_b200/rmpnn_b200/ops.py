@@ -1,0 +1,215 @@
+"""Tensor-level wrappers over the C ABI (include/rmpnn_b200.h).
+
+Each function checks that its tensors live on a CUDA device, allocates outputs with
+torch (the library never allocates), and enqueues the kernels on torch's current
+stream.  No function here computes anything in PyTorch.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional, Sequence
+
+import torch
+
+from . import _lib
+from ._lib import EPI_NORMALIZE, EPI_RESID_LN, EPI_SEGSUM, EPI_STORE, MlpDesc, check, lib
+
+HIDDEN = 128
+NODE_RAW = 101
+EDGE_RAW = 115
+MAX_K = 128
+
+# torch.linspace(0, 20, 16) bit patterns (rdesign/model/feature.py:54) -- passed to the kernels
+_RBF_MU = (C.c_float * 16)(*torch.linspace(0.0, 20.0, 16).tolist())
+
+
+def _stream() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("rmpnn_b200 runs on CUDA tensors only (no CPU fallback); got a "
+                               f"{t.device} tensor")
+
+
+def _f32c(t: torch.Tensor) -> torch.Tensor:
+    return t.detach().to(torch.float32).contiguous()
+
+
+# --------------------------------------------------------------------------- graph
+@dataclass
+class Graph:
+    """Valid-only flattened kNN graph of a padded batch (device int32 bookkeeping)."""
+    B: int
+    N: int
+    K: int
+    Nv: int
+    Ne: int
+    node_map: torch.Tensor     # [B*N] dense -> flat (-1 masked)
+    node_src: torch.Tensor     # [B*N] flat -> dense (first Nv)
+    sinfo: torch.Tensor        # [B,4] L, deg, node_off, edge_off
+    row_ptr: torch.Tensor      # [B*N+1] CSR offsets (first Nv+1)
+    counts: torch.Tensor       # [2] Nv, Ne
+    E_dense: torch.Tensor      # [B,N,K] int64
+    D_neighbors: torch.Tensor  # [B,N,K] fp32
+    ctr: torch.Tensor          # [Ne] int32 centre flat id
+    nbr: torch.Tensor          # [Ne] int32 neighbour flat id
+    E_flat: torch.Tensor       # [2,Ne] int64
+
+
+def knn(X: torch.Tensor, mask: torch.Tensor, top_k: int, atom: int = 0):
+    """``RNAFeatures._dist`` (rdesign/model/feature.py:42-50) -> (D_neighbors, E_idx)."""
+    _need_cuda(X, mask)
+    X, mask = _f32c(X), _f32c(mask)
+    B, N, A, _ = X.shape
+    K = min(int(top_k), N)
+    E = torch.empty(B, N, K, dtype=torch.int64, device=X.device)
+    D = torch.empty(B, N, K, dtype=torch.float32, device=X.device)
+    check(lib().rmp_knn(_ptr(X), _ptr(mask), B, N, A, atom, K, _ptr(E), _ptr(D), _stream()), "rmp_knn")
+    return D, E
+
+
+def build_graph(X: torch.Tensor, mask: torch.Tensor, top_k: int, sizes=None) -> Graph:
+    """kNN + valid-only flattening (rdesign/model/feature.py:170-177, 227-237).
+
+    ``sizes=(Nv, Ne)`` lets a caller that already knows the lengths on the host skip the
+    one device->host read of the two counters.
+    """
+    _need_cuda(X, mask)
+    X, mask = _f32c(X), _f32c(mask)
+    B, N, A, _ = X.shape
+    K = min(int(top_k), N)
+    dev = X.device
+    i32 = dict(dtype=torch.int32, device=dev)
+    node_map = torch.empty(B * N, **i32)
+    node_src = torch.empty(B * N, **i32)
+    sinfo = torch.empty(B, 4, **i32)
+    row_ptr = torch.empty(B * N + 1, **i32)
+    counts = torch.empty(2, **i32)
+    L = lib()
+    check(L.rmp_graph_index(_ptr(mask), B, N, K, _ptr(node_map), _ptr(node_src), _ptr(sinfo), _ptr(row_ptr),
+                            _ptr(counts), _stream()), "rmp_graph_index")
+    D, E = knn(X, mask, K)
+    if sizes is None:
+        Nv, Ne = (int(v) for v in counts.tolist())        # the one host sync of the featurizer
+    else:
+        Nv, Ne = int(sizes[0]), int(sizes[1])
+    ctr = torch.empty(Ne, **i32)
+    nbr = torch.empty(Ne, **i32)
+    E_flat = torch.empty(2, Ne, dtype=torch.int64, device=dev)
+    check(L.rmp_edge_list(_ptr(E), _ptr(node_map), _ptr(node_src), _ptr(sinfo), _ptr(row_ptr), _ptr(counts),
+                          B, N, K, Ne, _ptr(ctr), _ptr(nbr), _ptr(E_flat), _stream()), "rmp_edge_list")
+    return Graph(B, N, K, Nv, Ne, node_map, node_src, sinfo, row_ptr, counts, E, D, ctr, nbr, E_flat)
+
+
+def raw_features(X: torch.Tensor, g: Graph):
+    """node_raw [Nv,101], edge_raw [Ne,115] (rdesign/model/feature.py:179-220)."""
+    _need_cuda(X)
+    X = _f32c(X[:, :, :6, :])
+    dev = X.device
+    frames = torch.empty(g.B * g.N, 9, dtype=torch.float32, device=dev)
+    node_raw = torch.empty(g.Nv, NODE_RAW, dtype=torch.float32, device=dev)
+    edge_raw = torch.empty(g.Ne, EDGE_RAW, dtype=torch.float32, device=dev)
+    check(lib().rmp_rdesign_raw_features(_ptr(X), g.B, g.N, _ptr(g.node_src), _ptr(g.ctr), _ptr(g.nbr),
+                                         _ptr(g.counts), g.Nv, g.Ne, C.cast(_RBF_MU, C.c_void_p),
+                                         _ptr(frames), _ptr(node_raw), _ptr(edge_raw), _stream()),
+          "rmp_rdesign_raw_features")
+    return node_raw, edge_raw
+
+
+# --------------------------------------------------------------------------- fused row MLP
+@dataclass
+class PackedLinear:
+    """nn.Linear weights in the kernel's layout: Wt[k_pad][n_out] (transposed, zero padded)."""
+    Wt: torch.Tensor
+    bias: Optional[torch.Tensor]
+    k_in: int
+    n_out: int
+
+
+def pack_linear(weight: torch.Tensor, bias: Optional[torch.Tensor]) -> PackedLinear:
+    _need_cuda(weight, bias)
+    n_out, k_in = weight.shape
+    if n_out % 128:
+        raise ValueError(f"rmpnn_b200 row MLP needs output widths that are multiples of 128, got {n_out}")
+    k_pad = (k_in + 31) // 32 * 32
+    Wt = torch.zeros(k_pad, n_out, dtype=torch.float32, device=weight.device)
+    Wt[:k_in] = weight.detach().to(torch.float32).t()
+    return PackedLinear(Wt.contiguous(), None if bias is None else _f32c(bias), k_in, n_out)
+
+
+def row_mlp(segments: Sequence, stages: Sequence, epilogue: int, out: torch.Tensor, rows: int,
+            gain=None, beta=None, resid=None, seg_id=None, alpha: float = 1.0,
+            rows_dev: Optional[torch.Tensor] = None, rows_slot: int = 0):
+    """One fused launch: concat(gathered segments) -> chained Linear(+GELU) -> epilogue.
+
+    segments: [(src [*, width] fp32, idx int32 [rows] or None), ...]
+    stages:   [(PackedLinear, gelu: bool), ...]
+    """
+    d = MlpDesc()
+    if not 1 <= len(segments) <= _lib.MAX_SEGS or not 1 <= len(stages) <= _lib.MAX_STAGES:
+        raise ValueError("row_mlp: 1..3 input segments and 1..4 stages per launch")
+    keep = []
+    for s, (src, idx) in enumerate(segments):
+        _need_cuda(src, idx)
+        assert src.dtype == torch.float32 and src.is_contiguous()
+        assert idx is None or (idx.dtype == torch.int32 and idx.is_contiguous())
+        d.seg_src[s], d.seg_idx[s], d.seg_width[s] = _ptr(src), _ptr(idx), src.shape[-1]
+        keep.append((src, idx))
+    d.num_segs = len(segments)
+    for s, (pl, gelu) in enumerate(stages):
+        d.Wt[s], d.bias[s], d.k_in[s], d.n_out[s], d.gelu[s] = _ptr(pl.Wt), _ptr(pl.bias), pl.k_in, pl.n_out, int(gelu)
+    d.num_stages = len(stages)
+    d.epilogue = epilogue
+    _need_cuda(out, gain, beta, resid, seg_id, rows_dev)
+    d.gain, d.beta, d.resid, d.seg_id = _ptr(gain), _ptr(beta), _ptr(resid), _ptr(seg_id)
+    d.alpha = float(alpha)
+    d.out = _ptr(out)
+    d.rows_dev, d.rows_slot, d.rows_cap = _ptr(rows_dev), rows_slot, int(rows)
+    check(lib().rmp_row_mlp(C.byref(d), _stream()), "rmp_row_mlp")
+    return out
+
+
+def add_layernorm(a, b, gamma, beta, eps=1e-5, zero_b=False, out=None, rows_dev=None, rows_slot=0):
+    """out = LayerNorm(a + b) over 128 channels (norm1, rdesign/model/mpnn.py:35)."""
+    _need_cuda(a, b, gamma, beta)
+    rows = a.shape[0]
+    if out is None:
+        out = torch.empty_like(a)
+    check(lib().rmp_add_layernorm(_ptr(a), _ptr(b), _ptr(gamma), _ptr(beta), float(eps), _ptr(rows_dev),
+                                  rows_slot, rows, int(zero_b), _ptr(out), _stream()), "rmp_add_layernorm")
+    return out
+
+
+def readout_head(h, weight, bias, temperature: float = 0.0, seed: int = 0, want_probs=True, want_samples=True):
+    """Final Linear(->4) + softmax + argmax / temperature sampling
+    (rdesign/model/functional.py:121-127, rdesign/model/rdesign.py:112-115)."""
+    _need_cuda(h, weight, bias)
+    rows, k_in = h.shape
+    dev = h.device
+    logits = torch.empty(rows, 4, dtype=torch.float32, device=dev)
+    probs = torch.empty(rows, 4, dtype=torch.float32, device=dev) if want_probs else None
+    samples = torch.empty(rows, dtype=torch.int64, device=dev) if want_samples else None
+    check(lib().rmp_readout_head(_ptr(h), k_in, _ptr(weight), _ptr(bias), float(temperature), int(seed), None, 0,
+                                 rows, _ptr(logits), _ptr(probs), _ptr(samples), _stream()), "rmp_readout_head")
+    return logits, probs, samples
+
+
+def cast_bf16(src: torch.Tensor) -> torch.Tensor:
+    _need_cuda(src)
+    src = _f32c(src)
+    dst = torch.empty(src.shape, dtype=torch.bfloat16, device=src.device)
+    check(lib().rmp_cast_bf16(_ptr(src), _ptr(dst), src.numel(), _stream()), "rmp_cast_bf16")
+    return dst
+
+
+__all__ = ["Graph", "PackedLinear", "knn", "build_graph", "raw_features", "pack_linear", "row_mlp",
+           "add_layernorm", "readout_head", "cast_bf16", "EPI_STORE", "EPI_NORMALIZE", "EPI_RESID_LN",
+           "EPI_SEGSUM", "HIDDEN", "NODE_RAW", "EDGE_RAW", "MAX_K"]

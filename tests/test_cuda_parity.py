@@ -1,0 +1,220 @@
+"""GPU parity tests: the CUDA path (through the C ABI) against the CPU oracle and the
+golden vectors of the unmodified reference.  Run on the B200 box: pytest -m gpu.
+
+Tolerances (BASELINE.json north_star): neighbour indices bit-exact under the documented
+(distance, index) tie-break; fp32 logits within 1e-4 abs; identical argmax sequences.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rdesign_oracle as O
+from oracle.weights import RDesignConfig, make_state_dict, synthetic_backbones
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL_FP32 = 1e-4
+RAW_TOL = 1e-5
+EMBED_TOL = 5e-5
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from rmpnn_b200 import ops as _ops
+    return _ops
+
+
+def _engine(params, cfg, **kw):
+    from rmpnn_b200.engine import RDesignEngine
+    return RDesignEngine(params, cfg.k_neighbors, cfg.scale, device="cuda", **kw)
+
+
+# --------------------------------------------------------------------------- kNN (a-1)
+def test_knn_bit_exact_on_golden_inputs(golden, ops):
+    X, mask, cfg = golden["X"], golden["mask"], golden["config"]
+    D_o, I_o = O.knn(X[:, :, 0, :], mask, cfg.k_neighbors)
+    D_c, I_c = ops.knn(X.cuda(), mask.cuda(), cfg.k_neighbors)
+    assert torch.equal(I_c.cpu(), I_o)
+    assert torch.equal(D_c.cpu(), D_o)                      # distances bit for bit
+    # and the reference's own topk distances (sorted) are the same numbers
+    assert torch.equal(D_c.cpu(), torch.sort(torch.from_numpy(golden["D_neighbors"]), -1).values)
+
+
+@pytest.mark.parametrize("B,N,K,lengths", [
+    (4, 256, 30, None), (3, 300, 48, [300, 77, 20]), (2, 1000, 25, [1000, 999]), (5, 33, 64, [33, 32, 31, 2, 1]),
+    (1, 1, 5, None), (2, 130, 128, [130, 129]),
+])
+def test_knn_bit_exact_random(ops, B, N, K, lengths):
+    X, S, mask = synthetic_backbones(B, N, 900 + N + K, lengths=lengths)
+    D_o, I_o = O.knn(X[:, :, 0, :], mask, K)
+    D_c, I_c = ops.knn(X.cuda(), mask.cuda(), K)
+    assert torch.equal(I_c.cpu(), I_o)
+    assert torch.equal(D_c.cpu(), D_o)
+
+
+def test_knn_ties_lower_index_first(ops):
+    # all atoms coincide -> every distance ties; canonical order is 0..K-1
+    X = torch.zeros(1, 40, 6, 3)
+    mask = torch.ones(1, 40)
+    D, I = ops.knn(X.cuda(), mask.cuda(), 7)
+    assert torch.equal(I.cpu(), torch.arange(7).expand(1, 40, 7))
+    # integer lattice: many exact ties, oracle (stable sort) must agree
+    g = torch.Generator().manual_seed(3)
+    X = torch.randint(0, 3, (2, 64, 6, 3), generator=g).float()
+    D_o, I_o = O.knn(X[:, :, 0, :], torch.ones(2, 64), 9)
+    D_c, I_c = ops.knn(X.cuda(), torch.ones(2, 64).cuda(), 9)
+    assert torch.equal(I_c.cpu(), I_o) and torch.equal(D_c.cpu(), D_o)
+
+
+def test_knn_non_prefix_mask(ops):
+    X, S, mask = synthetic_backbones(2, 50, 5)
+    mask[0, 3:9] = 0
+    mask[1, ::4] = 0
+    D_o, I_o = O.knn(X[:, :, 0, :], mask, 12)
+    D_c, I_c = ops.knn(X.cuda(), mask.cuda(), 12)
+    assert torch.equal(I_c.cpu(), I_o) and torch.equal(D_c.cpu(), D_o)
+
+
+def test_knn_long_chain_global_memory_path(ops):
+    # N > 8192 takes the non-staged path
+    X, S, mask = synthetic_backbones(1, 8200, 31)
+    K = 16
+    D_c, I_c = ops.knn(X.cuda(), mask.cuda(), K)
+    rows = torch.tensor([0, 1, 4099, 8199])
+    P = X[0, :, 0, :]
+    for r in rows.tolist():
+        d = P - P[r]
+        dist = torch.sqrt((d * d)[:, 0] + (d * d)[:, 1] + (d * d)[:, 2] + 1e-6)
+        ds, idx = torch.sort(dist, stable=True)
+        assert torch.equal(I_c[0, r].cpu(), idx[:K]) and torch.equal(D_c[0, r].cpu(), ds[:K])
+
+
+# --------------------------------------------------------------------------- graph (a-2)
+def test_flat_graph_matches_oracle(golden, ops):
+    X, mask, cfg = golden["X"], golden["mask"], golden["config"]
+    g = ops.build_graph(X.cuda(), mask.cuda(), cfg.k_neighbors)
+    _, I_o = O.knn(X[:, :, 0, :], mask, cfg.k_neighbors)
+    E_o, batch_id = O.flatten_graph(mask, I_o)
+    assert (g.Nv, g.Ne) == (int(mask.sum()), E_o.shape[1])
+    assert torch.equal(g.E_flat.cpu(), E_o)
+    assert torch.equal(g.ctr.cpu().long(), E_o[0]) and torch.equal(g.nbr.cpu().long(), E_o[1])
+    # centres identical to the reference's own flattening; whole list where it is tie free
+    assert np.array_equal(g.E_flat[0].cpu().numpy(), golden["E_idx"][0])
+    src = g.node_src[: g.Nv].cpu().long()
+    assert torch.equal(src // mask.shape[1], batch_id)
+    rp = g.row_ptr[: g.Nv + 1].cpu().long()
+    assert torch.equal(rp[1:] - rp[:-1], torch.bincount(E_o[0], minlength=g.Nv))
+
+
+def test_flat_graph_non_prefix_mask(ops):
+    X, S, mask = synthetic_backbones(3, 37, 8, lengths=[37, 20, 3])
+    mask[0, 5:11] = 0
+    mask[1, 0] = 0
+    g = ops.build_graph(X.cuda(), mask.cuda(), 6)
+    _, I_o = O.knn(X[:, :, 0, :], mask, 6)
+    E_o, _ = O.flatten_graph(mask, I_o)
+    assert torch.equal(g.E_flat.cpu(), E_o)
+
+
+# --------------------------------------------------------------------------- features (a-3..a-6)
+def test_raw_features_match_oracle_and_reference(golden, ops):
+    X, mask, cfg = golden["X"], golden["mask"], golden["config"]
+    g = ops.build_graph(X.cuda(), mask.cuda(), cfg.k_neighbors)
+    node_c, edge_c = ops.raw_features(X.cuda(), g)
+    node_o, edge_o, _ = O.raw_features(X, mask, cfg.k_neighbors, E_idx=g.E_dense.cpu())
+    np.testing.assert_allclose(node_c.cpu().numpy(), node_o.numpy(), atol=RAW_TOL, rtol=0)
+    np.testing.assert_allclose(edge_c.cpu().numpy(), edge_o.numpy(), atol=RAW_TOL, rtol=0)
+    # node features do not depend on neighbour order: compare with the reference directly
+    np.testing.assert_allclose(node_c.cpu().numpy(), golden["node_raw"], atol=RAW_TOL, rtol=0)
+    if np.array_equal(g.E_flat.cpu().numpy(), golden["E_idx"]):
+        st = int(golden["edge_stride"])
+        np.testing.assert_allclose(edge_c.cpu().numpy()[::st], golden["edge_raw"], atol=RAW_TOL, rtol=0)
+
+
+def test_embeddings_match_reference(golden):
+    X, mask, cfg = golden["X"], golden["mask"], golden["config"]
+    eng = _engine(golden["params"], cfg)
+    g = eng.graph(X.cuda(), mask.cuda())
+    h_V, h_E = eng.embed(X.cuda(), g)
+    np.testing.assert_allclose(h_V.cpu().numpy(), golden["h_V0"], atol=EMBED_TOL, rtol=0)
+    if np.array_equal(g.E_flat.cpu().numpy(), golden["E_idx"]):
+        st = int(golden["edge_stride"])
+        np.testing.assert_allclose(h_E.cpu().numpy()[::st], golden["h_E"], atol=EMBED_TOL, rtol=0)
+
+
+# --------------------------------------------------------------------------- layers + head (a-7..a-9)
+def test_forward_fp32_matches_oracle(golden):
+    X, S, mask, cfg = golden["X"], golden["S"], golden["mask"], golden["config"]
+    eng = _engine(golden["params"], cfg)
+    h_V, h_E, g, layers = eng.encode(X.cuda(), mask.cuda(), return_layers=True)
+    logits, probs, samples = eng.readout(h_V)
+    ref = O.forward(golden["params"], X, S, mask, cfg.k_neighbors, cfg.scale, E_idx=g.E_dense.cpu(),
+                    return_layers=True)
+    assert torch.equal(g.E_flat.cpu(), ref["E_idx"])
+    for l, (a, b) in enumerate(zip(layers, ref["layers"])):
+        np.testing.assert_allclose(a.cpu().numpy(), b.numpy(), atol=1e-4, rtol=0, err_msg=f"layer {l}")
+    np.testing.assert_allclose(logits.cpu().numpy(), ref["logits"].numpy(), atol=LOGIT_TOL_FP32, rtol=0)
+    np.testing.assert_allclose(probs.cpu().numpy(), ref["probs"].numpy(), atol=LOGIT_TOL_FP32, rtol=0)
+    assert torch.equal(samples.cpu(), ref["samples"])
+
+
+def test_forward_fp32_matches_reference_golden(golden):
+    """Directly against the unmodified reference's stored outputs (graphs without ties)."""
+    X, mask, cfg = golden["X"], golden["mask"], golden["config"]
+    eng = _engine(golden["params"], cfg)
+    out = eng.forward(X.cuda(), mask.cuda())
+    if not np.array_equal(out["graph"].E_flat.cpu().numpy(), golden["E_idx"]):
+        pytest.skip("reference topk broke ties differently on this case; covered via the oracle")
+    np.testing.assert_allclose(out["logits"].cpu().numpy(), golden["logits"], atol=LOGIT_TOL_FP32, rtol=0)
+    assert np.array_equal(out["samples"].cpu().numpy(), golden["samples"])
+
+
+@pytest.mark.parametrize("B,L,K,lengths", [(4, 256, 30, None), (6, 190, 25, [190, 150, 101, 64, 17, 3])])
+def test_forward_fp32_default_model_medium_batch(B, L, K, lengths):
+    cfg = RDesignConfig(k_neighbors=K)
+    params = make_state_dict(cfg, 42)
+    X, S, mask = synthetic_backbones(B, L, 1002, lengths=lengths)
+    ref = O.forward(params, X, S, mask, K, cfg.scale)
+    out = _engine(params, cfg).forward(X.cuda(), mask.cuda())
+    assert torch.equal(out["graph"].E_flat.cpu(), ref["E_idx"])
+    np.testing.assert_allclose(out["logits"].cpu().numpy(), ref["logits"].numpy(), atol=LOGIT_TOL_FP32, rtol=0)
+    assert torch.equal(out["samples"].cpu(), ref["samples"])
+
+
+def test_sizes_hint_skips_host_sync_and_matches():
+    cfg = RDesignConfig(k_neighbors=10, num_mpnn_layers=1)
+    params = make_state_dict(cfg, 3)
+    X, S, mask = synthetic_backbones(2, 30, 4, lengths=[30, 12])
+    eng = _engine(params, cfg)
+    a = eng.forward(X.cuda(), mask.cuda())
+    b = eng.forward(X.cuda(), mask.cuda(), sizes=(42, 30 * 10 + 12 * 10))
+    assert torch.equal(a["logits"], b["logits"])
+
+
+# --------------------------------------------------------------------------- sampling
+def test_sampling_temperature(ops):
+    g = torch.Generator().manual_seed(0)
+    h = torch.randn(20000, 128, generator=g).cuda()
+    W = (torch.randn(4, 128, generator=g) * 0.05).cuda()
+    b = torch.zeros(4).cuda()
+    logits, probs, greedy = ops.readout_head(h, W, b, 0.0)
+    ref_logits = h.cpu() @ W.cpu().t()
+    np.testing.assert_allclose(logits.cpu().numpy(), ref_logits.numpy(), atol=1e-5, rtol=0)
+    assert torch.equal(greedy.cpu(), torch.softmax(ref_logits, -1).argmax(-1))
+    # T -> 0 reproduces argmax
+    _, _, cold = ops.readout_head(h, W, b, 1e-4, seed=7)
+    assert (cold == greedy).float().mean().item() > 0.999
+    # T = 1: empirical class frequencies follow the mean softmax; draws depend on the seed
+    _, _, s1 = ops.readout_head(h, W, b, 1.0, seed=1)
+    _, _, s2 = ops.readout_head(h, W, b, 1.0, seed=2)
+    _, _, s1b = ops.readout_head(h, W, b, 1.0, seed=1)
+    assert torch.equal(s1, s1b) and not torch.equal(s1, s2)
+    freq = torch.bincount(s1.cpu(), minlength=4).float() / s1.numel()
+    np.testing.assert_allclose(freq.numpy(), probs.cpu().mean(0).numpy(), atol=0.02)
+
+
+# --------------------------------------------------------------------------- errors
+def test_error_paths(ops):
+    X, S, mask = synthetic_backbones(1, 200, 1)
+    with pytest.raises(RuntimeError, match="RMP_MAX_K|exceeds"):
+        ops.knn(X.cuda(), mask.cuda(), 150)
