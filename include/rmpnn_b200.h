@@ -156,11 +156,14 @@ typedef struct rmp_mlp_desc {
 
 int rmp_row_mlp(const rmp_mlp_desc* desc, void* stream);
 
-/* out[r,:] = LayerNorm(a[r,:] + b[r,:]) over 128 channels (norm1, rdesign/model/mpnn.py:35);
- * b may be NULL.  If zero_b != 0 the rows of b are zeroed after being read (re-arms the
- * segmented-sum buffer for the next layer). */
+/* out[r,:] = norm(a[r,:] + b[r,:]) over 128 channels; b may be NULL.
+ *   variant 0: nn.LayerNorm, biased variance (norm1, rdesign/model/mpnn.py:35)
+ *   variant 1: reference Normalize, unbiased variance, gain*(x-mu)/(sqrt(var+eps)+eps)+bias
+ *              (rdesign/model/functional.py:79-96)
+ * If zero_b != 0 the rows of b are zeroed after being read (re-arms the segmented-sum
+ * buffer for the next layer). */
 int rmp_add_layernorm(const float* a, float* b, const float* gamma, const float* beta, float eps,
-                      const int32_t* rows_dev, int rows_slot, int rows_cap, int zero_b,
+                      const int32_t* rows_dev, int rows_slot, int rows_cap, int zero_b, int variant,
                       float* out, void* stream);
 
 /* ------------------------------------------------------------------ head (a-9)

@@ -221,7 +221,8 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
                                                            const float* __restrict__ gamma,
                                                            const float* __restrict__ beta, float eps,
                                                            const int32_t* __restrict__ rows_dev, int rows_slot,
-                                                           int rows_cap, int zero_b, float* __restrict__ out) {
+                                                           int rows_cap, int zero_b, int variant,
+                                                           float* __restrict__ out) {
     const int nrows = rows_dev ? min(rows_dev[rows_slot], rows_cap) : rows_cap;
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
     if (r >= nrows) return;
@@ -235,8 +236,9 @@ __global__ void __launch_bounds__(256) add_layernorm_kernel(const float* __restr
     }
     const float mu = warp_sum(x.x + x.y + x.z + x.w) * (1.f / 128.f);
     x.x -= mu; x.y -= mu; x.z -= mu; x.w -= mu;
-    const float var = warp_sum(x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w) * (1.f / 128.f);
-    const float inv = 1.f / sqrtf(var + eps);
+    const float ss = warp_sum(x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w);
+    // variant 0: nn.LayerNorm (biased variance); 1: reference Normalize (unbiased, eps inside and outside)
+    const float inv = variant ? 1.f / (sqrtf(ss * (1.f / 127.f) + eps) + eps) : 1.f / sqrtf(ss * (1.f / 128.f) + eps);
     const float4 g = reinterpret_cast<const float4*>(gamma)[lane];
     const float4 bt = reinterpret_cast<const float4*>(beta)[lane];
     reinterpret_cast<float4*>(out + (size_t)r * 128)[lane] =
@@ -396,14 +398,14 @@ extern "C" int rmp_row_mlp(const rmp_mlp_desc* dp, void* stream) {
 }
 
 extern "C" int rmp_add_layernorm(const float* a, float* b, const float* gamma, const float* beta, float eps,
-                                 const int32_t* rows_dev, int rows_slot, int rows_cap, int zero_b, float* out,
-                                 void* stream) {
+                                 const int32_t* rows_dev, int rows_slot, int rows_cap, int zero_b, int variant,
+                                 float* out, void* stream) {
     RMP_REQUIRE(a && gamma && beta && out, RMP_E_ARG, "rmp_add_layernorm: null pointer");
     RMP_REQUIRE(aligned16(a) && aligned16(out) && aligned16(gamma) && aligned16(beta) && (!b || aligned16(b)),
                 RMP_E_ALIGN, "rmp_add_layernorm: pointers must be 16-byte aligned");
     if (rows_cap <= 0) return RMP_OK;
     add_layernorm_kernel<<<ceil_div(rows_cap, 8), 256, 0, (cudaStream_t)stream>>>(a, b, gamma, beta, eps, rows_dev,
-                                                                                  rows_slot, rows_cap, zero_b, out);
+                                                                                  rows_slot, rows_cap, zero_b, variant, out);
     return check_launch("rmp_add_layernorm");
 }
 

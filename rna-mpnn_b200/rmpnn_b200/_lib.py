@@ -54,7 +54,7 @@ SIGNATURES = {
     "rmp_edge_list": [P, P, P, P, P, P, I, I, I, I, P, P, P, P],
     "rmp_rdesign_raw_features": [P, I, I, P, P, P, P, I, I, P, P, P, P, P],
     "rmp_row_mlp": [C.POINTER(MlpDesc), P],
-    "rmp_add_layernorm": [P, P, P, P, F, P, I, I, I, P, P],
+    "rmp_add_layernorm": [P, P, P, P, F, P, I, I, I, I, P, P],
     "rmp_readout_head": [P, I, P, P, F, U64, P, I, I, P, P, P, P],
     "rmp_cast_bf16": [P, P, I64, P],
 }

@@ -177,14 +177,17 @@ def row_mlp(segments: Sequence, stages: Sequence, epilogue: int, out: torch.Tens
     return out
 
 
-def add_layernorm(a, b, gamma, beta, eps=1e-5, zero_b=False, out=None, rows_dev=None, rows_slot=0):
-    """out = LayerNorm(a + b) over 128 channels (norm1, rdesign/model/mpnn.py:35)."""
+def add_layernorm(a, b, gamma, beta, eps=1e-5, zero_b=False, out=None, rows_dev=None, rows_slot=0,
+                  reference_normalize=False):
+    """out = LayerNorm(a + b) over 128 channels (norm1, rdesign/model/mpnn.py:35); with
+    ``reference_normalize`` the reference's ``Normalize`` (rdesign/model/functional.py:79-96)."""
     _need_cuda(a, b, gamma, beta)
     rows = a.shape[0]
     if out is None:
         out = torch.empty_like(a)
     check(lib().rmp_add_layernorm(_ptr(a), _ptr(b), _ptr(gamma), _ptr(beta), float(eps), _ptr(rows_dev),
-                                  rows_slot, rows, int(zero_b), _ptr(out), _stream()), "rmp_add_layernorm")
+                                  rows_slot, rows, int(zero_b), int(reference_normalize), _ptr(out), _stream()),
+          "rmp_add_layernorm")
     return out
 
 
