@@ -27,15 +27,25 @@ ATOM_P, ATOM_O5, ATOM_C5, ATOM_C4, ATOM_C3, ATOM_O3 = range(6)
 
 
 # --------------------------------------------------------------------------- a-1
-def pairwise_p_distance(P: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+def sqrt_rn(x: torch.Tensor) -> torch.Tensor:
+    """Correctly rounded fp32 square root (via fp64).  torch's CPU ``sqrt`` on this build
+    (MKL VML, high-accuracy mode) is only faithful to < 1 ulp, so the reference's own
+    distances can sit 1 ulp off the IEEE value; the canonical kNN is defined on the IEEE
+    value, which is what ``sqrt.rn.f32`` gives on the GPU."""
+    return torch.sqrt(x.double()).float()
+
+
+def pairwise_p_distance(P: torch.Tensor, mask: torch.Tensor, exact_sqrt: bool = True) -> torch.Tensor:
     """Adjusted P-P distance matrix [B,N,N]   (rdesign/model/feature.py:42-48).
 
     valid pair   -> sqrt(((dx*dx + dy*dy) + dz*dz) + 1e-6)
     invalid pair -> 10000 + (rowmax + 1)
+    ``exact_sqrt=False`` uses torch's CPU sqrt exactly as the reference does.
     """
     pair_ok = mask[:, None, :] * mask[:, :, None]
     diff = P[:, None, :, :] - P[:, :, None, :]
-    D = (1.0 - pair_ok) * 10000 + pair_ok * torch.sqrt((diff ** 2).sum(3) + 1e-6)
+    root = sqrt_rn if exact_sqrt else torch.sqrt
+    D = (1.0 - pair_ok) * 10000 + pair_ok * root((diff ** 2).sum(3) + 1e-6)
     row_max = D.max(-1, keepdim=True).values
     return D + (1.0 - pair_ok) * (row_max + 1)
 
@@ -43,16 +53,17 @@ def pairwise_p_distance(P: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
 def knn_reference_order(P, mask, top_k):
     """``torch.topk`` selection exactly as the reference calls it
     (rdesign/model/feature.py:49).  Tie order is whatever ATen gives."""
-    D = pairwise_p_distance(P, mask)
+    D = pairwise_p_distance(P, mask, exact_sqrt=False)
     return torch.topk(D, min(top_k, D.shape[-1]), dim=-1, largest=False)
 
 
 def knn(P, mask, top_k):
-    """Canonical kNN: ascending adjusted distance, ties broken by LOWER index.
+    """Canonical kNN: ascending adjusted distance (IEEE-rounded sqrt), ties broken by
+    LOWER index.
 
-    This is the documented tie-break the CUDA kernel implements (the reference's
-    ``topk`` order among exact ties is unspecified); a stable ascending sort
-    realises it.  Returns (D_neighbors [B,N,K'], E_idx [B,N,K'] int64).
+    This is the documented rule the CUDA kernel implements (the reference's ``topk``
+    order among exact ties is unspecified, and its CPU sqrt is 1-ulp faithful only); a
+    stable ascending sort realises it.  Returns (D_neighbors [B,N,K'], E_idx [B,N,K'] int64).
     """
     D = pairwise_p_distance(P, mask)
     Ds, idx = torch.sort(D, dim=-1, stable=True)
