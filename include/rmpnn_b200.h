@@ -184,6 +184,21 @@ int rmp_readout_head(const float* h, int k_in, const float* W, const float* b,
  * (tcgen05 / TMEM / TMA).  Declared here, implemented in layer_tc.cu.
  */
 
+/* Fused edge-message kernel: for every edge e (rows of h_E, centre ctr[e], neighbour nbr[e])
+ *   m = GELU(W_S-1 .. GELU(W_1 GELU(W_0e h_E[e] + Pc[ctr[e]] + Pn[nbr[e]]) + b_1) .. + b_S-1)
+ *   agg[ctr[e], :] += alpha * m
+ * Replaces rdesign/model/rdesign.py:85 (gather + cat) and rdesign/model/mpnn.py:33-34 (message MLP,
+ * scatter_sum / scale) with W_0 = [W_0e | W_0c | W_0n] split by column block and
+ * Pc = h_V W_0c^T + b_0, Pn = h_V W_0n^T computed per node by the caller (rmp_row_mlp).
+ *   h_E_bf16 [n_edges,128] bf16; W_bf16 [num_stages*128,128] bf16 = rows of W_0e, W_1, .. (nn.Linear layout)
+ *   bias[s] fp32 [128] for s >= 1 (bias[0] unused: folded into Pc); Pc, Pn fp32 with row stride ld_p
+ *   agg [Nv,128] fp32 must be zero on entry (edges of a node may span two tiles);
+ *   debug: NULL, or [num_stages][n_edges][128] fp32 receiving every stage's activations (tests).
+ * Edges of one centre must be contiguous (they are in the valid-only flattening). */
+int rmp_edge_mlp_bf16(const void* h_E_bf16, const void* W_bf16, int num_stages, const float* const* bias,
+                      const float* Pc, const float* Pn, int ld_p, const int32_t* ctr, const int32_t* nbr,
+                      int n_edges, float alpha, float* agg, float* debug, void* stream);
+
 /* fp32 -> bf16 row conversion (h_E storage for the bf16 path), n elements */
 int rmp_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
 

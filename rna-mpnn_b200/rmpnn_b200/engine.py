@@ -27,6 +27,10 @@ class LayerWeights:
     norm1_b: torch.Tensor
     norm2_w: torch.Tensor
     norm2_b: torch.Tensor
+    # bf16 tensor-core arm: W_0 split by column block (edge | centre | neighbour)
+    msg_w16: Optional[torch.Tensor] = None        # [S*128,128] bf16: W_0e, W_1, ..
+    msg_bias: Optional[List[Optional[torch.Tensor]]] = None
+    proj: Optional[ops.PackedLinear] = None       # h_V -> [Pc | Pn]  (128 -> 256, bias [b_0 | 0])
 
 
 def _indexed(params: Mapping[str, torch.Tensor], prefix: str):
@@ -55,8 +59,17 @@ class RDesignWeights:
             den = [ops.pack_linear(w, b) for w, b in _indexed(p, pre + "dense.")]
             if len(msg) > 4 or len(den) > 4:
                 raise ValueError("rmpnn_b200 fuses at most 4 Linear stages per launch")
-            self.layers.append(LayerWeights(msg, den, p[pre + "norm1.weight"], p[pre + "norm1.bias"],
-                                            p[pre + "norm2.weight"], p[pre + "norm2.bias"]))
+            lw = LayerWeights(msg, den, p[pre + "norm1.weight"], p[pre + "norm1.bias"],
+                              p[pre + "norm2.weight"], p[pre + "norm2.bias"])
+            mw = _indexed(p, pre + "message_layers.")
+            H = ops.HIDDEN
+            if mw[0][0].shape == (H, 3 * H) and all(w.shape == (H, H) for w, _ in mw[1:]):
+                W0, b0 = mw[0]
+                lw.msg_w16 = torch.cat([W0[:, :H]] + [w for w, _ in mw[1:]], 0).to(torch.bfloat16).contiguous()
+                lw.msg_bias = [None] + [b for _, b in mw[1:]]
+                lw.proj = ops.pack_linear(torch.cat([W0[:, H:2 * H], W0[:, 2 * H:]], 0),
+                                          torch.cat([b0, torch.zeros_like(b0)], 0))
+            self.layers.append(lw)
         ro = _indexed(p, "readout.readout_layers.")
         self.readout_hidden = [ops.pack_linear(w, b) for w, b in ro[:-1]]
         self.readout_w, self.readout_b = ro[-1]
@@ -78,6 +91,8 @@ class RDesignEngine:
             raise ValueError("precision must be RMP_PREC_FP32 or RMP_PREC_BF16")
 
     def dominant_kernel_name(self) -> str:
+        if self.precision == PREC_BF16:
+            return "edge_mlp_tc_kernel (edge message MLP + neighbour sum, bf16 tcgen05/TMEM/TMA)"
         return "row_mlp_kernel<64> (edge message MLP + segmented sum, fp32 CUDA cores)"
 
     # ---- stages -----------------------------------------------------------------
@@ -104,8 +119,18 @@ class RDesignEngine:
         if self.kernel_timer is not None:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record(torch.cuda.current_stream())
-        ops.row_mlp([(h_E, None), (h_V, g.ctr), (h_V, g.nbr)], [(m, True) for m in lw.message],
-                    ops.EPI_SEGSUM, agg, g.Ne, seg_id=g.ctr, alpha=1.0 / self.scale)
+        if self.precision == PREC_BF16:
+            if lw.msg_w16 is None:
+                raise ValueError("bf16 layer kernels need message layers of shape 384->128->128..")
+            # per-node projections of W_0's centre / neighbour column blocks, then the tcgen05 edge kernel
+            P = torch.empty(g.Nv, 2 * ops.HIDDEN, dtype=torch.float32, device=h_V.device)
+            ops.row_mlp([(h_V, None)], [(lw.proj, False)], ops.EPI_STORE, P, g.Nv)
+            if self.kernel_timer is not None:
+                ev[0].record(torch.cuda.current_stream())
+            ops.edge_mlp_bf16(h_E, lw.msg_w16, lw.msg_bias, P, g.ctr, g.nbr, agg, 1.0 / self.scale)
+        else:
+            ops.row_mlp([(h_E, None), (h_V, g.ctr), (h_V, g.nbr)], [(m, True) for m in lw.message],
+                        ops.EPI_SEGSUM, agg, g.Ne, seg_id=g.ctr, alpha=1.0 / self.scale)
         if self.kernel_timer is not None:
             ev[1].record(torch.cuda.current_stream())
             self.kernel_timer.append(ev)
@@ -118,6 +143,8 @@ class RDesignEngine:
     def encode(self, X, mask, sizes=None, return_layers=False):
         g = self.graph(X, mask, sizes)
         h_V, h_E = self.embed(X, g)
+        if self.precision == PREC_BF16:
+            h_E = ops.cast_bf16(h_E)              # h_E is layer-invariant: stored once as bf16
         agg = torch.zeros_like(h_V)
         layers = []
         for l in range(len(self.w.layers)):

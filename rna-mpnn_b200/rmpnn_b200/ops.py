@@ -205,6 +205,24 @@ def readout_head(h, weight, bias, temperature: float = 0.0, seed: int = 0, want_
     return logits, probs, samples
 
 
+def edge_mlp_bf16(h_E16, W16, biases, P, ctr, nbr, agg, alpha: float, debug=None):
+    """tcgen05 edge-message kernel (rmp_edge_mlp_bf16).
+
+    h_E16 [Ne,128] bf16; W16 [S*128,128] bf16 (rows of W_0e, W_1, ..); biases: list of S fp32 [128]
+    tensors (entry 0 ignored); P [Nv,256] fp32 = [Pc | Pn] node projections; agg [Nv,128] fp32 zeroed.
+    """
+    _need_cuda(h_E16, W16, P, ctr, nbr, agg, debug, *[b for b in biases if b is not None])
+    S = W16.shape[0] // 128
+    assert h_E16.dtype == torch.bfloat16 and W16.dtype == torch.bfloat16 and h_E16.is_contiguous() and W16.is_contiguous()
+    assert P.dtype == torch.float32 and P.is_contiguous() and P.shape[1] == 256
+    barr = (C.c_void_p * 4)(*([_ptr(b) if b is not None else None for b in biases] + [None] * (4 - len(biases))))
+    pc = P.data_ptr()
+    check(lib().rmp_edge_mlp_bf16(_ptr(h_E16), _ptr(W16), S, C.cast(barr, C.c_void_p), pc, pc + 128 * 4, 256,
+                                  _ptr(ctr), _ptr(nbr), h_E16.shape[0], float(alpha), _ptr(agg), _ptr(debug),
+                                  _stream()), "rmp_edge_mlp_bf16")
+    return agg
+
+
 def cast_bf16(src: torch.Tensor) -> torch.Tensor:
     _need_cuda(src)
     src = _f32c(src)
@@ -213,6 +231,6 @@ def cast_bf16(src: torch.Tensor) -> torch.Tensor:
     return dst
 
 
-__all__ = ["Graph", "PackedLinear", "knn", "build_graph", "raw_features", "pack_linear", "row_mlp",
+__all__ = ["Graph", "PackedLinear", "edge_mlp_bf16", "knn", "build_graph", "raw_features", "pack_linear", "row_mlp",
            "add_layernorm", "readout_head", "cast_bf16", "EPI_STORE", "EPI_NORMALIZE", "EPI_RESID_LN",
            "EPI_SEGSUM", "HIDDEN", "NODE_RAW", "EDGE_RAW", "MAX_K"]

@@ -1,0 +1,106 @@
+"""bf16 tensor-core arm (tcgen05 / TMEM / TMA) against plain fp32 PyTorch references of
+the same ops, and the whole bf16 forward against the oracle (2e-2 logit budget)."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from oracle import rdesign_oracle as O
+from oracle.weights import RDesignConfig, make_state_dict, synthetic_backbones
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL_BF16 = 2e-2
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+def _edge_reference(hE, W, biases, P, ctr, nbr, alpha, Nv):
+    """fp32 reference of rmp_edge_mlp_bf16 with the kernel's rounding points: bf16 h_E / weights /
+    inter-stage activations, fp32 accumulation and fp32 gathered projections."""
+    S = W.shape[0] // 128
+    acts = []
+    x = _bf(hE)
+    for s in range(S):
+        pre = x @ _bf(W[s * 128:(s + 1) * 128]).t()
+        pre = pre + (P[ctr.long(), :128] + P[nbr.long(), 128:] if s == 0 else biases[s])
+        a = F.gelu(pre)
+        acts.append(a)
+        x = _bf(a)
+    agg = torch.zeros(Nv, 128).index_add_(0, ctr.long(), x) * alpha
+    return acts, agg
+
+
+def _segments(Nv, degs):
+    ctr = torch.repeat_interleave(torch.arange(Nv), torch.as_tensor(degs))
+    return ctr.to(torch.int32)
+
+
+@pytest.mark.parametrize("Nv,deg,S", [(4, 32, 3), (129, 30, 3), (1600, 25, 3), (300, 2, 3), (500, 1, 2), (37, 48, 2),
+                                      (3, 128, 3)])
+def test_edge_mlp_tc_matches_fp32_reference(Nv, deg, S):
+    from rmpnn_b200 import ops
+    g = torch.Generator().manual_seed(Nv * 7 + deg)
+    degs = [deg] * Nv
+    if Nv > 10:
+        degs[3] = max(1, deg // 2)                     # ragged: one short segment
+    ctr = _segments(Nv, degs)
+    Ne = ctr.numel()
+    nbr = torch.randint(0, Nv, (Ne,), generator=g, dtype=torch.int32)
+    hE = torch.randn(Ne, 128, generator=g)
+    W = torch.randn(S * 128, 128, generator=g) / 128 ** 0.5
+    biases = [None] + [0.1 * torch.randn(128, generator=g) for _ in range(S - 1)]
+    P = torch.randn(Nv, 256, generator=g) * 0.5
+    alpha = 1.0 / 30
+    acts_ref, agg_ref = _edge_reference(hE, W, biases, P, ctr, nbr, alpha, Nv)
+
+    dbg = torch.zeros(S, Ne, 128, device="cuda")
+    agg = torch.zeros(Nv, 128, device="cuda")
+    ops.edge_mlp_bf16(hE.cuda().to(torch.bfloat16), W.cuda().to(torch.bfloat16),
+                      [None] + [b.cuda() for b in biases[1:]], P.cuda(), ctr.cuda(), nbr.cuda(), agg, alpha, debug=dbg)
+    torch.cuda.synchronize()
+    for s in range(S):
+        tol = 2e-4 if s == 0 else 6e-3                  # later stages see bf16 re-rounding of the previous one
+        np.testing.assert_allclose(dbg[s].cpu().numpy(), acts_ref[s].numpy(), atol=tol, rtol=0, err_msg=f"stage {s}")
+    np.testing.assert_allclose(agg.cpu().numpy(), agg_ref.numpy(), atol=6e-3 * max(1.0, deg / 30), rtol=0)
+
+
+def test_edge_mlp_tc_accumulates_into_agg_and_is_repeatable():
+    from rmpnn_b200 import ops
+    g = torch.Generator().manual_seed(1)
+    Nv, deg = 700, 30
+    ctr = _segments(Nv, [deg] * Nv).cuda()
+    Ne = ctr.numel()
+    nbr = torch.randint(0, Nv, (Ne,), generator=g, dtype=torch.int32).cuda()
+    hE = torch.randn(Ne, 128, generator=g).cuda().to(torch.bfloat16)
+    W = (torch.randn(384, 128, generator=g) / 11.3).cuda().to(torch.bfloat16)
+    b = [None, torch.zeros(128).cuda(), torch.zeros(128).cuda()]
+    P = torch.randn(Nv, 256, generator=g).cuda()
+    outs = []
+    for _ in range(3):
+        agg = torch.zeros(Nv, 128, device="cuda")
+        ops.edge_mlp_bf16(hE, W, b, P, ctr, nbr, agg, 1.0)
+        outs.append(agg.clone())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])   # <= 2 partial sums per node
+    agg2 = outs[0].clone()
+    ops.edge_mlp_bf16(hE, W, b, P, ctr, nbr, agg2, 1.0)
+    np.testing.assert_allclose(agg2.cpu().numpy(), 2 * outs[0].cpu().numpy(), rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("B,L,K,lengths", [(2, 64, 25, [64, 50]), (4, 256, 30, None), (3, 100, 48, [100, 61, 7])])
+def test_forward_bf16_within_budget(B, L, K, lengths):
+    from rmpnn_b200._lib import PREC_BF16
+    from rmpnn_b200.engine import RDesignEngine
+    cfg = RDesignConfig(k_neighbors=K)
+    params = make_state_dict(cfg, 42)
+    X, S, mask = synthetic_backbones(B, L, 1002, lengths=lengths)
+    ref = O.forward(params, X, S, mask, K, cfg.scale)
+    eng = RDesignEngine(params, K, cfg.scale, device="cuda", precision=PREC_BF16)
+    out = eng.forward(X.cuda(), mask.cuda())
+    assert torch.equal(out["graph"].E_flat.cpu(), ref["E_idx"])
+    err = (out["logits"].cpu() - ref["logits"]).abs().max().item()
+    assert err < LOGIT_TOL_BF16, err
+    agree = (out["samples"].cpu() == ref["samples"]).float().mean().item()
+    assert agree > 0.97, agree          # argmax may flip only where two logits are within the bf16 budget
