@@ -199,6 +199,21 @@ int rmp_edge_mlp_bf16(const void* h_E_bf16, const void* W_bf16, int num_stages, 
                       const float* Pc, const float* Pn, int ld_p, const int32_t* ctr, const int32_t* nbr,
                       int n_edges, float alpha, float* agg, float* debug, void* stream);
 
+/* Fused node-update kernel on 128-node tiles (tcgen05, weights streamed by TMA):
+ *   x1 = prologue_ln ? LayerNorm1(h_in + agg) : h_in      (agg rows are re-zeroed after being read)
+ *   then num_stages chained Linear stages, stage s: K[s] -> N[s] (N in {128,256}), W_bf16[s] = nn.Linear
+ *   weight [N][K] as bf16, bias[s] fp32, kind[s]:
+ *     0  bias + GELU (tanh form)                          -> operand of the next stage
+ *     1  bias + residual x1 + LayerNorm2 (eps 1e-5)       -> h_out [n_rows,128] (and next operand)
+ *     2  bias                                             -> p_out [n_rows,N] fp32 (last stage only)
+ * Replaces rdesign/model/mpnn.py:35-37 (norm1, dense FFN, norm2); a trailing kind-2 stage emits the
+ * next layer's per-node projections [Pc | Pn] consumed by rmp_edge_mlp_bf16.
+ * x1_scratch [n_rows,128] fp32 is a caller-provided workspace for the residual. */
+int rmp_node_mlp_bf16(const float* h_in, float* agg, int prologue_ln, const float* ln1_g, const float* ln1_b,
+                      int num_stages, const void* const* W_bf16, const int32_t* K, const int32_t* N,
+                      const int32_t* kind, const float* const* bias, const float* ln2_g, const float* ln2_b,
+                      float* x1_scratch, float* h_out, float* p_out, int n_rows, void* stream);
+
 /* fp32 -> bf16 row conversion (h_E storage for the bf16 path), n elements */
 int rmp_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
 

@@ -132,6 +132,23 @@ __device__ __forceinline__ uint32_t sw128_chunk(int r, int j) {
     return (uint32_t)((r >> 3) * 1024 + (r & 7) * 128 + ((j ^ (r & 7)) << 4));
 }
 
+// GELU for the bf16 arm: tanh form on the hardware tanh unit (MUFU.TANH), 5 FP32 ops + 1 MUFU.
+// |tanh-form - erf-form| <= 5e-4 abs, below the bf16 rounding (2^-9 relative) applied to the result;
+// the fp32 arm (rowmlp.cu) keeps the exact erf form.
+__device__ __forceinline__ float gelu_tanh_fast(float x) {
+    const float x2 = x * x;
+    const float inner = x * fmaf(x2, 0.0356774081f, 0.7978845608f);     // sqrt(2/pi) * (x + 0.044715 x^3)
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(inner));
+    const float hx = 0.5f * x;
+    return fmaf(hx, t, hx);
+}
+
+// fire-and-forget fp32 vector reduction into global memory (REDG.E.ADD.F32x4)
+__device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
+    asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<const uint32_t*>(&h);
@@ -160,7 +177,7 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
                    const EdgeParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by the 128B swizzle atoms
-    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sW = smem;                                         // [S][2][128][64] bf16
     uint8_t* sA = sW + (size_t)p.num_stages * kTileBytes;       // [2 buffers][2][128][64] bf16
     uint8_t* sSel = sA + 2 * kTileBytes;                        // [2][128][64] bf16 selector
@@ -304,26 +321,33 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
 
             // ---- chained stage epilogues: TMEM -> (+gather / +bias) -> GELU -> bf16 -> smem A operand ----
             for (int s = 0; s < S; ++s) {
+                float4 g0[8], g1[8];                       // gathered projections of one 32-column chunk
+                auto gather = [&](int col0) {
+                    const float4* pc = reinterpret_cast<const float4*>(p.Pc + (size_t)c * p.ld_p + col0);
+                    const float4* pn = reinterpret_cast<const float4*>(p.Pn + (size_t)nb * p.ld_p + col0);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) { g0[q] = __ldg(pc + q); g1[q] = __ldg(pn + q); }
+                };
+                if (s == 0 && valid) gather(half * 64);    // in flight while the MMA runs
                 mbar_wait(&bars->acc_full, ph_acc); ph_acc ^= 1;
                 tc_fence_after();
 #pragma unroll
                 for (int ch = 0; ch < 2; ++ch) {
                     const int col0 = half * 64 + ch * 32;
                     float v[32];
+                    if (s == 0 && valid && ch == 1) gather(col0);
                     tmem_ld32(t_row + (uint32_t)col0, v);
                     if (s == 0) {
                         if (valid) {
-                            const float4* pc = reinterpret_cast<const float4*>(p.Pc + (size_t)c * p.ld_p + col0);
-                            const float4* pn = reinterpret_cast<const float4*>(p.Pn + (size_t)nb * p.ld_p + col0);
 #pragma unroll
                             for (int q = 0; q < 8; ++q) {
-                                const float4 x = __ldg(pc + q), y = __ldg(pn + q);
-                                v[4 * q + 0] += x.x + y.x; v[4 * q + 1] += x.y + y.y;
-                                v[4 * q + 2] += x.z + y.z; v[4 * q + 3] += x.w + y.w;
+                                v[4 * q + 0] += g0[q].x + g1[q].x; v[4 * q + 1] += g0[q].y + g1[q].y;
+                                v[4 * q + 2] += g0[q].z + g1[q].z; v[4 * q + 3] += g0[q].w + g1[q].w;
                             }
                         }
                     } else {
-                        const float4* bs = reinterpret_cast<const float4*>(p.bias[s] + col0);
+                        const float* bsp = s == 1 ? p.bias[1] : (s == 2 ? p.bias[2] : p.bias[3]);
+                        const float4* bs = reinterpret_cast<const float4*>(bsp + col0);
 #pragma unroll
                         for (int q = 0; q < 8; ++q) {
                             const float4 x = __ldg(bs + q);
@@ -331,7 +355,7 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
                         }
                     }
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) v[q] = gelu_erf(v[q]);
+                    for (int q = 0; q < 32; ++q) v[q] = gelu_tanh_fast(v[q]);
                     if (p.debug && valid) {
                         float* dbg = p.debug + ((size_t)s * p.n_edges + e) * 128 + col0;
 #pragma unroll
@@ -361,7 +385,9 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
                     if (row < nslots) {
                         float* dst = p.agg + (size_t)(first_node + row) * 128 + col0;
 #pragma unroll
-                        for (int q = 0; q < 32; ++q) atomicAdd(dst + q, v[q] * p.alpha);
+                        for (int q = 0; q < 8; ++q)
+                            red_add_v4(dst + 4 * q, v[4 * q] * p.alpha, v[4 * q + 1] * p.alpha, v[4 * q + 2] * p.alpha,
+                                       v[4 * q + 3] * p.alpha);
                     }
                 }
             }
@@ -370,6 +396,269 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
         }
     }
 
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// =================================================================================================
+// Node kernel: per tile of 128 nodes
+//     x1 = LayerNorm1(h_V + agg)                       (prologue, also re-zeroes agg for the next layer)
+//     d  = W_last(GELU(.. GELU(W_a x1 + b_a) ..)) + b  (tcgen05 chain, weights streamed by TMA)
+//     h' = LayerNorm2(x1 + d)                          -> h_out (fp32)
+//     P  = [W0c | W0n] h' + [b0 | 0]                   -> next layer's per-node projections
+// (rdesign/model/mpnn.py:35-37 and the h_V[E_idx] operand of rdesign/model/rdesign.py:85 for the
+// next layer).  Stage kinds: 0 = bias+GELU -> bf16 A operand, 1 = bias+residual+LN -> h_out (+A),
+// 2 = bias -> fp32 store (projection).  Hidden width <= 256 columns of TMEM.
+// =================================================================================================
+constexpr int kNodeMaxStages = 5;
+constexpr int kRing = 4;                          // weight ring slots of 32 KB ([256 rows][64 k])
+constexpr int kSlotBytes = 256 * 128;
+
+struct NodeStage {
+    int K, N, kind;
+    const float* bias;
+};
+struct NodeParams {
+    const float* h_in;          // [n_rows,128]
+    float* agg;                 // [n_rows,128] neighbour sums (already scaled); zeroed after reading; may be NULL
+    int prologue_ln;            // 1: x1 = LN1(h_in + agg), 0: x1 = h_in
+    const float* ln1_g; const float* ln1_b;
+    const float* ln2_g; const float* ln2_b;
+    float* x1;                  // [n_rows,128] fp32 scratch (residual), needed when a kind-1 stage exists
+    float* h_out;               // [n_rows,128]
+    float* p_out;               // [n_rows,256]
+    NodeStage st[kNodeMaxStages];
+    int S;
+    int n_rows;
+};
+struct alignas(8) NodeBarriers {
+    uint64_t w_full[kRing], w_empty[kRing], acc_full, act_ready;
+};
+
+__device__ __forceinline__ void store_act_chunk(uint8_t* a_buf, int row, int col0, const float (&v)[32]) {
+    // 32 consecutive columns starting at col0 -> K-block col0/64, 16-byte chunks (col0%64)/8 ..
+    uint8_t* kb = a_buf + (col0 >> 6) * kKBlockBytes;
+    const int j0 = (col0 & 63) >> 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint4 pk = make_uint4(pack_bf16(v[8 * j + 0], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                    pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+        *reinterpret_cast<uint4*>(kb + sw128_chunk(row, j0 + j)) = pk;
+    }
+}
+
+__global__ void __launch_bounds__(kThreads, 1)
+node_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
+                   const __grid_constant__ CUtensorMap tm2, const __grid_constant__ CUtensorMap tm3,
+                   const __grid_constant__ CUtensorMap tm4, const NodeParams p) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sA = smem;                                  // [4 K-blocks][128][64] bf16 activation (in place)
+    uint8_t* sW = sA + 4 * kKBlockBytes;                 // weight ring
+    NodeBarriers* bars = reinterpret_cast<NodeBarriers*>(sW + kRing * kSlotBytes);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 1);
+    float* s_red = reinterpret_cast<float*>(s_tmem + 4);  // [2 stats][2 halves][128 rows]
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = (p.n_rows + kTileM - 1) / kTileM;
+    const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    const int S = p.S;
+
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kRing; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
+        mbar_init(&bars->acc_full, 1);
+        mbar_init(&bars->act_ready, kEpiThreads);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(s_tmem, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+    const CUtensorMap* maps[kNodeMaxStages] = {&tm0, &tm1, &tm2, &tm3, &tm4};
+
+    if (warp == 0) {
+        // ===================== TMA producer: weight slabs [N rows][64 k] through the ring =====================
+        if (lane == 0) {
+            for (int s = 0; s < S; ++s) tma_prefetch_desc(maps[s]);
+            uint32_t n = 0;
+            for (int i = 0; i < my_tiles; ++i)
+                for (int s = 0; s < S; ++s)
+                    for (int kb = 0; kb < p.st[s].K / 64; ++kb, ++n) {
+                        const uint32_t slot = n % kRing;
+                        mbar_wait(&bars->w_empty[slot], ((n / kRing) & 1) ^ 1);
+                        mbar_expect_tx(&bars->w_full[slot], (uint32_t)(p.st[s].N * 128));
+                        tma_load_2d(sW + slot * kSlotBytes, maps[s], &bars->w_full[slot], kb * 64, 0);
+                    }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        // ===================== MMA issuer =====================
+        if (lane == 0) {
+            uint32_t n = 0, ph_act = 0;
+            const uint32_t a_addr = smem_u32(sA);
+            for (int i = 0; i < my_tiles; ++i)
+                for (int s = 0; s < S; ++s) {
+                    const uint32_t idesc = instr_desc_bf16(128, p.st[s].N, 0);
+                    mbar_wait(&bars->act_ready, ph_act); ph_act ^= 1;
+                    tc_fence_after();
+                    for (int kb = 0; kb < p.st[s].K / 64; ++kb, ++n) {
+                        const uint32_t slot = n % kRing;
+                        mbar_wait(&bars->w_full[slot], (n / kRing) & 1);
+                        tc_fence_after();
+                        const uint32_t w_addr = smem_u32(sW + slot * kSlotBytes);
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            umma_bf16(tmem_base, smem_desc_sw128(a_addr + kb * kKBlockBytes + k * 32, 16, 1024),
+                                      smem_desc_sw128(w_addr + k * 32, 16, 1024), idesc, (kb | k) > 0);
+                        umma_commit(&bars->w_empty[slot]);
+                    }
+                    umma_commit(&bars->acc_full);
+                }
+        }
+        __syncwarp();
+    } else {
+        // ===================== prologue / epilogue warps =====================
+        const int half = (warp - 2) >> 2;
+        const int lane_grp = warp & 3;
+        const int row = lane_grp * 32 + lane;
+        const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+        float* red_sum = s_red;                    // [2][128]
+        float* red_sq = s_red + 2 * kTileM;        // [2][128]
+        uint32_t ph_acc = 0;
+
+        // LayerNorm over the 128 channels of a row held as 64 + 64 by the two column halves
+        auto layer_norm64 = [&](float (&x)[64], const float* gamma, const float* beta, int c0) {
+            float sm = 0.f;
+#pragma unroll
+            for (int q = 0; q < 64; ++q) sm += x[q];
+            red_sum[half * kTileM + row] = sm;
+            epi_bar_sync();
+            const float mu = (sm + red_sum[(half ^ 1) * kTileM + row]) * (1.f / 128.f);
+            float sq = 0.f;
+#pragma unroll
+            for (int q = 0; q < 64; ++q) { x[q] -= mu; sq = fmaf(x[q], x[q], sq); }
+            red_sq[half * kTileM + row] = sq;
+            epi_bar_sync();
+            const float inv = 1.f / sqrtf((sq + red_sq[(half ^ 1) * kTileM + row]) * (1.f / 128.f) + 1e-5f);
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c0) + q);
+                const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c0) + q);
+                x[4 * q + 0] = fmaf(x[4 * q + 0] * inv, g.x, b.x); x[4 * q + 1] = fmaf(x[4 * q + 1] * inv, g.y, b.y);
+                x[4 * q + 2] = fmaf(x[4 * q + 2] * inv, g.z, b.z); x[4 * q + 3] = fmaf(x[4 * q + 3] * inv, g.w, b.w);
+            }
+        };
+        auto store_row64 = [&](float* dst, const float (&x)[64]) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+                reinterpret_cast<float4*>(dst)[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+        };
+        auto to_operand64 = [&](const float (&x)[64], int c0) {
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                float v[32];
+#pragma unroll
+                for (int q = 0; q < 32; ++q) v[q] = x[ch * 32 + q];
+                store_act_chunk(sA, row, c0 + ch * 32, v);
+            }
+        };
+
+        for (int i = 0; i < my_tiles; ++i) {
+            const int tile = blockIdx.x + i * gridDim.x;
+            const int r = tile * kTileM + row;
+            const bool valid = r < p.n_rows;
+            const int c0 = half * 64;
+            // ---- prologue: x1 = LN1(h + agg) (or h), kept in global for the residual, bf16 copy -> A ----
+            {
+                float x[64];
+#pragma unroll
+                for (int q = 0; q < 64; ++q) x[q] = 0.f;
+                if (valid) {
+                    const float4* hp = reinterpret_cast<const float4*>(p.h_in + (size_t)r * 128 + c0);
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const float4 a = __ldg(hp + q);
+                        x[4 * q] = a.x; x[4 * q + 1] = a.y; x[4 * q + 2] = a.z; x[4 * q + 3] = a.w;
+                    }
+                    if (p.prologue_ln && p.agg) {
+                        float4* ap = reinterpret_cast<float4*>(p.agg + (size_t)r * 128 + c0);
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) {
+                            const float4 a = ap[q];
+                            x[4 * q] += a.x; x[4 * q + 1] += a.y; x[4 * q + 2] += a.z; x[4 * q + 3] += a.w;
+                            ap[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        }
+                    }
+                }
+                if (p.prologue_ln) {
+                    layer_norm64(x, p.ln1_g, p.ln1_b, c0);
+                    if (valid && p.x1) store_row64(p.x1 + (size_t)r * 128 + c0, x);
+                }
+                to_operand64(x, c0);
+                tc_fence_before();
+                fence_proxy_async();
+                mbar_arrive(&bars->act_ready);
+            }
+            // ---- stage epilogues ----
+            for (int s = 0; s < S; ++s) {
+                const NodeStage stg = p.st[s];
+                mbar_wait(&bars->acc_full, ph_acc); ph_acc ^= 1;
+                tc_fence_after();
+                const int ncols = stg.N >> 1;                 // columns of this half
+                const int cb = half * ncols;
+                if (stg.kind == 1) {                          // N == 128: bias + residual + LN2 -> h_out (+ operand)
+                    float x[64];
+#pragma unroll
+                    for (int ch = 0; ch < 2; ++ch) {
+                        float v[32];
+                        tmem_ld32(t_row + (uint32_t)(cb + ch * 32), v);
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) x[ch * 32 + q] = v[q];
+                    }
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(stg.bias + cb) + q);
+                        float4 rsd = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (valid) rsd = reinterpret_cast<const float4*>(p.x1 + (size_t)r * 128 + cb)[q];
+                        x[4 * q] += b.x + rsd.x; x[4 * q + 1] += b.y + rsd.y;
+                        x[4 * q + 2] += b.z + rsd.z; x[4 * q + 3] += b.w + rsd.w;
+                    }
+                    layer_norm64(x, p.ln2_g, p.ln2_b, cb);
+                    if (valid) store_row64(p.h_out + (size_t)r * 128 + cb, x);
+                    if (s + 1 < S) to_operand64(x, cb);
+                } else {
+                    for (int ch = 0; ch < ncols / 32; ++ch) {
+                        const int col0 = cb + ch * 32;
+                        float v[32];
+                        tmem_ld32(t_row + (uint32_t)col0, v);
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 b = __ldg(reinterpret_cast<const float4*>(stg.bias + col0) + q);
+                            v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+                        }
+                        if (stg.kind == 0) {
+#pragma unroll
+                            for (int q = 0; q < 32; ++q) v[q] = gelu_tanh_fast(v[q]);
+                            store_act_chunk(sA, row, col0, v);
+                        } else if (valid) {                   // kind 2: fp32 projection store
+                            float4* dst = reinterpret_cast<float4*>(p.p_out + (size_t)r * stg.N + col0);
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                        }
+                    }
+                }
+                tc_fence_before();
+                if (s + 1 < S) {
+                    fence_proxy_async();
+                    mbar_arrive(&bars->act_ready);
+                } else {
+                    epi_bar_sync();          // every TMEM read of this tile is done before the next prologue arrives
+                }
+            }
+        }
+    }
     tc_fence_before();
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
@@ -392,19 +681,22 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// bf16 row-major [rows][128] tensor, box = 64 columns x 128 rows, 128-byte swizzle
-static int make_map_bf16_rows128(CUtensorMap* map, const void* base, uint64_t rows) {
+// bf16 row-major [rows][cols] tensor, box = 64 columns x box_rows rows, 128-byte swizzle
+static int make_map_bf16(CUtensorMap* map, const void* base, uint64_t rows, uint64_t cols, uint32_t box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) { set_error("cuTensorMapEncodeTiled entry point not found"); return RMP_E_ARCH; }
-    const cuuint64_t dims[2] = {128, rows};
-    const cuuint64_t strides[1] = {256};
-    const cuuint32_t box[2] = {64, 128};
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {cols * 2};
+    const cuuint32_t box[2] = {64, box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed (%d)", (int)r); return RMP_E_ARG; }
     return RMP_OK;
+}
+static int make_map_bf16_rows128(CUtensorMap* map, const void* base, uint64_t rows) {
+    return make_map_bf16(map, base, rows, 128, 128);
 }
 
 }  // namespace tc
@@ -441,4 +733,44 @@ extern "C" int rmp_edge_mlp_bf16(const void* h_E_bf16, const void* W_bf16, int n
     const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
     tc::edge_mlp_tc_kernel<<<grid, tc::kThreads, smem, (cudaStream_t)stream>>>(tm_e, tm_w, p);
     return check_launch("rmp_edge_mlp_bf16");
+}
+
+extern "C" int rmp_node_mlp_bf16(const float* h_in, float* agg, int prologue_ln, const float* ln1_g, const float* ln1_b,
+                                 int num_stages, const void* const* W_bf16, const int32_t* K, const int32_t* N,
+                                 const int32_t* kind, const float* const* bias, const float* ln2_g, const float* ln2_b,
+                                 float* x1_scratch, float* h_out, float* p_out, int n_rows, void* stream) {
+    RMP_REQUIRE(h_in && W_bf16 && K && N && kind && bias, RMP_E_ARG, "rmp_node_mlp_bf16: null pointer");
+    RMP_REQUIRE(num_stages >= 1 && num_stages <= tc::kNodeMaxStages, RMP_E_SHAPE, "rmp_node_mlp_bf16: 1..5 stages");
+    RMP_REQUIRE(!prologue_ln || (ln1_g && ln1_b), RMP_E_ARG, "rmp_node_mlp_bf16: LayerNorm-1 parameters missing");
+    if (n_rows <= 0) return RMP_OK;
+    tc::NodeParams p{};
+    CUtensorMap maps[tc::kNodeMaxStages];
+    memset(maps, 0, sizeof(maps));
+    int width = 128;
+    for (int s = 0; s < num_stages; ++s) {
+        RMP_REQUIRE(W_bf16[s] && bias[s] && aligned16(W_bf16[s]) && aligned16(bias[s]), RMP_E_ALIGN,
+                    "rmp_node_mlp_bf16: stage %d weights/bias null or unaligned", s);
+        RMP_REQUIRE(K[s] == width && (N[s] == 128 || N[s] == 256), RMP_E_SHAPE,
+                    "rmp_node_mlp_bf16: stage %d is %d->%d, expected %d->{128,256}", s, K[s], N[s], width);
+        RMP_REQUIRE(kind[s] >= 0 && kind[s] <= 2, RMP_E_ARG, "rmp_node_mlp_bf16: stage kind");
+        if (kind[s] == 1) RMP_REQUIRE(N[s] == 128 && ln2_g && ln2_b && x1_scratch && h_out && prologue_ln, RMP_E_ARG,
+                                      "rmp_node_mlp_bf16: residual+LayerNorm stage needs 128 outputs, LN params, scratch");
+        if (kind[s] == 2) RMP_REQUIRE(p_out && s == num_stages - 1, RMP_E_ARG,
+                                      "rmp_node_mlp_bf16: projection stage must be last and needs p_out");
+        int rc = tc::make_map_bf16(&maps[s], W_bf16[s], (uint64_t)N[s], (uint64_t)K[s], (uint32_t)N[s]);
+        if (rc) return rc;
+        p.st[s].K = K[s]; p.st[s].N = N[s]; p.st[s].kind = kind[s]; p.st[s].bias = bias[s];
+        width = N[s];
+    }
+    p.h_in = h_in; p.agg = agg; p.prologue_ln = prologue_ln; p.ln1_g = ln1_g; p.ln1_b = ln1_b;
+    p.ln2_g = ln2_g; p.ln2_b = ln2_b; p.x1 = x1_scratch; p.h_out = h_out; p.p_out = p_out;
+    p.S = num_stages; p.n_rows = n_rows;
+    const size_t smem = 1024 + 4 * tc::kKBlockBytes + tc::kRing * tc::kSlotBytes + sizeof(tc::NodeBarriers) + 16 +
+                        4 * tc::kTileM * sizeof(float);
+    cudaFuncSetAttribute(tc::node_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int n_tiles = ceil_div(n_rows, tc::kTileM);
+    const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
+    tc::node_mlp_tc_kernel<<<grid, tc::kThreads, smem, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3],
+                                                                              maps[4], p);
+    return check_launch("rmp_node_mlp_bf16");
 }

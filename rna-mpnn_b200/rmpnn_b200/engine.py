@@ -31,6 +31,8 @@ class LayerWeights:
     msg_w16: Optional[torch.Tensor] = None        # [S*128,128] bf16: W_0e, W_1, ..
     msg_bias: Optional[List[Optional[torch.Tensor]]] = None
     proj: Optional[ops.PackedLinear] = None       # h_V -> [Pc | Pn]  (128 -> 256, bias [b_0 | 0])
+    proj16: Optional[tuple] = None                # (W bf16 [256,128], bias fp32 [256]) for the tcgen05 node kernel
+    dense16: Optional[list] = None                # [(W bf16 [N,K], bias fp32 [N])] dense stages, or None if unsupported
 
 
 def _indexed(params: Mapping[str, torch.Tensor], prefix: str):
@@ -67,8 +69,14 @@ class RDesignWeights:
                 W0, b0 = mw[0]
                 lw.msg_w16 = torch.cat([W0[:, :H]] + [w for w, _ in mw[1:]], 0).to(torch.bfloat16).contiguous()
                 lw.msg_bias = [None] + [b for _, b in mw[1:]]
-                lw.proj = ops.pack_linear(torch.cat([W0[:, H:2 * H], W0[:, 2 * H:]], 0),
-                                          torch.cat([b0, torch.zeros_like(b0)], 0))
+                Wp = torch.cat([W0[:, H:2 * H], W0[:, 2 * H:]], 0)
+                bp = torch.cat([b0, torch.zeros_like(b0)], 0).contiguous()
+                lw.proj = ops.pack_linear(Wp, bp)
+                lw.proj16 = (Wp.to(torch.bfloat16).contiguous(), bp)
+            dw = _indexed(p, pre + "dense.")
+            widths_ok = all(w.shape[0] in (128, 256) and w.shape[1] in (128, 256) for w, _ in dw)
+            if widths_ok and dw[0][0].shape[1] == H and dw[-1][0].shape[0] == H and len(dw) <= 4:
+                lw.dense16 = [(w.to(torch.bfloat16).contiguous(), b.contiguous()) for w, b in dw]
             self.layers.append(lw)
         ro = _indexed(p, "readout.readout_layers.")
         self.readout_hidden = [ops.pack_linear(w, b) for w, b in ro[:-1]]
@@ -122,9 +130,13 @@ class RDesignEngine:
         if self.precision == PREC_BF16:
             if lw.msg_w16 is None:
                 raise ValueError("bf16 layer kernels need message layers of shape 384->128->128..")
-            # per-node projections of W_0's centre / neighbour column blocks, then the tcgen05 edge kernel
-            P = torch.empty(g.Nv, 2 * ops.HIDDEN, dtype=torch.float32, device=h_V.device)
-            ops.row_mlp([(h_V, None)], [(lw.proj, False)], ops.EPI_STORE, P, g.Nv)
+            # per-node projections of W_0's centre / neighbour column blocks: emitted by the previous
+            # layer's node kernel, or computed here for the first layer
+            P = getattr(self, "_next_P", None)
+            self._next_P = None
+            if P is None or P.shape[0] != g.Nv:
+                P = torch.empty(g.Nv, 2 * ops.HIDDEN, dtype=torch.float32, device=h_V.device)
+                ops.node_mlp_bf16(h_V, [(*lw.proj16, 2)], g.Nv, p_out=P)
             if self.kernel_timer is not None:
                 ev[0].record(torch.cuda.current_stream())
             ops.edge_mlp_bf16(h_E, lw.msg_w16, lw.msg_bias, P, g.ctr, g.nbr, agg, 1.0 / self.scale)
@@ -134,10 +146,28 @@ class RDesignEngine:
         if self.kernel_timer is not None:
             ev[1].record(torch.cuda.current_stream())
             self.kernel_timer.append(ev)
+        if self.precision == PREC_BF16 and lw.dense16 is not None:
+            return self._node_update_tc(l, h_V, agg, g)
         x1 = ops.add_layernorm(h_V, agg, lw.norm1_w, lw.norm1_b, 1e-5, zero_b=True)
         out = torch.empty_like(h_V)
         stages = [(d, True) for d in lw.dense[:-1]] + [(lw.dense[-1], False)]
         ops.row_mlp([(x1, None)], stages, ops.EPI_RESID_LN, out, g.Nv, gain=lw.norm2_w, beta=lw.norm2_b, resid=x1)
+        return out
+
+    def _node_update_tc(self, l, h_V, agg, g):
+        """norm1 + dense FFN + norm2 on tcgen05, plus the next layer's [Pc | Pn] projections."""
+        lw = self.w.layers[l]
+        stages = [(w, b, 0) for w, b in lw.dense16[:-1]] + [(*lw.dense16[-1], 1)]
+        nxt = self.w.layers[l + 1] if l + 1 < len(self.w.layers) else None
+        p_out = None
+        if nxt is not None and nxt.proj16 is not None:
+            stages.append((*nxt.proj16, 2))
+            p_out = torch.empty(g.Nv, 2 * ops.HIDDEN, dtype=torch.float32, device=h_V.device)
+        out = torch.empty_like(h_V)
+        x1 = torch.empty_like(h_V)
+        ops.node_mlp_bf16(h_V, stages, g.Nv, agg=agg, ln1=(lw.norm1_w, lw.norm1_b), ln2=(lw.norm2_w, lw.norm2_b),
+                          x1=x1, h_out=out, p_out=p_out)
+        self._next_P = p_out
         return out
 
     def encode(self, X, mask, sizes=None, return_layers=False):
@@ -147,6 +177,7 @@ class RDesignEngine:
             h_E = ops.cast_bf16(h_E)              # h_E is layer-invariant: stored once as bf16
         agg = torch.zeros_like(h_V)
         layers = []
+        self._next_P = None
         for l in range(len(self.w.layers)):
             h_V = self.layer(l, h_V, h_E, g, agg)
             if return_layers:

@@ -223,6 +223,31 @@ def edge_mlp_bf16(h_E16, W16, biases, P, ctr, nbr, agg, alpha: float, debug=None
     return agg
 
 
+def node_mlp_bf16(h_in, stages, n_rows, agg=None, ln1=None, ln2=None, x1=None, h_out=None, p_out=None):
+    """tcgen05 node-update kernel (rmp_node_mlp_bf16).
+
+    stages: [(W bf16 [N,K], bias fp32 [N], kind)], kind 0 = GELU, 1 = residual + LayerNorm2 -> h_out,
+    2 = fp32 projection store -> p_out.  ln1 = (gamma, beta) enables x1 = LayerNorm1(h_in + agg).
+    """
+    _need_cuda(h_in, agg, x1, h_out, p_out, *(ln1 or ()), *(ln2 or ()))
+    n = len(stages)
+    Ws = (C.c_void_p * n)(*[_ptr(w) for w, _, _ in stages])
+    Bs = (C.c_void_p * n)(*[_ptr(b) for _, b, _ in stages])
+    Ks = (C.c_int32 * n)(*[w.shape[1] for w, _, _ in stages])
+    Ns = (C.c_int32 * n)(*[w.shape[0] for w, _, _ in stages])
+    kinds = (C.c_int32 * n)(*[k for _, _, k in stages])
+    for w, b, _ in stages:
+        _need_cuda(w, b)
+        assert w.dtype == torch.bfloat16 and w.is_contiguous() and b.dtype == torch.float32
+    g1, b1 = ln1 if ln1 is not None else (None, None)
+    g2, b2 = ln2 if ln2 is not None else (None, None)
+    check(lib().rmp_node_mlp_bf16(_ptr(h_in), _ptr(agg), int(ln1 is not None), _ptr(g1), _ptr(b1), n,
+                                  C.cast(Ws, C.c_void_p), C.cast(Ks, C.c_void_p), C.cast(Ns, C.c_void_p),
+                                  C.cast(kinds, C.c_void_p), C.cast(Bs, C.c_void_p), _ptr(g2), _ptr(b2), _ptr(x1),
+                                  _ptr(h_out), _ptr(p_out), int(n_rows), _stream()), "rmp_node_mlp_bf16")
+    return h_out, p_out
+
+
 def cast_bf16(src: torch.Tensor) -> torch.Tensor:
     _need_cuda(src)
     src = _f32c(src)
@@ -231,6 +256,6 @@ def cast_bf16(src: torch.Tensor) -> torch.Tensor:
     return dst
 
 
-__all__ = ["Graph", "PackedLinear", "edge_mlp_bf16", "knn", "build_graph", "raw_features", "pack_linear", "row_mlp",
+__all__ = ["Graph", "PackedLinear", "edge_mlp_bf16", "node_mlp_bf16", "knn", "build_graph", "raw_features", "pack_linear", "row_mlp",
            "add_layernorm", "readout_head", "cast_bf16", "EPI_STORE", "EPI_NORMALIZE", "EPI_RESID_LN",
            "EPI_SEGSUM", "HIDDEN", "NODE_RAW", "EDGE_RAW", "MAX_K"]

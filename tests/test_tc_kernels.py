@@ -26,7 +26,7 @@ def _edge_reference(hE, W, biases, P, ctr, nbr, alpha, Nv):
     for s in range(S):
         pre = x @ _bf(W[s * 128:(s + 1) * 128]).t()
         pre = pre + (P[ctr.long(), :128] + P[nbr.long(), 128:] if s == 0 else biases[s])
-        a = F.gelu(pre)
+        a = F.gelu(pre, approximate="tanh")     # the bf16 arm evaluates the tanh form on MUFU.TANH
         acts.append(a)
         x = _bf(a)
     agg = torch.zeros(Nv, 128).index_add_(0, ctr.long(), x) * alpha
@@ -62,7 +62,7 @@ def test_edge_mlp_tc_matches_fp32_reference(Nv, deg, S):
                       [None] + [b.cuda() for b in biases[1:]], P.cuda(), ctr.cuda(), nbr.cuda(), agg, alpha, debug=dbg)
     torch.cuda.synchronize()
     for s in range(S):
-        tol = 2e-4 if s == 0 else 6e-3                  # later stages see bf16 re-rounding of the previous one
+        tol = 2e-3 if s == 0 else 6e-3      # tanh.approx.f32 is 2^-11 accurate; later stages see bf16 re-rounding
         np.testing.assert_allclose(dbg[s].cpu().numpy(), acts_ref[s].numpy(), atol=tol, rtol=0, err_msg=f"stage {s}")
     np.testing.assert_allclose(agg.cpu().numpy(), agg_ref.numpy(), atol=6e-3 * max(1.0, deg / 30), rtol=0)
 
@@ -87,6 +87,62 @@ def test_edge_mlp_tc_accumulates_into_agg_and_is_repeatable():
     agg2 = outs[0].clone()
     ops.edge_mlp_bf16(hE, W, b, P, ctr, nbr, agg2, 1.0)
     np.testing.assert_allclose(agg2.cpu().numpy(), 2 * outs[0].cpu().numpy(), rtol=1e-5, atol=1e-5)
+
+
+def _ln(x, g, b):
+    return F.layer_norm(x, (128,), g, b, 1e-5)
+
+
+@pytest.mark.parametrize("n_rows,widths,with_proj", [(128, [256, 256, 256], True), (300, [256, 256, 256], True),
+                                                     (77, [256], False), (20000, [256, 256], True),
+                                                     (130, [128, 128], False)])
+def test_node_mlp_tc_matches_fp32_reference(n_rows, widths, with_proj):
+    from rmpnn_b200 import ops
+    g = torch.Generator().manual_seed(n_rows)
+    h = torch.randn(n_rows, 128, generator=g)
+    agg = 0.3 * torch.randn(n_rows, 128, generator=g)
+    ln1 = (1 + 0.1 * torch.randn(128, generator=g), 0.1 * torch.randn(128, generator=g))
+    ln2 = (1 + 0.1 * torch.randn(128, generator=g), 0.1 * torch.randn(128, generator=g))
+    dims = [128] + widths + [128]
+    lin = [(torch.randn(dims[i + 1], dims[i], generator=g) / dims[i] ** 0.5, 0.1 * torch.randn(dims[i + 1], generator=g))
+           for i in range(len(dims) - 1)]
+    proj = (torch.randn(256, 128, generator=g) / 128 ** 0.5, 0.1 * torch.randn(256, generator=g))
+    # fp32 reference with the kernel's rounding points
+    x1 = _ln(h + agg, *ln1)
+    x = _bf(x1)
+    for W, b in lin[:-1]:
+        x = _bf(F.gelu(x @ _bf(W).t() + b, approximate="tanh"))
+    h_ref = _ln(x1 + x @ _bf(lin[-1][0]).t() + lin[-1][1], *ln2)
+    p_ref = _bf(h_ref) @ _bf(proj[0]).t() + proj[1]
+
+    dev = "cuda"
+    stages = [(W.to(dev).to(torch.bfloat16), b.to(dev), 0) for W, b in lin[:-1]]
+    stages.append((lin[-1][0].to(dev).to(torch.bfloat16), lin[-1][1].to(dev), 1))
+    if with_proj:
+        stages.append((proj[0].to(dev).to(torch.bfloat16), proj[1].to(dev), 2))
+    agg_d = agg.to(dev)
+    h_out = torch.empty(n_rows, 128, device=dev)
+    x1_d = torch.empty(n_rows, 128, device=dev)
+    p_out = torch.empty(n_rows, 256, device=dev) if with_proj else None
+    ops.node_mlp_bf16(h.to(dev), stages, n_rows, agg=agg_d, ln1=tuple(t.to(dev) for t in ln1),
+                      ln2=tuple(t.to(dev) for t in ln2), x1=x1_d, h_out=h_out, p_out=p_out)
+    torch.cuda.synchronize()
+    np.testing.assert_allclose(x1_d.cpu().numpy(), x1.numpy(), atol=2e-5, rtol=0)
+    np.testing.assert_allclose(h_out.cpu().numpy(), h_ref.numpy(), atol=2e-2, rtol=0)
+    assert (h_out.cpu() - h_ref).abs().mean().item() < 2e-3
+    assert float(agg_d.abs().max()) == 0.0                     # neighbour-sum buffer re-armed for the next layer
+    if with_proj:
+        np.testing.assert_allclose(p_out.cpu().numpy(), p_ref.numpy(), atol=3e-2, rtol=0)
+
+
+def test_node_mlp_tc_projection_only():
+    from rmpnn_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    h = torch.randn(1000, 128, generator=g)
+    W, b = torch.randn(256, 128, generator=g) / 11.3, 0.1 * torch.randn(256, generator=g)
+    P = torch.empty(1000, 256, device="cuda")
+    ops.node_mlp_bf16(h.cuda(), [(W.cuda().to(torch.bfloat16), b.cuda(), 2)], 1000, p_out=P)
+    np.testing.assert_allclose(P.cpu().numpy(), (_bf(h) @ _bf(W).t() + b).numpy(), atol=1e-4, rtol=0)
 
 
 @pytest.mark.parametrize("B,L,K,lengths", [(2, 64, 25, [64, 50]), (4, 256, 30, None), (3, 100, 48, [100, 61, 7])])
