@@ -168,25 +168,69 @@ struct EdgeParams {
     float* debug;                    // optional [num_stages][n_edges][128] post-activation dump
 };
 
+// Two edge tiles are in flight per CTA: epilogue group g (8 warps) owns the tiles with local index
+// i % 2 == g, the single MMA thread serves whichever tile has its next operand ready, and the TMA
+// producer keeps a 3-deep ring of h_E tiles.  While one group runs a stage epilogue on the CUDA cores
+// the other group's GEMM runs on the tensor pipe.
+constexpr int kGroups = 2;
+constexpr int kABufs = 3;
+constexpr int kEdgeThreads = 64 + kGroups * kEpiThreads;       // 576
+constexpr int kSelSlots = 16;                                  // node slots per tile served by the selector MMA
+constexpr int kSelBytes = 2 * kSelSlots * 128;                 // [2 K-blocks][16 slots][64 edges] bf16
+constexpr uint32_t kEdgeTmemCols = 512;                        // acc g at 128*g, neighbour sums g at 256 + 32*g
+
 struct alignas(8) Barriers {
-    uint64_t w_full, a_full[2], a_empty[2], acc_full, act_ready, agg_full, agg_empty;
+    uint64_t w_full, a_full[kABufs], a_empty[kABufs];
+    uint64_t acc_full[kGroups], act_ready[kGroups], agg_full[kGroups], agg_empty[kGroups];
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void group_bar_sync(int g) {
+    asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(kEpiThreads) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+// Instruction descriptor with A MN-major (the [edge][channel] activation read as A = m3^T), B K-major
+__host__ __device__ constexpr uint32_t instr_desc_bf16_amn(int M, int N) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__global__ void __launch_bounds__(kEdgeThreads, 1)
 edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant__ CUtensorMap tm_w,
                    const EdgeParams p) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     // 1024-byte alignment is required by the 128B swizzle atoms
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
-    uint8_t* sW = smem;                                         // [S][2][128][64] bf16
-    uint8_t* sA = sW + (size_t)p.num_stages * kTileBytes;       // [2 buffers][2][128][64] bf16
-    uint8_t* sSel = sA + 2 * kTileBytes;                        // [2][128][64] bf16 selector
-    Barriers* bars = reinterpret_cast<Barriers*>(sSel + kTileBytes);
+    uint8_t* sW = smem;                                         // [S][2][128][64] bf16, resident
+    uint8_t* sA = sW + (size_t)p.num_stages * kTileBytes;       // [3 buffers][2][128][64] bf16
+    uint8_t* sSel = sA + kABufs * kTileBytes;                   // [2 groups][2][16][64] bf16 selector
+    Barriers* bars = reinterpret_cast<Barriers*>(sSel + kGroups * kSelBytes);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 1);
-    int* s_ctr = reinterpret_cast<int*>(s_tmem + 4);            // [128]
-    int* s_start = s_ctr + kTileM;                              // [128]
-    int* s_end = s_start + kTileM;                              // [128]
-    int* s_misc = s_end + kTileM;                               // [0] = nslots
+    int* s_int = reinterpret_cast<int*>(s_tmem + 4);            // per group: ctr[128] start[128] end[128] misc[4]
+    constexpr int kIntsPerGroup = 3 * kTileM + 4;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = (p.n_edges + kTileM - 1) / kTileM;
@@ -195,14 +239,16 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
 
     if (threadIdx.x == 0) {
         mbar_init(&bars->w_full, 1);
-        for (int b = 0; b < 2; ++b) { mbar_init(&bars->a_full[b], 1); mbar_init(&bars->a_empty[b], 1); }
-        mbar_init(&bars->acc_full, 1);
-        mbar_init(&bars->act_ready, kEpiThreads);
-        mbar_init(&bars->agg_full, 1);
-        mbar_init(&bars->agg_empty, kEpiThreads);
+        for (int b = 0; b < kABufs; ++b) { mbar_init(&bars->a_full[b], 1); mbar_init(&bars->a_empty[b], 1); }
+        for (int g = 0; g < kGroups; ++g) {
+            mbar_init(&bars->acc_full[g], 1);
+            mbar_init(&bars->act_ready[g], kEpiThreads);
+            mbar_init(&bars->agg_full[g], 1);
+            mbar_init(&bars->agg_empty[g], kEpiThreads);
+        }
         fence_barrier_init();
     }
-    if (warp == 1) tmem_alloc(s_tmem, kTmemCols);
+    if (warp == 1) tmem_alloc(s_tmem, kEdgeTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -218,9 +264,9 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
                 for (int kb = 0; kb < 2; ++kb)
                     tma_load_2d(sW + (size_t)s * kTileBytes + kb * kKBlockBytes, &tm_w, &bars->w_full, kb * 64, s * 128);
             for (int i = 0; i < my_tiles; ++i) {
-                const int b = i & 1;
+                const int b = i % kABufs;
                 const int tile = blockIdx.x + i * gridDim.x;
-                mbar_wait(&bars->a_empty[b], ((i >> 1) & 1) ^ 1);
+                mbar_wait(&bars->a_empty[b], ((i / kABufs) & 1) ^ 1);
                 mbar_expect_tx(&bars->a_full[b], kTileBytes);
                 for (int kb = 0; kb < 2; ++kb)
                     tma_load_2d(sA + (size_t)b * kTileBytes + kb * kKBlockBytes, &tm_e, &bars->a_full[b], kb * 64,
@@ -229,65 +275,91 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===================== MMA issuer =====================
+        // ===================== MMA issuer: serves the two in-flight tiles as their operands become ready ====
         if (lane == 0) {
-            constexpr uint32_t idesc_kk = instr_desc_bf16(128, 128, 0);
-            constexpr uint32_t idesc_kmn = instr_desc_bf16(128, 128, 1);
-            const uint32_t acc = tmem_base, agg = tmem_base + 128;
-            uint32_t ph_act = 0, ph_ae = 0;
+            constexpr uint32_t idesc_stage = instr_desc_bf16(128, 128, 0);
+            constexpr uint32_t idesc_sel = instr_desc_bf16_amn(128, kSelSlots);
+            int ti[kGroups], st[kGroups];
+            uint32_t ph_act[kGroups], ph_ae[kGroups];
+            for (int g = 0; g < kGroups; ++g) { ti[g] = g; st[g] = 0; ph_act[g] = 0; ph_ae[g] = 0; }
             mbar_wait(&bars->w_full, 0);
-            for (int i = 0; i < my_tiles; ++i) {
-                const int b = i & 1;
-                const uint32_t a_addr = smem_u32(sA + (size_t)b * kTileBytes);
-                mbar_wait(&bars->a_full[b], (i >> 1) & 1);
-                for (int s = 0; s < S; ++s) {
-                    if (s > 0) { mbar_wait(&bars->act_ready, ph_act); ph_act ^= 1; }
+            int remaining = my_tiles;
+            while (remaining > 0) {
+#pragma unroll
+                for (int g = 0; g < kGroups; ++g) {
+                    if (ti[g] >= my_tiles) continue;
+                    const int i = ti[g], b = i % kABufs, s = st[g];
+                    bool ready;
+                    if (s == 0) ready = mbar_test(&bars->a_full[b], (i / kABufs) & 1);
+                    else if (s < S) ready = mbar_test(&bars->act_ready[g], ph_act[g]);
+                    else ready = mbar_test(&bars->act_ready[g], ph_act[g]) && mbar_test(&bars->agg_empty[g], ph_ae[g] ^ 1);
+                    if (!ready) continue;
                     tc_fence_after();
-                    const uint32_t w_addr = smem_u32(sW + (size_t)s * kTileBytes);
+                    const uint32_t a_addr = smem_u32(sA + (size_t)b * kTileBytes);
+                    if (s < S) {
+                        if (s > 0) ph_act[g] ^= 1;
+                        const uint32_t w_addr = smem_u32(sW + (size_t)s * kTileBytes);
+                        const uint32_t acc = tmem_base + (uint32_t)(g * 128);
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) {               // K = 128 = 8 x UMMA_K(16)
-                        const uint32_t off = (uint32_t)((k >> 2) * kKBlockBytes + (k & 3) * 32);
-                        umma_bf16(acc, smem_desc_sw128(a_addr + off, 16, 1024), smem_desc_sw128(w_addr + off, 16, 1024),
-                                  idesc_kk, k > 0);
+                        for (int k = 0; k < 8; ++k) {               // K = 128 = 8 x UMMA_K(16)
+                            const uint32_t off = (uint32_t)((k >> 2) * kKBlockBytes + (k & 3) * 32);
+                            umma_bf16(acc, smem_desc_sw128(a_addr + off, 16, 1024),
+                                      smem_desc_sw128(w_addr + off, 16, 1024), idesc_stage, k > 0);
+                        }
+                        umma_commit(&bars->acc_full[g]);
+                        st[g] = s + 1;
+                    } else {
+                        // neighbour sums, transposed: aggT[ch][slot] = sum_r m3[r][ch] * Sel[slot][r].
+                        // A = m3 read MN-major in place, B = 16-slot selector (K-major).
+                        ph_act[g] ^= 1; ph_ae[g] ^= 1;
+                        const int* misc = s_int + g * kIntsPerGroup + 3 * kTileM;
+                        if (*reinterpret_cast<const volatile int*>(misc + 1) == 0) {   // selector path (<= 16 node slots)
+                            const uint32_t sel_addr = smem_u32(sSel + g * kSelBytes);
+                            const uint32_t agg = tmem_base + 256u + (uint32_t)(g * 32);
+#pragma unroll
+                            for (int k = 0; k < 8; ++k) {           // K = 128 edge rows = 8 x 16
+                                const uint32_t a_off = (uint32_t)(k * 2048);            // 16 rows of 128 B
+                                const uint32_t b_off = (uint32_t)((k >> 2) * (kSelSlots * 128) + (k & 3) * 32);
+                                umma_bf16(agg, smem_desc_sw128(a_addr + a_off, kKBlockBytes, 1024),
+                                          smem_desc_sw128(sel_addr + b_off, 16, 1024), idesc_sel, k > 0);
+                            }
+                        }
+                        umma_commit(&bars->agg_full[g]);
+                        umma_commit(&bars->a_empty[b]);
+                        st[g] = 0;
+                        ti[g] = i + kGroups;
+                        --remaining;
                     }
-                    umma_commit(&bars->acc_full);
                 }
-                // neighbour sums: agg[slot][ch] = sum_r Sel[slot][r] * m3[r][ch]; m3 is read MN-major in place
-                mbar_wait(&bars->act_ready, ph_act); ph_act ^= 1;
-                mbar_wait(&bars->agg_empty, ph_ae ^ 1); ph_ae ^= 1;
-                tc_fence_after();
-                const uint32_t sel_addr = smem_u32(sSel);
-#pragma unroll
-                for (int k = 0; k < 8; ++k) {                   // K = 128 edge rows = 8 x 16
-                    const uint32_t a_off = (uint32_t)((k >> 2) * kKBlockBytes + (k & 3) * 32);
-                    const uint32_t b_off = (uint32_t)(k * 2048);     // 16 rows of 128 B
-                    umma_bf16(agg, smem_desc_sw128(sel_addr + a_off, 16, 1024),
-                              smem_desc_sw128(a_addr + b_off, kKBlockBytes, 1024), idesc_kmn, k > 0);
-                }
-                umma_commit(&bars->agg_full);
-                umma_commit(&bars->a_empty[b]);
             }
         }
         __syncwarp();
     } else {
-        // ===================== epilogue warps =====================
-        const int half = (warp - 2) >> 2;            // output column half == K-block of the next stage
-        const int lane_grp = warp & 3;               // TMEM lanes this warp may touch: 32*(warp%4)..+31
+        // ===================== epilogue groups =====================
+        const int g = (warp - 2) >> 3;                   // group 0: warps 2..9, group 1: warps 10..17
+        const int half = ((warp - 2) >> 2) & 1;          // output column half == K-block of the next stage
+        const int lane_grp = warp & 3;                   // TMEM lanes this warp may touch: 32*(warp%4)..+31
         const int row = lane_grp * 32 + lane;
         const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+        const uint32_t t_acc = t_row + (uint32_t)(g * 128);
+        const uint32_t t_agg = t_row + 256u + (uint32_t)(g * 32);
+        int* s_ctr = s_int + g * kIntsPerGroup;
+        int* s_start = s_ctr + kTileM;
+        int* s_end = s_start + kTileM;
+        int* s_misc = s_end + kTileM;                    // [0] = nslots, [1] = 1 if the tile bypasses the selector MMA
+        uint8_t* sel = sSel + g * kSelBytes;
         uint32_t ph_acc = 0, ph_agg = 0;
-        for (int i = 0; i < my_tiles; ++i) {
-            const int b = i & 1;
+        for (int i = g; i < my_tiles; i += kGroups) {
             const int tile = blockIdx.x + i * gridDim.x;
             const int e = tile * kTileM + row;
             const bool valid = e < p.n_edges;
             const int c = valid ? __ldg(p.ctr + e) : -1;
             const int nb = valid ? __ldg(p.nbr + e) : 0;
-            uint8_t* a_buf = sA + (size_t)b * kTileBytes;
+            uint8_t* a_buf = sA + (size_t)(i % kABufs) * kTileBytes;
 
             // ---- segment bookkeeping + selector matrix (edges of a node are contiguous) ----
             if (half == 0) s_ctr[row] = c;
-            epi_bar_sync();
+            group_bar_sync(g);
             const int first_node = s_ctr[0];
             {
                 const int prev = row > 0 ? s_ctr[row - 1] : -2;
@@ -296,14 +368,15 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
                     if (c != prev) s_start[c - first_node] = row;
                     if (c != next) {
                         s_end[c - first_node] = row + 1;
-                        if (next < 0) s_misc[0] = c - first_node + 1;
+                        if (next < 0) { s_misc[0] = c - first_node + 1; s_misc[1] = (c - first_node + 1) > kSelSlots; }
                     }
                 }
             }
-            epi_bar_sync();
+            group_bar_sync(g);
             const int nslots = s_misc[0];
-            if (row < nslots) {
-                const int st = s_start[row], en = s_end[row];
+            const bool bypass = nslots > kSelSlots;      // tiny-degree nodes: sum with vector reductions instead
+            if (!bypass && row < kSelSlots) {
+                const int st = row < nslots ? s_start[row] : 0, en = row < nslots ? s_end[row] : 0;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     uint32_t w[4];
@@ -314,35 +387,29 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
                         const uint32_t hi = (r0 + 1 >= st && r0 + 1 < en) ? 0x3F80u : 0u;
                         w[q] = lo | (hi << 16);
                     }
-                    *reinterpret_cast<uint4*>(sSel + half * kKBlockBytes + sw128_chunk(row, j)) =
+                    *reinterpret_cast<uint4*>(sel + half * (kSelSlots * 128) + sw128_chunk(row, j)) =
                         make_uint4(w[0], w[1], w[2], w[3]);
                 }
             }
 
             // ---- chained stage epilogues: TMEM -> (+gather / +bias) -> GELU -> bf16 -> smem A operand ----
             for (int s = 0; s < S; ++s) {
-                float4 g0[8], g1[8];                       // gathered projections of one 32-column chunk
-                auto gather = [&](int col0) {
-                    const float4* pc = reinterpret_cast<const float4*>(p.Pc + (size_t)c * p.ld_p + col0);
-                    const float4* pn = reinterpret_cast<const float4*>(p.Pn + (size_t)nb * p.ld_p + col0);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) { g0[q] = __ldg(pc + q); g1[q] = __ldg(pn + q); }
-                };
-                if (s == 0 && valid) gather(half * 64);    // in flight while the MMA runs
-                mbar_wait(&bars->acc_full, ph_acc); ph_acc ^= 1;
+                mbar_wait(&bars->acc_full[g], ph_acc); ph_acc ^= 1;
                 tc_fence_after();
 #pragma unroll
                 for (int ch = 0; ch < 2; ++ch) {
                     const int col0 = half * 64 + ch * 32;
                     float v[32];
-                    if (s == 0 && valid && ch == 1) gather(col0);
-                    tmem_ld32(t_row + (uint32_t)col0, v);
+                    tmem_ld32(t_acc + (uint32_t)col0, v);
                     if (s == 0) {
                         if (valid) {
+                            const float4* pc = reinterpret_cast<const float4*>(p.Pc + (size_t)c * p.ld_p + col0);
+                            const float4* pn = reinterpret_cast<const float4*>(p.Pn + (size_t)nb * p.ld_p + col0);
 #pragma unroll
                             for (int q = 0; q < 8; ++q) {
-                                v[4 * q + 0] += g0[q].x + g1[q].x; v[4 * q + 1] += g0[q].y + g1[q].y;
-                                v[4 * q + 2] += g0[q].z + g1[q].z; v[4 * q + 3] += g0[q].w + g1[q].w;
+                                const float4 x = __ldg(pc + q), y = __ldg(pn + q);
+                                v[4 * q + 0] += x.x + y.x; v[4 * q + 1] += x.y + y.y;
+                                v[4 * q + 2] += x.z + y.z; v[4 * q + 3] += x.w + y.w;
                             }
                         }
                     } else {
@@ -361,44 +428,47 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
 #pragma unroll
                         for (int q = 0; q < 32; ++q) dbg[q] = v[q];
                     }
+                    if (s == S - 1 && bypass) {
+                        if (valid) {
+                            float* dst = p.agg + (size_t)c * 128 + col0;
 #pragma unroll
-                    for (int j = 0; j < 4; ++j) {
-                        const uint4 pk = make_uint4(pack_bf16(v[8 * j + 0], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                                    pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-                        *reinterpret_cast<uint4*>(a_buf + half * kKBlockBytes + sw128_chunk(row, ch * 4 + j)) = pk;
+                            for (int q = 0; q < 8; ++q)
+                                red_add_v4(dst + 4 * q, v[4 * q] * p.alpha, v[4 * q + 1] * p.alpha,
+                                           v[4 * q + 2] * p.alpha, v[4 * q + 3] * p.alpha);
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint4 pk = make_uint4(pack_bf16(v[8 * j + 0], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                                        pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+                            *reinterpret_cast<uint4*>(a_buf + half * kKBlockBytes + sw128_chunk(row, ch * 4 + j)) = pk;
+                        }
                     }
                 }
                 tc_fence_before();
                 fence_proxy_async();
-                mbar_arrive(&bars->act_ready);
+                mbar_arrive(&bars->act_ready[g]);
             }
 
-            // ---- neighbour sums out of TMEM: one row per node slot ----
-            mbar_wait(&bars->agg_full, ph_agg); ph_agg ^= 1;
+            // ---- neighbour sums out of TMEM: lane = channel, column = node slot ----
+            mbar_wait(&bars->agg_full[g], ph_agg); ph_agg ^= 1;
             tc_fence_after();
-            if (lane_grp * 32 < nslots) {                   // warp-uniform
+            if (!bypass && half == 0) {
+                float v[16];
+                tmem_ld16(t_agg, v);
+                float* dst = p.agg + (size_t)first_node * 128 + row;       // row == channel here
 #pragma unroll
-                for (int ch = 0; ch < 2; ++ch) {
-                    const int col0 = half * 64 + ch * 32;
-                    float v[32];
-                    tmem_ld32(t_row + (uint32_t)(128 + col0), v);
-                    if (row < nslots) {
-                        float* dst = p.agg + (size_t)(first_node + row) * 128 + col0;
-#pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            red_add_v4(dst + 4 * q, v[4 * q] * p.alpha, v[4 * q + 1] * p.alpha, v[4 * q + 2] * p.alpha,
-                                       v[4 * q + 3] * p.alpha);
-                    }
-                }
+                for (int n = 0; n < kSelSlots; ++n)
+                    if (n < nslots) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + n * 128), "f"(v[n] * p.alpha) : "memory");
             }
             tc_fence_before();
-            mbar_arrive(&bars->agg_empty);
+            mbar_arrive(&bars->agg_empty[g]);
         }
     }
 
     tc_fence_before();
     __syncthreads();
-    if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+    if (warp == 1) tmem_dealloc(tmem_base, kEdgeTmemCols);
 }
 
 // =================================================================================================
@@ -725,13 +795,13 @@ extern "C" int rmp_edge_mlp_bf16(const void* h_E_bf16, const void* W_bf16, int n
         p.bias[s] = bias[s];
     }
     p.num_stages = num_stages; p.alpha = alpha; p.agg = agg; p.n_edges = n_edges; p.debug = debug;
-    const size_t smem = 1024 + (size_t)(num_stages + 3) * tc::kTileBytes + sizeof(tc::Barriers) + 16 +
-                        (3 * tc::kTileM + 4) * sizeof(int);
+    const size_t smem = 1024 + (size_t)(num_stages + tc::kABufs) * tc::kTileBytes + tc::kGroups * tc::kSelBytes +
+                        sizeof(tc::Barriers) + 16 + tc::kGroups * (3 * tc::kTileM + 4) * sizeof(int);
     RMP_REQUIRE(smem <= 227 * 1024, RMP_E_SHAPE, "rmp_edge_mlp_bf16: %zu B of shared memory needed", smem);
     cudaFuncSetAttribute(tc::edge_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int n_tiles = ceil_div(n_edges, tc::kTileM);
     const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
-    tc::edge_mlp_tc_kernel<<<grid, tc::kThreads, smem, (cudaStream_t)stream>>>(tm_e, tm_w, p);
+    tc::edge_mlp_tc_kernel<<<grid, tc::kEdgeThreads, smem, (cudaStream_t)stream>>>(tm_e, tm_w, p);
     return check_launch("rmp_edge_mlp_bf16");
 }
 
