@@ -191,13 +191,21 @@ int rmp_readout_head(const float* h, int k_in, const float* W, const float* b,
  * scatter_sum / scale) with W_0 = [W_0e | W_0c | W_0n] split by column block and
  * Pc = h_V W_0c^T + b_0, Pn = h_V W_0n^T computed per node by the caller (rmp_row_mlp).
  *   h_E_bf16 [n_edges,128] bf16; W_bf16 [num_stages*128,128] bf16 = rows of W_0e, W_1, .. (nn.Linear layout)
- *   bias[s] fp32 [128] for s >= 1 (bias[0] unused: folded into Pc); Pc, Pn fp32 with row stride ld_p
+ *   bias[s] fp32 [128] for s >= 1 (bias[0] unused: folded into Pc); Pc [Nv,128] fp32, Pn [Nv,128] bf16
  *   agg [Nv,128] fp32 must be zero on entry (edges of a node may span two tiles);
  *   debug: NULL, or [num_stages][n_edges][128] fp32 receiving every stage's activations (tests).
- * Edges of one centre must be contiguous (they are in the valid-only flattening). */
+ * Edges of one centre must be contiguous (they are in the valid-only flattening): row_ptr [Nv+1] are the
+ * CSR offsets of the centres (ctr[e] == v  <=>  row_ptr[v] <= e < row_ptr[v+1]). */
 int rmp_edge_mlp_bf16(const void* h_E_bf16, const void* W_bf16, int num_stages, const float* const* bias,
-                      const float* Pc, const float* Pn, int ld_p, const int32_t* ctr, const int32_t* nbr,
-                      int n_edges, float alpha, float* agg, float* debug, void* stream);
+                      const float* Pc, const void* Pn_bf16, const int32_t* ctr, const int32_t* nbr,
+                      const int32_t* row_ptr, int n_edges, float alpha, float* agg, float* debug, void* stream);
+
+/* Same, with an optional device buffer `timeline` (int64 [8000]) that receives (tag, clock64) pairs of
+ * CTA 0's first epilogue thread -- a tuning aid used by scripts/edge_timeline.py; NULL disables it. */
+int rmp_edge_mlp_bf16_traced(const void* h_E_bf16, const void* W_bf16, int num_stages, const float* const* bias,
+                             const float* Pc, const void* Pn_bf16, const int32_t* ctr, const int32_t* nbr,
+                             const int32_t* row_ptr, int n_edges, float alpha, float* agg, float* debug,
+                             long long* timeline, void* stream);
 
 /* Fused node-update kernel on 128-node tiles (tcgen05, weights streamed by TMA):
  *   x1 = prologue_ln ? LayerNorm1(h_in + agg) : h_in      (agg rows are re-zeroed after being read)
@@ -205,14 +213,15 @@ int rmp_edge_mlp_bf16(const void* h_E_bf16, const void* W_bf16, int num_stages, 
  *   weight [N][K] as bf16, bias[s] fp32, kind[s]:
  *     0  bias + GELU (tanh form)                          -> operand of the next stage
  *     1  bias + residual x1 + LayerNorm2 (eps 1e-5)       -> h_out [n_rows,128] (and next operand)
- *     2  bias                                             -> p_out [n_rows,N] fp32 (last stage only)
+ *     2  bias (N = 256, last stage only)                  -> p_out [n_rows,128] fp32 = columns 0..127 (Pc),
+ *                                                            pn_out [n_rows,128] bf16 = columns 128..255 (Pn)
  * Replaces rdesign/model/mpnn.py:35-37 (norm1, dense FFN, norm2); a trailing kind-2 stage emits the
  * next layer's per-node projections [Pc | Pn] consumed by rmp_edge_mlp_bf16.
  * x1_scratch [n_rows,128] fp32 is a caller-provided workspace for the residual. */
 int rmp_node_mlp_bf16(const float* h_in, float* agg, int prologue_ln, const float* ln1_g, const float* ln1_b,
                       int num_stages, const void* const* W_bf16, const int32_t* K, const int32_t* N,
                       const int32_t* kind, const float* const* bias, const float* ln2_g, const float* ln2_b,
-                      float* x1_scratch, float* h_out, float* p_out, int n_rows, void* stream);
+                      float* x1_scratch, float* h_out, float* p_out, void* pn_out_bf16, int n_rows, void* stream);
 
 /* fp32 -> bf16 row conversion (h_E storage for the bf16 path), n elements */
 int rmp_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);

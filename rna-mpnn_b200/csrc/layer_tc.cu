@@ -17,6 +17,8 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <type_traits>
+
 namespace rmp {
 namespace tc {
 
@@ -144,6 +146,13 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
     return fmaf(hx, t, hx);
 }
 
+// 256-bit read-only global load (LDG.E.256): one full 32-byte sector per thread and instruction
+__device__ __forceinline__ void ldg256(const void* ptr, uint32_t (&r)[8]) {
+    asm volatile("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(ptr));
+}
+
 // fire-and-forget fp32 vector reduction into global memory (REDG.E.ADD.F32x4)
 __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
     asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -154,18 +163,32 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<const uint32_t*>(&h);
 }
 
+__device__ __forceinline__ void store_act_chunk(uint8_t* a_buf, int row, int col0, const float (&v)[32]) {
+    // 32 consecutive columns starting at col0 -> K-block col0/64, 16-byte chunks (col0%64)/8 ..
+    uint8_t* kb = a_buf + (col0 >> 6) * kKBlockBytes;
+    const int j0 = (col0 & 63) >> 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const uint4 pk = make_uint4(pack_bf16(v[8 * j + 0], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                    pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+        *reinterpret_cast<uint4*>(kb + sw128_chunk(row, j0 + j)) = pk;
+    }
+}
+
 struct EdgeParams {
-    const float* Pc;                 // [Nv, ld_p] centre projection incl. stage-0 bias
-    const float* Pn;                 // [Nv, ld_p] neighbour projection
-    int ld_p;
+    const float* Pc;                 // [Nv, ld_pc] fp32 centre projection incl. stage-0 bias (L1-resident rows)
+    const uint16_t* Pn;              // [Nv, ld_pn] bf16 neighbour projection (random rows: gathered from L2)
+    int ld_pc, ld_pn;
     const int32_t* ctr;
     const int32_t* nbr;
+    const int32_t* row_ptr;          // [Nv+1] CSR edge offsets (edges of a node are contiguous)
     const float* bias[kMaxStages];   // stages >= 1
     int num_stages;
     float alpha;
     float* agg;                      // [Nv,128] fp32, pre-zeroed
     int n_edges;
     float* debug;                    // optional [num_stages][n_edges][128] post-activation dump
+    long long* timeline;             // optional clock64 trace of CTA 0 / first epilogue warp (tests, tuning)
 };
 
 // Two edge tiles are in flight per CTA: epilogue group g (8 warps) owns the tiles with local index
@@ -197,6 +220,11 @@ __device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
+// wait used by the role threads that are not latency critical: poll, then sleep, so the single
+// spinning lane does not take issue slots from the epilogue warps of its SM sub-partition
+__device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity, unsigned ns) {
+    while (!mbar_test(bar, parity)) __nanosleep(ns);
+}
 __device__ __forceinline__ void group_bar_sync(int g) {
     asm volatile("bar.sync %0, %1;" ::"r"(g + 1), "n"(kEpiThreads) : "memory");
 }
@@ -213,11 +241,22 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
 #pragma unroll
     for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld4(uint32_t taddr, float (&v)[4]) {
+    uint32_t r[4];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 4; ++i) v[i] = __uint_as_float(r[i]);
+}
 // Instruction descriptor with A MN-major (the [edge][channel] activation read as A = m3^T), B K-major
 __host__ __device__ constexpr uint32_t instr_desc_bf16_amn(int M, int N) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (1u << 15) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
+// 18 warps: the register file is allocated to a CTA in 4-warp granules (20 x 32 x 96 = 61440), so 96 is the cap
 __global__ void __launch_bounds__(kEdgeThreads, 1)
 edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant__ CUtensorMap tm_w,
                    const EdgeParams p) {
@@ -242,9 +281,9 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
         for (int b = 0; b < kABufs; ++b) { mbar_init(&bars->a_full[b], 1); mbar_init(&bars->a_empty[b], 1); }
         for (int g = 0; g < kGroups; ++g) {
             mbar_init(&bars->acc_full[g], 1);
-            mbar_init(&bars->act_ready[g], kEpiThreads);
+            mbar_init(&bars->act_ready[g], kGroups * kEpiThreads);
             mbar_init(&bars->agg_full[g], 1);
-            mbar_init(&bars->agg_empty[g], kEpiThreads);
+            mbar_init(&bars->agg_empty[g], kGroups * kEpiThreads);
         }
         fence_barrier_init();
     }
@@ -266,7 +305,7 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
             for (int i = 0; i < my_tiles; ++i) {
                 const int b = i % kABufs;
                 const int tile = blockIdx.x + i * gridDim.x;
-                mbar_wait(&bars->a_empty[b], ((i / kABufs) & 1) ^ 1);
+                mbar_wait_relaxed(&bars->a_empty[b], ((i / kABufs) & 1) ^ 1, 400);
                 mbar_expect_tx(&bars->a_full[b], kTileBytes);
                 for (int kb = 0; kb < 2; ++kb)
                     tma_load_2d(sA + (size_t)b * kTileBytes + kb * kKBlockBytes, &tm_e, &bars->a_full[b], kb * 64,
@@ -285,6 +324,7 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
             mbar_wait(&bars->w_full, 0);
             int remaining = my_tiles;
             while (remaining > 0) {
+                bool progressed = false;
 #pragma unroll
                 for (int g = 0; g < kGroups; ++g) {
                     if (ti[g] >= my_tiles) continue;
@@ -294,6 +334,7 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
                     else if (s < S) ready = mbar_test(&bars->act_ready[g], ph_act[g]);
                     else ready = mbar_test(&bars->act_ready[g], ph_act[g]) && mbar_test(&bars->agg_empty[g], ph_ae[g] ^ 1);
                     if (!ready) continue;
+                    progressed = true;
                     tc_fence_after();
                     const uint32_t a_addr = smem_u32(sA + (size_t)b * kTileBytes);
                     if (s < S) {
@@ -331,139 +372,220 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
                         --remaining;
                     }
                 }
+                if (!progressed) __nanosleep(120);     // do not steal issue slots from the epilogue warps
             }
         }
         __syncwarp();
     } else {
-        // ===================== epilogue groups =====================
-        const int g = (warp - 2) >> 3;                   // group 0: warps 2..9, group 1: warps 10..17
-        const int half = ((warp - 2) >> 2) & 1;          // output column half == K-block of the next stage
+        // ===================== epilogue: 16 warps, time-multiplexed over the two in-flight tiles ==========
+        // warp -> (TMEM lane group = warp % 4, column quarter): thread = one edge row x 32 columns.  All 16
+        // warps run stage s of tile A, then stage s of tile B; while they work on one tile the tensor pipe
+        // runs the next GEMM of the other, so neither side waits for the other in steady state.
+        const int ew = warp - 2;
+        const int quarter = ew >> 2;                     // 32-column slice; K-block = quarter / 2
         const int lane_grp = warp & 3;                   // TMEM lanes this warp may touch: 32*(warp%4)..+31
         const int row = lane_grp * 32 + lane;
+        const int col0 = quarter * 32;
         const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
-        const uint32_t t_acc = t_row + (uint32_t)(g * 128);
-        const uint32_t t_agg = t_row + 256u + (uint32_t)(g * 32);
-        int* s_ctr = s_int + g * kIntsPerGroup;
-        int* s_start = s_ctr + kTileM;
-        int* s_end = s_start + kTileM;
-        int* s_misc = s_end + kTileM;                    // [0] = nslots, [1] = 1 if the tile bypasses the selector MMA
-        uint8_t* sel = sSel + g * kSelBytes;
-        uint32_t ph_acc = 0, ph_agg = 0;
-        for (int i = g; i < my_tiles; i += kGroups) {
-            const int tile = blockIdx.x + i * gridDim.x;
-            const int e = tile * kTileM + row;
-            const bool valid = e < p.n_edges;
-            const int c = valid ? __ldg(p.ctr + e) : -1;
-            const int nb = valid ? __ldg(p.nbr + e) : 0;
-            uint8_t* a_buf = sA + (size_t)(i % kABufs) * kTileBytes;
+        uint32_t ph_acc[kGroups] = {0, 0}, ph_agg[kGroups] = {0, 0};
+        int tl_n = 0;
+        const bool tl_on = p.timeline != nullptr && blockIdx.x == 0 && threadIdx.x == 64;
+        auto stamp = [&](int tag) {
+            if (tl_on && tl_n < 4000) { p.timeline[tl_n * 2] = tag; p.timeline[tl_n * 2 + 1] = clock64(); ++tl_n; }
+        };
 
-            // ---- segment bookkeeping + selector matrix (edges of a node are contiguous) ----
-            if (half == 0) s_ctr[row] = c;
-            group_bar_sync(g);
-            const int first_node = s_ctr[0];
-            {
-                const int prev = row > 0 ? s_ctr[row - 1] : -2;
-                const int next = row < kTileM - 1 ? s_ctr[row + 1] : -2;
-                if (half == 0 && valid) {
-                    if (c != prev) s_start[c - first_node] = row;
-                    if (c != next) {
-                        s_end[c - first_node] = row + 1;
-                        if (next < 0) { s_misc[0] = c - first_node + 1; s_misc[1] = (c - first_node + 1) > kSelSlots; }
-                    }
-                }
+        // (centre, neighbour) node of this thread's edge row in local tile i; -1 marks rows past the end
+        auto load_idx = [&](int i, int& c, int& nb) {
+            c = -1; nb = 0;
+            if (i < my_tiles) {
+                const int e = (blockIdx.x + i * gridDim.x) * kTileM + row;
+                if (e < p.n_edges) { c = __ldg(p.ctr + e); nb = __ldg(p.nbr + e); }
             }
-            group_bar_sync(g);
-            const int nslots = s_misc[0];
-            const bool bypass = nslots > kSelSlots;      // tiny-degree nodes: sum with vector reductions instead
-            if (!bypass && row < kSelSlots) {
-                const int st = row < nslots ? s_start[row] : 0, en = row < nslots ? s_end[row] : 0;
-#pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    uint32_t w[4];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        const int r0 = half * 64 + j * 8 + q * 2;
-                        const uint32_t lo = (r0 >= st && r0 < en) ? 0x3F80u : 0u;
-                        const uint32_t hi = (r0 + 1 >= st && r0 + 1 < en) ? 0x3F80u : 0u;
-                        w[q] = lo | (hi << 16);
-                    }
-                    *reinterpret_cast<uint4*>(sel + half * (kSelSlots * 128) + sw128_chunk(row, j)) =
-                        make_uint4(w[0], w[1], w[2], w[3]);
-                }
-            }
+        };
+        int c_nx0, nb_nx0, c_nx1, nb_nx1;
+        load_idx(0, c_nx0, nb_nx0);
+        load_idx(1, c_nx1, nb_nx1);
+        // stage biases (stages >= 1) live in shared memory: broadcast LDS instead of global loads per chunk
+        float* s_bias = reinterpret_cast<float*>(s_int + kGroups * kIntsPerGroup);       // [kMaxStages][128]
+        s_bias += (4 - ((smem_u32(s_bias) >> 2) & 3)) & 3;                                // 16-byte aligned for LDS.128
+        for (int t = threadIdx.x - 64; t < (S - 1) * 128; t += kGroups * kEpiThreads) {
+            const int st = 1 + t / 128;
+            const float* bsp = st == 1 ? p.bias[1] : (st == 2 ? p.bias[2] : p.bias[3]);
+            s_bias[st * 128 + (t & 127)] = __ldg(bsp + (t & 127));
+        }
+        asm volatile("bar.sync 1, %0;" ::"n"(kGroups * kEpiThreads) : "memory");
 
-            // ---- chained stage epilogues: TMEM -> (+gather / +bias) -> GELU -> bf16 -> smem A operand ----
-            for (int s = 0; s < S; ++s) {
-                mbar_wait(&bars->acc_full[g], ph_acc); ph_acc ^= 1;
+        for (int i0 = 0; i0 < my_tiles; i0 += kGroups) {
+            stamp(90);
+            const int c_cur[kGroups] = {c_nx0, c_nx1}, nb_cur[kGroups] = {nb_nx0, nb_nx1};
+            int fn[kGroups] = {0, 0}, ns[kGroups] = {0, 0};
+
+            // stage-0 addend of this row's 32 columns: Pc[centre] + Pn[neighbour], combined while the GEMM runs
+            float4 add[8];
+            auto gather_addend = [&](int g) {
+                if (c_cur[g] >= 0) {
+                    const float* pc = p.Pc + (size_t)c_cur[g] * p.ld_pc + col0;
+                    const uint16_t* pn = p.Pn + (size_t)nb_cur[g] * p.ld_pn + col0;
+                    uint32_t w[2][8], f[4][8];
+                    ldg256(pn, w[0]); ldg256(pn + 16, w[1]);                 // 32 bf16 = two 32-byte sectors
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) ldg256(pc + 8 * q, f[q]);    // 32 fp32 = four sectors
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {                            // columns 4q .. 4q+3
+                        const uint32_t w0 = w[q >> 2][(q & 3) * 2], w1 = w[q >> 2][(q & 3) * 2 + 1];
+                        const uint32_t* fq = &f[q >> 1][(q & 1) * 4];
+                        add[q].x = __uint_as_float(fq[0]) + __uint_as_float(w0 << 16);
+                        add[q].y = __uint_as_float(fq[1]) + __uint_as_float(w0 & 0xffff0000u);
+                        add[q].z = __uint_as_float(fq[2]) + __uint_as_float(w1 << 16);
+                        add[q].w = __uint_as_float(fq[3]) + __uint_as_float(w1 & 0xffff0000u);
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) add[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+            };
+            gather_addend(0);
+            stamp(95);
+            // streaming index loads (HBM) are issued only now, after the L2 gather was consumed, so that nothing
+            // on the critical path shares a scoreboard with them; they land during the stage epilogues
+            load_idx(i0 + kGroups, c_nx0, nb_nx0);       // indices of the next pair, a whole pair of tiles ahead
+            load_idx(i0 + kGroups + 1, c_nx1, nb_nx1);
+#pragma unroll
+            for (int g = 0; g < kGroups; ++g)            // node slots of the two tiles, consumed after stage 0
+                if (i0 + g < my_tiles) {
+                    const int e_base = (blockIdx.x + (i0 + g) * gridDim.x) * kTileM;
+                    fn[g] = __ldg(p.ctr + e_base);
+                    ns[g] = __ldg(p.ctr + min(e_base + kTileM, p.n_edges) - 1);
+                }
+
+            // one (tile, stage) epilogue; FIRST selects the stage-0 flavour at compile time so that the gathered
+            // addend registers are live in that code only
+            auto stage = [&](auto first_tag, int s, int g) {
+                constexpr bool FIRST = decltype(first_tag)::value;
+                const int i = i0 + g;
+                if (i >= my_tiles) return;
+                const bool valid = c_cur[g] >= 0;
+                const bool bypass = (ns[g] - fn[g] + 1) > kSelSlots;
+                uint8_t* a_buf = sA + (size_t)(i % kABufs) * kTileBytes;
+                stamp(100 + s * 10 + g);                       // about to wait for the accumulator
+                mbar_wait(&bars->acc_full[g], ph_acc[g]); ph_acc[g] ^= 1;
                 tc_fence_after();
+                stamp(200 + s * 10 + g);                       // accumulator ready
+                float v[32];
+                tmem_ld32(t_row + (uint32_t)(g * 128 + col0), v);
+                stamp(300 + s * 10 + g);                       // TMEM load done
+                if constexpr (FIRST) {
 #pragma unroll
-                for (int ch = 0; ch < 2; ++ch) {
-                    const int col0 = half * 64 + ch * 32;
-                    float v[32];
-                    tmem_ld32(t_acc + (uint32_t)col0, v);
-                    if (s == 0) {
-                        if (valid) {
-                            const float4* pc = reinterpret_cast<const float4*>(p.Pc + (size_t)c * p.ld_p + col0);
-                            const float4* pn = reinterpret_cast<const float4*>(p.Pn + (size_t)nb * p.ld_p + col0);
+                    for (int q = 0; q < 8; ++q) {
+                        v[4 * q + 0] += add[q].x; v[4 * q + 1] += add[q].y;
+                        v[4 * q + 2] += add[q].z; v[4 * q + 3] += add[q].w;
+                    }
+                } else {
+                    const float4* bs = reinterpret_cast<const float4*>(s_bias + s * 128 + col0);
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) {
-                                const float4 x = __ldg(pc + q), y = __ldg(pn + q);
-                                v[4 * q + 0] += x.x + y.x; v[4 * q + 1] += x.y + y.y;
-                                v[4 * q + 2] += x.z + y.z; v[4 * q + 3] += x.w + y.w;
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 x = bs[q];
+                        v[4 * q + 0] += x.x; v[4 * q + 1] += x.y; v[4 * q + 2] += x.z; v[4 * q + 3] += x.w;
+                    }
+                }
+                stamp(400 + s * 10 + g);                       // gathers / bias added
+#pragma unroll
+                for (int q0 = 0; q0 < 32; q0 += 8) {           // 8 independent GELUs in flight
+                    float in[8], hx[8];
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float x = v[q0 + q];
+                        in[q] = x * fmaf(x * x, 0.0356774081f, 0.7978845608f);
+                        hx[q] = 0.5f * x;
+                    }
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) asm("tanh.approx.f32 %0, %1;" : "=f"(in[q]) : "f"(in[q]));
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) v[q0 + q] = fmaf(hx[q], in[q], hx[q]);
+                }
+                stamp(500 + s * 10 + g);                       // GELU done
+                if (p.debug && valid) {
+                    const int e = (blockIdx.x + i * gridDim.x) * kTileM + row;
+                    float* dbg = p.debug + ((size_t)s * p.n_edges + e) * 128 + col0;
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) dbg[q] = v[q];
+                }
+                if (s == S - 1 && bypass) {
+                    if (valid) {
+                        float* dst = p.agg + (size_t)c_cur[g] * 128 + col0;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            red_add_v4(dst + 4 * q, v[4 * q] * p.alpha, v[4 * q + 1] * p.alpha,
+                                       v[4 * q + 2] * p.alpha, v[4 * q + 3] * p.alpha);
+                    }
+                } else {
+                    store_act_chunk(a_buf, row, col0, v);
+                }
+                stamp(600 + s * 10 + g);                       // operand stored
+                if constexpr (FIRST) {
+                    if (g == 0) gather_addend(1);              // v[] is dead: start the other tile's gather
+                    // selector matrix of this tile (rows = node slots, K = the tile's 128 edge rows); the MMA
+                    // thread reads it (and the bypass flag) only after the last stage's act_ready
+                    if (threadIdx.x == 64) (s_int + g * kIntsPerGroup + 3 * kTileM)[1] = bypass;
+                    if (!bypass && row < kSelSlots && quarter < 2) {
+                        const int e_base = (blockIdx.x + i * gridDim.x) * kTileM;
+                        int st = 0, en = 0;
+                        if (row < ns[g] - fn[g] + 1) {
+                            st = max(__ldg(p.row_ptr + fn[g] + row) - e_base, 0);
+                            en = min(__ldg(p.row_ptr + fn[g] + row + 1) - e_base, kTileM);
+                        }
+                        uint8_t* sel = sSel + g * kSelBytes + quarter * (kSelSlots * 128);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            uint32_t w[4];
+#pragma unroll
+                            for (int q = 0; q < 4; ++q) {
+                                const int r0 = quarter * 64 + j * 8 + q * 2;
+                                const uint32_t lo = (r0 >= st && r0 < en) ? 0x3F80u : 0u;
+                                const uint32_t hi = (r0 + 1 >= st && r0 + 1 < en) ? 0x3F80u : 0u;
+                                w[q] = lo | (hi << 16);
                             }
-                        }
-                    } else {
-                        const float* bsp = s == 1 ? p.bias[1] : (s == 2 ? p.bias[2] : p.bias[3]);
-                        const float4* bs = reinterpret_cast<const float4*>(bsp + col0);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 x = __ldg(bs + q);
-                            v[4 * q + 0] += x.x; v[4 * q + 1] += x.y; v[4 * q + 2] += x.z; v[4 * q + 3] += x.w;
-                        }
-                    }
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) v[q] = gelu_tanh_fast(v[q]);
-                    if (p.debug && valid) {
-                        float* dbg = p.debug + ((size_t)s * p.n_edges + e) * 128 + col0;
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) dbg[q] = v[q];
-                    }
-                    if (s == S - 1 && bypass) {
-                        if (valid) {
-                            float* dst = p.agg + (size_t)c * 128 + col0;
-#pragma unroll
-                            for (int q = 0; q < 8; ++q)
-                                red_add_v4(dst + 4 * q, v[4 * q] * p.alpha, v[4 * q + 1] * p.alpha,
-                                           v[4 * q + 2] * p.alpha, v[4 * q + 3] * p.alpha);
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint4 pk = make_uint4(pack_bf16(v[8 * j + 0], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                                        pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-                            *reinterpret_cast<uint4*>(a_buf + half * kKBlockBytes + sw128_chunk(row, ch * 4 + j)) = pk;
+                            *reinterpret_cast<uint4*>(sel + sw128_chunk(row, j)) = make_uint4(w[0], w[1], w[2], w[3]);
                         }
                     }
                 }
                 tc_fence_before();
                 fence_proxy_async();
                 mbar_arrive(&bars->act_ready[g]);
+                stamp(700 + s * 10 + g);                       // fences + arrive done
+            };
+            stage(std::true_type{}, 0, 0);
+            stage(std::true_type{}, 0, 1);
+            for (int s = 1; s < S; ++s) {
+                stage(std::false_type{}, s, 0);
+                stage(std::false_type{}, s, 1);
             }
 
-            // ---- neighbour sums out of TMEM: lane = channel, column = node slot ----
-            mbar_wait(&bars->agg_full[g], ph_agg); ph_agg ^= 1;
-            tc_fence_after();
-            if (!bypass && half == 0) {
-                float v[16];
-                tmem_ld16(t_agg, v);
-                float* dst = p.agg + (size_t)first_node * 128 + row;       // row == channel here
+            // ---- neighbour sums out of TMEM: lane = channel, columns = node slots, 4 slots per column quarter ----
 #pragma unroll
-                for (int n = 0; n < kSelSlots; ++n)
-                    if (n < nslots) asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + n * 128), "f"(v[n] * p.alpha) : "memory");
+            for (int g = 0; g < kGroups; ++g) {
+                const int i = i0 + g;
+                if (i >= my_tiles) continue;
+                stamp(800 + g);
+                mbar_wait(&bars->agg_full[g], ph_agg[g]); ph_agg[g] ^= 1;
+                tc_fence_after();
+                stamp(810 + g);
+                const int nslots = ns[g] - fn[g] + 1;
+                if (nslots <= kSelSlots && quarter * 4 < nslots) {       // warp-uniform
+                    float v[4];
+                    tmem_ld4(t_row + 256u + (uint32_t)(g * 32 + quarter * 4), v);
+                    float* dst = p.agg + (size_t)(fn[g] + quarter * 4) * 128 + row;      // row == channel here
+#pragma unroll
+                    for (int n = 0; n < 4; ++n)
+                        if (quarter * 4 + n < nslots)
+                            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + n * 128), "f"(v[n] * p.alpha) : "memory");
+                }
+                tc_fence_before();
+                mbar_arrive(&bars->agg_empty[g]);
+                stamp(820 + g);
             }
-            tc_fence_before();
-            mbar_arrive(&bars->agg_empty[g]);
         }
+        if (tl_on) p.timeline[7999] = tl_n;
     }
 
     tc_fence_before();
@@ -497,7 +619,8 @@ struct NodeParams {
     const float* ln2_g; const float* ln2_b;
     float* x1;                  // [n_rows,128] fp32 scratch (residual), needed when a kind-1 stage exists
     float* h_out;               // [n_rows,128]
-    float* p_out;               // [n_rows,256]
+    float* p_out;               // kind-2 stage: columns [0,128) fp32 [n_rows,128] (centre projection)
+    uint16_t* pn_out;           //               columns [128,256) bf16 [n_rows,128] (neighbour projection)
     NodeStage st[kNodeMaxStages];
     int S;
     int n_rows;
@@ -505,18 +628,6 @@ struct NodeParams {
 struct alignas(8) NodeBarriers {
     uint64_t w_full[kRing], w_empty[kRing], acc_full, act_ready;
 };
-
-__device__ __forceinline__ void store_act_chunk(uint8_t* a_buf, int row, int col0, const float (&v)[32]) {
-    // 32 consecutive columns starting at col0 -> K-block col0/64, 16-byte chunks (col0%64)/8 ..
-    uint8_t* kb = a_buf + (col0 >> 6) * kKBlockBytes;
-    const int j0 = (col0 & 63) >> 3;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        const uint4 pk = make_uint4(pack_bf16(v[8 * j + 0], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                    pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
-        *reinterpret_cast<uint4*>(kb + sw128_chunk(row, j0 + j)) = pk;
-    }
-}
 
 __global__ void __launch_bounds__(kThreads, 1)
 node_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
@@ -712,10 +823,19 @@ node_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
 #pragma unroll
                             for (int q = 0; q < 32; ++q) v[q] = gelu_tanh_fast(v[q]);
                             store_act_chunk(sA, row, col0, v);
-                        } else if (valid) {                   // kind 2: fp32 projection store
-                            float4* dst = reinterpret_cast<float4*>(p.p_out + (size_t)r * stg.N + col0);
+                        } else if (valid) {                   // kind 2: projections, centre fp32 | neighbour bf16
+                            if (col0 < 128) {
+                                float4* dst = reinterpret_cast<float4*>(p.p_out + (size_t)r * 128 + col0);
 #pragma unroll
-                            for (int q = 0; q < 8; ++q) dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                                for (int q = 0; q < 8; ++q)
+                                    dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                            } else {
+                                uint4* dst = reinterpret_cast<uint4*>(p.pn_out + (size_t)r * 128 + (col0 - 128));
+#pragma unroll
+                                for (int j = 0; j < 4; ++j)
+                                    dst[j] = make_uint4(pack_bf16(v[8 * j + 0], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
+                                                        pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+                            }
                         }
                     }
                 }
@@ -774,12 +894,28 @@ static int make_map_bf16_rows128(CUtensorMap* map, const void* base, uint64_t ro
 
 using namespace rmp;
 
+extern "C" int rmp_edge_mlp_bf16_traced(const void* h_E_bf16, const void* W_bf16, int num_stages,
+                                        const float* const* bias, const float* Pc, const void* Pn_bf16,
+                                        const int32_t* ctr, const int32_t* nbr, const int32_t* row_ptr, int n_edges,
+                                        float alpha, float* agg, float* debug, long long* timeline, void* stream);
+
 extern "C" int rmp_edge_mlp_bf16(const void* h_E_bf16, const void* W_bf16, int num_stages, const float* const* bias,
-                                 const float* Pc, const float* Pn, int ld_p, const int32_t* ctr, const int32_t* nbr,
-                                 int n_edges, float alpha, float* agg, float* debug, void* stream) {
+                                 const float* Pc, const void* Pn_bf16, const int32_t* ctr, const int32_t* nbr,
+                                 const int32_t* row_ptr, int n_edges, float alpha, float* agg, float* debug,
+                                 void* stream) {
+    return rmp_edge_mlp_bf16_traced(h_E_bf16, W_bf16, num_stages, bias, Pc, Pn_bf16, ctr, nbr, row_ptr, n_edges, alpha,
+                                    agg, debug, nullptr, stream);
+}
+
+extern "C" int rmp_edge_mlp_bf16_traced(const void* h_E_bf16, const void* W_bf16, int num_stages,
+                                        const float* const* bias, const float* Pc, const void* Pn_bf16,
+                                        const int32_t* ctr, const int32_t* nbr, const int32_t* row_ptr, int n_edges,
+                                        float alpha, float* agg, float* debug, long long* timeline, void* stream) {
+    const void* Pn = Pn_bf16;
+    RMP_REQUIRE(row_ptr, RMP_E_ARG, "rmp_edge_mlp_bf16: row_ptr is null");
     RMP_REQUIRE(h_E_bf16 && W_bf16 && Pc && Pn && ctr && nbr && agg && bias, RMP_E_ARG, "rmp_edge_mlp_bf16: null pointer");
     RMP_REQUIRE(num_stages >= 1 && num_stages <= tc::kMaxStages, RMP_E_SHAPE, "rmp_edge_mlp_bf16: 1..4 message layers");
-    RMP_REQUIRE(n_edges >= 0 && ld_p >= 128 && (ld_p & 3) == 0, RMP_E_ARG, "rmp_edge_mlp_bf16: bad sizes");
+    RMP_REQUIRE(n_edges >= 0, RMP_E_ARG, "rmp_edge_mlp_bf16: bad sizes");
     RMP_REQUIRE(aligned16(h_E_bf16) && aligned16(W_bf16) && aligned16(Pc) && aligned16(Pn), RMP_E_ALIGN,
                 "rmp_edge_mlp_bf16: pointers must be 16-byte aligned");
     if (n_edges == 0) return RMP_OK;
@@ -789,14 +925,17 @@ extern "C" int rmp_edge_mlp_bf16(const void* h_E_bf16, const void* W_bf16, int n
     rc = tc::make_map_bf16_rows128(&tm_w, W_bf16, (uint64_t)num_stages * 128);
     if (rc) return rc;
     tc::EdgeParams p{};
-    p.Pc = Pc; p.Pn = Pn; p.ld_p = ld_p; p.ctr = ctr; p.nbr = nbr;
+    p.Pc = Pc; p.Pn = reinterpret_cast<const uint16_t*>(Pn); p.ld_pc = 128; p.ld_pn = 128; p.ctr = ctr; p.nbr = nbr;
+    p.row_ptr = row_ptr;
     for (int s = 1; s < num_stages; ++s) {
         RMP_REQUIRE(bias[s] && aligned16(bias[s]), RMP_E_ALIGN, "rmp_edge_mlp_bf16: bias[%d] null or unaligned", s);
         p.bias[s] = bias[s];
     }
     p.num_stages = num_stages; p.alpha = alpha; p.agg = agg; p.n_edges = n_edges; p.debug = debug;
+    p.timeline = timeline;
     const size_t smem = 1024 + (size_t)(num_stages + tc::kABufs) * tc::kTileBytes + tc::kGroups * tc::kSelBytes +
-                        sizeof(tc::Barriers) + 16 + tc::kGroups * (3 * tc::kTileM + 4) * sizeof(int);
+                        sizeof(tc::Barriers) + 16 + tc::kGroups * (3 * tc::kTileM + 4) * sizeof(int) +
+                        tc::kMaxStages * 128 * sizeof(float) + 16;
     RMP_REQUIRE(smem <= 227 * 1024, RMP_E_SHAPE, "rmp_edge_mlp_bf16: %zu B of shared memory needed", smem);
     cudaFuncSetAttribute(tc::edge_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int n_tiles = ceil_div(n_edges, tc::kTileM);
@@ -808,7 +947,8 @@ extern "C" int rmp_edge_mlp_bf16(const void* h_E_bf16, const void* W_bf16, int n
 extern "C" int rmp_node_mlp_bf16(const float* h_in, float* agg, int prologue_ln, const float* ln1_g, const float* ln1_b,
                                  int num_stages, const void* const* W_bf16, const int32_t* K, const int32_t* N,
                                  const int32_t* kind, const float* const* bias, const float* ln2_g, const float* ln2_b,
-                                 float* x1_scratch, float* h_out, float* p_out, int n_rows, void* stream) {
+                                 float* x1_scratch, float* h_out, float* p_out, void* pn_out_bf16, int n_rows,
+                                 void* stream) {
     RMP_REQUIRE(h_in && W_bf16 && K && N && kind && bias, RMP_E_ARG, "rmp_node_mlp_bf16: null pointer");
     RMP_REQUIRE(num_stages >= 1 && num_stages <= tc::kNodeMaxStages, RMP_E_SHAPE, "rmp_node_mlp_bf16: 1..5 stages");
     RMP_REQUIRE(!prologue_ln || (ln1_g && ln1_b), RMP_E_ARG, "rmp_node_mlp_bf16: LayerNorm-1 parameters missing");
@@ -825,8 +965,8 @@ extern "C" int rmp_node_mlp_bf16(const float* h_in, float* agg, int prologue_ln,
         RMP_REQUIRE(kind[s] >= 0 && kind[s] <= 2, RMP_E_ARG, "rmp_node_mlp_bf16: stage kind");
         if (kind[s] == 1) RMP_REQUIRE(N[s] == 128 && ln2_g && ln2_b && x1_scratch && h_out && prologue_ln, RMP_E_ARG,
                                       "rmp_node_mlp_bf16: residual+LayerNorm stage needs 128 outputs, LN params, scratch");
-        if (kind[s] == 2) RMP_REQUIRE(p_out && s == num_stages - 1, RMP_E_ARG,
-                                      "rmp_node_mlp_bf16: projection stage must be last and needs p_out");
+        if (kind[s] == 2) RMP_REQUIRE(p_out && pn_out_bf16 && s == num_stages - 1 && N[s] == 256, RMP_E_ARG,
+                                      "rmp_node_mlp_bf16: projection stage must be last, 256 wide, with p_out and pn_out");
         int rc = tc::make_map_bf16(&maps[s], W_bf16[s], (uint64_t)N[s], (uint64_t)K[s], (uint32_t)N[s]);
         if (rc) return rc;
         p.st[s].K = K[s]; p.st[s].N = N[s]; p.st[s].kind = kind[s]; p.st[s].bias = bias[s];
@@ -834,6 +974,7 @@ extern "C" int rmp_node_mlp_bf16(const float* h_in, float* agg, int prologue_ln,
     }
     p.h_in = h_in; p.agg = agg; p.prologue_ln = prologue_ln; p.ln1_g = ln1_g; p.ln1_b = ln1_b;
     p.ln2_g = ln2_g; p.ln2_b = ln2_b; p.x1 = x1_scratch; p.h_out = h_out; p.p_out = p_out;
+    p.pn_out = reinterpret_cast<uint16_t*>(pn_out_bf16);
     p.S = num_stages; p.n_rows = n_rows;
     const size_t smem = 1024 + 4 * tc::kKBlockBytes + tc::kRing * tc::kSlotBytes + sizeof(tc::NodeBarriers) + 16 +
                         4 * tc::kTileM * sizeof(float);

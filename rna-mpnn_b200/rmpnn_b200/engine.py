@@ -134,12 +134,12 @@ class RDesignEngine:
             # layer's node kernel, or computed here for the first layer
             P = getattr(self, "_next_P", None)
             self._next_P = None
-            if P is None or P.shape[0] != g.Nv:
-                P = torch.empty(g.Nv, 2 * ops.HIDDEN, dtype=torch.float32, device=h_V.device)
-                ops.node_mlp_bf16(h_V, [(*lw.proj16, 2)], g.Nv, p_out=P)
+            if P is None or P[0].shape[0] != g.Nv:
+                P = self._proj_buffers(g.Nv, h_V.device)
+                ops.node_mlp_bf16(h_V, [(*lw.proj16, 2)], g.Nv, p_out=P[0], pn_out=P[1])
             if self.kernel_timer is not None:
                 ev[0].record(torch.cuda.current_stream())
-            ops.edge_mlp_bf16(h_E, lw.msg_w16, lw.msg_bias, P, g.ctr, g.nbr, agg, 1.0 / self.scale)
+            ops.edge_mlp_bf16(h_E, lw.msg_w16, lw.msg_bias, P[0], P[1], g.ctr, g.nbr, g.row_ptr, agg, 1.0 / self.scale)
         else:
             ops.row_mlp([(h_E, None), (h_V, g.ctr), (h_V, g.nbr)], [(m, True) for m in lw.message],
                         ops.EPI_SEGSUM, agg, g.Ne, seg_id=g.ctr, alpha=1.0 / self.scale)
@@ -159,16 +159,21 @@ class RDesignEngine:
         lw = self.w.layers[l]
         stages = [(w, b, 0) for w, b in lw.dense16[:-1]] + [(*lw.dense16[-1], 1)]
         nxt = self.w.layers[l + 1] if l + 1 < len(self.w.layers) else None
-        p_out = None
+        pc = pn = None
         if nxt is not None and nxt.proj16 is not None:
             stages.append((*nxt.proj16, 2))
-            p_out = torch.empty(g.Nv, 2 * ops.HIDDEN, dtype=torch.float32, device=h_V.device)
+            pc, pn = self._proj_buffers(g.Nv, h_V.device)
         out = torch.empty_like(h_V)
         x1 = torch.empty_like(h_V)
         ops.node_mlp_bf16(h_V, stages, g.Nv, agg=agg, ln1=(lw.norm1_w, lw.norm1_b), ln2=(lw.norm2_w, lw.norm2_b),
-                          x1=x1, h_out=out, p_out=p_out)
-        self._next_P = p_out
+                          x1=x1, h_out=out, p_out=pc, pn_out=pn)
+        self._next_P = (pc, pn) if pc is not None else None
         return out
+
+    @staticmethod
+    def _proj_buffers(n, device):
+        return (torch.empty(n, ops.HIDDEN, dtype=torch.float32, device=device),
+                torch.empty(n, ops.HIDDEN, dtype=torch.bfloat16, device=device))
 
     def encode(self, X, mask, sizes=None, return_layers=False):
         g = self.graph(X, mask, sizes)

@@ -205,31 +205,32 @@ def readout_head(h, weight, bias, temperature: float = 0.0, seed: int = 0, want_
     return logits, probs, samples
 
 
-def edge_mlp_bf16(h_E16, W16, biases, P, ctr, nbr, agg, alpha: float, debug=None):
+def edge_mlp_bf16(h_E16, W16, biases, Pc, Pn16, ctr, nbr, row_ptr, agg, alpha: float, debug=None):
     """tcgen05 edge-message kernel (rmp_edge_mlp_bf16).
 
     h_E16 [Ne,128] bf16; W16 [S*128,128] bf16 (rows of W_0e, W_1, ..); biases: list of S fp32 [128]
-    tensors (entry 0 ignored); P [Nv,256] fp32 = [Pc | Pn] node projections; agg [Nv,128] fp32 zeroed.
+    tensors (entry 0 ignored); Pc [Nv,128] fp32 / Pn16 [Nv,128] bf16 node projections; agg [Nv,128] fp32 zeroed.
     """
-    _need_cuda(h_E16, W16, P, ctr, nbr, agg, debug, *[b for b in biases if b is not None])
+    _need_cuda(h_E16, W16, Pc, Pn16, ctr, nbr, row_ptr, agg, debug, *[b for b in biases if b is not None])
     S = W16.shape[0] // 128
     assert h_E16.dtype == torch.bfloat16 and W16.dtype == torch.bfloat16 and h_E16.is_contiguous() and W16.is_contiguous()
-    assert P.dtype == torch.float32 and P.is_contiguous() and P.shape[1] == 256
+    assert Pc.dtype == torch.float32 and Pc.is_contiguous() and Pc.shape[1] == 128
+    assert Pn16.dtype == torch.bfloat16 and Pn16.is_contiguous() and Pn16.shape[1] == 128
     barr = (C.c_void_p * 4)(*([_ptr(b) if b is not None else None for b in biases] + [None] * (4 - len(biases))))
-    pc = P.data_ptr()
-    check(lib().rmp_edge_mlp_bf16(_ptr(h_E16), _ptr(W16), S, C.cast(barr, C.c_void_p), pc, pc + 128 * 4, 256,
-                                  _ptr(ctr), _ptr(nbr), h_E16.shape[0], float(alpha), _ptr(agg), _ptr(debug),
+    check(lib().rmp_edge_mlp_bf16(_ptr(h_E16), _ptr(W16), S, C.cast(barr, C.c_void_p), _ptr(Pc), _ptr(Pn16),
+                                  _ptr(ctr), _ptr(nbr), _ptr(row_ptr), h_E16.shape[0], float(alpha), _ptr(agg), _ptr(debug),
                                   _stream()), "rmp_edge_mlp_bf16")
     return agg
 
 
-def node_mlp_bf16(h_in, stages, n_rows, agg=None, ln1=None, ln2=None, x1=None, h_out=None, p_out=None):
+def node_mlp_bf16(h_in, stages, n_rows, agg=None, ln1=None, ln2=None, x1=None, h_out=None, p_out=None, pn_out=None):
     """tcgen05 node-update kernel (rmp_node_mlp_bf16).
 
     stages: [(W bf16 [N,K], bias fp32 [N], kind)], kind 0 = GELU, 1 = residual + LayerNorm2 -> h_out,
-    2 = fp32 projection store -> p_out.  ln1 = (gamma, beta) enables x1 = LayerNorm1(h_in + agg).
+    2 = projection store -> p_out [n,128] fp32 (columns 0..127) + pn_out [n,128] bf16 (columns 128..255).
+    ln1 = (gamma, beta) enables x1 = LayerNorm1(h_in + agg).
     """
-    _need_cuda(h_in, agg, x1, h_out, p_out, *(ln1 or ()), *(ln2 or ()))
+    _need_cuda(h_in, agg, x1, h_out, p_out, pn_out, *(ln1 or ()), *(ln2 or ()))
     n = len(stages)
     Ws = (C.c_void_p * n)(*[_ptr(w) for w, _, _ in stages])
     Bs = (C.c_void_p * n)(*[_ptr(b) for _, b, _ in stages])
@@ -244,8 +245,8 @@ def node_mlp_bf16(h_in, stages, n_rows, agg=None, ln1=None, ln2=None, x1=None, h
     check(lib().rmp_node_mlp_bf16(_ptr(h_in), _ptr(agg), int(ln1 is not None), _ptr(g1), _ptr(b1), n,
                                   C.cast(Ws, C.c_void_p), C.cast(Ks, C.c_void_p), C.cast(Ns, C.c_void_p),
                                   C.cast(kinds, C.c_void_p), C.cast(Bs, C.c_void_p), _ptr(g2), _ptr(b2), _ptr(x1),
-                                  _ptr(h_out), _ptr(p_out), int(n_rows), _stream()), "rmp_node_mlp_bf16")
-    return h_out, p_out
+                                  _ptr(h_out), _ptr(p_out), _ptr(pn_out), int(n_rows), _stream()), "rmp_node_mlp_bf16")
+    return h_out, p_out, pn_out
 
 
 def cast_bf16(src: torch.Tensor) -> torch.Tensor:

@@ -25,7 +25,7 @@ def _edge_reference(hE, W, biases, P, ctr, nbr, alpha, Nv):
     x = _bf(hE)
     for s in range(S):
         pre = x @ _bf(W[s * 128:(s + 1) * 128]).t()
-        pre = pre + (P[ctr.long(), :128] + P[nbr.long(), 128:] if s == 0 else biases[s])
+        pre = pre + (P[ctr.long(), :128] + _bf(P[nbr.long(), 128:]) if s == 0 else biases[s])
         a = F.gelu(pre, approximate="tanh")     # the bf16 arm evaluates the tanh form on MUFU.TANH
         acts.append(a)
         x = _bf(a)
@@ -36,6 +36,11 @@ def _edge_reference(hE, W, biases, P, ctr, nbr, alpha, Nv):
 def _segments(Nv, degs):
     ctr = torch.repeat_interleave(torch.arange(Nv), torch.as_tensor(degs))
     return ctr.to(torch.int32)
+
+
+def _row_ptr(ctr, Nv):
+    counts = torch.bincount(ctr.long(), minlength=Nv)
+    return torch.cat([torch.zeros(1, dtype=torch.long), torch.cumsum(counts, 0)]).to(torch.int32)
 
 
 @pytest.mark.parametrize("Nv,deg,S", [(4, 32, 3), (129, 30, 3), (1600, 25, 3), (300, 2, 3), (500, 1, 2), (37, 48, 2),
@@ -59,11 +64,13 @@ def test_edge_mlp_tc_matches_fp32_reference(Nv, deg, S):
     dbg = torch.zeros(S, Ne, 128, device="cuda")
     agg = torch.zeros(Nv, 128, device="cuda")
     ops.edge_mlp_bf16(hE.cuda().to(torch.bfloat16), W.cuda().to(torch.bfloat16),
-                      [None] + [b.cuda() for b in biases[1:]], P.cuda(), ctr.cuda(), nbr.cuda(), agg, alpha, debug=dbg)
+                      [None] + [b.cuda() for b in biases[1:]], P[:, :128].contiguous().cuda(),
+                      P[:, 128:].contiguous().cuda().to(torch.bfloat16), ctr.cuda(), nbr.cuda(),
+                      _row_ptr(ctr, Nv).cuda(), agg, alpha, debug=dbg)
     torch.cuda.synchronize()
     for s in range(S):
         tol = 2e-3 if s == 0 else 6e-3      # tanh.approx.f32 is 2^-11 accurate; later stages see bf16 re-rounding
-        np.testing.assert_allclose(dbg[s].cpu().numpy(), acts_ref[s].numpy(), atol=tol, rtol=0, err_msg=f"stage {s}")
+        np.testing.assert_allclose(dbg[s].cpu().numpy(), acts_ref[s].numpy(), atol=tol, rtol=4e-3, err_msg=f"stage {s}")
     np.testing.assert_allclose(agg.cpu().numpy(), agg_ref.numpy(), atol=6e-3 * max(1.0, deg / 30), rtol=0)
 
 
@@ -72,20 +79,22 @@ def test_edge_mlp_tc_accumulates_into_agg_and_is_repeatable():
     g = torch.Generator().manual_seed(1)
     Nv, deg = 700, 30
     ctr = _segments(Nv, [deg] * Nv).cuda()
+    rp = _row_ptr(ctr.cpu(), Nv).cuda()
     Ne = ctr.numel()
     nbr = torch.randint(0, Nv, (Ne,), generator=g, dtype=torch.int32).cuda()
     hE = torch.randn(Ne, 128, generator=g).cuda().to(torch.bfloat16)
     W = (torch.randn(384, 128, generator=g) / 11.3).cuda().to(torch.bfloat16)
     b = [None, torch.zeros(128).cuda(), torch.zeros(128).cuda()]
     P = torch.randn(Nv, 256, generator=g).cuda()
+    Pc, Pn = P[:, :128].contiguous(), P[:, 128:].contiguous().to(torch.bfloat16)
     outs = []
     for _ in range(3):
         agg = torch.zeros(Nv, 128, device="cuda")
-        ops.edge_mlp_bf16(hE, W, b, P, ctr, nbr, agg, 1.0)
+        ops.edge_mlp_bf16(hE, W, b, Pc, Pn, ctr, nbr, rp, agg, 1.0)
         outs.append(agg.clone())
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[1], outs[2])   # <= 2 partial sums per node
     agg2 = outs[0].clone()
-    ops.edge_mlp_bf16(hE, W, b, P, ctr, nbr, agg2, 1.0)
+    ops.edge_mlp_bf16(hE, W, b, Pc, Pn, ctr, nbr, rp, agg2, 1.0)
     np.testing.assert_allclose(agg2.cpu().numpy(), 2 * outs[0].cpu().numpy(), rtol=1e-5, atol=1e-5)
 
 
@@ -123,16 +132,18 @@ def test_node_mlp_tc_matches_fp32_reference(n_rows, widths, with_proj):
     agg_d = agg.to(dev)
     h_out = torch.empty(n_rows, 128, device=dev)
     x1_d = torch.empty(n_rows, 128, device=dev)
-    p_out = torch.empty(n_rows, 256, device=dev) if with_proj else None
+    p_out = torch.empty(n_rows, 128, device=dev) if with_proj else None
+    pn_out = torch.empty(n_rows, 128, device=dev, dtype=torch.bfloat16) if with_proj else None
     ops.node_mlp_bf16(h.to(dev), stages, n_rows, agg=agg_d, ln1=tuple(t.to(dev) for t in ln1),
-                      ln2=tuple(t.to(dev) for t in ln2), x1=x1_d, h_out=h_out, p_out=p_out)
+                      ln2=tuple(t.to(dev) for t in ln2), x1=x1_d, h_out=h_out, p_out=p_out, pn_out=pn_out)
     torch.cuda.synchronize()
     np.testing.assert_allclose(x1_d.cpu().numpy(), x1.numpy(), atol=2e-5, rtol=0)
     np.testing.assert_allclose(h_out.cpu().numpy(), h_ref.numpy(), atol=2e-2, rtol=0)
     assert (h_out.cpu() - h_ref).abs().mean().item() < 2e-3
     assert float(agg_d.abs().max()) == 0.0                     # neighbour-sum buffer re-armed for the next layer
     if with_proj:
-        np.testing.assert_allclose(p_out.cpu().numpy(), p_ref.numpy(), atol=3e-2, rtol=0)
+        got = torch.cat([p_out.cpu(), pn_out.float().cpu()], 1)
+        np.testing.assert_allclose(got.numpy(), p_ref.numpy(), atol=4e-2, rtol=0)
 
 
 def test_node_mlp_tc_projection_only():
@@ -140,9 +151,12 @@ def test_node_mlp_tc_projection_only():
     g = torch.Generator().manual_seed(5)
     h = torch.randn(1000, 128, generator=g)
     W, b = torch.randn(256, 128, generator=g) / 11.3, 0.1 * torch.randn(256, generator=g)
-    P = torch.empty(1000, 256, device="cuda")
-    ops.node_mlp_bf16(h.cuda(), [(W.cuda().to(torch.bfloat16), b.cuda(), 2)], 1000, p_out=P)
-    np.testing.assert_allclose(P.cpu().numpy(), (_bf(h) @ _bf(W).t() + b).numpy(), atol=1e-4, rtol=0)
+    Pc = torch.empty(1000, 128, device="cuda")
+    Pn = torch.empty(1000, 128, device="cuda", dtype=torch.bfloat16)
+    ops.node_mlp_bf16(h.cuda(), [(W.cuda().to(torch.bfloat16), b.cuda(), 2)], 1000, p_out=Pc, pn_out=Pn)
+    ref = _bf(h) @ _bf(W).t() + b
+    np.testing.assert_allclose(Pc.cpu().numpy(), ref[:, :128].numpy(), atol=1e-4, rtol=0)
+    np.testing.assert_allclose(Pn.float().cpu().numpy(), _bf(ref[:, 128:]).numpy(), atol=2e-2, rtol=0)
 
 
 @pytest.mark.parametrize("B,L,K,lengths", [(2, 64, 25, [64, 50]), (4, 256, 30, None), (3, 100, 48, [100, 61, 7])])
