@@ -223,6 +223,16 @@ int rmp_node_mlp_bf16(const float* h_in, float* agg, int prologue_ln, const floa
                       const int32_t* kind, const float* const* bias, const float* ln2_g, const float* ln2_b,
                       float* x1_scratch, float* h_out, float* p_out, void* pn_out_bf16, int n_rows, void* stream);
 
+/* Fused edge featurizer of the bf16 arm: raw edge features (a-4, a-5) -> Linear(115->128) on tcgen05 ->
+ * reference Normalize -> h_E as bf16.  Replaces rdesign/model/feature.py:193-206, :215-220, :224 (edge half).
+ *   X [B*N,6,3] fp32, frames [B*N,9] (from rmp_rdesign_raw_features), node_src/ctr/nbr as in rmp_edge_list
+ *   W_perm_bf16 [128,128] bf16: edge_embedding.weight with its input columns permuted to the kernel's
+ *   feature order [rbf 96 | quaternion 4 | direction 15 | 13 zero columns]; bias/gain/beta fp32 [128]
+ *   h_E_bf16 [n_edges,128] bf16 */
+int rmp_edge_embed_bf16(const float* X, const float* frames, const int32_t* node_src, const int32_t* ctr,
+                        const int32_t* nbr, int n_edges, const float* rbf_mu, const void* W_perm_bf16,
+                        const float* bias, const float* gain, const float* beta, void* h_E_bf16, void* stream);
+
 /* fp32 -> bf16 row conversion (h_E storage for the bf16 path), n elements */
 int rmp_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
 

@@ -4,55 +4,9 @@
 // _quaternions, _orientations_coarse, _dihedrals) and :179-220 (feature order).
 // Nothing [B,N,N]-shaped is ever materialised: every node / edge recomputes its
 // few distances from the 6x3 coordinates of its one or two residues.
-#include "common.cuh"
+#include "geom.cuh"
 
 namespace rmp {
-
-struct V3 {
-    float x, y, z;
-};
-__device__ __forceinline__ V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
-__device__ __forceinline__ V3 cross(V3 a, V3 b) {
-    return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x};
-}
-__device__ __forceinline__ float dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
-__device__ __forceinline__ V3 ld3(const float* p) { return {p[0], p[1], p[2]}; }
-
-// v / |v| with 0/0 -> 0  (rdesign/utils/data.py:164-171)
-__device__ __forceinline__ V3 unit_nan0(V3 v) {
-    const float n = sqrtf(dot(v, v));
-    V3 r = {v.x / n, v.y / n, v.z / n};
-    if (isnan(r.x)) r.x = 0.f;
-    if (isnan(r.y)) r.y = 0.f;
-    if (isnan(r.z)) r.z = 0.f;
-    return r;
-}
-// F.normalize: v / max(|v|, eps)
-__device__ __forceinline__ V3 unit_eps(V3 v, float eps) {
-    const float n = fmaxf(sqrtf(dot(v, v)), eps);
-    return {v.x / n, v.y / n, v.z / n};
-}
-__device__ __forceinline__ float sign_of(float v) { return (v > 0.f) ? 1.f : ((v < 0.f) ? -1.f : 0.f); }
-
-// sqrt(|a-b|^2 + 1e-6)   (rdesign/model/feature.py:62,65)
-__device__ __forceinline__ float eps_dist(V3 a, V3 b) {
-    const V3 d = a - b;
-    return sqrtf(dot(d, d) + 1e-6f);
-}
-
-struct RbfMu {
-    float mu[16];
-};
-
-// 16 Gaussian bumps  exp(-((d - mu)/1.25)^2)   (rdesign/model/feature.py:52-58)
-template <typename Store>
-__device__ __forceinline__ void rbf16(float d, const RbfMu& c, Store&& st) {
-#pragma unroll
-    for (int r = 0; r < 16; ++r) {
-        const float z = __fdiv_rn(d - c.mu[r], 1.25f);
-        st(r, expf(-(z * z)));
-    }
-}
 
 // --------------------------------------------------------------------------------
 // local frames: one thread per dense residue  (feature.py:90-107)
@@ -77,11 +31,6 @@ __global__ void __launch_bounds__(256) frames_kernel(const float* __restrict__ X
     q[0] = b1.x; q[1] = b1.y; q[2] = b1.z;
     q[3] = n0.x; q[4] = n0.y; q[5] = n0.z;
     q[6] = t.x;  q[7] = t.y;  q[8] = t.z;
-}
-
-__device__ __forceinline__ V3 rotate(const float* q, V3 d) {
-    return {q[0] * d.x + q[1] * d.y + q[2] * d.z, q[3] * d.x + q[4] * d.y + q[5] * d.z,
-            q[6] * d.x + q[7] * d.y + q[8] * d.z};
 }
 
 // --------------------------------------------------------------------------------
@@ -179,18 +128,9 @@ __global__ void __launch_bounds__(kEdgeTile) edge_raw_kernel(const float* __rest
 #pragma unroll
         for (int c = 0; c < 9; ++c) { Qi[c] = qi[c]; Qj[c] = qj[c]; }
         // orientation quaternion of R = Qi^T Qj   (feature.py:70-88, :124)
-        float R[3][3];
-#pragma unroll
-        for (int r = 0; r < 3; ++r)
-#pragma unroll
-            for (int c = 0; c < 3; ++c) R[r][c] = Qi[0 + r] * Qj[0 + c] + Qi[3 + r] * Qj[3 + c] + Qi[6 + r] * Qj[6 + c];
-        const float Rxx = R[0][0], Ryy = R[1][1], Rzz = R[2][2];
-        float qx = sign_of(R[2][1] - R[1][2]) * (0.5f * sqrtf(fabsf(1.f + (Rxx - Ryy - Rzz))));
-        float qy = sign_of(R[0][2] - R[2][0]) * (0.5f * sqrtf(fabsf(1.f + (-Rxx + Ryy - Rzz))));
-        float qz = sign_of(R[1][0] - R[0][1]) * (0.5f * sqrtf(fabsf(1.f + (-Rxx - Ryy + Rzz))));
-        float qw = sqrtf(fmaxf(1.f + (Rxx + Ryy + Rzz), 0.f)) / 2.f;
-        const float qn = fmaxf(sqrtf(qx * qx + qy * qy + qz * qz + qw * qw), 1e-12f);
-        f[0] = qx / qn; f[1] = qy / qn; f[2] = qz / qn; f[3] = qw / qn;
+        float quat[4];
+        frame_quaternion(Qi, Qj, quat);
+        f[0] = quat[0]; f[1] = quat[1]; f[2] = quat[2]; f[3] = quat[3];
         // distance: atom a of the CENTRE to P of the NEIGHBOUR   (feature.py:200-206, :62-63)
         const V3 pj = ld3(xj);
 #pragma unroll

@@ -57,6 +57,7 @@ SIGNATURES = {
     "rmp_add_layernorm": [P, P, P, P, F, P, I, I, I, I, P, P],
     "rmp_readout_head": [P, I, P, P, F, U64, P, I, I, P, P, P, P],
     "rmp_cast_bf16": [P, P, I64, P],
+    "rmp_edge_embed_bf16": [P, P, P, P, P, I, P, P, P, P, P, P, P],
     "rmp_node_mlp_bf16": [P, P, I, P, P, I, P, P, P, P, P, P, P, P, P, P, P, I, P],
     "rmp_edge_mlp_bf16": [P, P, I, P, P, P, P, P, P, I, F, P, P, P],
     "rmp_edge_mlp_bf16_traced": [P, P, I, P, P, P, P, P, P, I, F, P, P, P, P],

@@ -53,6 +53,8 @@ class RDesignWeights:
         self.edge_emb = ops.pack_linear(p["features.edge_embedding.weight"], p["features.edge_embedding.bias"])
         self.norm_nodes = (p["features.norm_nodes.gain"], p["features.norm_nodes.bias"])
         self.norm_edges = (p["features.norm_edges.gain"], p["features.norm_edges.bias"])
+        self.edge_emb16 = ops.pack_edge_embedding(p["features.edge_embedding.weight"])
+        self.edge_emb_bias = p["features.edge_embedding.bias"]
         n_layers = 1 + max(int(k.split(".")[1]) for k in p if k.startswith("mpnn_layers."))
         self.layers: List[LayerWeights] = []
         for l in range(n_layers):
@@ -109,14 +111,20 @@ class RDesignEngine:
 
     def embed(self, X, g: ops.Graph):
         """h_V [Nv,128], h_E [Ne,128]   (rdesign/model/feature.py:179-224)."""
-        node_raw, edge_raw = ops.raw_features(X, g)
+        bf16 = self.precision == PREC_BF16
+        node_raw, edge_raw, frames = ops.raw_features(X, g, want_edges=not bf16, return_frames=True)
         dev = node_raw.device
         h_V = torch.empty(g.Nv, ops.HIDDEN, dtype=torch.float32, device=dev)
-        h_E = torch.empty(g.Ne, ops.HIDDEN, dtype=torch.float32, device=dev)
         ops.row_mlp([(node_raw, None)], [(self.w.node_emb, False)], ops.EPI_NORMALIZE, h_V, g.Nv,
                     gain=self.w.norm_nodes[0], beta=self.w.norm_nodes[1])
-        ops.row_mlp([(edge_raw, None)], [(self.w.edge_emb, False)], ops.EPI_NORMALIZE, h_E, g.Ne,
-                    gain=self.w.norm_edges[0], beta=self.w.norm_edges[1])
+        if bf16:
+            # fused tcgen05 edge featurizer: h_E is produced directly as bf16 (it is layer-invariant)
+            h_E = ops.edge_embed_bf16(X, frames, g, self.w.edge_emb16, self.w.edge_emb_bias,
+                                      self.w.norm_edges[0], self.w.norm_edges[1])
+        else:
+            h_E = torch.empty(g.Ne, ops.HIDDEN, dtype=torch.float32, device=dev)
+            ops.row_mlp([(edge_raw, None)], [(self.w.edge_emb, False)], ops.EPI_NORMALIZE, h_E, g.Ne,
+                        gain=self.w.norm_edges[0], beta=self.w.norm_edges[1])
         return h_V, h_E
 
     def layer(self, l: int, h_V, h_E, g: ops.Graph, agg: Optional[torch.Tensor] = None):
@@ -178,8 +186,6 @@ class RDesignEngine:
     def encode(self, X, mask, sizes=None, return_layers=False):
         g = self.graph(X, mask, sizes)
         h_V, h_E = self.embed(X, g)
-        if self.precision == PREC_BF16:
-            h_E = ops.cast_bf16(h_E)              # h_E is layer-invariant: stored once as bf16
         agg = torch.zeros_like(h_V)
         layers = []
         self._next_P = None

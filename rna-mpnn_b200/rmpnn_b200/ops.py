@@ -109,19 +109,45 @@ def build_graph(X: torch.Tensor, mask: torch.Tensor, top_k: int, sizes=None) -> 
     return Graph(B, N, K, Nv, Ne, node_map, node_src, sinfo, row_ptr, counts, E, D, ctr, nbr, E_flat)
 
 
-def raw_features(X: torch.Tensor, g: Graph):
+def raw_features(X: torch.Tensor, g: Graph, want_edges: bool = True, return_frames: bool = False):
     """node_raw [Nv,101], edge_raw [Ne,115] (rdesign/model/feature.py:179-220)."""
     _need_cuda(X)
     X = _f32c(X[:, :, :6, :])
     dev = X.device
     frames = torch.empty(g.B * g.N, 9, dtype=torch.float32, device=dev)
     node_raw = torch.empty(g.Nv, NODE_RAW, dtype=torch.float32, device=dev)
-    edge_raw = torch.empty(g.Ne, EDGE_RAW, dtype=torch.float32, device=dev)
+    edge_raw = torch.empty(g.Ne, EDGE_RAW, dtype=torch.float32, device=dev) if want_edges else None
     check(lib().rmp_rdesign_raw_features(_ptr(X), g.B, g.N, _ptr(g.node_src), _ptr(g.ctr), _ptr(g.nbr),
                                          _ptr(g.counts), g.Nv, g.Ne, C.cast(_RBF_MU, C.c_void_p),
                                          _ptr(frames), _ptr(node_raw), _ptr(edge_raw), _stream()),
           "rmp_rdesign_raw_features")
+    if return_frames:
+        return node_raw, edge_raw, frames
     return node_raw, edge_raw
+
+
+# kernel feature order of rmp_edge_embed_bf16: rbf (reference columns 4..99) | quaternion (0..3) |
+# direction (100..114) | 13 zero columns
+_EDGE_PERM = list(range(4, 100)) + list(range(0, 4)) + list(range(100, 115))
+
+
+def pack_edge_embedding(weight: torch.Tensor) -> torch.Tensor:
+    """edge_embedding.weight [128,115] -> bf16 [128,128] with columns in the fused kernel's order."""
+    _need_cuda(weight)
+    W = torch.zeros(128, 128, dtype=torch.float32, device=weight.device)
+    W[:, :EDGE_RAW] = weight.detach().to(torch.float32)[:, _EDGE_PERM]
+    return W.to(torch.bfloat16).contiguous()
+
+
+def edge_embed_bf16(X: torch.Tensor, frames: torch.Tensor, g: Graph, W_perm16, bias, gain, beta) -> torch.Tensor:
+    """Fused tcgen05 edge featurizer: coordinates -> h_E [Ne,128] bf16 (rmp_edge_embed_bf16)."""
+    _need_cuda(X, frames, W_perm16, bias, gain, beta)
+    X = _f32c(X[:, :, :6, :])
+    h_E = torch.empty(g.Ne, HIDDEN, dtype=torch.bfloat16, device=X.device)
+    check(lib().rmp_edge_embed_bf16(_ptr(X), _ptr(frames), _ptr(g.node_src), _ptr(g.ctr), _ptr(g.nbr), g.Ne,
+                                    C.cast(_RBF_MU, C.c_void_p), _ptr(W_perm16), _ptr(bias), _ptr(gain), _ptr(beta),
+                                    _ptr(h_E), _stream()), "rmp_edge_embed_bf16")
+    return h_E
 
 
 # --------------------------------------------------------------------------- fused row MLP
@@ -257,6 +283,6 @@ def cast_bf16(src: torch.Tensor) -> torch.Tensor:
     return dst
 
 
-__all__ = ["Graph", "PackedLinear", "edge_mlp_bf16", "node_mlp_bf16", "knn", "build_graph", "raw_features", "pack_linear", "row_mlp",
+__all__ = ["Graph", "PackedLinear", "edge_embed_bf16", "pack_edge_embedding", "edge_mlp_bf16", "node_mlp_bf16", "knn", "build_graph", "raw_features", "pack_linear", "row_mlp",
            "add_layernorm", "readout_head", "cast_bf16", "EPI_STORE", "EPI_NORMALIZE", "EPI_RESID_LN",
            "EPI_SEGSUM", "HIDDEN", "NODE_RAW", "EDGE_RAW", "MAX_K"]

@@ -159,6 +159,25 @@ def test_node_mlp_tc_projection_only():
     np.testing.assert_allclose(Pn.float().cpu().numpy(), _bf(ref[:, 128:]).numpy(), atol=2e-2, rtol=0)
 
 
+@pytest.mark.parametrize("B,L,K,lengths", [(2, 64, 25, [64, 50]), (3, 100, 48, [100, 61, 7]), (1, 300, 30, None)])
+def test_edge_embed_tc_matches_oracle(B, L, K, lengths):
+    from rmpnn_b200._lib import PREC_BF16
+    from rmpnn_b200.engine import RDesignEngine
+    cfg = RDesignConfig(k_neighbors=K, num_mpnn_layers=1)
+    params = make_state_dict(cfg, 42)
+    X, S, mask = synthetic_backbones(B, L, 77, lengths=lengths)
+    eng = RDesignEngine(params, K, cfg.scale, device="cuda", precision=PREC_BF16)
+    g = eng.graph(X.cuda(), mask.cuda())
+    h_V, h_E = eng.embed(X.cuda(), g)
+    assert h_E.dtype == torch.bfloat16
+    ref = O.features(params, X, S, mask, K)
+    assert torch.equal(g.E_flat.cpu(), ref[4])
+    np.testing.assert_allclose(h_V.cpu().numpy(), ref[2].numpy(), atol=3e-4, rtol=0)   # fp32 node path (acos near +-1)
+    err = (h_E.float().cpu() - ref[3]).abs()
+    # bf16 raw features x bf16 weights, bf16 output: a few bf16 ulps of an O(1..4) normalised value
+    assert err.max().item() < 8e-2 and err.mean().item() < 6e-3, (err.max().item(), err.mean().item())
+
+
 @pytest.mark.parametrize("B,L,K,lengths", [(2, 64, 25, [64, 50]), (4, 256, 30, None), (3, 100, 48, [100, 61, 7])])
 def test_forward_bf16_within_budget(B, L, K, lengths):
     from rmpnn_b200._lib import PREC_BF16
@@ -171,6 +190,7 @@ def test_forward_bf16_within_budget(B, L, K, lengths):
     out = eng.forward(X.cuda(), mask.cuda())
     assert torch.equal(out["graph"].E_flat.cpu(), ref["E_idx"])
     err = (out["logits"].cpu() - ref["logits"]).abs().max().item()
+    print(f"bf16 forward max |dlogit| = {err:.4f}")
     assert err < LOGIT_TOL_BF16, err
     agree = (out["samples"].cpu() == ref["samples"]).float().mean().item()
     assert agree > 0.97, agree          # argmax may flip only where two logits are within the bf16 budget
