@@ -40,6 +40,15 @@ METRIC = "RNA nucleotides/sec (enc+dec fwd)"
 UNIT = "nt/s"
 
 
+def ncu_traffic(kernel_key):
+    """DRAM bytes per launch of the dominant kernel from the committed ncu --set full capture."""
+    path = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get(kernel_key)
+    return None
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -251,7 +260,7 @@ def run_ours(args):
         peak_tf = pk["bf16_tflops_sustained"]
         achieved = flop_launch / (k_ms * 1e-3) / 1e12 if k_ms > 0 else 0.0
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
-                    "frac": achieved / peak_tf, "traffic": None,
+                    "frac": achieved / peak_tf, "traffic": ncu_traffic(f"{args.precision}:{args.workload}"),
                     "kernel": eng.dominant_kernel_name(), "kernel_ms": k_ms,
                     "kernel_share_of_step": sum(ktimes) / total_ms if total_ms else None,
                     "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
@@ -283,7 +292,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("RMPNN_PRECISION", "fp32"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("RMPNN_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

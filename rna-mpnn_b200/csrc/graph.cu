@@ -116,7 +116,9 @@ __global__ void __launch_bounds__(256) node_finalize_kernel(int B, int N, const 
 // --------------------------------------------------------------------------------
 typedef unsigned long long u64;
 constexpr u64 kKeyMax = ~0ull;
-constexpr int kKnnRowsPerWarp = 8;
+// rows handled by one warp: more rows amortise staging the structure in shared memory, fewer rows give
+// more warps in flight; the selection is latency bound (dependent shuffles), so short chains get 1
+__host__ __device__ inline int knn_rows_per_warp(int N) { return N <= 1024 ? 1 : (N <= 4096 ? 2 : 8); }
 constexpr int kKnnWarps = 8;
 constexpr int kKnnSmemPoints = 8192;      // structures up to this length are staged in smem
 
@@ -160,8 +162,8 @@ __device__ __forceinline__ float ref_pair_distance(float4 a, float4 b) {
 template <int R, bool SMEM>
 __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(const float* __restrict__ X,
                                                              const float* __restrict__ mask, int N, int A,
-                                                             int atom, int K, int64_t* __restrict__ E_idx,
-                                                             float* __restrict__ D_out) {
+                                                             int atom, int K, int rows_per_warp,
+                                                             int64_t* __restrict__ E_idx, float* __restrict__ D_out) {
     extern __shared__ float4 s_pts[];
     const int b = blockIdx.y, t = threadIdx.x, lane = t & 31, w = t >> 5;
     const float* Xb = X + (size_t)b * N * A * 3 + (size_t)atom * 3;
@@ -174,8 +176,8 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(const float* __rest
         for (int j = t; j < N; j += kKnnWarps * 32) s_pts[j] = load_point(j);
         __syncthreads();
     }
-    const int row0 = (blockIdx.x * kKnnWarps + w) * kKnnRowsPerWarp;
-    for (int rr = 0; rr < kKnnRowsPerWarp; ++rr) {
+    const int row0 = (blockIdx.x * kKnnWarps + w) * rows_per_warp;
+    for (int rr = 0; rr < rows_per_warp; ++rr) {
         const int i = row0 + rr;
         if (i >= N) break;                                   // warp-uniform
         const float4 pi = SMEM ? s_pts[i] : load_point(i);
@@ -217,14 +219,15 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(const float* __rest
 template <int R>
 static int launch_knn(const float* X, const float* mask, int B, int N, int A, int atom, int K,
                       int64_t* E_idx, float* D, cudaStream_t st) {
-    dim3 grid(ceil_div(N, kKnnWarps * kKnnRowsPerWarp), B);
+    const int rpw = knn_rows_per_warp(N);
+    dim3 grid(ceil_div(N, kKnnWarps * rpw), B);
     if (N <= kKnnSmemPoints) {
         const size_t smem = (size_t)N * sizeof(float4);
         auto k = knn_kernel<R, true>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        k<<<grid, kKnnWarps * 32, smem, st>>>(X, mask, N, A, atom, K, E_idx, D);
+        k<<<grid, kKnnWarps * 32, smem, st>>>(X, mask, N, A, atom, K, rpw, E_idx, D);
     } else {
-        knn_kernel<R, false><<<grid, kKnnWarps * 32, 0, st>>>(X, mask, N, A, atom, K, E_idx, D);
+        knn_kernel<R, false><<<grid, kKnnWarps * 32, 0, st>>>(X, mask, N, A, atom, K, rpw, E_idx, D);
     }
     return check_launch("rmp_knn");
 }
