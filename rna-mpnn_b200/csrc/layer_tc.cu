@@ -282,37 +282,30 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
                     }
                 }
                 stamp(400 + s * 10 + g);                       // gathers / bias added
+                stamp(500 + s * 10 + g);
+                if (p.debug != nullptr || (s == S - 1 && bypass)) {
+                    // fp32 GELU: debug dump (tests) and the tiny-degree bypass that sums with vector reductions
 #pragma unroll
-                for (int q0 = 0; q0 < 32; q0 += 8) {           // 8 independent GELUs in flight
-                    float in[8], hx[8];
+                    for (int q = 0; q < 32; ++q) v[q] = gelu_tanh_fast(v[q]);
+                    if (p.debug && valid) {
+                        const int e = (blockIdx.x + i * gridDim.x) * kTileM + row;
+                        float* dbg = p.debug + ((size_t)s * p.n_edges + e) * 128 + col0;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float x = v[q0 + q];
-                        in[q] = x * fmaf(x * x, 0.0356774081f, 0.7978845608f);
-                        hx[q] = 0.5f * x;
+                        for (int q = 0; q < 32; ++q) dbg[q] = v[q];
                     }
+                    if (s == S - 1 && bypass) {
+                        if (valid) {
+                            float* dst = p.agg + (size_t)c_cur[g] * 128 + col0;
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) asm("tanh.approx.f32 %0, %1;" : "=f"(in[q]) : "f"(in[q]));
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) v[q0 + q] = fmaf(hx[q], in[q], hx[q]);
-                }
-                stamp(500 + s * 10 + g);                       // GELU done
-                if (p.debug && valid) {
-                    const int e = (blockIdx.x + i * gridDim.x) * kTileM + row;
-                    float* dbg = p.debug + ((size_t)s * p.n_edges + e) * 128 + col0;
-#pragma unroll
-                    for (int q = 0; q < 32; ++q) dbg[q] = v[q];
-                }
-                if (s == S - 1 && bypass) {
-                    if (valid) {
-                        float* dst = p.agg + (size_t)c_cur[g] * 128 + col0;
-#pragma unroll
-                        for (int q = 0; q < 8; ++q)
-                            red_add_v4(dst + 4 * q, v[4 * q] * p.alpha, v[4 * q + 1] * p.alpha,
-                                       v[4 * q + 2] * p.alpha, v[4 * q + 3] * p.alpha);
+                            for (int q = 0; q < 8; ++q)
+                                red_add_v4(dst + 4 * q, v[4 * q] * p.alpha, v[4 * q + 1] * p.alpha,
+                                           v[4 * q + 2] * p.alpha, v[4 * q + 3] * p.alpha);
+                        }
+                    } else {
+                        store_act_chunk(a_buf, row, col0, v);
                     }
                 } else {
-                    store_act_chunk(a_buf, row, col0, v);
+                    store_gelu_chunk(a_buf, row, col0, v);     // packed bf16x2 GELU straight into the A operand
                 }
                 stamp(600 + s * 10 + g);                       // operand stored
                 if constexpr (FIRST) {
@@ -613,9 +606,7 @@ node_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
                             v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
                         }
                         if (stg.kind == 0) {
-#pragma unroll
-                            for (int q = 0; q < 32; ++q) v[q] = gelu_tanh_fast(v[q]);
-                            store_act_chunk(sA, row, col0, v);
+                            store_gelu_chunk(sA, row, col0, v);
                         } else if (valid) {                   // kind 2: projections, centre fp32 | neighbour bf16
                             if (col0 < 128) {
                                 float4* dst = reinterpret_cast<float4*>(p.p_out + (size_t)r * 128 + col0);

@@ -135,6 +135,22 @@ __device__ __forceinline__ float gelu_tanh_fast(float x) {
     return fmaf(hx, t, hx);
 }
 
+// Packed GELU of two fp32 values -> bf16x2 (tanh form, bf16 FMAs + MUFU.TANH.BF16).  The result feeds a
+// bf16 tensor-core operand, so evaluating the polynomial in bf16 adds ~1 extra bf16 ulp to a value that
+// is rounded to bf16 anyway; measured end-to-end |dlogit| stays < 4e-3 (budget 2e-2).
+__device__ __forceinline__ uint32_t gelu_bf16x2(float a, float b) {
+    const __nv_bfloat162 x = __floats2bfloat162_rn(a, b);
+    const __nv_bfloat162 c1 = __float2bfloat162_rn(0.0356774081f), c0 = __float2bfloat162_rn(0.7978845608f);
+    const __nv_bfloat162 inner = __hmul2(x, __hfma2(__hmul2(x, x), c1, c0));
+    uint32_t t;
+    asm("tanh.approx.bf16x2 %0, %1;" : "=r"(t) : "r"(*reinterpret_cast<const uint32_t*>(&inner)));
+    const __nv_bfloat162 hx = __hmul2(x, __float2bfloat162_rn(0.5f));
+    const __nv_bfloat162 y = __hfma2(hx, *reinterpret_cast<const __nv_bfloat162*>(&t), hx);
+    return *reinterpret_cast<const uint32_t*>(&y);
+}
+// GELU + pack of 32 consecutive columns, written as the next stage's swizzled A operand
+__device__ __forceinline__ void store_gelu_chunk(uint8_t* a_buf, int row, int col0, const float (&v)[32]);
+
 // 256-bit read-only global load (LDG.E.256): one full 32-byte sector per thread and instruction
 __device__ __forceinline__ void ldg256(const void* ptr, uint32_t (&r)[8]) {
     asm volatile("ld.global.nc.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
@@ -150,6 +166,16 @@ __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c
 __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     const __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi);
     return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+__device__ __forceinline__ void store_gelu_chunk(uint8_t* a_buf, int row, int col0, const float (&v)[32]) {
+    uint8_t* kb = a_buf + (col0 >> 6) * kKBlockBytes;
+    const int j0 = (col0 & 63) >> 3;
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        *reinterpret_cast<uint4*>(kb + sw128_chunk(row, j0 + j)) =
+            make_uint4(gelu_bf16x2(v[8 * j + 0], v[8 * j + 1]), gelu_bf16x2(v[8 * j + 2], v[8 * j + 3]),
+                       gelu_bf16x2(v[8 * j + 4], v[8 * j + 5]), gelu_bf16x2(v[8 * j + 6], v[8 * j + 7]));
 }
 
 __device__ __forceinline__ void store_act_chunk(uint8_t* a_buf, int row, int col0, const float (&v)[32]) {

@@ -72,6 +72,15 @@ def test_edge_mlp_tc_matches_fp32_reference(Nv, deg, S):
         tol = 2e-3 if s == 0 else 6e-3      # tanh.approx.f32 is 2^-11 accurate; later stages see bf16 re-rounding
         np.testing.assert_allclose(dbg[s].cpu().numpy(), acts_ref[s].numpy(), atol=tol, rtol=4e-3, err_msg=f"stage {s}")
     np.testing.assert_allclose(agg.cpu().numpy(), agg_ref.numpy(), atol=6e-3 * max(1.0, deg / 30), rtol=0)
+    # production path (no dump): packed bf16x2 GELU written straight into the next operand
+    agg2 = torch.zeros(Nv, 128, device="cuda")
+    ops.edge_mlp_bf16(hE.cuda().to(torch.bfloat16), W.cuda().to(torch.bfloat16),
+                      [None] + [b.cuda() for b in biases[1:]], P[:, :128].contiguous().cuda(),
+                      P[:, 128:].contiguous().cuda().to(torch.bfloat16), ctr.cuda(), nbr.cuda(),
+                      _row_ptr(ctr, Nv).cuda(), agg2, alpha)
+    err = (agg2.cpu() - agg_ref).abs()
+    assert err.max().item() < 2.5e-2 * max(1.0, deg / 30) and err.mean().item() < 2e-3 * max(1.0, deg / 30), \
+        (err.max().item(), err.mean().item())
 
 
 def test_edge_mlp_tc_accumulates_into_agg_and_is_repeatable():
