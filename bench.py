@@ -196,13 +196,23 @@ def run_ours(args):
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)     # > 126 MB L2
     stream = torch.cuda.current_stream()
 
+    replay = static = None
+    if args.graph:
+        # the ~30 launches of one forward are captured once and replayed with a single graph launch
+        replay, static = eng.capture(Xd, md, sizes)
+
     def step_resident():
-        return eng.forward(Xd, md, sizes=sizes)
+        return replay() if replay else eng.forward(Xd, md, sizes=sizes)
 
     def step_e2e():
-        xd = Xp.to(dev, non_blocking=True)
-        mk = mp.to(dev, non_blocking=True)
-        out = eng.forward(xd, mk, sizes=sizes)
+        if replay:
+            static["X"].copy_(Xp, non_blocking=True)
+            static["mask"].copy_(mp, non_blocking=True)
+            out = replay()
+        else:
+            xd = Xp.to(dev, non_blocking=True)
+            mk = mp.to(dev, non_blocking=True)
+            out = eng.forward(xd, mk, sizes=sizes)
         samples_host.copy_(out["samples"], non_blocking=True)
         return out
 
@@ -217,7 +227,9 @@ def run_ours(args):
     barrier()
 
     # ---- device-resident timing (value) + dominant-kernel timing (roofline) ----
-    eng.kernel_timer = []                # the engine records (start, end) events around the message kernel
+    # the engine records (start, end) events around the dominant kernel; under graph replay that kernel is
+    # timed in a separate eager pass right after the timed region instead
+    eng.kernel_timer = [] if not replay else None
     ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
     launches0 = L_.rmp_launch_count()
     with ClockSampler(local) as clocks:
@@ -231,6 +243,17 @@ def run_ours(args):
     launches = (L_.rmp_launch_count() - launches0) // args.steps
     step_ms = [s.elapsed_time(e) for s, e in ev]
     total_ms = sum(step_ms)
+    k_passes = args.steps
+    if replay:
+        # a graph replay bumps no host-side counters: count launches and time the dominant kernel in an eager pass
+        eng.kernel_timer = []
+        k_passes = 3
+        launches0 = L_.rmp_launch_count()
+        for _ in range(k_passes):
+            flush.zero_()
+            eng.forward(Xd, md, sizes=sizes)
+        torch.cuda.synchronize()
+        launches = (L_.rmp_launch_count() - launches0) // k_passes
     ktimes = [s.elapsed_time(e) for s, e in eng.kernel_timer]
     eng.kernel_timer = None
 
@@ -262,7 +285,7 @@ def run_ours(args):
         roofline = {"bound": "tensor", "achieved": achieved, "peak": peak_tf, "unit": "TFLOP/s",
                     "frac": achieved / peak_tf, "traffic": ncu_traffic(f"{args.precision}:{args.workload}"),
                     "kernel": eng.dominant_kernel_name(), "kernel_ms": k_ms,
-                    "kernel_share_of_step": sum(ktimes) / total_ms if total_ms else None,
+                    "kernel_share_of_step": (sum(ktimes) / k_passes) / (total_ms / args.steps) if total_ms else None,
                     "peak_source": pk["source"] + " bf16 sustained (kernel timed inside a long step)",
                     "algorithmic_flop_per_launch": flop_launch}
         cb = None
@@ -276,7 +299,8 @@ def run_ours(args):
                                        "RNAModel default (9 layers, H=128), kNN+featurizer+layers+readout/argmax",
                            "sharding": "whole structures per rank, no data-path collective",
                            "l2": "256 MiB flush buffer written between timed iterations",
-                           "precision": args.precision},
+                           "precision": args.precision,
+                           "launch": "CUDA graph replay" if replay else "eager (one host call per kernel)"},
                 "roofline": roofline, "cpu_baseline": cb,
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": Xp.numel() * 4 + mp.numel() * 4,
                         "d2h_bytes_per_step": samples_host.numel() * 8},
@@ -295,6 +319,8 @@ def main():
     ap.add_argument("--precision", default=os.environ.get("RMPNN_PRECISION", "bf16"), choices=["fp32", "bf16"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--graph", dest="graph", action="store_true", default=True, help="replay the forward as a CUDA graph")
+    ap.add_argument("--no-graph", dest="graph", action="store_false")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

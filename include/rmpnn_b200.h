@@ -233,6 +233,10 @@ int rmp_edge_embed_bf16(const float* X, const float* frames, const int32_t* node
                         const int32_t* nbr, int n_edges, const float* rbf_mu, const void* W_perm_bf16,
                         const float* bias, const float* gain, const float* beta, void* h_E_bf16, void* stream);
 
+/* tuning aid: int64 [800] device buffer that receives a clock64 trace of the node kernel while the environment
+ * variable RMP_NODE_TIMELINE is set (scripts/node_timeline.py); NULL disables it */
+void rmp_set_node_timeline(void* buf);
+
 /* fp32 -> bf16 row conversion (h_E storage for the bf16 path), n elements */
 int rmp_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
 

@@ -410,6 +410,7 @@ struct NodeParams {
     NodeStage st[kNodeMaxStages];
     int S;
     int n_rows;
+    long long* timeline;        // optional clock64 trace of CTA 0's first epilogue thread
 };
 struct alignas(8) NodeBarriers {
     uint64_t w_full[kRing], w_empty[kRing], acc_full, act_ready;
@@ -494,6 +495,12 @@ node_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
         float* red_sum = s_red;                    // [2][128]
         float* red_sq = s_red + 2 * kTileM;        // [2][128]
         uint32_t ph_acc = 0;
+        int tl_n = 0;
+        const bool tl_on = p.timeline != nullptr && blockIdx.x == 0 && threadIdx.x == 64;
+        auto stamp = [&](int tag) {
+            if (tl_on && tl_n < 400) { p.timeline[tl_n * 2] = tag; p.timeline[tl_n * 2 + 1] = clock64(); ++tl_n; }
+        };
+        stamp(1);
 
         // LayerNorm over the 128 channels of a row held as 64 + 64 by the two column halves
         auto layer_norm64 = [&](float (&x)[64], const float* gamma, const float* beta, int c0) {
@@ -517,10 +524,9 @@ node_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
                 x[4 * q + 2] = fmaf(x[4 * q + 2] * inv, g.z, b.z); x[4 * q + 3] = fmaf(x[4 * q + 3] * inv, g.w, b.w);
             }
         };
-        auto store_row64 = [&](float* dst, const float (&x)[64]) {
+        auto store_row64 = [&](float* dst, const float (&x)[64]) {      // 8 full 32-byte sectors per thread
 #pragma unroll
-            for (int q = 0; q < 16; ++q)
-                reinterpret_cast<float4*>(dst)[q] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+            for (int q = 0; q < 8; ++q) stg256f(dst + 8 * q, &x[8 * q]);
         };
         auto to_operand64 = [&](const float (&x)[64], int c0) {
 #pragma unroll
@@ -537,42 +543,55 @@ node_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
             const int r = tile * kTileM + row;
             const bool valid = r < p.n_rows;
             const int c0 = half * 64;
-            // ---- prologue: x1 = LN1(h + agg) (or h), kept in global for the residual, bf16 copy -> A ----
+            // ---- prologue: x1 = LN1(h + agg) (or h).  One warp per row, lanes across the 128 channels: fully
+            //      coalesced 512-byte row accesses, LayerNorm by warp shuffles, bf16 copy -> swizzled A operand ----
             {
-                float x[64];
-#pragma unroll
-                for (int q = 0; q < 64; ++q) x[q] = 0.f;
-                if (valid) {
-                    const float4* hp = reinterpret_cast<const float4*>(p.h_in + (size_t)r * 128 + c0);
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        const float4 a = __ldg(hp + q);
-                        x[4 * q] = a.x; x[4 * q + 1] = a.y; x[4 * q + 2] = a.z; x[4 * q + 3] = a.w;
-                    }
-                    if (p.prologue_ln && p.agg) {
-                        float4* ap = reinterpret_cast<float4*>(p.agg + (size_t)r * 128 + c0);
-#pragma unroll
-                        for (int q = 0; q < 16; ++q) {
-                            const float4 a = ap[q];
-                            x[4 * q] += a.x; x[4 * q + 1] += a.y; x[4 * q + 2] += a.z; x[4 * q + 3] += a.w;
-                            ap[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+                const int ew = warp - 2;                               // 8 warps x 16 rows
+                float4 g1 = make_float4(1.f, 1.f, 1.f, 1.f), b1 = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (p.prologue_ln) {
+                    g1 = __ldg(reinterpret_cast<const float4*>(p.ln1_g) + lane);
+                    b1 = __ldg(reinterpret_cast<const float4*>(p.ln1_b) + lane);
+                }
+#pragma unroll 4
+                for (int rr = 0; rr < 16; ++rr) {
+                    const int rl = ew * 16 + rr;                       // row inside the tile
+                    const int rg = tile * kTileM + rl;
+                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rg < p.n_rows) {
+                        x = __ldg(reinterpret_cast<const float4*>(p.h_in + (size_t)rg * 128) + lane);
+                        if (p.prologue_ln && p.agg) {
+                            float4* ap = reinterpret_cast<float4*>(p.agg + (size_t)rg * 128) + lane;
+                            const float4 a = *ap;
+                            x.x += a.x; x.y += a.y; x.z += a.z; x.w += a.w;
+                            *ap = make_float4(0.f, 0.f, 0.f, 0.f);     // re-arm the neighbour-sum buffer
                         }
                     }
+                    if (p.prologue_ln) {
+                        const float mu = warp_sum(x.x + x.y + x.z + x.w) * (1.f / 128.f);
+                        x.x -= mu; x.y -= mu; x.z -= mu; x.w -= mu;
+                        const float var = warp_sum(x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w) * (1.f / 128.f);
+                        const float inv = 1.f / sqrtf(var + 1e-5f);
+                        x.x = fmaf(x.x * inv, g1.x, b1.x); x.y = fmaf(x.y * inv, g1.y, b1.y);
+                        x.z = fmaf(x.z * inv, g1.z, b1.z); x.w = fmaf(x.w * inv, g1.w, b1.w);
+                        if (rg < p.n_rows && p.x1) reinterpret_cast<float4*>(p.x1 + (size_t)rg * 128)[lane] = x;
+                    }
+                    // columns 4*lane .. 4*lane+3 -> K-block lane/16, 16-byte chunk (lane%16)/2, 8-byte half lane%2
+                    *reinterpret_cast<uint2*>(sA + (lane >> 4) * kKBlockBytes + sw128_chunk(rl, (lane & 15) >> 1) + (lane & 1) * 8) =
+                        make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
                 }
-                if (p.prologue_ln) {
-                    layer_norm64(x, p.ln1_g, p.ln1_b, c0);
-                    if (valid && p.x1) store_row64(p.x1 + (size_t)r * 128 + c0, x);
-                }
-                to_operand64(x, c0);
+                stamp(3);
                 tc_fence_before();
                 fence_proxy_async();
                 mbar_arrive(&bars->act_ready);
+                epi_bar_sync();                                        // x1 rows written above are re-read by other warps
+                stamp(4);
             }
             // ---- stage epilogues ----
             for (int s = 0; s < S; ++s) {
                 const NodeStage stg = p.st[s];
                 mbar_wait(&bars->acc_full, ph_acc); ph_acc ^= 1;
                 tc_fence_after();
+                stamp(10 + s);
                 const int ncols = stg.N >> 1;                 // columns of this half
                 const int cb = half * ncols;
                 if (stg.kind == 1) {                          // N == 128: bias + residual + LN2 -> h_out (+ operand)
@@ -585,12 +604,15 @@ node_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
                         for (int q = 0; q < 32; ++q) x[ch * 32 + q] = v[q];
                     }
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(stg.bias + cb) + q);
-                        float4 rsd = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (valid) rsd = reinterpret_cast<const float4*>(p.x1 + (size_t)r * 128 + cb)[q];
-                        x[4 * q] += b.x + rsd.x; x[4 * q + 1] += b.y + rsd.y;
-                        x[4 * q + 2] += b.z + rsd.z; x[4 * q + 3] += b.w + rsd.w;
+                    for (int q = 0; q < 8; ++q) {
+                        float rsd[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        if (valid) ldg256f(p.x1 + (size_t)r * 128 + cb + 8 * q, rsd);
+                        const float4 ba = __ldg(reinterpret_cast<const float4*>(stg.bias + cb) + 2 * q);
+                        const float4 bb = __ldg(reinterpret_cast<const float4*>(stg.bias + cb) + 2 * q + 1);
+                        x[8 * q + 0] += ba.x + rsd[0]; x[8 * q + 1] += ba.y + rsd[1];
+                        x[8 * q + 2] += ba.z + rsd[2]; x[8 * q + 3] += ba.w + rsd[3];
+                        x[8 * q + 4] += bb.x + rsd[4]; x[8 * q + 5] += bb.y + rsd[5];
+                        x[8 * q + 6] += bb.z + rsd[6]; x[8 * q + 7] += bb.w + rsd[7];
                     }
                     layer_norm64(x, p.ln2_g, p.ln2_b, cb);
                     if (valid) store_row64(p.h_out + (size_t)r * 128 + cb, x);
@@ -609,21 +631,20 @@ node_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
                             store_gelu_chunk(sA, row, col0, v);
                         } else if (valid) {                   // kind 2: projections, centre fp32 | neighbour bf16
                             if (col0 < 128) {
-                                float4* dst = reinterpret_cast<float4*>(p.p_out + (size_t)r * 128 + col0);
 #pragma unroll
-                                for (int q = 0; q < 8; ++q)
-                                    dst[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                                for (int q = 0; q < 4; ++q) stg256f(p.p_out + (size_t)r * 128 + col0 + 8 * q, &v[8 * q]);
                             } else {
-                                uint4* dst = reinterpret_cast<uint4*>(p.pn_out + (size_t)r * 128 + (col0 - 128));
+                                uint32_t pk[16];
 #pragma unroll
-                                for (int j = 0; j < 4; ++j)
-                                    dst[j] = make_uint4(pack_bf16(v[8 * j + 0], v[8 * j + 1]), pack_bf16(v[8 * j + 2], v[8 * j + 3]),
-                                                        pack_bf16(v[8 * j + 4], v[8 * j + 5]), pack_bf16(v[8 * j + 6], v[8 * j + 7]));
+                                for (int q = 0; q < 16; ++q) pk[q] = pack_bf16(v[2 * q], v[2 * q + 1]);
+                                stg256u(p.pn_out + (size_t)r * 128 + (col0 - 128), &pk[0]);
+                                stg256u(p.pn_out + (size_t)r * 128 + (col0 - 128) + 16, &pk[8]);
                             }
                         }
                     }
                 }
                 tc_fence_before();
+                stamp(20 + s);
                 if (s + 1 < S) {
                     fence_proxy_async();
                     mbar_arrive(&bars->act_ready);
@@ -632,6 +653,7 @@ node_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
                 }
             }
         }
+        if (tl_on) p.timeline[799] = tl_n;
     }
     tc_fence_before();
     __syncthreads();
@@ -693,6 +715,10 @@ extern "C" int rmp_edge_mlp_bf16_traced(const void* h_E_bf16, const void* W_bf16
     return check_launch("rmp_edge_mlp_bf16");
 }
 
+static void* g_node_timeline = nullptr;
+// tuning aid: device buffer (int64 [800]) receiving the node kernel's clock64 trace when RMP_NODE_TIMELINE is set
+extern "C" void rmp_set_node_timeline(void* buf) { g_node_timeline = buf; }
+
 extern "C" int rmp_node_mlp_bf16(const float* h_in, float* agg, int prologue_ln, const float* ln1_g, const float* ln1_b,
                                  int num_stages, const void* const* W_bf16, const int32_t* K, const int32_t* N,
                                  const int32_t* kind, const float* const* bias, const float* ln2_g, const float* ln2_b,
@@ -725,6 +751,7 @@ extern "C" int rmp_node_mlp_bf16(const float* h_in, float* agg, int prologue_ln,
     p.ln2_g = ln2_g; p.ln2_b = ln2_b; p.x1 = x1_scratch; p.h_out = h_out; p.p_out = p_out;
     p.pn_out = reinterpret_cast<uint16_t*>(pn_out_bf16);
     p.S = num_stages; p.n_rows = n_rows;
+    p.timeline = reinterpret_cast<long long*>(getenv("RMP_NODE_TIMELINE") ? g_node_timeline : nullptr);
     const size_t smem = 1024 + 4 * tc::kKBlockBytes + tc::kRing * tc::kSlotBytes + sizeof(tc::NodeBarriers) + 16 +
                         4 * tc::kTileM * sizeof(float);
     cudaFuncSetAttribute(tc::node_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

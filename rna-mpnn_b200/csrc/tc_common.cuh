@@ -158,6 +158,22 @@ __device__ __forceinline__ void ldg256(const void* ptr, uint32_t (&r)[8]) {
                  : "l"(ptr));
 }
 
+__device__ __forceinline__ void ldg256f(const float* ptr, float (&r)[8]) {
+    asm volatile("ld.global.v8.f32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(r[0]), "=f"(r[1]), "=f"(r[2]), "=f"(r[3]), "=f"(r[4]), "=f"(r[5]), "=f"(r[6]), "=f"(r[7])
+                 : "l"(ptr));
+}
+__device__ __forceinline__ void stg256f(float* ptr, const float* r) {
+    asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "f"(r[0]), "f"(r[1]), "f"(r[2]),
+                 "f"(r[3]), "f"(r[4]), "f"(r[5]), "f"(r[6]), "f"(r[7])
+                 : "memory");
+}
+__device__ __forceinline__ void stg256u(void* ptr, const uint32_t* r) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(r[0]), "r"(r[1]), "r"(r[2]),
+                 "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+                 : "memory");
+}
+
 // fire-and-forget fp32 vector reduction into global memory (REDG.E.ADD.F32x4)
 __device__ __forceinline__ void red_add_v4(float* dst, float a, float b, float c, float d) {
     asm volatile("red.global.v4.f32.add [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");

@@ -205,6 +205,31 @@ class RDesignEngine:
         return ops.readout_head(x, self.w.readout_w, self.w.readout_b, temperature, seed)
 
     @torch.no_grad()
+    def capture(self, X, mask, sizes, temperature: float = 0.0, seed: int = 0):
+        """Capture one forward for fixed shapes into a CUDA graph.
+
+        Returns ``(replay, static)``: ``static["X"]`` / ``static["mask"]`` are the input buffers to
+        overwrite, ``replay()`` launches the whole forward (about 30 kernels) with one graph launch and
+        returns the same dict as :meth:`forward` (tensors are reused between replays).  ``sizes=(Nv, Ne)``
+        must be given: a captured forward cannot read the two counters back to the host.
+        """
+        static = {"X": X.clone(), "mask": mask.clone()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                       # warm-up outside the capture (lazy init, attributes)
+            for _ in range(2):
+                self.forward(static["X"], static["mask"], sizes, temperature, seed)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self.forward(static["X"], static["mask"], sizes, temperature, seed)
+
+        def replay():
+            graph.replay()
+            return out
+        return replay, static
+
+    @torch.no_grad()
     def forward(self, X, mask, sizes=None, temperature: float = 0.0, seed: int = 0) -> Dict[str, torch.Tensor]:
         h_V, h_E, g = self.encode(X, mask, sizes)
         logits, probs, samples = self.readout(h_V, temperature, seed)
