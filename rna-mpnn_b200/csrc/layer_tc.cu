@@ -552,32 +552,48 @@ node_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
                     g1 = __ldg(reinterpret_cast<const float4*>(p.ln1_g) + lane);
                     b1 = __ldg(reinterpret_cast<const float4*>(p.ln1_b) + lane);
                 }
-#pragma unroll 4
-                for (int rr = 0; rr < 16; ++rr) {
-                    const int rl = ew * 16 + rr;                       // row inside the tile
-                    const int rg = tile * kTileM + rl;
-                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (rg < p.n_rows) {
-                        x = __ldg(reinterpret_cast<const float4*>(p.h_in + (size_t)rg * 128) + lane);
-                        if (p.prologue_ln && p.agg) {
-                            float4* ap = reinterpret_cast<float4*>(p.agg + (size_t)rg * 128) + lane;
-                            const float4 a = *ap;
-                            x.x += a.x; x.y += a.y; x.z += a.z; x.w += a.w;
-                            *ap = make_float4(0.f, 0.f, 0.f, 0.f);     // re-arm the neighbour-sum buffer
+                for (int r0 = 0; r0 < 16; r0 += 8) {                  // 8 rows per batch: 16 independent loads in flight
+                    float4 xs[8];
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+                        const int rg = tile * kTileM + ew * 16 + r0 + rr;
+                        xs[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (rg < p.n_rows) xs[rr] = __ldg(reinterpret_cast<const float4*>(p.h_in + (size_t)rg * 128) + lane);
+                    }
+                    if (p.prologue_ln && p.agg) {
+                        float4 as[8];
+#pragma unroll
+                        for (int rr = 0; rr < 8; ++rr) {
+                            const int rg = tile * kTileM + ew * 16 + r0 + rr;
+                            as[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
+                            if (rg < p.n_rows) as[rr] = reinterpret_cast<const float4*>(p.agg + (size_t)rg * 128)[lane];
+                        }
+#pragma unroll
+                        for (int rr = 0; rr < 8; ++rr) {
+                            const int rg = tile * kTileM + ew * 16 + r0 + rr;
+                            xs[rr].x += as[rr].x; xs[rr].y += as[rr].y; xs[rr].z += as[rr].z; xs[rr].w += as[rr].w;
+                            if (rg < p.n_rows)                         // re-arm the neighbour-sum buffer
+                                reinterpret_cast<float4*>(p.agg + (size_t)rg * 128)[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
                         }
                     }
-                    if (p.prologue_ln) {
-                        const float mu = warp_sum(x.x + x.y + x.z + x.w) * (1.f / 128.f);
-                        x.x -= mu; x.y -= mu; x.z -= mu; x.w -= mu;
-                        const float var = warp_sum(x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w) * (1.f / 128.f);
-                        const float inv = 1.f / sqrtf(var + 1e-5f);
-                        x.x = fmaf(x.x * inv, g1.x, b1.x); x.y = fmaf(x.y * inv, g1.y, b1.y);
-                        x.z = fmaf(x.z * inv, g1.z, b1.z); x.w = fmaf(x.w * inv, g1.w, b1.w);
-                        if (rg < p.n_rows && p.x1) reinterpret_cast<float4*>(p.x1 + (size_t)rg * 128)[lane] = x;
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+                        const int rl = ew * 16 + r0 + rr;              // row inside the tile
+                        const int rg = tile * kTileM + rl;
+                        float4 x = xs[rr];
+                        if (p.prologue_ln) {
+                            const float mu = warp_sum(x.x + x.y + x.z + x.w) * (1.f / 128.f);
+                            x.x -= mu; x.y -= mu; x.z -= mu; x.w -= mu;
+                            const float var = warp_sum(x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w) * (1.f / 128.f);
+                            const float inv = 1.f / sqrtf(var + 1e-5f);
+                            x.x = fmaf(x.x * inv, g1.x, b1.x); x.y = fmaf(x.y * inv, g1.y, b1.y);
+                            x.z = fmaf(x.z * inv, g1.z, b1.z); x.w = fmaf(x.w * inv, g1.w, b1.w);
+                            if (rg < p.n_rows && p.x1) reinterpret_cast<float4*>(p.x1 + (size_t)rg * 128)[lane] = x;
+                        }
+                        // columns 4*lane .. 4*lane+3 -> K-block lane/16, 16-byte chunk (lane%16)/2, 8-byte half lane%2
+                        *reinterpret_cast<uint2*>(sA + (lane >> 4) * kKBlockBytes + sw128_chunk(rl, (lane & 15) >> 1) + (lane & 1) * 8) =
+                            make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
                     }
-                    // columns 4*lane .. 4*lane+3 -> K-block lane/16, 16-byte chunk (lane%16)/2, 8-byte half lane%2
-                    *reinterpret_cast<uint2*>(sA + (lane >> 4) * kKBlockBytes + sw128_chunk(rl, (lane & 15) >> 1) + (lane & 1) * 8) =
-                        make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
                 }
                 stamp(3);
                 tc_fence_before();
