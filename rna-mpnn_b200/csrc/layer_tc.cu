@@ -10,8 +10,8 @@
 // [Ne,H] activations of the reference (rdesign/model/mpnn.py:33) never reach HBM: per edge the
 // kernel reads 256 B of bf16 h_E and the L2-resident projections, nothing else.
 //
-// Roles (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner,
-// warps 2..9 = epilogue (thread = one edge row, two column halves).
+// Roles (704 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 = gather
+// (accumulator pre-initialisation with the gathered projections), warps 6..21 = two epilogue groups.
 #include "tc_common.cuh"
 
 namespace rmp {
@@ -30,26 +30,56 @@ struct EdgeParams {
     float* agg;                      // [Nv,128] fp32, pre-zeroed
     int n_edges;
     float* debug;                    // optional [num_stages][n_edges][128] post-activation dump
-    long long* timeline;             // optional clock64 trace of CTA 0 / first epilogue warp (tests, tuning)
+    long long* timeline;             // optional int64[32768] clock64 trace of CTA 0 (per epilogue warp + MMA thread; tuning)
 };
 
-// Two edge tiles are in flight per CTA: epilogue group g (8 warps) owns the tiles with local index
-// i % 2 == g, the single MMA thread serves whichever tile has its next operand ready, and the TMA
-// producer keeps a 3-deep ring of h_E tiles.  While one group runs a stage epilogue on the CUDA cores
-// the other group's GEMM runs on the tensor pipe.
+// Pipeline.  A tile owns slot = i % 3: one 32 KB A buffer (h_E, then the activations in place) and one
+// 128-column TMEM accumulator.
+//   gather warps : acc[slot] <- Pc[centre] + Pn[neighbour]          (tcgen05.st, a tile or more ahead)
+//   MMA thread   : acc[slot] += h_E . W1e^T as soon as the TMA tile and the pre-initialised accumulator are
+//                  there, so the stage-0 pre-activation of tile i+2 is complete before an epilogue group asks
+//   epilogue     : group g (8 warps) owns the tiles with i % 2 == g and runs their stage epilogues
+//                  (bias + GELU -> bf16 A operand in place); the two groups are decoupled, so while one is on
+//                  the CUDA cores / MUFU the other group's GEMM is on the tensor pipe.
+// The epilogue never touches global memory on its critical path: its only inputs are TMEM and shared memory.
 constexpr int kGroups = 2;
-constexpr int kABufs = 3;
-constexpr int kEdgeThreads = 64 + kGroups * kEpiThreads;       // 576
+constexpr int kSlots = 3;
+constexpr int kGatherThreads = 128;
+constexpr int kEdgeThreads = 64 + kGatherThreads + kGroups * kEpiThreads;   // 704
 constexpr int kSelSlots = 16;                                  // node slots per tile served by the selector MMA
 constexpr int kSelBytes = 2 * kSelSlots * 128;                 // [2 K-blocks][16 slots][64 edges] bf16
-constexpr uint32_t kEdgeTmemCols = 512;                        // acc g at 128*g, neighbour sums g at 256 + 32*g
+constexpr uint32_t kEdgeTmemCols = 512;                        // acc slot s at 128*s, neighbour sums g at 384 + 32*g
+constexpr uint32_t kAggCol = 384;
 
 struct alignas(8) Barriers {
-    uint64_t w_full, a_full[kABufs], a_empty[kABufs];
-    uint64_t acc_full[kGroups], act_ready[kGroups], agg_full[kGroups], agg_empty[kGroups];
+    uint64_t w_full, a_full[kSlots], a_empty[kSlots];
+    uint64_t init_done[kSlots], acc_free[kSlots], acc_full[kSlots], act_ready[kSlots];
+    uint64_t agg_full[kGroups], agg_empty[kGroups];
 };
 
-// 18 warps: the register file is allocated to a CTA in 4-warp granules (20 x 32 x 96 = 61440), so 96 is the cap
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+        "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+        "f"(v[0]), "f"(v[1]), "f"(v[2]), "f"(v[3]), "f"(v[4]), "f"(v[5]), "f"(v[6]), "f"(v[7]), "f"(v[8]), "f"(v[9]),
+        "f"(v[10]), "f"(v[11]), "f"(v[12]), "f"(v[13]), "f"(v[14]), "f"(v[15]), "f"(v[16]), "f"(v[17]), "f"(v[18]),
+        "f"(v[19]), "f"(v[20]), "f"(v[21]), "f"(v[22]), "f"(v[23]), "f"(v[24]), "f"(v[25]), "f"(v[26]), "f"(v[27]),
+        "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
+    uint32_t r[8];
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+
 __global__ void __launch_bounds__(kEdgeThreads, 1)
 edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant__ CUtensorMap tm_w,
                    const EdgeParams p) {
@@ -57,12 +87,13 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
     // 1024-byte alignment is required by the 128B swizzle atoms
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sW = smem;                                         // [S][2][128][64] bf16, resident
-    uint8_t* sA = sW + (size_t)p.num_stages * kTileBytes;       // [3 buffers][2][128][64] bf16
-    uint8_t* sSel = sA + kABufs * kTileBytes;                   // [2 groups][2][16][64] bf16 selector
+    uint8_t* sA = sW + (size_t)p.num_stages * kTileBytes;       // [3 slots][2][128][64] bf16
+    uint8_t* sSel = sA + kSlots * kTileBytes;                   // [2 groups][2][16][64] bf16 selector
     Barriers* bars = reinterpret_cast<Barriers*>(sSel + kGroups * kSelBytes);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 1);
-    int* s_int = reinterpret_cast<int*>(s_tmem + 4);            // per group: ctr[128] start[128] end[128] misc[4]
-    constexpr int kIntsPerGroup = 3 * kTileM + 4;
+    int* s_meta = reinterpret_cast<int*>(s_tmem + 4);           // per slot: first node, last node of the tile
+    float* s_bias = reinterpret_cast<float*>(s_meta + 2 * kSlots + 2);                // [kMaxStages][128]
+    s_bias += (4 - ((smem_u32(s_bias) >> 2) & 3)) & 3;                                // 16-byte aligned for LDS.128
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = (p.n_edges + kTileM - 1) / kTileM;
@@ -71,14 +102,21 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
 
     if (threadIdx.x == 0) {
         mbar_init(&bars->w_full, 1);
-        for (int b = 0; b < kABufs; ++b) { mbar_init(&bars->a_full[b], 1); mbar_init(&bars->a_empty[b], 1); }
-        for (int g = 0; g < kGroups; ++g) {
-            mbar_init(&bars->acc_full[g], 1);
-            mbar_init(&bars->act_ready[g], kGroups * kEpiThreads);
-            mbar_init(&bars->agg_full[g], 1);
-            mbar_init(&bars->agg_empty[g], kGroups * kEpiThreads);
+        for (int b = 0; b < kSlots; ++b) {
+            mbar_init(&bars->a_full[b], 1); mbar_init(&bars->a_empty[b], 1);
+            mbar_init(&bars->init_done[b], kGatherThreads);
+            mbar_init(&bars->acc_free[b], kEpiThreads);
+            mbar_init(&bars->acc_full[b], 1);
+            mbar_init(&bars->act_ready[b], kEpiThreads);
         }
+        for (int g = 0; g < kGroups; ++g) { mbar_init(&bars->agg_full[g], 1); mbar_init(&bars->agg_empty[g], kEpiThreads); }
         fence_barrier_init();
+    }
+    // stage biases (stages >= 1) live in shared memory: broadcast LDS instead of global loads per chunk
+    for (int t = threadIdx.x; t < (S - 1) * 128; t += kEdgeThreads) {
+        const int st = 1 + t / 128;
+        const float* bsp = st == 1 ? p.bias[1] : (st == 2 ? p.bias[2] : p.bias[3]);
+        s_bias[st * 128 + (t & 127)] = __ldg(bsp + (t & 127));
     }
     if (warp == 1) tmem_alloc(s_tmem, kEdgeTmemCols);
     tc_fence_before();
@@ -96,9 +134,9 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
                 for (int kb = 0; kb < 2; ++kb)
                     tma_load_2d(sW + (size_t)s * kTileBytes + kb * kKBlockBytes, &tm_w, &bars->w_full, kb * 64, s * 128);
             for (int i = 0; i < my_tiles; ++i) {
-                const int b = i % kABufs;
+                const int b = i % kSlots;
                 const int tile = blockIdx.x + i * gridDim.x;
-                mbar_wait_relaxed(&bars->a_empty[b], ((i / kABufs) & 1) ^ 1, 400);
+                mbar_wait_relaxed(&bars->a_empty[b], ((i / kSlots) & 1) ^ 1, 200);
                 mbar_expect_tx(&bars->a_full[b], kTileBytes);
                 for (int kb = 0; kb < 2; ++kb)
                     tma_load_2d(sA + (size_t)b * kTileBytes + kb * kKBlockBytes, &tm_e, &bars->a_full[b], kb * 64,
@@ -107,87 +145,93 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
         }
         __syncwarp();
     } else if (warp == 1) {
-        // ===================== MMA issuer: serves the two in-flight tiles as their operands become ready ====
+        // ===================== MMA issuer: serves the tiles in flight as their operands become ready ====
         if (lane == 0) {
             constexpr uint32_t idesc_stage = instr_desc_bf16(128, 128, 0);
             constexpr uint32_t idesc_sel = instr_desc_bf16_amn(128, kSelSlots);
-            int ti[kGroups], st[kGroups];
-            uint32_t ph_act[kGroups], ph_ae[kGroups];
-            for (int g = 0; g < kGroups; ++g) { ti[g] = g; st[g] = 0; ph_act[g] = 0; ph_ae[g] = 0; }
+            int ti[kSlots], st[kSlots];
+            bool sel_path[kSlots];             // latched at stage-0 issue: s_meta[slot] is rewritten once acc_free fires
+#pragma unroll
+            for (int b = 0; b < kSlots; ++b) { ti[b] = b; st[b] = 0; sel_path[b] = true; }
             mbar_wait(&bars->w_full, 0);
             int remaining = my_tiles;
+            int tlm = 0;
+            const bool tlm_on = p.timeline != nullptr && blockIdx.x == 0;
+            auto mstamp = [&](int tag) {        // MMA-thread trace lives in the upper half of the buffer
+                if (tlm_on && tlm < 1990) { p.timeline[25600 + tlm * 2] = tag; p.timeline[25601 + tlm * 2] = clock64(); ++tlm; }
+            };
             while (remaining > 0) {
                 bool progressed = false;
+                // pass 0: later stages of tiles in flight (an epilogue group is waiting for these);
+                // pass 1: stage-0 GEMMs of tiles ahead (nobody waits yet) -- only when pass 0 found nothing
 #pragma unroll
-                for (int g = 0; g < kGroups; ++g) {
-                    if (ti[g] >= my_tiles) continue;
-                    const int i = ti[g], b = i % kABufs, s = st[g];
-                    bool ready;
-                    if (s == 0) ready = mbar_test(&bars->a_full[b], (i / kABufs) & 1);
-                    else if (s < S) ready = mbar_test(&bars->act_ready[g], ph_act[g]);
-                    else ready = mbar_test(&bars->act_ready[g], ph_act[g]) && mbar_test(&bars->agg_empty[g], ph_ae[g] ^ 1);
-                    if (!ready) continue;
-                    progressed = true;
-                    tc_fence_after();
-                    const uint32_t a_addr = smem_u32(sA + (size_t)b * kTileBytes);
-                    if (s < S) {
-                        if (s > 0) ph_act[g] ^= 1;
-                        const uint32_t w_addr = smem_u32(sW + (size_t)s * kTileBytes);
-                        const uint32_t acc = tmem_base + (uint32_t)(g * 128);
+                for (int pass = 0; pass < 2; ++pass) {
+                    if (pass == 1 && progressed) break;
 #pragma unroll
-                        for (int k = 0; k < 8; ++k) {               // K = 128 = 8 x UMMA_K(16)
-                            const uint32_t off = (uint32_t)((k >> 2) * kKBlockBytes + (k & 3) * 32);
-                            umma_bf16(acc, smem_desc_sw128(a_addr + off, 16, 1024),
-                                      smem_desc_sw128(w_addr + off, 16, 1024), idesc_stage, k > 0);
+                    for (int b = 0; b < kSlots; ++b) {
+                        const int i = ti[b], s = st[b];
+                        if (i >= my_tiles || (pass == 0) != (s > 0)) continue;
+                        const uint32_t par_tile = (uint32_t)((i / kSlots) & 1);
+                        const int g = i & 1, k_g = i >> 1;           // group and per-group tile counter
+                        bool ready;
+                        if (s == 0) ready = mbar_test(&bars->a_full[b], par_tile) && mbar_test(&bars->init_done[b], par_tile);
+                        else {
+                            ready = mbar_test(&bars->act_ready[b], (uint32_t)((S * (i / kSlots) + s - 1) & 1));
+                            if (s == S && k_g > 0) ready = ready && mbar_test(&bars->agg_empty[g], (uint32_t)((k_g - 1) & 1));
                         }
-                        umma_commit(&bars->acc_full[g]);
-                        st[g] = s + 1;
-                    } else {
-                        // neighbour sums, transposed: aggT[ch][slot] = sum_r m3[r][ch] * Sel[slot][r].
-                        // A = m3 read MN-major in place, B = 16-slot selector (K-major).
-                        ph_act[g] ^= 1; ph_ae[g] ^= 1;
-                        const int* misc = s_int + g * kIntsPerGroup + 3 * kTileM;
-                        if (*reinterpret_cast<const volatile int*>(misc + 1) == 0) {   // selector path (<= 16 node slots)
-                            const uint32_t sel_addr = smem_u32(sSel + g * kSelBytes);
-                            const uint32_t agg = tmem_base + 256u + (uint32_t)(g * 32);
+                        if (!ready) continue;
+                        progressed = true;
+                        tc_fence_after();
+                        mstamp(1000 * (i + 1) + s);
+                        const uint32_t a_addr = smem_u32(sA + (size_t)b * kTileBytes);
+                        if (s < S) {
+                            const uint32_t w_addr = smem_u32(sW + (size_t)s * kTileBytes);
+                            const uint32_t acc = tmem_base + (uint32_t)(b * 128);
 #pragma unroll
-                            for (int k = 0; k < 8; ++k) {           // K = 128 edge rows = 8 x 16
-                                const uint32_t a_off = (uint32_t)(k * 2048);            // 16 rows of 128 B
-                                const uint32_t b_off = (uint32_t)((k >> 2) * (kSelSlots * 128) + (k & 3) * 32);
-                                umma_bf16(agg, smem_desc_sw128(a_addr + a_off, kKBlockBytes, 1024),
-                                          smem_desc_sw128(sel_addr + b_off, 16, 1024), idesc_sel, k > 0);
+                            for (int k = 0; k < 8; ++k) {               // K = 128 = 8 x UMMA_K(16)
+                                const uint32_t off = (uint32_t)((k >> 2) * kKBlockBytes + (k & 3) * 32);
+                                // stage 0 accumulates onto the gathered projections the gather warps stored
+                                umma_bf16(acc, smem_desc_sw128(a_addr + off, 16, 1024),
+                                          smem_desc_sw128(w_addr + off, 16, 1024), idesc_stage, (s == 0) || (k > 0));
                             }
+                            umma_commit(&bars->acc_full[b]);
+                            if (s == 0) {
+                                const volatile int* meta = s_meta + 2 * b;
+                                sel_path[b] = meta[1] - meta[0] + 1 <= kSelSlots;
+                            }
+                            st[b] = s + 1;
+                        } else {
+                            // neighbour sums, transposed: aggT[ch][slot] = sum_r m3[r][ch] * Sel[slot][r].
+                            // A = m3 read MN-major in place, B = 16-slot selector (K-major).
+                            if (sel_path[b]) {                              // selector path (<= 16 node slots)
+                                const uint32_t sel_addr = smem_u32(sSel + g * kSelBytes);
+                                const uint32_t agg = tmem_base + kAggCol + (uint32_t)(g * 32);
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) {           // K = 128 edge rows = 8 x 16
+                                    const uint32_t a_off = (uint32_t)(k * 2048);            // 16 rows of 128 B
+                                    const uint32_t b_off = (uint32_t)((k >> 2) * (kSelSlots * 128) + (k & 3) * 32);
+                                    umma_bf16(agg, smem_desc_sw128(a_addr + a_off, kKBlockBytes, 1024),
+                                              smem_desc_sw128(sel_addr + b_off, 16, 1024), idesc_sel, k > 0);
+                                }
+                            }
+                            umma_commit(&bars->agg_full[g]);
+                            umma_commit(&bars->a_empty[b]);
+                            st[b] = 0;
+                            ti[b] = i + kSlots;
+                            --remaining;
                         }
-                        umma_commit(&bars->agg_full[g]);
-                        umma_commit(&bars->a_empty[b]);
-                        st[g] = 0;
-                        ti[g] = i + kGroups;
-                        --remaining;
                     }
                 }
-                if (!progressed) __nanosleep(120);     // do not steal issue slots from the epilogue warps
+                if (!progressed) __nanosleep(32);      // do not steal issue slots from the epilogue warps
             }
+            if (tlm_on) p.timeline[32016] = tlm;
         }
         __syncwarp();
-    } else {
-        // ===================== epilogue: 16 warps, time-multiplexed over the two in-flight tiles ==========
-        // warp -> (TMEM lane group = warp % 4, column quarter): thread = one edge row x 32 columns.  All 16
-        // warps run stage s of tile A, then stage s of tile B; while they work on one tile the tensor pipe
-        // runs the next GEMM of the other, so neither side waits for the other in steady state.
-        const int ew = warp - 2;
-        const int quarter = ew >> 2;                     // 32-column slice; K-block = quarter / 2
-        const int lane_grp = warp & 3;                   // TMEM lanes this warp may touch: 32*(warp%4)..+31
+    } else if (warp < 2 + kGatherThreads / 32) {
+        // ===================== gather warps: acc[slot] <- Pc[centre] + Pn[neighbour] (thread = edge row) =====
+        const int lane_grp = warp & 3;
         const int row = lane_grp * 32 + lane;
-        const int col0 = quarter * 32;
         const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
-        uint32_t ph_acc[kGroups] = {0, 0}, ph_agg[kGroups] = {0, 0};
-        int tl_n = 0;
-        const bool tl_on = p.timeline != nullptr && blockIdx.x == 0 && threadIdx.x == 64;
-        auto stamp = [&](int tag) {
-            if (tl_on && tl_n < 4000) { p.timeline[tl_n * 2] = tag; p.timeline[tl_n * 2 + 1] = clock64(); ++tl_n; }
-        };
-
-        // (centre, neighbour) node of this thread's edge row in local tile i; -1 marks rows past the end
         auto load_idx = [&](int i, int& c, int& nb) {
             c = -1; nb = 0;
             if (i < my_tiles) {
@@ -195,183 +239,180 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
                 if (e < p.n_edges) { c = __ldg(p.ctr + e); nb = __ldg(p.nbr + e); }
             }
         };
-        int c_nx0, nb_nx0, c_nx1, nb_nx1;
-        load_idx(0, c_nx0, nb_nx0);
-        load_idx(1, c_nx1, nb_nx1);
-        // stage biases (stages >= 1) live in shared memory: broadcast LDS instead of global loads per chunk
-        float* s_bias = reinterpret_cast<float*>(s_int + kGroups * kIntsPerGroup);       // [kMaxStages][128]
-        s_bias += (4 - ((smem_u32(s_bias) >> 2) & 3)) & 3;                                // 16-byte aligned for LDS.128
-        for (int t = threadIdx.x - 64; t < (S - 1) * 128; t += kGroups * kEpiThreads) {
-            const int st = 1 + t / 128;
-            const float* bsp = st == 1 ? p.bias[1] : (st == 2 ? p.bias[2] : p.bias[3]);
-            s_bias[st * 128 + (t & 127)] = __ldg(bsp + (t & 127));
+        int c_nx, nb_nx;
+        load_idx(0, c_nx, nb_nx);
+        for (int i = 0; i < my_tiles; ++i) {
+            const int b = i % kSlots;
+            const int c = c_nx, nb = nb_nx;
+            const int e_base = (blockIdx.x + i * gridDim.x) * kTileM;
+            const int last_row = min(kTileM, p.n_edges - e_base) - 1;
+            const float* pc = p.Pc + (size_t)max(c, 0) * p.ld_pc;
+            const uint16_t* pn = p.Pn + (size_t)nb * p.ld_pn;
+            // first half of the neighbour row is requested before the (possibly blocking) wait for the accumulator
+            uint32_t w[4][8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ldg256(pn + 16 * q, w[q]);
+            load_idx(i + 1, c_nx, nb_nx);                      // streaming index loads of the next tile
+            mbar_wait(&bars->acc_free[b], (uint32_t)(((i / kSlots) & 1) ^ 1));
+            tc_fence_after();
+            if (row == 0) s_meta[2 * b] = c;
+            if (row == last_row) s_meta[2 * b + 1] = c;
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (h == 1) {
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) ldg256(pn + 64 + 16 * q, w[q]);
+                }
+#pragma unroll
+                for (int q2 = 0; q2 < 2; ++q2) {               // 32 columns: h*64 + q2*32
+                    const int col0 = h * 64 + q2 * 32;
+                    uint32_t f[4][8];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) ldg256(pc + col0 + 8 * q, f[q]);
+                    float v[32];
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) {             // bf16 pair q of this 32-column chunk
+                        const uint32_t ww = w[q2 * 2 + (q >> 3)][q & 7];
+                        v[2 * q] = __uint_as_float(f[q >> 2][(2 * q) & 7]) + __uint_as_float(ww << 16);
+                        v[2 * q + 1] = __uint_as_float(f[q >> 2][(2 * q + 1) & 7]) + __uint_as_float(ww & 0xffff0000u);
+                    }
+                    if (c < 0) {
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) v[q] = 0.f;
+                    }
+                    tmem_st32(t_row + (uint32_t)(b * 128 + col0), v);
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            mbar_arrive(&bars->init_done[b]);
         }
-        asm volatile("bar.sync 1, %0;" ::"n"(kGroups * kEpiThreads) : "memory");
+    } else {
+        // ===================== epilogue: two decoupled groups of 8 warps, group g owns tiles i % 2 == g ==========
+        // warp -> (TMEM lane group = warp % 4, column half): thread = one edge row x 64 columns (two chunks of 32)
+        const int ew = warp - (2 + kGatherThreads / 32);
+        const int g = ew >> 3;
+        const int half = (ew >> 2) & 1;
+        const int lane_grp = warp & 3;                   // TMEM lanes this warp may touch: 32*(warp%4)..+31
+        const int row = lane_grp * 32 + lane;
+        const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+        int tl_n = 0;
+        const bool tl_on = p.timeline != nullptr && blockIdx.x == 0 && lane == 0;
+        long long* tl_buf = p.timeline + ew * 1600;
+        auto stamp = [&](int tag) {
+            if (tl_on && tl_n < 799) { tl_buf[tl_n * 2] = tag; tl_buf[tl_n * 2 + 1] = clock64(); ++tl_n; }
+        };
 
-        for (int i0 = 0; i0 < my_tiles; i0 += kGroups) {
+        for (int i = g; i < my_tiles; i += kGroups) {
+            const int b = i % kSlots;
+            const int pb = S * (i / kSlots);
+            const int e_base = (blockIdx.x + i * gridDim.x) * kTileM;
+            const bool valid = e_base + row < p.n_edges;
+            uint8_t* a_buf = sA + (size_t)b * kTileBytes;
+            const uint32_t t_acc = t_row + (uint32_t)(b * 128 + half * 64);
+            int fn = 0, nslots = 1;
+            bool bypass = false;
             stamp(90);
-            const int c_cur[kGroups] = {c_nx0, c_nx1}, nb_cur[kGroups] = {nb_nx0, nb_nx1};
-            int fn[kGroups] = {0, 0}, ns[kGroups] = {0, 0};
-
-            // stage-0 addend of this row's 32 columns: Pc[centre] + Pn[neighbour], combined while the GEMM runs
-            float4 add[8];
-            auto gather_addend = [&](int g) {
-                if (c_cur[g] >= 0) {
-                    const float* pc = p.Pc + (size_t)c_cur[g] * p.ld_pc + col0;
-                    const uint16_t* pn = p.Pn + (size_t)nb_cur[g] * p.ld_pn + col0;
-                    uint32_t w[2][8], f[4][8];
-                    ldg256(pn, w[0]); ldg256(pn + 16, w[1]);                 // 32 bf16 = two 32-byte sectors
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) ldg256(pc + 8 * q, f[q]);    // 32 fp32 = four sectors
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {                            // columns 4q .. 4q+3
-                        const uint32_t w0 = w[q >> 2][(q & 3) * 2], w1 = w[q >> 2][(q & 3) * 2 + 1];
-                        const uint32_t* fq = &f[q >> 1][(q & 1) * 4];
-                        add[q].x = __uint_as_float(fq[0]) + __uint_as_float(w0 << 16);
-                        add[q].y = __uint_as_float(fq[1]) + __uint_as_float(w0 & 0xffff0000u);
-                        add[q].z = __uint_as_float(fq[2]) + __uint_as_float(w1 << 16);
-                        add[q].w = __uint_as_float(fq[3]) + __uint_as_float(w1 & 0xffff0000u);
-                    }
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) add[q] = make_float4(0.f, 0.f, 0.f, 0.f);
-                }
-            };
-            gather_addend(0);
-            stamp(95);
-            // streaming index loads (HBM) are issued only now, after the L2 gather was consumed, so that nothing
-            // on the critical path shares a scoreboard with them; they land during the stage epilogues
-            load_idx(i0 + kGroups, c_nx0, nb_nx0);       // indices of the next pair, a whole pair of tiles ahead
-            load_idx(i0 + kGroups + 1, c_nx1, nb_nx1);
-#pragma unroll
-            for (int g = 0; g < kGroups; ++g)            // node slots of the two tiles, consumed after stage 0
-                if (i0 + g < my_tiles) {
-                    const int e_base = (blockIdx.x + (i0 + g) * gridDim.x) * kTileM;
-                    fn[g] = __ldg(p.ctr + e_base);
-                    ns[g] = __ldg(p.ctr + min(e_base + kTileM, p.n_edges) - 1);
-                }
-
-            // one (tile, stage) epilogue; FIRST selects the stage-0 flavour at compile time so that the gathered
-            // addend registers are live in that code only
-            auto stage = [&](auto first_tag, int s, int g) {
-                constexpr bool FIRST = decltype(first_tag)::value;
-                const int i = i0 + g;
-                if (i >= my_tiles) return;
-                const bool valid = c_cur[g] >= 0;
-                const bool bypass = (ns[g] - fn[g] + 1) > kSelSlots;
-                uint8_t* a_buf = sA + (size_t)(i % kABufs) * kTileBytes;
-                stamp(100 + s * 10 + g);                       // about to wait for the accumulator
-                mbar_wait(&bars->acc_full[g], ph_acc[g]); ph_acc[g] ^= 1;
+            for (int s = 0; s < S; ++s) {
+                stamp(100 + s * 10);                           // about to wait for the accumulator
+                mbar_wait(&bars->acc_full[b], (uint32_t)((pb + s) & 1));
                 tc_fence_after();
-                stamp(200 + s * 10 + g);                       // accumulator ready
-                float v[32];
-                tmem_ld32(t_row + (uint32_t)(g * 128 + col0), v);
-                stamp(300 + s * 10 + g);                       // TMEM load done
-                if constexpr (FIRST) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        v[4 * q + 0] += add[q].x; v[4 * q + 1] += add[q].y;
-                        v[4 * q + 2] += add[q].z; v[4 * q + 3] += add[q].w;
-                    }
-                } else {
-                    const float4* bs = reinterpret_cast<const float4*>(s_bias + s * 128 + col0);
-#pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 x = bs[q];
-                        v[4 * q + 0] += x.x; v[4 * q + 1] += x.y; v[4 * q + 2] += x.z; v[4 * q + 3] += x.w;
-                    }
+                stamp(200 + s * 10);                           // accumulator ready
+                if (s == 0) {
+                    fn = reinterpret_cast<const volatile int*>(s_meta)[2 * b];
+                    nslots = reinterpret_cast<const volatile int*>(s_meta)[2 * b + 1] - fn + 1;
+                    bypass = nslots > kSelSlots;
                 }
-                stamp(400 + s * 10 + g);                       // gathers / bias added
-                stamp(500 + s * 10 + g);
-                if (p.debug != nullptr || (s == S - 1 && bypass)) {
-                    // fp32 GELU: debug dump (tests) and the tiny-degree bypass that sums with vector reductions
+                const bool slow = p.debug != nullptr || (s == S - 1 && bypass);
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) v[q] = gelu_tanh_fast(v[q]);
-                    if (p.debug && valid) {
-                        const int e = (blockIdx.x + i * gridDim.x) * kTileM + row;
-                        float* dbg = p.debug + ((size_t)s * p.n_edges + e) * 128 + col0;
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) dbg[q] = v[q];
+                for (int ch = 0; ch < 2; ++ch) {
+                    const int col0 = half * 64 + ch * 32;
+                    float v[32];
+                    tmem_ld32(t_acc + (uint32_t)(ch * 32), v);
+                    if (s == S - 1 && ch == 1) {               // this thread is done with the accumulator
+                        tc_fence_before();
+                        mbar_arrive(&bars->acc_free[b]);
                     }
-                    if (s == S - 1 && bypass) {
-                        if (valid) {
-                            float* dst = p.agg + (size_t)c_cur[g] * 128 + col0;
+                    if (s > 0) {
+                        const float4* bs = reinterpret_cast<const float4*>(s_bias + s * 128 + col0);
 #pragma unroll
-                            for (int q = 0; q < 8; ++q)
-                                red_add_v4(dst + 4 * q, v[4 * q] * p.alpha, v[4 * q + 1] * p.alpha,
-                                           v[4 * q + 2] * p.alpha, v[4 * q + 3] * p.alpha);
+                        for (int q = 0; q < 8; ++q) {
+                            const float4 x = bs[q];
+                            v[4 * q + 0] += x.x; v[4 * q + 1] += x.y; v[4 * q + 2] += x.z; v[4 * q + 3] += x.w;
+                        }
+                    }
+                    if (slow) {
+                        // fp32 GELU: debug dump (tests) and the tiny-degree bypass that sums with vector reductions
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) v[q] = gelu_tanh_fast(v[q]);
+                        if (p.debug && valid) {
+                            float* dbg = p.debug + ((size_t)s * p.n_edges + e_base + row) * 128 + col0;
+#pragma unroll
+                            for (int q = 0; q < 32; ++q) dbg[q] = v[q];
+                        }
+                        if (s == S - 1 && bypass) {
+                            if (valid) {
+                                float* dst = p.agg + (size_t)__ldg(p.ctr + e_base + row) * 128 + col0;
+#pragma unroll
+                                for (int q = 0; q < 8; ++q)
+                                    red_add_v4(dst + 4 * q, v[4 * q] * p.alpha, v[4 * q + 1] * p.alpha,
+                                               v[4 * q + 2] * p.alpha, v[4 * q + 3] * p.alpha);
+                            }
+                        } else {
+                            store_act_chunk(a_buf, row, col0, v);
                         }
                     } else {
-                        store_act_chunk(a_buf, row, col0, v);
+                        store_gelu_chunk(a_buf, row, col0, v);     // packed bf16x2 GELU straight into the A operand
                     }
-                } else {
-                    store_gelu_chunk(a_buf, row, col0, v);     // packed bf16x2 GELU straight into the A operand
                 }
-                stamp(600 + s * 10 + g);                       // operand stored
-                if constexpr (FIRST) {
-                    if (g == 0) gather_addend(1);              // v[] is dead: start the other tile's gather
-                    // selector matrix of this tile (rows = node slots, K = the tile's 128 edge rows); the MMA
-                    // thread reads it (and the bypass flag) only after the last stage's act_ready
-                    if (threadIdx.x == 64) (s_int + g * kIntsPerGroup + 3 * kTileM)[1] = bypass;
-                    if (!bypass && row < kSelSlots && quarter < 2) {
-                        const int e_base = (blockIdx.x + i * gridDim.x) * kTileM;
-                        int st = 0, en = 0;
-                        if (row < ns[g] - fn[g] + 1) {
-                            st = max(__ldg(p.row_ptr + fn[g] + row) - e_base, 0);
-                            en = min(__ldg(p.row_ptr + fn[g] + row + 1) - e_base, kTileM);
-                        }
-                        uint8_t* sel = sSel + g * kSelBytes + quarter * (kSelSlots * 128);
+                stamp(600 + s * 10);                           // operand stored
+                if (s == 0 && !bypass && row < kSelSlots) {
+                    // selector matrix of this tile (rows = node slots, K = the tile's 128 edge rows; this thread
+                    // fills K-block `half` of slot `row`); the previous tile of this group is done with it
+                    int st = 0, en = 0;
+                    if (row < nslots) {
+                        st = max(__ldg(p.row_ptr + fn + row) - e_base, 0);
+                        en = min(__ldg(p.row_ptr + fn + row + 1) - e_base, kTileM);
+                    }
+                    uint8_t* sel = sSel + g * kSelBytes + half * (kSelSlots * 128);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            uint32_t w[4];
+                    for (int j = 0; j < 8; ++j) {
+                        uint32_t w[4];
 #pragma unroll
-                            for (int q = 0; q < 4; ++q) {
-                                const int r0 = quarter * 64 + j * 8 + q * 2;
-                                const uint32_t lo = (r0 >= st && r0 < en) ? 0x3F80u : 0u;
-                                const uint32_t hi = (r0 + 1 >= st && r0 + 1 < en) ? 0x3F80u : 0u;
-                                w[q] = lo | (hi << 16);
-                            }
-                            *reinterpret_cast<uint4*>(sel + sw128_chunk(row, j)) = make_uint4(w[0], w[1], w[2], w[3]);
+                        for (int q = 0; q < 4; ++q) {
+                            const int r0 = half * 64 + j * 8 + q * 2;
+                            const uint32_t lo = (r0 >= st && r0 < en) ? 0x3F80u : 0u;
+                            const uint32_t hi = (r0 + 1 >= st && r0 + 1 < en) ? 0x3F80u : 0u;
+                            w[q] = lo | (hi << 16);
                         }
+                        *reinterpret_cast<uint4*>(sel + sw128_chunk(row, j)) = make_uint4(w[0], w[1], w[2], w[3]);
                     }
                 }
                 tc_fence_before();
                 fence_proxy_async();
-                mbar_arrive(&bars->act_ready[g]);
-                stamp(700 + s * 10 + g);                       // fences + arrive done
-            };
-            stage(std::true_type{}, 0, 0);
-            stage(std::true_type{}, 0, 1);
-            for (int s = 1; s < S; ++s) {
-                stage(std::false_type{}, s, 0);
-                stage(std::false_type{}, s, 1);
+                mbar_arrive(&bars->act_ready[b]);
+                stamp(700 + s * 10);                           // fences + arrive done
             }
 
-            // ---- neighbour sums out of TMEM: lane = channel, columns = node slots, 4 slots per column quarter ----
+            // ---- neighbour sums out of TMEM: lane = channel, columns = node slots, 8 slots per column half ----
+            stamp(800);
+            mbar_wait(&bars->agg_full[g], (uint32_t)((i >> 1) & 1));
+            tc_fence_after();
+            stamp(810);
+            if (!bypass && half * 8 < nslots) {                          // warp-uniform
+                float v[8];
+                tmem_ld8(t_row + kAggCol + (uint32_t)(g * 32 + half * 8), v);
+                float* dst = p.agg + (size_t)(fn + half * 8) * 128 + row;          // row == channel here
 #pragma unroll
-            for (int g = 0; g < kGroups; ++g) {
-                const int i = i0 + g;
-                if (i >= my_tiles) continue;
-                stamp(800 + g);
-                mbar_wait(&bars->agg_full[g], ph_agg[g]); ph_agg[g] ^= 1;
-                tc_fence_after();
-                stamp(810 + g);
-                const int nslots = ns[g] - fn[g] + 1;
-                if (nslots <= kSelSlots && quarter * 4 < nslots) {       // warp-uniform
-                    float v[4];
-                    tmem_ld4(t_row + 256u + (uint32_t)(g * 32 + quarter * 4), v);
-                    float* dst = p.agg + (size_t)(fn[g] + quarter * 4) * 128 + row;      // row == channel here
-#pragma unroll
-                    for (int n = 0; n < 4; ++n)
-                        if (quarter * 4 + n < nslots)
-                            asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + n * 128), "f"(v[n] * p.alpha) : "memory");
-                }
-                tc_fence_before();
-                mbar_arrive(&bars->agg_empty[g]);
-                stamp(820 + g);
+                for (int n = 0; n < 8; ++n)
+                    if (half * 8 + n < nslots)
+                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + n * 128), "f"(v[n] * p.alpha) : "memory");
             }
+            tc_fence_before();
+            mbar_arrive(&bars->agg_empty[g]);
+            stamp(820);
         }
-        if (tl_on) p.timeline[7999] = tl_n;
+        if (tl_on) p.timeline[32000 + ew] = tl_n;
     }
 
     tc_fence_before();
@@ -720,8 +761,8 @@ extern "C" int rmp_edge_mlp_bf16_traced(const void* h_E_bf16, const void* W_bf16
     }
     p.num_stages = num_stages; p.alpha = alpha; p.agg = agg; p.n_edges = n_edges; p.debug = debug;
     p.timeline = timeline;
-    const size_t smem = 1024 + (size_t)(num_stages + tc::kABufs) * tc::kTileBytes + tc::kGroups * tc::kSelBytes +
-                        sizeof(tc::Barriers) + 16 + tc::kGroups * (3 * tc::kTileM + 4) * sizeof(int) +
+    const size_t smem = 1024 + (size_t)(num_stages + tc::kSlots) * tc::kTileBytes + tc::kGroups * tc::kSelBytes +
+                        sizeof(tc::Barriers) + 16 + (2 * tc::kSlots + 2) * sizeof(int) +
                         tc::kMaxStages * 128 * sizeof(float) + 16;
     RMP_REQUIRE(smem <= 227 * 1024, RMP_E_SHAPE, "rmp_edge_mlp_bf16: %zu B of shared memory needed", smem);
     cudaFuncSetAttribute(tc::edge_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);

@@ -1,5 +1,5 @@
-"""Tuning aid: clock64 trace of one epilogue thread of the tcgen05 edge kernel (CTA 0)."""
-import ctypes as C, os, sys
+"""Tuning aid: clock64 trace of the tcgen05 edge kernel (CTA 0): every epilogue warp and the MMA thread."""
+import ctypes as C, os, sys, collections
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path[:0] = [ROOT, os.path.join(ROOT, "rna-mpnn_b200")]
 import torch
@@ -15,27 +15,53 @@ W = (torch.randn(384, 128) / 11.3).cuda().to(torch.bfloat16)
 b = [None, torch.zeros(128).cuda(), torch.zeros(128).cuda()]
 Pc = torch.randn(Nv, 128).cuda(); Pn = torch.randn(Nv, 128).cuda().to(torch.bfloat16)
 agg = torch.zeros(Nv, 128).cuda()
-tl = torch.zeros(8000, dtype=torch.int64).cuda()
+tl = torch.zeros(32768, dtype=torch.int64).cuda()
 barr = (C.c_void_p * 4)(None, b[1].data_ptr(), b[2].data_ptr(), None)
 L = _lib.lib()
-for _ in range(3):
+def launch(t):
     _lib.check(L.rmp_edge_mlp_bf16_traced(hE.data_ptr(), W.data_ptr(), 3, C.cast(barr, C.c_void_p), Pc.data_ptr(),
                Pn.data_ptr(), ctr.data_ptr(), nbr.data_ptr(), rp.data_ptr(), Ne, 1 / 30, agg.data_ptr(), None,
-               tl.data_ptr(), torch.cuda.current_stream().cuda_stream))
+               t, torch.cuda.current_stream().cuda_stream))
+for _ in range(3):
+    launch(tl.data_ptr())
 torch.cuda.synchronize()
+e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(20):
+    launch(None)
+e1.record(); torch.cuda.synchronize()
+print("untraced launch us", e0.elapsed_time(e1) * 1000 / 20)
 t = tl.cpu().tolist()
-n = t[7999]
-ev = [(t[2 * i], t[2 * i + 1]) for i in range(n)]
-t0 = ev[0][1]
-print("events", n, "total cycles", ev[-1][1] - t0)
-# per-kind average deltas to the previous event
-import collections
-acc = collections.defaultdict(list)
-for (a, ta), (b_, tb) in zip(ev[:-1], ev[1:]):
-    acc[(a, b_)].append(tb - ta)
-for k in sorted(acc, key=lambda k: -sum(acc[k])):
-    v = acc[k]
-    print(f"{k[0]:4d} -> {k[1]:4d}: n={len(v):4d} mean={sum(v)/len(v):8.0f} total={sum(v):9d}")
-print("first 60 events:")
-for a, ta in ev[:60]:
-    print(a, ta - t0)
+warps = {}
+for ew in range(16):
+    n = t[32000 + ew]
+    warps[ew] = [(t[ew * 1600 + 2 * i], t[ew * 1600 + 2 * i + 1]) for i in range(n)]
+t0 = min(w[0][1] for w in warps.values() if w)
+print("total cycles (warp 0)", warps[0][-1][1] - warps[0][0][1])
+for ew in (0, 8):
+    ev = warps[ew]
+    acc = collections.defaultdict(list)
+    for (a, ta), (b_, tb) in zip(ev[:-1], ev[1:]):
+        acc[(a, b_)].append(tb - ta)
+    print(f"--- epilogue warp {ew} (group {ew >> 3}) mean deltas")
+    for k in sorted(acc, key=lambda k: -sum(acc[k])):
+        v = acc[k]
+        print(f"{k[0]:4d} -> {k[1]:4d}: n={len(v):4d} mean={sum(v)/len(v):8.0f} total={sum(v):9d}")
+# per (tile, stage): when each warp got the accumulator (2x0) and when it arrived (7x0)
+print("--- per group-tile stage windows: min/max over the 8 warps of acc-ready (200+10s) and arrive (700+10s)")
+for g in range(2):
+    ws = [warps[g * 8 + j] for j in range(8)]
+    ntile = sum(1 for tag, _ in ws[0] if tag == 90)
+    for k in range(3, min(ntile, 7)):
+        for s in range(3):
+            rdy = [[ts for tag, ts in w if tag == 200 + 10 * s][k] - t0 for w in ws]
+            arr = [[ts for tag, ts in w if tag == 700 + 10 * s][k] - t0 for w in ws]
+            print(f"g{g} tile#{k} s{s}: ready {min(rdy)}..{max(rdy)}  arrive {min(arr)}..{max(arr)}  "
+                  f"group E = {max(arr) - min(rdy)}  per-warp E = {[a - r for a, r in zip(arr, rdy)]}")
+m = t[32016]
+print("MMA thread issues (tile+1)*1000+stage, cycle, delta:")
+prev = None
+for i in range(min(m, 60)):
+    tag, ts = t[25600 + 2 * i], t[25601 + 2 * i]
+    print(tag, ts - t0, (ts - prev) if prev is not None else 0)
+    prev = ts
