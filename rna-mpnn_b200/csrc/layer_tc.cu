@@ -10,8 +10,8 @@
 // [Ne,H] activations of the reference (rdesign/model/mpnn.py:33) never reach HBM: per edge the
 // kernel reads 256 B of bf16 h_E and the L2-resident projections, nothing else.
 //
-// Roles (704 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 2..5 = gather
-// (accumulator pre-initialisation with the gathered projections), warps 6..21 = two epilogue groups.
+// Roles (768 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 4..7 = gather /
+// drain (accumulator pre-initialisation, selector matrix, neighbour sums), warps 8..23 = epilogue.
 #include "tc_common.cuh"
 
 namespace rmp {
@@ -33,28 +33,34 @@ struct EdgeParams {
     long long* timeline;             // optional int64[32768] clock64 trace of CTA 0 (per epilogue warp + MMA thread; tuning)
 };
 
-// Pipeline.  A tile owns slot = i % 3: one 32 KB A buffer (h_E, then the activations in place) and one
-// 128-column TMEM accumulator.
-//   gather warps : acc[slot] <- Pc[centre] + Pn[neighbour]          (tcgen05.st, a tile or more ahead)
-//   MMA thread   : acc[slot] += h_E . W1e^T as soon as the TMA tile and the pre-initialised accumulator are
-//                  there, so the stage-0 pre-activation of tile i+2 is complete before an epilogue group asks
-//   epilogue     : group g (8 warps) owns the tiles with i % 2 == g and runs their stage epilogues
-//                  (bias + GELU -> bf16 A operand in place); the two groups are decoupled, so while one is on
-//                  the CUDA cores / MUFU the other group's GEMM is on the tensor pipe.
-// The epilogue never touches global memory on its critical path: its only inputs are TMEM and shared memory.
-constexpr int kGroups = 2;
+// Pipeline.  A tile owns slot = i % 3: one 32 KB smem buffer (h_E from TMA; at the end the last activation
+// m3), one 128-column TMEM accumulator X[slot] and one 4 KB selector matrix.
+//   gather warps : X[slot] <- Pc[centre] + Pn[neighbour] (tcgen05.st, a tile or more ahead), selector matrix of
+//                  the tile, and -- once the selector MMA of the slot's previous tile is done -- its neighbour
+//                  sums TMEM -> red.global.  They own every global load/store of the kernel.
+//   MMA thread   : stage 0  X += h_E . W1e^T          (A, B from smem)
+//                  stage s  X  = m_s . W_s^T          (A = the activations in TMEM, Y[tile & 1]; B from smem)
+//                  last     X[:, 0:16] = m3^T . Sel^T (A = m3 read MN-major from smem)
+//   epilogue     : X -> (+bias) -> GELU -> bf16 -> Y in TMEM (tcgen05.st; no shared-memory round trip, no proxy
+//                  fence), the last stage -> smem.  Its only inputs are TMEM and shared memory.
+// Schedule of the 16 epilogue warps (thread = row x 32 columns) over the two tiles in flight: stage s of the
+// even-tile stream, then a stage of the odd-tile stream, so the GEMM of one tile is hidden behind the epilogue
+// of the other.
+// Registers: the roles are rebalanced with setmaxnreg (warpgroup 0 = TMA/MMA 40, warpgroup 1 = gather 120; the CTA total stays 768 x 80,
+// warpgroups 2..5 = epilogue 80).
 constexpr int kSlots = 3;
 constexpr int kGatherThreads = 128;
-constexpr int kEdgeThreads = 64 + kGatherThreads + kGroups * kEpiThreads;   // 704
+constexpr int kEdgeEpiThreads = 512;
+constexpr int kEdgeThreads = 128 + kGatherThreads + kEdgeEpiThreads;        // 768
 constexpr int kSelSlots = 16;                                  // node slots per tile served by the selector MMA
 constexpr int kSelBytes = 2 * kSelSlots * 128;                 // [2 K-blocks][16 slots][64 edges] bf16
-constexpr uint32_t kEdgeTmemCols = 512;                        // acc slot s at 128*s, neighbour sums g at 384 + 32*g
-constexpr uint32_t kAggCol = 384;
+constexpr int kPcStride = 132;                                 // floats per row of the per-tile centre table
+constexpr uint32_t kEdgeTmemCols = 512;                        // X[s] at 128*s; Y[t] (bf16 A operand) at 384 + 64*t
+constexpr uint32_t kYCol = 384;
 
 struct alignas(8) Barriers {
     uint64_t w_full, a_full[kSlots], a_empty[kSlots];
-    uint64_t init_done[kSlots], acc_free[kSlots], acc_full[kSlots], act_ready[kSlots];
-    uint64_t agg_full[kGroups], agg_empty[kGroups];
+    uint64_t init_done[kSlots], acc_full[kSlots], act_ready[kSlots], agg_full[kSlots];
 };
 
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) {
@@ -68,18 +74,84 @@ __device__ __forceinline__ void tmem_st32(uint32_t taddr, const float (&v)[32]) 
         "f"(v[28]), "f"(v[29]), "f"(v[30]), "f"(v[31])
         : "memory");
 }
-__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
-__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float (&v)[8]) {
-    uint32_t r[8];
-    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
-                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
-                 : "r"(taddr)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&v)[16]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+        "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+        "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+        : "memory");
+}
+// split TMEM load: request 32 columns, and later wait for them (the registers are tied to the wait so that no use
+// can be scheduled before it)
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]),
+                   "+r"(r[16]), "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]),
+                   "+r"(r[23]), "+r"(r[24]), "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]),
+                   "+r"(r[30]), "+r"(r[31])
+                 :
                  : "memory");
-    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-#pragma unroll
-    for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[i]);
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// D[tmem] (+)= A[tmem] . B[smem]^T: the A operand (128 rows x 16 bf16 = 8 columns) is read from tensor memory
+__device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+        "}" ::"r"(d_tmem),
+        "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+        : "memory");
 }
 
+// 256-bit gather load that does not allocate in L1 (the neighbour rows are used once per tile)
+__device__ __forceinline__ void ldg256_stream(const void* ptr, uint32_t (&r)[8]) {
+    asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "l"(ptr));
+}
+// (a, b) += (x, y): one packed fp32x2 add
+__device__ __forceinline__ void add2(float& a, float& b, float x, float y) {
+    asm("{\n\t"
+        ".reg .b64 va, vx;\n\t"
+        "mov.b64 va, {%0, %1};\n\t"
+        "mov.b64 vx, {%2, %3};\n\t"
+        "add.rn.f32x2 va, va, vx;\n\t"
+        "mov.b64 {%0, %1}, va;\n\t"
+        "}"
+        : "+f"(a), "+f"(b)
+        : "f"(x), "f"(y));
+}
+template <int N>
+__device__ __forceinline__ void set_max_regs_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
+template <int N>
+__device__ __forceinline__ void set_max_regs_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" ::"n"(N)); }
+__device__ __forceinline__ void gather_bar_sync() { asm volatile("bar.sync 2, %0;" ::"n"(kGatherThreads) : "memory"); }
+
+// 16 packed bf16x2 GELU values of 32 fp32 pre-activations
+__device__ __forceinline__ void gelu_pack32(const float (&v)[32], uint32_t (&o)[16]) {
+#pragma unroll
+    for (int q = 0; q < 16; ++q) o[q] = gelu_bf16x2(v[2 * q], v[2 * q + 1]);
+}
+
+template <bool TRACE>
 __global__ void __launch_bounds__(kEdgeThreads, 1)
 edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant__ CUtensorMap tm_w,
                    const EdgeParams p) {
@@ -88,11 +160,14 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sW = smem;                                         // [S][2][128][64] bf16, resident
     uint8_t* sA = sW + (size_t)p.num_stages * kTileBytes;       // [3 slots][2][128][64] bf16
-    uint8_t* sSel = sA + kSlots * kTileBytes;                   // [2 groups][2][16][64] bf16 selector
-    Barriers* bars = reinterpret_cast<Barriers*>(sSel + kGroups * kSelBytes);
+    uint8_t* sSel = sA + kSlots * kTileBytes;                   // [3 slots][2][16][64] bf16 selector
+    float* s_pc = reinterpret_cast<float*>(sSel + kSlots * kSelBytes);                // [16][kPcStride] centre rows of a tile
+    Barriers* bars = reinterpret_cast<Barriers*>(s_pc + kSelSlots * kPcStride);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 1);
-    int* s_meta = reinterpret_cast<int*>(s_tmem + 4);           // per slot: first node, last node of the tile
-    float* s_bias = reinterpret_cast<float*>(s_meta + 2 * kSlots + 2);                // [kMaxStages][128]
+    // per (generation = (i / 3) & 1, slot): first node, node count of the tile.  Two generations, because the
+    // gather warps read the previous tile's entry (drain) while one of them already writes the next tile's
+    int* s_meta = reinterpret_cast<int*>(s_tmem + 4);
+    float* s_bias = reinterpret_cast<float*>(s_meta + 4 * kSlots + 4);                // [kMaxStages][128]
     s_bias += (4 - ((smem_u32(s_bias) >> 2) & 3)) & 3;                                // 16-byte aligned for LDS.128
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -105,11 +180,10 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
         for (int b = 0; b < kSlots; ++b) {
             mbar_init(&bars->a_full[b], 1); mbar_init(&bars->a_empty[b], 1);
             mbar_init(&bars->init_done[b], kGatherThreads);
-            mbar_init(&bars->acc_free[b], kEpiThreads);
             mbar_init(&bars->acc_full[b], 1);
-            mbar_init(&bars->act_ready[b], kEpiThreads);
+            mbar_init(&bars->act_ready[b], kEdgeEpiThreads);
+            mbar_init(&bars->agg_full[b], 1);
         }
-        for (int g = 0; g < kGroups; ++g) { mbar_init(&bars->agg_full[g], 1); mbar_init(&bars->agg_empty[g], kEpiThreads); }
         fence_barrier_init();
     }
     // stage biases (stages >= 1) live in shared memory: broadcast LDS instead of global loads per chunk
@@ -124,293 +198,335 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
 
-    if (warp == 0) {
-        // ===================== TMA producer =====================
-        if (lane == 0) {
-            tma_prefetch_desc(&tm_e);
-            tma_prefetch_desc(&tm_w);
-            mbar_expect_tx(&bars->w_full, (uint32_t)(S * kTileBytes));
-            for (int s = 0; s < S; ++s)
-                for (int kb = 0; kb < 2; ++kb)
-                    tma_load_2d(sW + (size_t)s * kTileBytes + kb * kKBlockBytes, &tm_w, &bars->w_full, kb * 64, s * 128);
-            for (int i = 0; i < my_tiles; ++i) {
-                const int b = i % kSlots;
-                const int tile = blockIdx.x + i * gridDim.x;
-                mbar_wait_relaxed(&bars->a_empty[b], ((i / kSlots) & 1) ^ 1, 200);
-                mbar_expect_tx(&bars->a_full[b], kTileBytes);
-                for (int kb = 0; kb < 2; ++kb)
-                    tma_load_2d(sA + (size_t)b * kTileBytes + kb * kKBlockBytes, &tm_e, &bars->a_full[b], kb * 64,
-                                tile * kTileM);
+    if (warp < 4) {
+        set_max_regs_dec<40>();
+        if (warp == 0) {
+            // ===================== TMA producer =====================
+            if (lane == 0) {
+                tma_prefetch_desc(&tm_e);
+                tma_prefetch_desc(&tm_w);
+                mbar_expect_tx(&bars->w_full, (uint32_t)(S * kTileBytes));
+                for (int s = 0; s < S; ++s)
+                    for (int kb = 0; kb < 2; ++kb)
+                        tma_load_2d(sW + (size_t)s * kTileBytes + kb * kKBlockBytes, &tm_w, &bars->w_full, kb * 64, s * 128);
+                for (int i = 0; i < my_tiles; ++i) {
+                    const int b = i % kSlots;
+                    const int tile = blockIdx.x + i * gridDim.x;
+                    mbar_wait_relaxed(&bars->a_empty[b], ((i / kSlots) & 1) ^ 1, 200);
+                    mbar_expect_tx(&bars->a_full[b], kTileBytes);
+                    for (int kb = 0; kb < 2; ++kb)
+                        tma_load_2d(sA + (size_t)b * kTileBytes + kb * kKBlockBytes, &tm_e, &bars->a_full[b], kb * 64,
+                                    tile * kTileM);
+                }
             }
-        }
-        __syncwarp();
-    } else if (warp == 1) {
-        // ===================== MMA issuer: serves the tiles in flight as their operands become ready ====
-        if (lane == 0) {
-            constexpr uint32_t idesc_stage = instr_desc_bf16(128, 128, 0);
-            constexpr uint32_t idesc_sel = instr_desc_bf16_amn(128, kSelSlots);
-            int ti[kSlots], st[kSlots];
-            bool sel_path[kSlots];             // latched at stage-0 issue: s_meta[slot] is rewritten once acc_free fires
+            __syncwarp();
+        } else if (warp == 1) {
+            // ===================== MMA issuer: serves the tiles in flight as their operands become ready ====
+            if (lane == 0) {
+                constexpr uint32_t idesc_stage = instr_desc_bf16(128, 128, 0);
+                constexpr uint32_t idesc_sel = instr_desc_bf16_amn(128, kSelSlots);
+                int ti[kSlots], st[kSlots];
+                bool sel_path[kSlots];
 #pragma unroll
-            for (int b = 0; b < kSlots; ++b) { ti[b] = b; st[b] = 0; sel_path[b] = true; }
-            mbar_wait(&bars->w_full, 0);
-            int remaining = my_tiles;
-            int tlm = 0;
-            const bool tlm_on = p.timeline != nullptr && blockIdx.x == 0;
-            auto mstamp = [&](int tag) {        // MMA-thread trace lives in the upper half of the buffer
-                if (tlm_on && tlm < 1990) { p.timeline[25600 + tlm * 2] = tag; p.timeline[25601 + tlm * 2] = clock64(); ++tlm; }
-            };
-            while (remaining > 0) {
-                bool progressed = false;
-                // pass 0: later stages of tiles in flight (an epilogue group is waiting for these);
-                // pass 1: stage-0 GEMMs of tiles ahead (nobody waits yet) -- only when pass 0 found nothing
+                for (int b = 0; b < kSlots; ++b) { ti[b] = b; st[b] = 0; sel_path[b] = true; }
+                const uint64_t d_a0 = smem_desc_sw128(smem_u32(sA), 16, 1024);              // h_E tile, K-major
+                const uint64_t d_am0 = smem_desc_sw128(smem_u32(sA), kKBlockBytes, 1024);   // m3 read MN-major
+                const uint64_t d_w0 = smem_desc_sw128(smem_u32(sW), 16, 1024);
+                const uint64_t d_sel0 = smem_desc_sw128(smem_u32(sSel), 16, 1024);
+                mbar_wait(&bars->w_full, 0);
+                int remaining = my_tiles;
+                int tlm = 0;
+                const bool tlm_on = TRACE && p.timeline != nullptr && blockIdx.x == 0;
+                auto mstamp = [&](int tag) {        // MMA-thread trace lives in the upper part of the buffer
+                    if constexpr (TRACE) {
+                        if (tlm_on && tlm < 1990) { p.timeline[25600 + tlm * 2] = tag; p.timeline[25601 + tlm * 2] = clock64(); ++tlm; }
+                    }
+                };
+                while (remaining > 0) {
+                    bool progressed = false;
+                    // pass 0: later stages of tiles in flight (the epilogue is waiting for these);
+                    // pass 1: stage-0 GEMMs of tiles ahead (nobody waits yet) -- only when pass 0 found nothing
 #pragma unroll
-                for (int pass = 0; pass < 2; ++pass) {
-                    if (pass == 1 && progressed) break;
+                    for (int pass = 0; pass < 2; ++pass) {
+                        if (pass == 1 && progressed) break;
 #pragma unroll
-                    for (int b = 0; b < kSlots; ++b) {
-                        const int i = ti[b], s = st[b];
-                        if (i >= my_tiles || (pass == 0) != (s > 0)) continue;
-                        const uint32_t par_tile = (uint32_t)((i / kSlots) & 1);
-                        const int g = i & 1, k_g = i >> 1;           // group and per-group tile counter
-                        bool ready;
-                        if (s == 0) ready = mbar_test(&bars->a_full[b], par_tile) && mbar_test(&bars->init_done[b], par_tile);
-                        else {
-                            ready = mbar_test(&bars->act_ready[b], (uint32_t)((S * (i / kSlots) + s - 1) & 1));
-                            if (s == S && k_g > 0) ready = ready && mbar_test(&bars->agg_empty[g], (uint32_t)((k_g - 1) & 1));
-                        }
-                        if (!ready) continue;
-                        progressed = true;
-                        tc_fence_after();
-                        mstamp(1000 * (i + 1) + s);
-                        const uint32_t a_addr = smem_u32(sA + (size_t)b * kTileBytes);
-                        if (s < S) {
-                            const uint32_t w_addr = smem_u32(sW + (size_t)s * kTileBytes);
+                        for (int b = 0; b < kSlots; ++b) {
+                            const int i = ti[b], s = st[b];
+                            if (i >= my_tiles || (pass == 0) != (s > 0)) continue;
+                            const uint32_t par_tile = (uint32_t)((i / kSlots) & 1);
+                            bool ready;
+                            if (s == 0) ready = mbar_test(&bars->a_full[b], par_tile) && mbar_test(&bars->init_done[b], par_tile);
+                            else ready = mbar_test(&bars->act_ready[b], (uint32_t)((S * (i / kSlots) + s - 1) & 1));
+                            if (!ready) continue;
+                            progressed = true;
+                            tc_fence_after();
+                            mstamp(1000 * (i + 1) + s);
+                            // descriptors are derived from four base descriptors by adding (byte offset >> 4) to the
+                            // 14-bit start-address field (keeps the single issuing thread inside its register budget)
+                            // (`zero` is opaque to the compiler so that it does not hoist ~50 precomputed descriptors
+                            // out of the polling loop and spill them)
+                            uint32_t zero;
+                            asm volatile("mov.u32 %0, 0;" : "=r"(zero));
+                            const uint64_t d_a = d_a0 + (uint64_t)(zero + b * (kTileBytes >> 4));
                             const uint32_t acc = tmem_base + (uint32_t)(b * 128);
-#pragma unroll
-                            for (int k = 0; k < 8; ++k) {               // K = 128 = 8 x UMMA_K(16)
-                                const uint32_t off = (uint32_t)((k >> 2) * kKBlockBytes + (k & 3) * 32);
-                                // stage 0 accumulates onto the gathered projections the gather warps stored
-                                umma_bf16(acc, smem_desc_sw128(a_addr + off, 16, 1024),
-                                          smem_desc_sw128(w_addr + off, 16, 1024), idesc_stage, (s == 0) || (k > 0));
-                            }
-                            umma_commit(&bars->acc_full[b]);
                             if (s == 0) {
-                                const volatile int* meta = s_meta + 2 * b;
-                                sel_path[b] = meta[1] - meta[0] + 1 <= kSelSlots;
-                            }
-                            st[b] = s + 1;
-                        } else {
-                            // neighbour sums, transposed: aggT[ch][slot] = sum_r m3[r][ch] * Sel[slot][r].
-                            // A = m3 read MN-major in place, B = 16-slot selector (K-major).
-                            if (sel_path[b]) {                              // selector path (<= 16 node slots)
-                                const uint32_t sel_addr = smem_u32(sSel + g * kSelBytes);
-                                const uint32_t agg = tmem_base + kAggCol + (uint32_t)(g * 32);
 #pragma unroll
-                                for (int k = 0; k < 8; ++k) {           // K = 128 edge rows = 8 x 16
-                                    const uint32_t a_off = (uint32_t)(k * 2048);            // 16 rows of 128 B
-                                    const uint32_t b_off = (uint32_t)((k >> 2) * (kSelSlots * 128) + (k & 3) * 32);
-                                    umma_bf16(agg, smem_desc_sw128(a_addr + a_off, kKBlockBytes, 1024),
-                                              smem_desc_sw128(sel_addr + b_off, 16, 1024), idesc_sel, k > 0);
+                                for (int k = 0; k < 8; ++k) {               // K = 128 = 8 x UMMA_K(16)
+                                    const uint64_t off = (uint64_t)(((k >> 2) * kKBlockBytes + (k & 3) * 32) >> 4);
+                                    // accumulates onto the gathered projections the gather warps stored
+                                    umma_bf16(acc, d_a + off, d_w0 + zero + off, idesc_stage, 1u);
                                 }
+                                umma_commit(&bars->acc_full[b]);
+                                const volatile int* meta = s_meta + 2 * (kSlots * (int)par_tile + b);
+                                sel_path[b] = meta[1] <= kSelSlots;
+                                st[b] = 1;
+                            } else if (s < S) {
+                                const uint64_t d_w = d_w0 + (uint64_t)(zero + s * (kTileBytes >> 4));
+                                const uint32_t a_tmem = tmem_base + kYCol + (uint32_t)((i & 1) * 64);
+#pragma unroll
+                                for (int k = 0; k < 8; ++k) {
+                                    const uint64_t off = (uint64_t)(((k >> 2) * kKBlockBytes + (k & 3) * 32) >> 4);
+                                    umma_bf16_ts(acc, a_tmem + (uint32_t)(k * 8), d_w + off, idesc_stage, (uint32_t)(k > 0));
+                                }
+                                umma_commit(&bars->acc_full[b]);
+                                st[b] = s + 1;
+                            } else {
+                                // neighbour sums, transposed: aggT[ch][slot] = sum_r m3[r][ch] * Sel[slot][r], written
+                                // over the (dead) first 16 accumulator columns.  A = m3 read MN-major from smem,
+                                // B = 16-slot selector (K-major).
+                                if (sel_path[b]) {
+                                    const uint64_t d_am = d_am0 + (uint64_t)(zero + b * (kTileBytes >> 4));
+                                    const uint64_t d_sel = d_sel0 + (uint64_t)(zero + b * (kSelBytes >> 4));
+#pragma unroll
+                                    for (int k = 0; k < 8; ++k) {           // K = 128 edge rows = 8 x 16
+                                        const uint64_t a_off = (uint64_t)((k * 2048) >> 4);       // 16 rows of 128 B
+                                        const uint64_t b_off = (uint64_t)(((k >> 2) * (kSelSlots * 128) + (k & 3) * 32) >> 4);
+                                        umma_bf16(acc, d_am + a_off, d_sel + b_off, idesc_sel, k > 0);
+                                    }
+                                }
+                                umma_commit(&bars->agg_full[b]);
+                                umma_commit(&bars->a_empty[b]);
+                                st[b] = 0;
+                                ti[b] = i + kSlots;
+                                --remaining;
                             }
-                            umma_commit(&bars->agg_full[g]);
-                            umma_commit(&bars->a_empty[b]);
-                            st[b] = 0;
-                            ti[b] = i + kSlots;
-                            --remaining;
                         }
                     }
+                    if (!progressed) __nanosleep(20);      // do not steal issue slots from the epilogue warps
                 }
-                if (!progressed) __nanosleep(32);      // do not steal issue slots from the epilogue warps
+                if (tlm_on) p.timeline[32016] = tlm;
             }
-            if (tlm_on) p.timeline[32016] = tlm;
+            __syncwarp();
         }
-        __syncwarp();
-    } else if (warp < 2 + kGatherThreads / 32) {
-        // ===================== gather warps: acc[slot] <- Pc[centre] + Pn[neighbour] (thread = edge row) =====
+    } else if (warp < 8) {
+        // ===================== gather / drain warps (thread = edge row, and = channel when draining) =====
+        set_max_regs_inc<120>();
         const int lane_grp = warp & 3;
         const int row = lane_grp * 32 + lane;
+        const int gt = threadIdx.x - 128;                          // 0..127
         const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
-        auto load_idx = [&](int i, int& c, int& nb) {
-            c = -1; nb = 0;
-            if (i < my_tiles) {
-                const int e = (blockIdx.x + i * gridDim.x) * kTileM + row;
-                if (e < p.n_edges) { c = __ldg(p.ctr + e); nb = __ldg(p.nbr + e); }
-            }
-        };
-        int c_nx, nb_nx;
-        load_idx(0, c_nx, nb_nx);
-        for (int i = 0; i < my_tiles; ++i) {
-            const int b = i % kSlots;
-            const int c = c_nx, nb = nb_nx;
-            const int e_base = (blockIdx.x + i * gridDim.x) * kTileM;
-            const int last_row = min(kTileM, p.n_edges - e_base) - 1;
-            const float* pc = p.Pc + (size_t)max(c, 0) * p.ld_pc;
-            const uint16_t* pn = p.Pn + (size_t)nb * p.ld_pn;
-            // first half of the neighbour row is requested before the (possibly blocking) wait for the accumulator
-            uint32_t w[4][8];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) ldg256(pn + 16 * q, w[q]);
-            load_idx(i + 1, c_nx, nb_nx);                      // streaming index loads of the next tile
-            mbar_wait(&bars->acc_free[b], (uint32_t)(((i / kSlots) & 1) ^ 1));
+        // neighbour sums of the tile that used slot b before: TMEM -> red.global (lane = channel, column = node slot)
+        auto drain = [&](int b, int j_prev) {
+            mbar_wait(&bars->agg_full[b], (uint32_t)((j_prev / kSlots) & 1));
             tc_fence_after();
-            if (row == 0) s_meta[2 * b] = c;
-            if (row == last_row) s_meta[2 * b + 1] = c;
+            const volatile int* meta = s_meta + 2 * (kSlots * ((j_prev / kSlots) & 1) + b);
+            const int fn = meta[0], nslots = meta[1];
+            if (nslots <= kSelSlots) {
+                float v[16];
+                tmem_ld16(t_row + (uint32_t)(b * 128), v);
+                float* dst = p.agg + (size_t)fn * 128 + row;
 #pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (h == 1) {
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) ldg256(pn + 64 + 16 * q, w[q]);
-                }
-#pragma unroll
-                for (int q2 = 0; q2 < 2; ++q2) {               // 32 columns: h*64 + q2*32
-                    const int col0 = h * 64 + q2 * 32;
-                    uint32_t f[4][8];
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) ldg256(pc + col0 + 8 * q, f[q]);
-                    float v[32];
-#pragma unroll
-                    for (int q = 0; q < 16; ++q) {             // bf16 pair q of this 32-column chunk
-                        const uint32_t ww = w[q2 * 2 + (q >> 3)][q & 7];
-                        v[2 * q] = __uint_as_float(f[q >> 2][(2 * q) & 7]) + __uint_as_float(ww << 16);
-                        v[2 * q + 1] = __uint_as_float(f[q >> 2][(2 * q + 1) & 7]) + __uint_as_float(ww & 0xffff0000u);
-                    }
-                    if (c < 0) {
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) v[q] = 0.f;
-                    }
-                    tmem_st32(t_row + (uint32_t)(b * 128 + col0), v);
-                }
-            }
-            tmem_st_wait();
-            tc_fence_before();
-            mbar_arrive(&bars->init_done[b]);
-        }
-    } else {
-        // ===================== epilogue: two decoupled groups of 8 warps, group g owns tiles i % 2 == g ==========
-        // warp -> (TMEM lane group = warp % 4, column half): thread = one edge row x 64 columns (two chunks of 32)
-        const int ew = warp - (2 + kGatherThreads / 32);
-        const int g = ew >> 3;
-        const int half = (ew >> 2) & 1;
-        const int lane_grp = warp & 3;                   // TMEM lanes this warp may touch: 32*(warp%4)..+31
-        const int row = lane_grp * 32 + lane;
-        const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
-        int tl_n = 0;
-        const bool tl_on = p.timeline != nullptr && blockIdx.x == 0 && lane == 0;
-        long long* tl_buf = p.timeline + ew * 1600;
-        auto stamp = [&](int tag) {
-            if (tl_on && tl_n < 799) { tl_buf[tl_n * 2] = tag; tl_buf[tl_n * 2 + 1] = clock64(); ++tl_n; }
-        };
-
-        for (int i = g; i < my_tiles; i += kGroups) {
-            const int b = i % kSlots;
-            const int pb = S * (i / kSlots);
-            const int e_base = (blockIdx.x + i * gridDim.x) * kTileM;
-            const bool valid = e_base + row < p.n_edges;
-            uint8_t* a_buf = sA + (size_t)b * kTileBytes;
-            const uint32_t t_acc = t_row + (uint32_t)(b * 128 + half * 64);
-            int fn = 0, nslots = 1;
-            bool bypass = false;
-            stamp(90);
-            for (int s = 0; s < S; ++s) {
-                stamp(100 + s * 10);                           // about to wait for the accumulator
-                mbar_wait(&bars->acc_full[b], (uint32_t)((pb + s) & 1));
-                tc_fence_after();
-                stamp(200 + s * 10);                           // accumulator ready
-                if (s == 0) {
-                    fn = reinterpret_cast<const volatile int*>(s_meta)[2 * b];
-                    nslots = reinterpret_cast<const volatile int*>(s_meta)[2 * b + 1] - fn + 1;
-                    bypass = nslots > kSelSlots;
-                }
-                const bool slow = p.debug != nullptr || (s == S - 1 && bypass);
-#pragma unroll
-                for (int ch = 0; ch < 2; ++ch) {
-                    const int col0 = half * 64 + ch * 32;
-                    float v[32];
-                    tmem_ld32(t_acc + (uint32_t)(ch * 32), v);
-                    if (s == S - 1 && ch == 1) {               // this thread is done with the accumulator
-                        tc_fence_before();
-                        mbar_arrive(&bars->acc_free[b]);
-                    }
-                    if (s > 0) {
-                        const float4* bs = reinterpret_cast<const float4*>(s_bias + s * 128 + col0);
-#pragma unroll
-                        for (int q = 0; q < 8; ++q) {
-                            const float4 x = bs[q];
-                            v[4 * q + 0] += x.x; v[4 * q + 1] += x.y; v[4 * q + 2] += x.z; v[4 * q + 3] += x.w;
-                        }
-                    }
-                    if (slow) {
-                        // fp32 GELU: debug dump (tests) and the tiny-degree bypass that sums with vector reductions
-#pragma unroll
-                        for (int q = 0; q < 32; ++q) v[q] = gelu_tanh_fast(v[q]);
-                        if (p.debug && valid) {
-                            float* dbg = p.debug + ((size_t)s * p.n_edges + e_base + row) * 128 + col0;
-#pragma unroll
-                            for (int q = 0; q < 32; ++q) dbg[q] = v[q];
-                        }
-                        if (s == S - 1 && bypass) {
-                            if (valid) {
-                                float* dst = p.agg + (size_t)__ldg(p.ctr + e_base + row) * 128 + col0;
-#pragma unroll
-                                for (int q = 0; q < 8; ++q)
-                                    red_add_v4(dst + 4 * q, v[4 * q] * p.alpha, v[4 * q + 1] * p.alpha,
-                                               v[4 * q + 2] * p.alpha, v[4 * q + 3] * p.alpha);
-                            }
-                        } else {
-                            store_act_chunk(a_buf, row, col0, v);
-                        }
-                    } else {
-                        store_gelu_chunk(a_buf, row, col0, v);     // packed bf16x2 GELU straight into the A operand
-                    }
-                }
-                stamp(600 + s * 10);                           // operand stored
-                if (s == 0 && !bypass && row < kSelSlots) {
-                    // selector matrix of this tile (rows = node slots, K = the tile's 128 edge rows; this thread
-                    // fills K-block `half` of slot `row`); the previous tile of this group is done with it
-                    int st = 0, en = 0;
-                    if (row < nslots) {
-                        st = max(__ldg(p.row_ptr + fn + row) - e_base, 0);
-                        en = min(__ldg(p.row_ptr + fn + row + 1) - e_base, kTileM);
-                    }
-                    uint8_t* sel = sSel + g * kSelBytes + half * (kSelSlots * 128);
-#pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        uint32_t w[4];
-#pragma unroll
-                        for (int q = 0; q < 4; ++q) {
-                            const int r0 = half * 64 + j * 8 + q * 2;
-                            const uint32_t lo = (r0 >= st && r0 < en) ? 0x3F80u : 0u;
-                            const uint32_t hi = (r0 + 1 >= st && r0 + 1 < en) ? 0x3F80u : 0u;
-                            w[q] = lo | (hi << 16);
-                        }
-                        *reinterpret_cast<uint4*>(sel + sw128_chunk(row, j)) = make_uint4(w[0], w[1], w[2], w[3]);
-                    }
-                }
-                tc_fence_before();
-                fence_proxy_async();
-                mbar_arrive(&bars->act_ready[b]);
-                stamp(700 + s * 10);                           // fences + arrive done
-            }
-
-            // ---- neighbour sums out of TMEM: lane = channel, columns = node slots, 8 slots per column half ----
-            stamp(800);
-            mbar_wait(&bars->agg_full[g], (uint32_t)((i >> 1) & 1));
-            tc_fence_after();
-            stamp(810);
-            if (!bypass && half * 8 < nslots) {                          // warp-uniform
-                float v[8];
-                tmem_ld8(t_row + kAggCol + (uint32_t)(g * 32 + half * 8), v);
-                float* dst = p.agg + (size_t)(fn + half * 8) * 128 + row;          // row == channel here
-#pragma unroll
-                for (int n = 0; n < 8; ++n)
-                    if (half * 8 + n < nslots)
+                for (int n = 0; n < 16; ++n)
+                    if (n < nslots)
                         asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + n * 128), "f"(v[n] * p.alpha) : "memory");
             }
             tc_fence_before();
-            mbar_arrive(&bars->agg_empty[g]);
-            stamp(820);
+        };
+        auto load_idx = [&](int i, int& c, int& nb, int& c_first, int& c_last) {
+            c = -1; nb = 0; c_first = 0; c_last = 0;
+            if (i < my_tiles) {
+                const int e_base = (blockIdx.x + i * gridDim.x) * kTileM;
+                const int e = e_base + row;
+                if (e < p.n_edges) { c = __ldg(p.ctr + e); nb = __ldg(p.nbr + e); }
+                c_first = __ldg(p.ctr + e_base);
+                c_last = __ldg(p.ctr + min(e_base + kTileM, p.n_edges) - 1);
+            }
+        };
+        int c_nx, nb_nx, cf_nx, cl_nx;
+        load_idx(0, c_nx, nb_nx, cf_nx, cl_nx);
+        for (int i = 0; i < my_tiles; ++i) {
+            const int b = i % kSlots;
+            const int c = c_nx, nb = nb_nx, fn = cf_nx, nslots = cl_nx - cf_nx + 1;
+            const bool table = nslots <= kSelSlots;            // else: tiny structures, > 16 nodes in the tile
+            // every load of the tile is requested up front: the whole neighbour row (random, L2) ...
+            const uint16_t* pn = p.Pn + (size_t)nb * p.ld_pn;
+            uint32_t w[8][8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) ldg256_stream(pn + 16 * q, w[q]);
+            // ... and this thread's 16 floats of the tile's <= 16 distinct centre rows (coalesced)
+            uint32_t pcf[2][8];
+            const bool fill = table && (gt >> 3) < nslots;
+            if (fill) {
+                const float* src = p.Pc + (size_t)(fn + (gt >> 3)) * p.ld_pc + (gt & 7) * 16;
+                ldg256(src, pcf[0]); ldg256(src + 8, pcf[1]);
+            }
+            load_idx(i + 1, c_nx, nb_nx, cf_nx, cl_nx);        // streaming index loads of the next tile
+            if (i >= kSlots) drain(b, i - kSlots);             // also: X[b], sel[b], s_meta[gen][b] are free from here on
+            gather_bar_sync();                                 // everybody is done with the previous tile's centre table
+            if (fill) {
+                float4* dst = reinterpret_cast<float4*>(s_pc + (gt >> 3) * kPcStride + (gt & 7) * 16);
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    dst[q] = make_float4(__uint_as_float(pcf[q >> 1][(q & 1) * 4 + 0]), __uint_as_float(pcf[q >> 1][(q & 1) * 4 + 1]),
+                                         __uint_as_float(pcf[q >> 1][(q & 1) * 4 + 2]), __uint_as_float(pcf[q >> 1][(q & 1) * 4 + 3]));
+            }
+            if (row == 0) {
+                int* meta = s_meta + 2 * (kSlots * ((i / kSlots) & 1) + b);
+                meta[0] = fn; meta[1] = nslots;
+            }
+            const int my_slot = c >= 0 ? c - fn : -1;
+            if (table) {
+                // column `row` of the selector matrix Sel[slot][edge] (K-major in the edge index, 128B swizzle)
+                uint8_t* sel = sSel + b * kSelBytes + (row >> 6) * (kSelSlots * 128) + (row & 7) * 2;
+#pragma unroll
+                for (int sl = 0; sl < kSelSlots; ++sl)
+                    *reinterpret_cast<uint16_t*>(sel + sw128_chunk(sl, (row & 63) >> 3)) = sl == my_slot ? 0x3F80 : 0;
+            }
+            gather_bar_sync();                                 // centre table complete
+            const float* pc_row = s_pc + max(my_slot, 0) * kPcStride;
+            const float* pc_glob = p.Pc + (size_t)max(c, 0) * p.ld_pc;
+#pragma unroll
+            for (int q4 = 0; q4 < 4; ++q4) {                   // 32 columns at a time
+                float v[32];
+                if (table) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 x = reinterpret_cast<const float4*>(pc_row + q4 * 32)[q];
+                        v[4 * q] = x.x; v[4 * q + 1] = x.y; v[4 * q + 2] = x.z; v[4 * q + 3] = x.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) v[q] = __ldg(pc_glob + q4 * 32 + q);
+                }
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {                 // bf16 pair q of this 32-column chunk
+                    const uint32_t ww = w[q4 * 2 + (q >> 3)][q & 7];
+                    v[2 * q] += __uint_as_float(ww << 16);
+                    v[2 * q + 1] += __uint_as_float(ww & 0xffff0000u);
+                }
+                if (c < 0) {
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) v[q] = 0.f;
+                }
+                tmem_st32(t_row + (uint32_t)(b * 128 + q4 * 32), v);
+            }
+            tmem_st_wait();
+            fence_proxy_async();                               // selector bytes -> visible to the tensor core
+            tc_fence_before();
+            mbar_arrive(&bars->init_done[b]);
+        }
+        for (int i = my_tiles; i < my_tiles + kSlots; ++i)     // neighbour sums of the last tiles
+            if (i >= kSlots) drain(i % kSlots, i - kSlots);
+    } else {
+        // ===================== epilogue warps: thread = one edge row x 32 columns ==========
+        // Two tile streams (even / odd tiles), one stage of each alternately, the odd stream lagging by half a
+        // tile: a stream's next GEMM runs while the other stream's epilogue is on the CUDA cores, tile starts are
+        // evenly spaced, and a finished tile's slot has four phases to be drained, re-initialised and refilled by
+        // TMA before its next owner asks for it.
+        const int ew = warp - 8;
+        const int lane_grp = warp & 3;                   // TMEM lanes this warp may touch: 32*(warp%4)..+31
+        const int row = lane_grp * 32 + lane;
+        const int col0 = (ew >> 2) * 32;                 // this thread's 32 columns
+        const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+        int tl_n = 0;
+        const bool tl_on = TRACE && p.timeline != nullptr && blockIdx.x == 0 && lane == 0;
+        long long* tl_buf = p.timeline + ew * 1600;
+        auto stamp = [&](int tag) {
+            if constexpr (TRACE) {
+                if (tl_on && tl_n < 799) { tl_buf[tl_n * 2] = tag; tl_buf[tl_n * 2 + 1] = clock64(); ++tl_n; }
+            }
+        };
+
+        // phase sequence: the even-tile stream at (pair k, stage sa), then the odd-tile stream S/2 stages behind it
+        const int off = S >> 1;
+        int seq_k = 0, seq_s = 0, seq_half = 0;
+        auto advance = [&](int& i, int& st) -> bool {
+            while (2 * seq_k < my_tiles + 2) {               // one extra pair index lets the lagging odd stream finish
+                if (seq_half == 0) {
+                    seq_half = 1;
+                    if (2 * seq_k < my_tiles) { i = 2 * seq_k; st = seq_s; return true; }
+                } else {
+                    seq_half = 0;
+                    const int kb = seq_s >= off ? seq_k : seq_k - 1;
+                    const int sb = seq_s >= off ? seq_s - off : seq_s - off + S;
+                    if (++seq_s == S) { seq_s = 0; ++seq_k; }
+                    if (kb >= 0 && 2 * kb + 1 < my_tiles) { i = 2 * kb + 1; st = sb; return true; }
+                }
+            }
+            return false;
+        };
+        int i = 0, st = 0;
+        while (advance(i, st)) {
+            const int b = i % kSlots;
+            const int e_base = (blockIdx.x + i * gridDim.x) * kTileM;
+            const bool valid = e_base + row < p.n_edges;
+            const bool last = st == S - 1;
+            stamp(100 + st * 10 + (i & 1));                    // about to wait for the accumulator
+            mbar_wait(&bars->acc_full[b], (uint32_t)((S * (i / kSlots) + st) & 1));
+            tc_fence_after();
+            stamp(200 + st * 10 + (i & 1));                    // accumulator ready
+            float v[32];
+            tmem_ld32(t_row + (uint32_t)(b * 128 + col0), v);
+            stamp(300 + st * 10 + (i & 1));
+            if (st > 0) {
+                const float4* bs = reinterpret_cast<const float4*>(s_bias + st * 128 + col0);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const float4 x = bs[q];
+                    add2(v[4 * q + 0], v[4 * q + 1], x.x, x.y);
+                    add2(v[4 * q + 2], v[4 * q + 3], x.z, x.w);
+                }
+            }
+            const bool bypass = last && reinterpret_cast<const volatile int*>(s_meta)[2 * (kSlots * ((i / kSlots) & 1) + b) + 1] > kSelSlots;
+            uint32_t o[16];
+            if (p.debug != nullptr || bypass) {
+                // fp32 GELU: debug dump (tests) and the tiny-degree bypass that sums with vector reductions
+#pragma unroll
+                for (int q = 0; q < 32; ++q) v[q] = gelu_tanh_fast(v[q]);
+                if (p.debug && valid) {
+                    float* dbg = p.debug + ((size_t)st * p.n_edges + e_base + row) * 128 + col0;
+#pragma unroll
+                    for (int q = 0; q < 32; ++q) dbg[q] = v[q];
+                }
+                if (bypass && valid) {
+                    float* dst = p.agg + (size_t)__ldg(p.ctr + e_base + row) * 128 + col0;
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        red_add_v4(dst + 4 * q, v[4 * q] * p.alpha, v[4 * q + 1] * p.alpha,
+                                   v[4 * q + 2] * p.alpha, v[4 * q + 3] * p.alpha);
+                }
+#pragma unroll
+                for (int q = 0; q < 16; ++q) o[q] = pack_bf16(v[2 * q], v[2 * q + 1]);
+            } else {
+                gelu_pack32(v, o);                             // packed bf16x2 GELU
+            }
+            stamp(500 + st * 10 + (i & 1));
+            if (last) {
+                if (!bypass) {                                 // m3 -> smem: A operand (MN-major) of the selector MMA
+                    uint8_t* kb = sA + (size_t)b * kTileBytes + (col0 >> 6) * kKBlockBytes;
+                    const int j0 = (col0 & 63) >> 3;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j)
+                        *reinterpret_cast<uint4*>(kb + sw128_chunk(row, j0 + j)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                }
+                fence_proxy_async();
+            } else {
+                tmem_st16(t_row + kYCol + (uint32_t)((i & 1) * 64 + col0 / 2), o);     // next stage's A operand, in TMEM
+                tmem_st_wait();
+            }
+            tc_fence_before();
+            mbar_arrive(&bars->act_ready[b]);
+            stamp(700 + st * 10 + (i & 1));
         }
         if (tl_on) p.timeline[32000 + ew] = tl_n;
     }
@@ -761,14 +877,19 @@ extern "C" int rmp_edge_mlp_bf16_traced(const void* h_E_bf16, const void* W_bf16
     }
     p.num_stages = num_stages; p.alpha = alpha; p.agg = agg; p.n_edges = n_edges; p.debug = debug;
     p.timeline = timeline;
-    const size_t smem = 1024 + (size_t)(num_stages + tc::kSlots) * tc::kTileBytes + tc::kGroups * tc::kSelBytes +
-                        sizeof(tc::Barriers) + 16 + (2 * tc::kSlots + 2) * sizeof(int) +
-                        tc::kMaxStages * 128 * sizeof(float) + 16;
+    const size_t smem = 1024 + (size_t)(num_stages + tc::kSlots) * tc::kTileBytes + tc::kSlots * tc::kSelBytes +
+                        tc::kSelSlots * tc::kPcStride * sizeof(float) + sizeof(tc::Barriers) + 16 +
+                        (4 * tc::kSlots + 4) * sizeof(int) + tc::kMaxStages * 128 * sizeof(float) + 16;
     RMP_REQUIRE(smem <= 227 * 1024, RMP_E_SHAPE, "rmp_edge_mlp_bf16: %zu B of shared memory needed", smem);
-    cudaFuncSetAttribute(tc::edge_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int n_tiles = ceil_div(n_edges, tc::kTileM);
     const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
-    tc::edge_mlp_tc_kernel<<<grid, tc::kEdgeThreads, smem, (cudaStream_t)stream>>>(tm_e, tm_w, p);
+    if (timeline) {
+        cudaFuncSetAttribute(tc::edge_mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        tc::edge_mlp_tc_kernel<true><<<grid, tc::kEdgeThreads, smem, (cudaStream_t)stream>>>(tm_e, tm_w, p);
+    } else {
+        cudaFuncSetAttribute(tc::edge_mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        tc::edge_mlp_tc_kernel<false><<<grid, tc::kEdgeThreads, smem, (cudaStream_t)stream>>>(tm_e, tm_w, p);
+    }
     return check_launch("rmp_edge_mlp_bf16");
 }
 

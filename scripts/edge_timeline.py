@@ -38,7 +38,7 @@ for ew in range(16):
     warps[ew] = [(t[ew * 1600 + 2 * i], t[ew * 1600 + 2 * i + 1]) for i in range(n)]
 t0 = min(w[0][1] for w in warps.values() if w)
 print("total cycles (warp 0)", warps[0][-1][1] - warps[0][0][1])
-for ew in (0, 8):
+for ew in (0, 5, 8):
     ev = warps[ew]
     acc = collections.defaultdict(list)
     for (a, ta), (b_, tb) in zip(ev[:-1], ev[1:]):
