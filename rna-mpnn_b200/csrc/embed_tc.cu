@@ -34,12 +34,17 @@ struct alignas(8) EmbedBarriers {
     uint64_t w_full, acc_full, act_ready;
 };
 
+// exp(-((d - mu) / 1.25)^2) = 2^(-t^2), t = (d - mu) * (0.8 * sqrt(log2 e)): one FMA, one multiply and one MUFU.EX2
+// per basis function.  The result is rounded to bf16 right away, so the fp32 arm's IEEE division (features.cu)
+// is not reproduced here.
 __device__ __forceinline__ void rbf16_bf16(float d, const float (&mu)[16], uint8_t* a_buf, int row, int chunk0) {
+    constexpr float kC = 0.96089792f;          // 0.8 * sqrt(log2(e))
+    const float dc = d * kC;
     float v[16];
 #pragma unroll
     for (int r = 0; r < 16; ++r) {
-        const float z = __fdiv_rn(d - mu[r], 1.25f);
-        v[r] = __expf(-(z * z));
+        const float t = fmaf(-mu[r], kC, dc);
+        asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(v[r]) : "f"(-(t * t)));
     }
 #pragma unroll
     for (int j = 0; j < 2; ++j)
@@ -108,12 +113,22 @@ edge_embed_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const EmbedParams
         float* red_sum = s_red;
         float* red_sq = s_red + 2 * kTileM;
         uint32_t ph_acc = 0;
+        // dense residue ids of this row's (centre, neighbour): a chain of two dependent global loads, fetched one
+        // tile ahead so that only the coordinate loads sit on a tile's critical path
+        auto load_ids = [&](int i, int& si, int& sj) {
+            si = sj = 0;
+            const int e = (blockIdx.x + i * gridDim.x) * kTileM + row;
+            if (i < my_tiles && e < p.n_edges) { si = __ldg(p.node_src + __ldg(p.ctr + e)); sj = __ldg(p.node_src + __ldg(p.nbr + e)); }
+        };
+        int si_nx, sj_nx;
+        load_ids(0, si_nx, sj_nx);
         for (int i = 0; i < my_tiles; ++i) {
             const int e = (blockIdx.x + i * gridDim.x) * kTileM + row;
             const bool valid = e < p.n_edges;
+            const int si = si_nx, sj = sj_nx;
+            load_ids(i + 1, si_nx, sj_nx);
             // ---- raw features of this row's half, straight into the swizzled A operand ----
             if (valid) {
-                const int si = __ldg(p.node_src + __ldg(p.ctr + e)), sj = __ldg(p.node_src + __ldg(p.nbr + e));
                 const float* xi = p.X + (size_t)si * 18;
                 const float* xj = p.X + (size_t)sj * 18;
                 const V3 pj = ld3(xj);

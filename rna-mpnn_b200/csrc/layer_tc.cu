@@ -151,7 +151,7 @@ __device__ __forceinline__ void gelu_pack32(const float (&v)[32], uint32_t (&o)[
     for (int q = 0; q < 16; ++q) o[q] = gelu_bf16x2(v[2 * q], v[2 * q + 1]);
 }
 
-template <bool TRACE>
+template <bool TRACE, bool DECOUPLED>
 __global__ void __launch_bounds__(kEdgeThreads, 1)
 edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant__ CUtensorMap tm_w,
                    const EdgeParams p) {
@@ -181,7 +181,7 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
             mbar_init(&bars->a_full[b], 1); mbar_init(&bars->a_empty[b], 1);
             mbar_init(&bars->init_done[b], kGatherThreads);
             mbar_init(&bars->acc_full[b], 1);
-            mbar_init(&bars->act_ready[b], kEdgeEpiThreads);
+            mbar_init(&bars->act_ready[b], DECOUPLED ? kEdgeEpiThreads / 2 : kEdgeEpiThreads);
             mbar_init(&bars->agg_full[b], 1);
         }
         fence_barrier_init();
@@ -436,7 +436,8 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
         const int ew = warp - 8;
         const int lane_grp = warp & 3;                   // TMEM lanes this warp may touch: 32*(warp%4)..+31
         const int row = lane_grp * 32 + lane;
-        const int col0 = (ew >> 2) * 32;                 // this thread's 32 columns
+        constexpr int kChunks = DECOUPLED ? 2 : 1;       // 32-column chunks per thread and phase
+        const int colb = DECOUPLED ? ((ew >> 2) & 1) * 64 : (ew >> 2) * 32;     // this thread's first column
         const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
         int tl_n = 0;
         const bool tl_on = TRACE && p.timeline != nullptr && blockIdx.x == 0 && lane == 0;
@@ -451,6 +452,12 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
         const int off = S >> 1;
         int seq_k = 0, seq_s = 0, seq_half = 0;
         auto advance = [&](int& i, int& st) -> bool {
+            if constexpr (DECOUPLED) {                       // group g = ew / 8 owns the tiles i % 2 == g, stage by stage
+                if (seq_half == 0) { seq_half = 1; seq_k = ew >> 3; seq_s = 0; }
+                else if (++seq_s == S) { seq_s = 0; seq_k += 2; }
+                i = seq_k; st = seq_s;
+                return seq_k < my_tiles;
+            }
             while (2 * seq_k < my_tiles + 2) {               // one extra pair index lets the lagging odd stream finish
                 if (seq_half == 0) {
                     seq_half = 1;
@@ -475,55 +482,59 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
             mbar_wait(&bars->acc_full[b], (uint32_t)((S * (i / kSlots) + st) & 1));
             tc_fence_after();
             stamp(200 + st * 10 + (i & 1));                    // accumulator ready
-            float v[32];
-            tmem_ld32(t_row + (uint32_t)(b * 128 + col0), v);
-            stamp(300 + st * 10 + (i & 1));
-            if (st > 0) {
-                const float4* bs = reinterpret_cast<const float4*>(s_bias + st * 128 + col0);
-#pragma unroll
-                for (int q = 0; q < 8; ++q) {
-                    const float4 x = bs[q];
-                    add2(v[4 * q + 0], v[4 * q + 1], x.x, x.y);
-                    add2(v[4 * q + 2], v[4 * q + 3], x.z, x.w);
-                }
-            }
             const bool bypass = last && reinterpret_cast<const volatile int*>(s_meta)[2 * (kSlots * ((i / kSlots) & 1) + b) + 1] > kSelSlots;
-            uint32_t o[16];
-            if (p.debug != nullptr || bypass) {
-                // fp32 GELU: debug dump (tests) and the tiny-degree bypass that sums with vector reductions
 #pragma unroll
-                for (int q = 0; q < 32; ++q) v[q] = gelu_tanh_fast(v[q]);
-                if (p.debug && valid) {
-                    float* dbg = p.debug + ((size_t)st * p.n_edges + e_base + row) * 128 + col0;
+            for (int ch = 0; ch < kChunks; ++ch) {
+                const int col0 = colb + ch * 32;
+                float v[32];
+                tmem_ld32(t_row + (uint32_t)(b * 128 + col0), v);
+                stamp(300 + st * 10 + (i & 1));
+                if (st > 0) {
+                    const float4* bs = reinterpret_cast<const float4*>(s_bias + st * 128 + col0);
 #pragma unroll
-                    for (int q = 0; q < 32; ++q) dbg[q] = v[q];
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 x = bs[q];
+                        add2(v[4 * q + 0], v[4 * q + 1], x.x, x.y);
+                        add2(v[4 * q + 2], v[4 * q + 3], x.z, x.w);
+                    }
                 }
-                if (bypass && valid) {
-                    float* dst = p.agg + (size_t)__ldg(p.ctr + e_base + row) * 128 + col0;
+                uint32_t o[16];
+                if (p.debug != nullptr || bypass) {
+                    // fp32 GELU: debug dump (tests) and the tiny-degree bypass that sums with vector reductions
 #pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        red_add_v4(dst + 4 * q, v[4 * q] * p.alpha, v[4 * q + 1] * p.alpha,
-                                   v[4 * q + 2] * p.alpha, v[4 * q + 3] * p.alpha);
+                    for (int q = 0; q < 32; ++q) v[q] = gelu_tanh_fast(v[q]);
+                    if (p.debug && valid) {
+                        float* dbg = p.debug + ((size_t)st * p.n_edges + e_base + row) * 128 + col0;
+#pragma unroll
+                        for (int q = 0; q < 32; ++q) dbg[q] = v[q];
+                    }
+                    if (bypass && valid) {
+                        float* dst = p.agg + (size_t)__ldg(p.ctr + e_base + row) * 128 + col0;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            red_add_v4(dst + 4 * q, v[4 * q] * p.alpha, v[4 * q + 1] * p.alpha,
+                                       v[4 * q + 2] * p.alpha, v[4 * q + 3] * p.alpha);
+                    }
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) o[q] = pack_bf16(v[2 * q], v[2 * q + 1]);
+                } else {
+                    gelu_pack32(v, o);                             // packed bf16x2 GELU
                 }
+                stamp(500 + st * 10 + (i & 1));
+                if (last) {
+                    if (!bypass) {                                 // m3 -> smem: A operand (MN-major) of the selector MMA
+                        uint8_t* kb = sA + (size_t)b * kTileBytes + (col0 >> 6) * kKBlockBytes;
+                        const int j0 = (col0 & 63) >> 3;
 #pragma unroll
-                for (int q = 0; q < 16; ++q) o[q] = pack_bf16(v[2 * q], v[2 * q + 1]);
-            } else {
-                gelu_pack32(v, o);                             // packed bf16x2 GELU
+                        for (int j = 0; j < 4; ++j)
+                            *reinterpret_cast<uint4*>(kb + sw128_chunk(row, j0 + j)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+                    }
+                } else {
+                    tmem_st16(t_row + kYCol + (uint32_t)((i & 1) * 64 + col0 / 2), o);     // next stage's A operand, in TMEM
+                }
             }
-            stamp(500 + st * 10 + (i & 1));
-            if (last) {
-                if (!bypass) {                                 // m3 -> smem: A operand (MN-major) of the selector MMA
-                    uint8_t* kb = sA + (size_t)b * kTileBytes + (col0 >> 6) * kKBlockBytes;
-                    const int j0 = (col0 & 63) >> 3;
-#pragma unroll
-                    for (int j = 0; j < 4; ++j)
-                        *reinterpret_cast<uint4*>(kb + sw128_chunk(row, j0 + j)) = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
-                }
-                fence_proxy_async();
-            } else {
-                tmem_st16(t_row + kYCol + (uint32_t)((i & 1) * 64 + col0 / 2), o);     // next stage's A operand, in TMEM
-                tmem_st_wait();
-            }
+            if (last) fence_proxy_async();
+            else tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&bars->act_ready[b]);
             stamp(700 + st * 10 + (i & 1));
@@ -717,6 +728,7 @@ node_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
                         xs[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
                         if (rg < p.n_rows) xs[rr] = __ldg(reinterpret_cast<const float4*>(p.h_in + (size_t)rg * 128) + lane);
                     }
+                    stamp(100 + r0);
                     if (p.prologue_ln && p.agg) {
                         float4 as[8];
 #pragma unroll
@@ -733,20 +745,43 @@ node_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
                                 reinterpret_cast<float4*>(p.agg + (size_t)rg * 128)[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
                         }
                     }
+                    stamp(110 + r0);
+                    if (p.prologue_ln) {
+                        // LayerNorm of the 8 rows at once: the 8 butterfly reductions of a step are independent
+                        // shuffles, so their latencies overlap instead of adding up row after row
+                        float sm[8], sq[8];
 #pragma unroll
-                    for (int rr = 0; rr < 8; ++rr) {
-                        const int rl = ew * 16 + r0 + rr;              // row inside the tile
-                        const int rg = tile * kTileM + rl;
-                        float4 x = xs[rr];
-                        if (p.prologue_ln) {
-                            const float mu = warp_sum(x.x + x.y + x.z + x.w) * (1.f / 128.f);
-                            x.x -= mu; x.y -= mu; x.z -= mu; x.w -= mu;
-                            const float var = warp_sum(x.x * x.x + x.y * x.y + x.z * x.z + x.w * x.w) * (1.f / 128.f);
-                            const float inv = 1.f / sqrtf(var + 1e-5f);
+                        for (int rr = 0; rr < 8; ++rr) sm[rr] = (xs[rr].x + xs[rr].y) + (xs[rr].z + xs[rr].w);
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                            for (int rr = 0; rr < 8; ++rr) sm[rr] += __shfl_xor_sync(0xffffffffu, sm[rr], o);
+                        }
+#pragma unroll
+                        for (int rr = 0; rr < 8; ++rr) {
+                            const float mu = sm[rr] * (1.f / 128.f);
+                            xs[rr].x -= mu; xs[rr].y -= mu; xs[rr].z -= mu; xs[rr].w -= mu;
+                            sq[rr] = (xs[rr].x * xs[rr].x + xs[rr].y * xs[rr].y) + (xs[rr].z * xs[rr].z + xs[rr].w * xs[rr].w);
+                        }
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                            for (int rr = 0; rr < 8; ++rr) sq[rr] += __shfl_xor_sync(0xffffffffu, sq[rr], o);
+                        }
+#pragma unroll
+                        for (int rr = 0; rr < 8; ++rr) {
+                            const int rg = tile * kTileM + ew * 16 + r0 + rr;
+                            const float inv = 1.f / sqrtf(sq[rr] * (1.f / 128.f) + 1e-5f);
+                            float4& x = xs[rr];
                             x.x = fmaf(x.x * inv, g1.x, b1.x); x.y = fmaf(x.y * inv, g1.y, b1.y);
                             x.z = fmaf(x.z * inv, g1.z, b1.z); x.w = fmaf(x.w * inv, g1.w, b1.w);
                             if (rg < p.n_rows && p.x1) reinterpret_cast<float4*>(p.x1 + (size_t)rg * 128)[lane] = x;
                         }
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+                        const int rl = ew * 16 + r0 + rr;              // row inside the tile
+                        const float4 x = xs[rr];
                         // columns 4*lane .. 4*lane+3 -> K-block lane/16, 16-byte chunk (lane%16)/2, 8-byte half lane%2
                         *reinterpret_cast<uint2*>(sA + (lane >> 4) * kKBlockBytes + sw128_chunk(rl, (lane & 15) >> 1) + (lane & 1) * 8) =
                             make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
@@ -762,30 +797,36 @@ node_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
             // ---- stage epilogues ----
             for (int s = 0; s < S; ++s) {
                 const NodeStage stg = p.st[s];
+                const int ncols = stg.N >> 1;                 // columns of this half
+                const int cb = half * ncols;
+                float x[64];
+                if (stg.kind == 1) {
+                    // residual x1 (written by this CTA's prologue, L2): requested before the accumulator wait
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        float rsd[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                        if (valid) ldg256f(p.x1 + (size_t)r * 128 + cb + 8 * q, rsd);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) x[8 * q + k] = rsd[k];
+                    }
+                }
                 mbar_wait(&bars->acc_full, ph_acc); ph_acc ^= 1;
                 tc_fence_after();
                 stamp(10 + s);
-                const int ncols = stg.N >> 1;                 // columns of this half
-                const int cb = half * ncols;
                 if (stg.kind == 1) {                          // N == 128: bias + residual + LN2 -> h_out (+ operand)
-                    float x[64];
 #pragma unroll
                     for (int ch = 0; ch < 2; ++ch) {
                         float v[32];
                         tmem_ld32(t_row + (uint32_t)(cb + ch * 32), v);
 #pragma unroll
-                        for (int q = 0; q < 32; ++q) x[ch * 32 + q] = v[q];
+                        for (int q = 0; q < 32; ++q) x[ch * 32 + q] += v[q];
                     }
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        float rsd[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                        if (valid) ldg256f(p.x1 + (size_t)r * 128 + cb + 8 * q, rsd);
                         const float4 ba = __ldg(reinterpret_cast<const float4*>(stg.bias + cb) + 2 * q);
                         const float4 bb = __ldg(reinterpret_cast<const float4*>(stg.bias + cb) + 2 * q + 1);
-                        x[8 * q + 0] += ba.x + rsd[0]; x[8 * q + 1] += ba.y + rsd[1];
-                        x[8 * q + 2] += ba.z + rsd[2]; x[8 * q + 3] += ba.w + rsd[3];
-                        x[8 * q + 4] += bb.x + rsd[4]; x[8 * q + 5] += bb.y + rsd[5];
-                        x[8 * q + 6] += bb.z + rsd[6]; x[8 * q + 7] += bb.w + rsd[7];
+                        x[8 * q + 0] += ba.x; x[8 * q + 1] += ba.y; x[8 * q + 2] += ba.z; x[8 * q + 3] += ba.w;
+                        x[8 * q + 4] += bb.x; x[8 * q + 5] += bb.y; x[8 * q + 6] += bb.z; x[8 * q + 7] += bb.w;
                     }
                     layer_norm64(x, p.ln2_g, p.ln2_b, cb);
                     if (valid) store_row64(p.h_out + (size_t)r * 128 + cb, x);
@@ -883,13 +924,13 @@ extern "C" int rmp_edge_mlp_bf16_traced(const void* h_E_bf16, const void* W_bf16
     RMP_REQUIRE(smem <= 227 * 1024, RMP_E_SHAPE, "rmp_edge_mlp_bf16: %zu B of shared memory needed", smem);
     const int n_tiles = ceil_div(n_edges, tc::kTileM);
     const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
-    if (timeline) {
-        cudaFuncSetAttribute(tc::edge_mlp_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        tc::edge_mlp_tc_kernel<true><<<grid, tc::kEdgeThreads, smem, (cudaStream_t)stream>>>(tm_e, tm_w, p);
-    } else {
-        cudaFuncSetAttribute(tc::edge_mlp_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        tc::edge_mlp_tc_kernel<false><<<grid, tc::kEdgeThreads, smem, (cudaStream_t)stream>>>(tm_e, tm_w, p);
-    }
+    static const bool decoupled = []() { const char* e = getenv("RMP_EDGE_SCHEDULE"); return e && e[0] == 'd'; }();
+    auto launch = [&](auto kernel) {
+        cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        kernel<<<grid, tc::kEdgeThreads, smem, (cudaStream_t)stream>>>(tm_e, tm_w, p);
+    };
+    if (timeline) { if (decoupled) launch(tc::edge_mlp_tc_kernel<true, true>); else launch(tc::edge_mlp_tc_kernel<true, false>); }
+    else { if (decoupled) launch(tc::edge_mlp_tc_kernel<false, true>); else launch(tc::edge_mlp_tc_kernel<false, false>); }
     return check_launch("rmp_edge_mlp_bf16");
 }
 
