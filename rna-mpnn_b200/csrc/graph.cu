@@ -110,33 +110,58 @@ __global__ void __launch_bounds__(256) node_finalize_kernel(int B, int N, const 
 // --------------------------------------------------------------------------------
 // kNN: one warp per query row, keys = (distance bits << 32 | index), ascending.
 // The K best keys live in a warp-distributed sorted list: slot s is register s/32
-// of lane s%32.  A candidate that beats the current K-th key is inserted by a
-// shuffle-based shift.  Ordering (distance, then index) is total, so the result is
-// deterministic and equals a stable ascending sort truncated to K.
+// of lane s%32.  Candidates that beat the current K-th key are compacted into a
+// per-warp ring in shared memory; every 32 of them are sorted (bitonic, across
+// lanes) and merged into the list block by block, then the threshold is refreshed.
+// Ordering (distance, then index) is total, so the result is deterministic and
+// equals a stable ascending sort truncated to K, whatever the batching.
 // --------------------------------------------------------------------------------
 typedef unsigned long long u64;
 constexpr u64 kKeyMax = ~0ull;
-// rows handled by one warp: more rows amortise staging the structure in shared memory, fewer rows give
-// more warps in flight; the selection is latency bound (dependent shuffles), so short chains get 1
+// rows handled by one warp: more rows amortise staging the structure in shared memory
 __host__ __device__ inline int knn_rows_per_warp(int N) { return N <= 1024 ? 1 : (N <= 4096 ? 2 : 8); }
 constexpr int kKnnWarps = 8;
 constexpr int kKnnSmemPoints = 8192;      // structures up to this length are staged in smem
+constexpr int kKnnRing = 64;              // candidate ring entries per warp
 
-template <int R>
-__device__ __forceinline__ void warp_sorted_insert(u64 (&slot)[R], u64 x, int lane) {
-    int p = 0;
+__device__ __forceinline__ u64 shfl_xor_u64(u64 v, int m) { return __shfl_xor_sync(0xffffffffu, v, m); }
+__device__ __forceinline__ u64 umin64(u64 a, u64 b) { return a < b ? a : b; }
+__device__ __forceinline__ u64 umax64(u64 a, u64 b) { return a < b ? b : a; }
+
+// bitonic (across the 32 lanes) -> ascending
+__device__ __forceinline__ u64 bitonic_merge32(u64 v, int lane) {
 #pragma unroll
-    for (int r = 0; r < R; ++r) p += __popc(__ballot_sync(0xffffffffu, slot[r] < x));
+    for (int m = 16; m > 0; m >>= 1) {
+        const u64 o = shfl_xor_u64(v, m);
+        v = (lane & m) ? umax64(v, o) : umin64(v, o);
+    }
+    return v;
+}
+// arbitrary -> ascending across the 32 lanes
+__device__ __forceinline__ u64 bitonic_sort32(u64 v, int lane) {
 #pragma unroll
-    for (int r = R - 1; r >= 0; --r) {
-        const u64 up = __shfl_up_sync(0xffffffffu, slot[r], 1);
-        u64 prev = up;
-        if (r > 0) {
-            const u64 carry = __shfl_sync(0xffffffffu, slot[r - 1], 31);
-            if (lane == 0) prev = carry;
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int m = k >> 1; m > 0; m >>= 1) {
+            const u64 o = shfl_xor_u64(v, m);
+            const bool up = ((lane & k) == 0) || k == 32;        // direction of this lane's k-block
+            const bool lower = (lane & m) == 0;
+            v = (lower == up) ? umin64(v, o) : umax64(v, o);
         }
-        const int s = r * 32 + lane;
-        slot[r] = (s < p) ? slot[r] : ((s == p) ? x : prev);
+    }
+    return v;
+}
+// merge 32 candidates (one per lane, any order) into the sorted list, dropping the 32 largest keys
+template <int R>
+__device__ __forceinline__ void warp_merge_batch(u64 (&slot)[R], u64 cand, int lane) {
+    u64 b = bitonic_sort32(cand, lane);
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+        // merge-split of two ascending blocks: the element-wise min / max against the reversed block are bitonic
+        const u64 rev = __shfl_sync(0xffffffffu, b, 31 - lane);
+        const u64 lo = umin64(slot[r], rev), hi = umax64(slot[r], rev);
+        slot[r] = bitonic_merge32(lo, lane);
+        b = bitonic_merge32(hi, lane);                           // the larger half moves up one block
     }
 }
 
@@ -165,6 +190,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(const float* __rest
                                                              int atom, int K, int rows_per_warp,
                                                              int64_t* __restrict__ E_idx, float* __restrict__ D_out) {
     extern __shared__ float4 s_pts[];
+    __shared__ u64 s_ring[kKnnWarps][kKnnRing];
     const int b = blockIdx.y, t = threadIdx.x, lane = t & 31, w = t >> 5;
     const float* Xb = X + (size_t)b * N * A * 3 + (size_t)atom * 3;
     const float* mb = mask + (size_t)b * N;
@@ -176,6 +202,8 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(const float* __rest
         for (int j = t; j < N; j += kKnnWarps * 32) s_pts[j] = load_point(j);
         __syncthreads();
     }
+    u64* ring = s_ring[w];
+    const unsigned lt_mask = (1u << lane) - 1u;
     const int row0 = (blockIdx.x * kKnnWarps + w) * rows_per_warp;
     for (int rr = 0; rr < rows_per_warp; ++rr) {
         const int i = row0 + rr;
@@ -185,6 +213,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(const float* __rest
 #pragma unroll
         for (int r = 0; r < R; ++r) slot[r] = kKeyMax;
         u64 thresh = kKeyMax;
+        int head = 0, cnt = 0;                               // ring state (warp-uniform)
         for (int base = 0; base < N; base += 32) {
             const int j = base + lane;
             u64 key = kKeyMax;
@@ -193,16 +222,26 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(const float* __rest
                 const float d = ref_pair_distance(pi, pj);
                 key = ((u64)__float_as_uint(d) << 32) | (unsigned)j;
             }
-            unsigned m = __ballot_sync(0xffffffffu, key < thresh);
-            while (m) {
-                const int src = __ffs(m) - 1;
-                m &= m - 1;
-                const u64 x = __shfl_sync(0xffffffffu, key, src);
-                if (x < thresh) {
-                    warp_sorted_insert<R>(slot, x, lane);
-                    thresh = warp_slot_read<R>(slot, K - 1);
-                }
+            const bool pass = key < thresh;
+            const unsigned m = __ballot_sync(0xffffffffu, pass);
+            if (m == 0) continue;
+            if (pass) ring[(head + cnt + __popc(m & lt_mask)) & (kKnnRing - 1)] = key;
+            cnt += __popc(m);
+            if (cnt >= 32) {
+                __syncwarp();
+                const u64 cand = ring[(head + lane) & (kKnnRing - 1)];
+                __syncwarp();
+                head = (head + 32) & (kKnnRing - 1);
+                cnt -= 32;
+                warp_merge_batch<R>(slot, cand, lane);
+                thresh = warp_slot_read<R>(slot, K - 1);
             }
+        }
+        if (cnt > 0) {                                       // the last, partial batch
+            __syncwarp();
+            const u64 cand = lane < cnt ? ring[(head + lane) & (kKnnRing - 1)] : kKeyMax;
+            __syncwarp();
+            warp_merge_batch<R>(slot, cand, lane);
         }
         const size_t o = ((size_t)b * N + i) * K;
 #pragma unroll
