@@ -47,3 +47,27 @@ def load_golden(name):
 @pytest.fixture(params=GOLDEN_CASES)
 def golden(request):
     return load_golden(request.param)
+
+
+RNAMPNN_GOLDEN_CASES = ["rnampnn_toy", "rnampnn_ragged", "rnampnn_default", "rnampnn_real", "rnampnn_alt",
+                        "rnampnn_tiny"]
+
+
+def load_rnampnn_golden(name):
+    """Golden vectors of the secondary (rnampnn) path (tests/golden/make_golden_rnampnn.py)."""
+    from oracle.weights import RNAMPNNConfig, make_rnampnn_state_dict
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    g = {k: z[k] for k in z.files}
+    fields = list(RNAMPNNConfig.__dataclass_fields__)
+    cfg = RNAMPNNConfig(**{f: int(v) for f, v in zip(fields, g["cfg"])})
+    g["name"] = name
+    g["config"] = cfg
+    g["params"] = make_rnampnn_state_dict(cfg, int(g["seed"]))
+    for k in ("coords", "mask"):
+        g[k] = torch.from_numpy(g[k])
+    return g
+
+
+@pytest.fixture(params=RNAMPNN_GOLDEN_CASES)
+def rgolden(request):
+    return load_rnampnn_golden(request.param)
