@@ -118,7 +118,7 @@ int rmp_rdesign_raw_features(const float* X, int B, int N,
  * Weights are passed TRANSPOSED and zero padded: Wt[k_pad][n_out], k_pad =
  * round_up(k_in, 32), n_out % 128 == 0 (see rmp_pack_rows()).
  */
-#define RMP_MAX_STAGES 4
+#define RMP_MAX_STAGES 6
 #define RMP_MAX_SEGS   3
 
 #define RMP_EPI_STORE      0  /* out[r,:] = y                                                          */
@@ -126,6 +126,8 @@ int rmp_rdesign_raw_features(const float* X, int B, int N,
                                  (rdesign/model/functional.py:79-96)                                   */
 #define RMP_EPI_RESID_LN   2  /* out = LayerNorm(resid + y), eps 1e-5 (rdesign/model/mpnn.py:37)        */
 #define RMP_EPI_SEGSUM     3  /* out[seg[r],:] += y * alpha   (scatter_sum / scale, mpnn.py:34)         */
+#define RMP_EPI_RESID_ADD  4  /* out[r,:] = resid[r,:] + y  (in-place edge update, rnampnn/model/mpnn.py:263;
+                                 out may alias resid)                                                   */
 
 typedef struct rmp_mlp_desc {
     /* input = concat over segments of src[idx ? idx[r] : r, 0:width] */
@@ -147,6 +149,8 @@ typedef struct rmp_mlp_desc {
     const float*   resid;                   /* RESID_LN: [rows, n]               */
     const int32_t* seg_id;                  /* SEGSUM: destination row per input row (non-decreasing) */
     float          alpha;                   /* SEGSUM scale (1/30)               */
+    const float*   row_scale;               /* optional [rows]: STORE / SEGSUM multiply row r's result by it
+                                               (row masks, 1/valid-neighbour-count; rnampnn/model/mpnn.py:192,219) */
     float*         out;
     /* rows: device count (rows_dev[rows_slot]) bounded by rows_cap */
     const int32_t* rows_dev;
@@ -179,6 +183,60 @@ int rmp_readout_head(const float* h, int k_in, const float* W, const float* b,
                      float temperature, uint64_t seed,
                      const int32_t* rows_dev, int rows_slot, int rows_cap,
                      float* logits, float* probs, int64_t* samples, void* stream);
+
+/* ================================================================== secondary path: rnampnn (a-10 .. a-16)
+ * The reference keeps the padded layout end to end: rows are dense residues b*N+i, edges are (row, slot k),
+ * edge_index [B,N,K] int64 holds the neighbour's index INSIDE its structure or -1.  The Linear stacks of this
+ * path (raw_project + RNABert FFN, edge embedding, ResMPNN message / edge MLPs, RawFFN, Readout) run on
+ * rmp_row_mlp; the entry points below are what is not a Linear.
+ */
+
+/* a-10.  Replaces ResFeature._get_res_graph, rnampnn/model/feature.py:205-256.
+ *   coords [B,N,A,3] fp32, mask [B,N]; centroid = mean of the A atoms (summed in torch-CPU's order 0,4,5,6,1,2,3
+ *   for A = 7), D = sqrt(((dx^2+dy^2)+dz^2)+1e-6) (IEEE), pairs with a padded end and the diagonal = 1e6;
+ *   ascending (D, index); then columns past N, "self", slots k > L_b-1 and padded rows -> -1.
+ *   edge_index [B,N,K] int64 (K = num_neighbours, may exceed N); D_neighbors [B,N,K] fp32 or NULL. */
+int rmp_res_graph(const float* coords, const float* mask, int B, int N, int A, int K,
+                  int64_t* edge_index, float* D_neighbors, void* stream);
+
+/* Per-edge bookkeeping derived from any edge_index (the module API accepts a caller-made one):
+ *   ctr_row/nbr_row [B*N*K] int32 dense rows of the centre and of the neighbour (-1 gathers row b*N+0 like the
+ *   reference's safe_edge_index, rnampnn/model/mpnn.py:173-174); edge_keep = (edge_index != -1) * mask_i
+ *   (feature.py:564-569); edge_w = (edge_index != -1) / max(#valid slots, 1) (mpnn.py:191, :215-219). */
+int rmp_res_edge_rows(const int64_t* edge_index, const float* mask, int B, int N, int K, int32_t* ctr_row,
+                      int32_t* nbr_row, float* edge_keep, float* edge_w, void* stream);
+
+/* a-11, a-12.  Replaces _inside_dists/_inside_angles/_inside_dihedrals and _cross_dists/_cross_angles/
+ * _cross_dihedrals (+ _gather_neighbours), rnampnn/model/feature.py:258-517.
+ *   raw      [B*N, nd(nd-1)/2 + na-2 + nh-3]          (padded rows: distances 1e6, cosines 0); NULL skips it
+ *   edge_raw [B*N*K, nd^2 + (na-1)^2 + (nh-2)^2]      (invalid edges: distances 1e6, cosines 0); NULL skips it */
+int rmp_res_raw_features(const float* coords, const float* mask, const int64_t* edge_index, int B, int N,
+                         int A, int K, int n_inside_dist, int n_inside_angle, int n_inside_dihedral,
+                         int n_cross_dist, int n_cross_angle, int n_cross_dihedral, float* raw,
+                         float* edge_raw, void* stream);
+
+/* a-13.  Replaces GraphNormalization.forward, rnampnn/model/functional.py:18-48, over 128 channels.
+ *   out = ((x - mean_b)/sqrt(var_b + 1e-6) * scale + shift) * mask,  x = a (+ b when b != NULL)
+ *   mean/var per structure and channel over the valid rows; the reference's variance also counts (0 - mean)^2
+ *   for each of the n_total - L_b padded rows it holds (n_total = N, or 4500 inside RNABert).
+ *   zero_b != 0 re-zeroes b after it is read (b doubles as the segmented-sum buffer of the message kernel).
+ *   stats_ws: caller workspace of B*257 doubles. */
+int rmp_graph_norm(const float* a, float* b, const float* mask, int B, int N, int n_total,
+                   const float* scale, const float* shift, int zero_b, double* stats_ws, float* out, void* stream);
+
+/* a-15.  Replaces nn.MultiheadAttention(query=key=value=x, key_padding_mask=~mask) inside RNABert.forward,
+ * rnampnn/model/functional.py:161-168, between in_proj and out_proj (both run on rmp_row_mlp).
+ *   qkv [B*N, 3E] = x in_proj_weight^T + in_proj_bias (q | k | v), E % heads == 0, head dim in {8,16,32}
+ *   out [B*N, E] = softmax(q k^T / sqrt(hd)) v per head over the VALID keys of the structure; padded query rows 0. */
+int rmp_res_attention(const float* qkv, const float* mask, int B, int N, int E, int heads, float* out, void* stream);
+
+/* x[r,:] *= w[r]  (row masks) */
+int rmp_scale_rows(float* x, const float* w, int64_t rows, int width, void* stream);
+
+/* a-16.  rmp_readout_head with logits *= row_mask before softmax / argmax (rnampnn/model/functional.py:86-88). */
+int rmp_readout_head_masked(const float* h, int k_in, const float* W, const float* b, const float* row_mask,
+                            float temperature, uint64_t seed, int rows, float* logits, float* probs,
+                            int64_t* samples, void* stream);
 
 /* ------------------------------------------------------------------ bf16 tensor-core layer path
  * (tcgen05 / TMEM / TMA).  Declared here, implemented in layer_tc.cu.

@@ -184,22 +184,59 @@ __device__ __forceinline__ float ref_pair_distance(float4 a, float4 b) {
     return __fsqrt_rn(__fadd_rn(s, 1e-6f));
 }
 
-template <int R, bool SMEM>
+// rnampnn variant (MODE 1, rnampnn/model/feature.py:218-227): pairs with a padded end and the diagonal sit at
+// exactly 1e6 (1e-3 + 1e6 rounds to 1e6 in fp32) and take part in the ordering like any other candidate.
+__device__ __forceinline__ float res_pair_distance(float4 a, float4 b, bool same) {
+    if (same || a.w == 0.0f || b.w == 0.0f) return 1e6f;
+    const float dx = __fsub_rn(b.x, a.x), dy = __fsub_rn(b.y, a.y), dz = __fsub_rn(b.z, a.z);
+    const float s = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    return __fsqrt_rn(__fadd_rn(s, 1e-6f));
+}
+
+// MODE 0: rdesign (one atom per residue, self included, E_idx [B,N,K] with K <= N).
+// MODE 1: rnampnn (centroid of the A atoms, self excluded, -1 sentinels, K may exceed N).
+template <int R, bool SMEM, int MODE>
 __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(const float* __restrict__ X,
                                                              const float* __restrict__ mask, int N, int A,
                                                              int atom, int K, int rows_per_warp,
                                                              int64_t* __restrict__ E_idx, float* __restrict__ D_out) {
     extern __shared__ float4 s_pts[];
     __shared__ u64 s_ring[kKnnWarps][kKnnRing];
+    __shared__ int s_len;
     const int b = blockIdx.y, t = threadIdx.x, lane = t & 31, w = t >> 5;
     const float* Xb = X + (size_t)b * N * A * 3 + (size_t)atom * 3;
     const float* mb = mask + (size_t)b * N;
     auto load_point = [&](int j) -> float4 {
         const float* p = Xb + (size_t)j * A * 3;
-        return make_float4(p[0], p[1], p[2], mb[j] == 1.0f ? 1.0f : 0.0f);
+        const float m = mb[j] == 1.0f ? 1.0f : 0.0f;
+        if (MODE == 0) return make_float4(p[0], p[1], p[2], m);
+        // coords.mean(dim=2): torch-CPU adds the seven atoms in the order 0,4,5,6,1,2,3, then divides
+        // (oracle/rnampnn_oracle.py: centroids); other atom counts are summed in index order
+        float c[3];
+#pragma unroll
+        for (int x = 0; x < 3; ++x) {
+            float s = p[x];
+            if (A == 7) {
+                s = __fadd_rn(s, p[12 + x]); s = __fadd_rn(s, p[15 + x]); s = __fadd_rn(s, p[18 + x]);
+                s = __fadd_rn(s, p[3 + x]);  s = __fadd_rn(s, p[6 + x]);  s = __fadd_rn(s, p[9 + x]);
+            } else {
+                for (int a = 1; a < A; ++a) s = __fadd_rn(s, p[a * 3 + x]);
+            }
+            c[x] = __fdiv_rn(s, (float)A);
+        }
+        return make_float4(c[0], c[1], c[2], m);
     };
     if (SMEM) {
         for (int j = t; j < N; j += kKnnWarps * 32) s_pts[j] = load_point(j);
+        __syncthreads();
+    }
+    if (MODE == 1) {                                         // L_b = number of valid residues of this structure
+        int cnt = 0;
+        for (int base = 0; base < N; base += kKnnWarps * 32) {
+            const int j = base + t;
+            cnt += __syncthreads_count(j < N && mb[j] == 1.0f);
+        }
+        if (t == 0) s_len = cnt;
         __syncthreads();
     }
     u64* ring = s_ring[w];
@@ -219,7 +256,7 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(const float* __rest
             u64 key = kKeyMax;
             if (j < N) {
                 const float4 pj = SMEM ? s_pts[j] : load_point(j);
-                const float d = ref_pair_distance(pi, pj);
+                const float d = MODE == 0 ? ref_pair_distance(pi, pj) : res_pair_distance(pi, pj, j == i);
                 key = ((u64)__float_as_uint(d) << 32) | (unsigned)j;
             }
             const bool pass = key < thresh;
@@ -248,27 +285,35 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(const float* __rest
         for (int r = 0; r < R; ++r) {
             const int s = r * 32 + lane;
             if (s < K) {
-                E_idx[o + s] = (int64_t)(slot[r] & 0xffffffffull);
+                if (MODE == 0) {
+                    E_idx[o + s] = (int64_t)(slot[r] & 0xffffffffull);
+                } else {
+                    // feature.py:236-254: columns past N, "self", slots k > valid_neighbours and padded rows -> -1
+                    const int j = (int)(slot[r] & 0xffffffffull);
+                    const int valid_nb = pi.w != 0.0f ? max(s_len - 1, 0) : 0;
+                    const bool dead = slot[r] == kKeyMax || j == i || s > valid_nb || pi.w == 0.0f;
+                    E_idx[o + s] = dead ? (int64_t)-1 : (int64_t)j;
+                }
                 if (D_out) D_out[o + s] = __uint_as_float((unsigned)(slot[r] >> 32));
             }
         }
     }
 }
 
-template <int R>
+template <int R, int MODE>
 static int launch_knn(const float* X, const float* mask, int B, int N, int A, int atom, int K,
                       int64_t* E_idx, float* D, cudaStream_t st) {
     const int rpw = knn_rows_per_warp(N);
     dim3 grid(ceil_div(N, kKnnWarps * rpw), B);
     if (N <= kKnnSmemPoints) {
         const size_t smem = (size_t)N * sizeof(float4);
-        auto k = knn_kernel<R, true>;
+        auto k = knn_kernel<R, true, MODE>;
         if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k<<<grid, kKnnWarps * 32, smem, st>>>(X, mask, N, A, atom, K, rpw, E_idx, D);
     } else {
-        knn_kernel<R, false><<<grid, kKnnWarps * 32, 0, st>>>(X, mask, N, A, atom, K, rpw, E_idx, D);
+        knn_kernel<R, false, MODE><<<grid, kKnnWarps * 32, 0, st>>>(X, mask, N, A, atom, K, rpw, E_idx, D);
     }
-    return check_launch("rmp_knn");
+    return check_launch(MODE == 0 ? "rmp_knn" : "rmp_res_graph");
 }
 
 // --------------------------------------------------------------------------------
@@ -341,9 +386,21 @@ extern "C" int rmp_knn(const float* X, const float* mask, int B, int N, int A, i
     RMP_REQUIRE(K <= RMP_MAX_K, RMP_E_SHAPE, "rmp_knn: K=%d exceeds RMP_MAX_K=%d", K, RMP_MAX_K);
     RMP_REQUIRE(B <= 65535, RMP_E_SHAPE, "rmp_knn: B=%d exceeds 65535 structures per call", B);
     cudaStream_t st = (cudaStream_t)stream;
-    if (K <= 32) return launch_knn<1>(X, mask, B, N, A, atom, K, E_idx, D_neighbors, st);
-    if (K <= 64) return launch_knn<2>(X, mask, B, N, A, atom, K, E_idx, D_neighbors, st);
-    return launch_knn<4>(X, mask, B, N, A, atom, K, E_idx, D_neighbors, st);
+    if (K <= 32) return launch_knn<1, 0>(X, mask, B, N, A, atom, K, E_idx, D_neighbors, st);
+    if (K <= 64) return launch_knn<2, 0>(X, mask, B, N, A, atom, K, E_idx, D_neighbors, st);
+    return launch_knn<4, 0>(X, mask, B, N, A, atom, K, E_idx, D_neighbors, st);
+}
+
+extern "C" int rmp_res_graph(const float* coords, const float* mask, int B, int N, int A, int K,
+                             int64_t* edge_index, float* D_neighbors, void* stream) {
+    RMP_REQUIRE(coords && mask && edge_index, RMP_E_ARG, "rmp_res_graph: null pointer");
+    RMP_REQUIRE(B > 0 && N > 0 && A > 0, RMP_E_ARG, "rmp_res_graph: bad sizes");
+    RMP_REQUIRE(K > 0 && K <= RMP_MAX_K, RMP_E_SHAPE, "rmp_res_graph: K=%d outside [1, %d]", K, RMP_MAX_K);
+    RMP_REQUIRE(B <= 65535, RMP_E_SHAPE, "rmp_res_graph: B=%d exceeds 65535 structures per call", B);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (K <= 32) return launch_knn<1, 1>(coords, mask, B, N, A, 0, K, edge_index, D_neighbors, st);
+    if (K <= 64) return launch_knn<2, 1>(coords, mask, B, N, A, 0, K, edge_index, D_neighbors, st);
+    return launch_knn<4, 1>(coords, mask, B, N, A, 0, K, edge_index, D_neighbors, st);
 }
 
 extern "C" int rmp_edge_list(const int64_t* E_idx, const int32_t* node_map, const int32_t* node_src,

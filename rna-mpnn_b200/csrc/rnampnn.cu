@@ -1,0 +1,427 @@
+// Kernels of the secondary (rnampnn) path, SURVEY.md section 8a rows a-10..a-16 (fp32 CUDA-core arm).
+//
+// Reference semantics: rnampnn/model/feature.py:205-571 (graph, 28 intra-residue and 90 cross-residue raw
+// features), rnampnn/model/functional.py:7-48 (GraphNormalization), :153-172 (RNABert: self-attention over
+// a 4500-row padding), rnampnn/model/mpnn.py:154-294 (ResMPNN).  The reference keeps the padded [B,N,..]
+// layout end to end and so do these kernels: rows are dense residues b*N+i, edges are (row, slot k).
+// The Linear stacks run on the fused row-MLP kernel (rowmlp.cu); this file holds what is not a Linear.
+#include "geom.cuh"
+
+namespace rmp {
+
+constexpr int kMaxAtoms = 7;
+
+// --------------------------------------------------------------------------------
+// per-edge bookkeeping from edge_index [B,N,K] (int64, -1 sentinel)
+//   nbr_row [B*N*K] : dense row of the neighbour, -1 -> row b*N+0 (mpnn.py:173-174, "safe" index)
+//   edge_keep       : 1 for edges that keep their embedding (edge_index != -1 and mask_i == 1), feature.py:564-569
+//   edge_w          : (edge_index != -1) / max(#valid slots of the row, 1)   (mpnn.py:191, :215-219)
+// --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) res_edge_rows_kernel(const int64_t* __restrict__ edge_index,
+                                                           const float* __restrict__ mask, int B, int N, int K,
+                                                           int32_t* __restrict__ ctr_row, int32_t* __restrict__ nbr_row,
+                                                           float* __restrict__ edge_keep, float* __restrict__ edge_w) {
+    const size_t row = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (row >= (size_t)B * N) return;
+    const int b = (int)(row / N);
+    const int64_t* ei = edge_index + row * K;
+    int cnt = 0;
+    for (int k = 0; k < K; ++k) cnt += ei[k] != -1;
+    const float inv = 1.0f / (float)(cnt > 0 ? cnt : 1);
+    const float mi = mask[row] == 0.0f ? 0.0f : 1.0f;
+    for (int k = 0; k < K; ++k) {
+        const int64_t j = ei[k];
+        const bool ok = j != -1;
+        ctr_row[row * K + k] = (int32_t)row;
+        nbr_row[row * K + k] = b * N + (ok ? (int)j : 0);
+        edge_keep[row * K + k] = ok ? mi : 0.0f;
+        edge_w[row * K + k] = ok ? inv : 0.0f;
+    }
+}
+
+// --------------------------------------------------------------------------------
+// intra-residue raw features (a-11): one thread per dense residue
+//   [nd*(nd-1)/2 distances | na-2 bond-angle cosines | nh-3 bond-plane cosines]
+// --------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128) res_inside_kernel(const float* __restrict__ coords, const float* __restrict__ mask,
+                                                        int rows, int A, int nd, int na, int nh, int raw_dim,
+                                                        float* __restrict__ raw) {
+    const int row = blockIdx.x * 128 + threadIdx.x;
+    if (row >= rows) return;
+    const float* p = coords + (size_t)row * A * 3;
+    float* out = raw + (size_t)row * raw_dim;
+    const bool ok = mask[row] != 0.0f;
+    V3 c[kMaxAtoms];
+#pragma unroll
+    for (int a = 0; a < kMaxAtoms; ++a) c[a] = a < A ? ld3(p + a * 3) : V3{0.f, 0.f, 0.f};
+    int o = 0;
+    // feature.py:316-329: upper triangle, row-major (a < b), padded rows -> 1e6
+#pragma unroll
+    for (int a = 0; a < kMaxAtoms; ++a)
+#pragma unroll
+        for (int b2 = a + 1; b2 < kMaxAtoms; ++b2)
+            if (b2 < nd) out[o++] = ok ? eps_dist(c[a], c[b2]) : 1e6f;
+    // feature.py:349-357: cos between consecutive bond vectors, dot / (|a||b| + 1e-6), * mask
+    V3 v[kMaxAtoms - 1];
+    float nrm[kMaxAtoms - 1];
+#pragma unroll
+    for (int a = 0; a < kMaxAtoms - 1; ++a) {
+        v[a] = c[a + 1] - c[a];
+        nrm[a] = sqrtf(dot(v[a], v[a]));
+    }
+#pragma unroll
+    for (int a = 0; a < kMaxAtoms - 2; ++a)
+        if (a < na - 2) out[o++] = ok ? dot(v[a], v[a + 1]) / (nrm[a] * nrm[a + 1] + 1e-6f) : 0.f;
+    // feature.py:377-383: unit bond vectors (eps 1e-6) -> unit plane normals (eps 1e-6) -> consecutive dots
+    V3 nor[kMaxAtoms - 2];
+#pragma unroll
+    for (int a = 0; a < kMaxAtoms - 2; ++a) nor[a] = unit_eps(cross(unit_eps(v[a], 1e-6f), unit_eps(v[a + 1], 1e-6f)), 1e-6f);
+#pragma unroll
+    for (int a = 0; a < kMaxAtoms - 3; ++a)
+        if (a < nh - 3) out[o++] = ok ? dot(nor[a + 1], nor[a]) : 0.f;
+}
+
+// --------------------------------------------------------------------------------
+// cross-residue raw features (a-12): 64 edges per block, staged in smem, written coalesced
+//   [nd*nd distances | (na-1)^2 bond cosines | (nh-2)^2 plane-normal cosines]
+// --------------------------------------------------------------------------------
+constexpr int kEdgeTile = 64;
+
+__global__ void __launch_bounds__(kEdgeTile) res_cross_kernel(const float* __restrict__ coords,
+                                                             const float* __restrict__ mask,
+                                                             const int64_t* __restrict__ edge_index, int B, int N,
+                                                             int A, int K, int nd, int na, int nh, int edge_dim,
+                                                             float* __restrict__ edge_raw) {
+    extern __shared__ float s_feat[];                  // [kEdgeTile][edge_dim + 1]
+    const size_t total = (size_t)B * N * K;
+    const size_t e0 = (size_t)blockIdx.x * kEdgeTile;
+    const size_t e = e0 + threadIdx.x;
+    const int stride = edge_dim + 1;
+    if (e < total) {
+        float* f = s_feat + (size_t)threadIdx.x * stride;
+        const size_t row = e / K;
+        const int b = (int)(row / N);
+        const int64_t j = edge_index[e];
+        const bool valid = j != -1 && mask[row] != 0.0f;   // feature.py:420: mask_i * (edge_index != -1)
+        if (!valid) {
+            for (int q = 0; q < nd * nd; ++q) f[q] = 1e6f;
+            for (int q = nd * nd; q < edge_dim; ++q) f[q] = 0.f;
+        } else {
+            const float* pi = coords + row * A * 3;
+            const float* pj = coords + ((size_t)b * N + (size_t)j) * A * 3;
+            V3 ci[kMaxAtoms], cj[kMaxAtoms];
+#pragma unroll
+            for (int a = 0; a < kMaxAtoms; ++a) {
+                ci[a] = a < A ? ld3(pi + a * 3) : V3{0.f, 0.f, 0.f};
+                cj[a] = a < A ? ld3(pj + a * 3) : V3{0.f, 0.f, 0.f};
+            }
+            int o = 0;
+            // feature.py:414-418: d(centre atom a, neighbour atom b), index a*nd + b
+#pragma unroll
+            for (int a = 0; a < kMaxAtoms; ++a)
+#pragma unroll
+                for (int b2 = 0; b2 < kMaxAtoms; ++b2)
+                    if (a < nd && b2 < nd) f[o++] = eps_dist(ci[a], cj[b2]);
+            V3 vi[kMaxAtoms - 1], vj[kMaxAtoms - 1];
+#pragma unroll
+            for (int a = 0; a < kMaxAtoms - 1; ++a) { vi[a] = ci[a + 1] - ci[a]; vj[a] = cj[a + 1] - cj[a]; }
+            // feature.py:451-464: unit bond vectors (F.normalize eps 1e-12), index a*(na-1) + b
+            {
+                V3 ui[kMaxAtoms - 1], uj[kMaxAtoms - 1];
+#pragma unroll
+                for (int a = 0; a < kMaxAtoms - 1; ++a) { ui[a] = unit_eps(vi[a], 1e-12f); uj[a] = unit_eps(vj[a], 1e-12f); }
+#pragma unroll
+                for (int a = 0; a < kMaxAtoms - 1; ++a)
+#pragma unroll
+                    for (int b2 = 0; b2 < kMaxAtoms - 1; ++b2)
+                        if (a < na - 1 && b2 < na - 1) f[o++] = dot(ui[a], uj[b2]);
+            }
+            // feature.py:493-512: normals of consecutive UN-normalised bond vectors (eps 1e-6), index a*(nh-2) + b
+            {
+                V3 ni[kMaxAtoms - 2], nj[kMaxAtoms - 2];
+#pragma unroll
+                for (int a = 0; a < kMaxAtoms - 2; ++a) {
+                    ni[a] = unit_eps(cross(vi[a], vi[a + 1]), 1e-6f);
+                    nj[a] = unit_eps(cross(vj[a], vj[a + 1]), 1e-6f);
+                }
+#pragma unroll
+                for (int a = 0; a < kMaxAtoms - 2; ++a)
+#pragma unroll
+                    for (int b2 = 0; b2 < kMaxAtoms - 2; ++b2)
+                        if (a < nh - 2 && b2 < nh - 2) f[o++] = dot(ni[a], nj[b2]);
+            }
+        }
+    }
+    __syncthreads();
+    const size_t n_here = total - e0 < (size_t)kEdgeTile ? total - e0 : (size_t)kEdgeTile;
+    float* dst = edge_raw + e0 * edge_dim;
+    for (size_t q = threadIdx.x; q < n_here * edge_dim; q += kEdgeTile) {
+        const int r = (int)(q / edge_dim), cidx = (int)(q % edge_dim);
+        dst[q] = s_feat[(size_t)r * stride + cidx];
+    }
+}
+
+// --------------------------------------------------------------------------------
+// GraphNormalization (a-13), two launches:
+//   stats : per (graph, channel) sum and sum of squares of x = (a + b) over VALID rows, fp64 accumulation
+//   apply : mean = S1/n, var = (S2 - n mean^2 + n_pad mean^2)/n  [padded rows add mean^2 each, functional.py:33-38],
+//           out = ((x - mean)/sqrt(var + 1e-6) * scale + shift) * mask
+// x = a + b fuses the residual adds that precede every GraphNorm in the reference (mpnn.py:222, functional.py:165).
+// --------------------------------------------------------------------------------
+constexpr int kGnRows = 64;       // rows per stats block
+
+__global__ void __launch_bounds__(128) graph_norm_stats_kernel(const float* __restrict__ a, const float* __restrict__ b,
+                                                              const float* __restrict__ mask, int N,
+                                                              double* __restrict__ stats) {
+    const int g = blockIdx.y, c = threadIdx.x;
+    const int r0 = blockIdx.x * kGnRows;
+    const int r1 = min(N, r0 + kGnRows);
+    double s1 = 0.0, s2 = 0.0;
+    int n = 0;
+    for (int r = r0; r < r1; ++r) {
+        const size_t row = (size_t)g * N + r;
+        if (mask[row] == 0.0f) continue;
+        float x = a[row * 128 + c];
+        if (b) x += b[row * 128 + c];
+        s1 += (double)x;
+        s2 += (double)x * (double)x;
+        ++n;
+    }
+    if (n == 0) return;
+    double* st = stats + (size_t)g * 257;
+    atomicAdd(st + c, s1);
+    atomicAdd(st + 128 + c, s2);
+    if (c == 0) atomicAdd(st + 256, (double)n);
+}
+
+__global__ void __launch_bounds__(256) graph_norm_apply_kernel(const float* __restrict__ a, float* __restrict__ b,
+                                                              const float* __restrict__ mask, int N, int n_total,
+                                                              const double* __restrict__ stats,
+                                                              const float* __restrict__ scale,
+                                                              const float* __restrict__ shift, int zero_b, size_t rows,
+                                                              float* __restrict__ out) {
+    const size_t row = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= rows) return;
+    const int lane = threadIdx.x & 31;
+    const int g = (int)(row / N);
+    float4* op = reinterpret_cast<float4*>(out + row * 128) + lane;
+    float4* bp = b ? reinterpret_cast<float4*>(b + row * 128) + lane : nullptr;
+    if (mask[row] == 0.0f) {
+        *op = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (bp && zero_b) *bp = make_float4(0.f, 0.f, 0.f, 0.f);
+        return;
+    }
+    float4 x = reinterpret_cast<const float4*>(a + row * 128)[lane];
+    if (bp) {
+        const float4 y = *bp;
+        x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
+        if (zero_b) *bp = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    const double* st = stats + (size_t)g * 257;
+    const double n = st[256] > 0.0 ? st[256] : 1.0;
+    const double n_pad = (double)n_total - st[256];
+    float xs[4] = {x.x, x.y, x.z, x.w}, ys[4];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int c = lane * 4 + q;
+        const double mean = st[c] / n;
+        double var = (st[128 + c] - n * mean * mean + n_pad * mean * mean) / n;
+        var = var > 0.0 ? var : 0.0;
+        const float mf = (float)mean;
+        const float sd = sqrtf((float)var + 1e-6f);
+        ys[q] = (xs[q] - mf) / sd * __ldg(scale + c) + __ldg(shift + c);
+    }
+    *op = make_float4(ys[0], ys[1], ys[2], ys[3]);
+}
+
+// --------------------------------------------------------------------------------
+// Self-attention over the valid rows of each structure (a-15).  One thread per query row, one block per
+// (128 queries, head, structure); keys/values of the head stream through shared memory in tiles of 128 rows,
+// online softmax in chunks of 8 keys.  The reference pads every structure to 4500 rows and masks the padded
+// keys (functional.py:161-168); only the L_b valid keys carry weight, so only those are visited.
+//   qkv [B*N, 3E] = in_proj(x): q | k | v, head h at columns h*HD.  out [B*N, E] (padded query rows -> 0).
+// --------------------------------------------------------------------------------
+constexpr int kAttnTile = 128;
+
+template <int HD>
+__global__ void __launch_bounds__(kAttnTile) res_attention_kernel(const float* __restrict__ qkv,
+                                                                 const float* __restrict__ mask, int N, int E,
+                                                                 float* __restrict__ out) {
+    __shared__ __align__(16) float s_k[kAttnTile][HD];
+    __shared__ __align__(16) float s_v[kAttnTile][HD];
+    __shared__ float s_ok[kAttnTile];
+    const int b = blockIdx.z, h = blockIdx.y, t = threadIdx.x;
+    const int qi = blockIdx.x * kAttnTile + t;
+    const size_t base = (size_t)b * N;
+    const bool q_ok = qi < N && mask[base + qi] != 0.0f;
+    float q[HD], acc[HD];
+    const float qs = 1.0f / sqrtf((float)HD);
+#pragma unroll
+    for (int d = 0; d < HD; ++d) { q[d] = 0.f; acc[d] = 0.f; }
+    if (q_ok) {
+        const float4* qp = reinterpret_cast<const float4*>(qkv + (base + qi) * 3 * E + h * HD);
+#pragma unroll
+        for (int d4 = 0; d4 < HD / 4; ++d4) {
+            const float4 v = qp[d4];
+            q[d4 * 4 + 0] = v.x * qs; q[d4 * 4 + 1] = v.y * qs; q[d4 * 4 + 2] = v.z * qs; q[d4 * 4 + 3] = v.w * qs;
+        }
+    }
+    float m = -INFINITY, l = 0.f;
+    for (int k0 = 0; k0 < N; k0 += kAttnTile) {
+        __syncthreads();
+        {
+            const int kj = k0 + t;
+            const bool ok = kj < N && mask[base + kj] != 0.0f;
+            s_ok[t] = ok ? 1.f : 0.f;
+            if (ok) {
+                const float4* kp = reinterpret_cast<const float4*>(qkv + (base + kj) * 3 * E + E + h * HD);
+                const float4* vp = reinterpret_cast<const float4*>(qkv + (base + kj) * 3 * E + 2 * E + h * HD);
+#pragma unroll
+                for (int d4 = 0; d4 < HD / 4; ++d4) {
+                    reinterpret_cast<float4*>(s_k[t])[d4] = kp[d4];
+                    reinterpret_cast<float4*>(s_v[t])[d4] = vp[d4];
+                }
+            }
+        }
+        __syncthreads();
+        const int kn = min(kAttnTile, N - k0);
+        for (int c0 = 0; c0 < kn; c0 += 8) {
+            float s[8];
+            float cmax = -INFINITY;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                const int kk = c0 + u;
+                s[u] = -INFINITY;
+                if (kk < kn && s_ok[kk] != 0.f) {               // uniform across the block
+                    float d0 = 0.f;
+#pragma unroll
+                    for (int d = 0; d < HD; ++d) d0 = fmaf(q[d], s_k[kk][d], d0);
+                    s[u] = d0;
+                    cmax = fmaxf(cmax, d0);
+                }
+            }
+            if (cmax == -INFINITY) continue;
+            const float m_new = fmaxf(m, cmax);
+            const float corr = expf(m - m_new);                 // exp(-inf) = 0 on the first chunk
+            l *= corr;
+#pragma unroll
+            for (int d = 0; d < HD; ++d) acc[d] *= corr;
+#pragma unroll
+            for (int u = 0; u < 8; ++u) {
+                if (s[u] == -INFINITY) continue;
+                const float p = expf(s[u] - m_new);
+                l += p;
+#pragma unroll
+                for (int d = 0; d < HD; ++d) acc[d] = fmaf(p, s_v[c0 + u][d], acc[d]);
+            }
+            m = m_new;
+        }
+    }
+    if (qi < N) {
+        float4* op = reinterpret_cast<float4*>(out + (base + qi) * E + h * HD);
+        const float inv = (q_ok && l > 0.f) ? 1.0f / l : 0.f;
+#pragma unroll
+        for (int d4 = 0; d4 < HD / 4; ++d4)
+            op[d4] = make_float4(acc[d4 * 4] * inv, acc[d4 * 4 + 1] * inv, acc[d4 * 4 + 2] * inv, acc[d4 * 4 + 3] * inv);
+    }
+}
+
+// rows of x [rows, width] times a per-row factor (logits *= mask, functional.py:88)
+__global__ void __launch_bounds__(256) scale_rows_kernel(float* __restrict__ x, const float* __restrict__ w, size_t rows,
+                                                        int width) {
+    const size_t i = (size_t)blockIdx.x * 256 + threadIdx.x;
+    if (i >= rows * width) return;
+    x[i] *= w[i / width];
+}
+
+}  // namespace rmp
+
+using namespace rmp;
+
+extern "C" int rmp_res_edge_rows(const int64_t* edge_index, const float* mask, int B, int N, int K, int32_t* ctr_row,
+                                 int32_t* nbr_row, float* edge_keep, float* edge_w, void* stream) {
+    RMP_REQUIRE(edge_index && mask && ctr_row && nbr_row && edge_keep && edge_w, RMP_E_ARG, "rmp_res_edge_rows: null pointer");
+    RMP_REQUIRE(B > 0 && N > 0 && K > 0, RMP_E_ARG, "rmp_res_edge_rows: bad sizes");
+    const size_t rows = (size_t)B * N;
+    res_edge_rows_kernel<<<(unsigned)((rows + 255) / 256), 256, 0, (cudaStream_t)stream>>>(edge_index, mask, B, N, K, ctr_row,
+                                                                                          nbr_row, edge_keep, edge_w);
+    return check_launch("rmp_res_edge_rows");
+}
+
+extern "C" int rmp_res_raw_features(const float* coords, const float* mask, const int64_t* edge_index, int B, int N,
+                                    int A, int K, int n_inside_dist, int n_inside_angle, int n_inside_dihedral,
+                                    int n_cross_dist, int n_cross_angle, int n_cross_dihedral, float* raw,
+                                    float* edge_raw, void* stream) {
+    RMP_REQUIRE(coords && mask, RMP_E_ARG, "rmp_res_raw_features: null pointer");
+    RMP_REQUIRE(B > 0 && N > 0 && A >= 4 && A <= kMaxAtoms, RMP_E_SHAPE, "rmp_res_raw_features: A=%d outside [4, %d]", A,
+                kMaxAtoms);
+    cudaStream_t st = (cudaStream_t)stream;
+    int launches = 0;
+    if (raw) {
+        const int nd = n_inside_dist, na = n_inside_angle, nh = n_inside_dihedral;
+        RMP_REQUIRE(nd >= 2 && nd <= A && na >= 3 && na <= A && nh >= 4 && nh <= A, RMP_E_SHAPE,
+                    "rmp_res_raw_features: inside atom counts (%d,%d,%d) need 2<=d, 3<=a, 4<=h, all <= A", nd, na, nh);
+        const int raw_dim = nd * (nd - 1) / 2 + na - 2 + nh - 3;
+        const int rows = B * N;
+        res_inside_kernel<<<ceil_div(rows, 128), 128, 0, st>>>(coords, mask, rows, A, nd, na, nh, raw_dim, raw);
+        ++launches;
+    }
+    if (edge_raw) {
+        const int nd = n_cross_dist, na = n_cross_angle, nh = n_cross_dihedral;
+        RMP_REQUIRE(edge_index && K > 0, RMP_E_ARG, "rmp_res_raw_features: edge_index missing");
+        RMP_REQUIRE(nd >= 2 && nd <= A && na >= 3 && na <= A && nh >= 4 && nh <= A, RMP_E_SHAPE,
+                    "rmp_res_raw_features: cross atom counts (%d,%d,%d) need 2<=d, 3<=a, 4<=h, all <= A", nd, na, nh);
+        const int edge_dim = nd * nd + (na - 1) * (na - 1) + (nh - 2) * (nh - 2);
+        const size_t total = (size_t)B * N * K;
+        const size_t smem = (size_t)kEdgeTile * (edge_dim + 1) * sizeof(float);
+        res_cross_kernel<<<(unsigned)((total + kEdgeTile - 1) / kEdgeTile), kEdgeTile, smem, st>>>(
+            coords, mask, edge_index, B, N, A, K, nd, na, nh, edge_dim, edge_raw);
+        ++launches;
+    }
+    return check_launch("rmp_res_raw_features", launches);
+}
+
+extern "C" int rmp_graph_norm(const float* a, float* b, const float* mask, int B, int N, int n_total,
+                              const float* scale, const float* shift, int zero_b, double* stats_ws, float* out,
+                              void* stream) {
+    RMP_REQUIRE(a && mask && scale && shift && stats_ws && out, RMP_E_ARG, "rmp_graph_norm: null pointer");
+    RMP_REQUIRE(B > 0 && N > 0 && n_total >= N, RMP_E_ARG, "rmp_graph_norm: bad sizes (n_total must be >= N)");
+    RMP_REQUIRE(aligned16(a) && aligned16(out) && (!b || aligned16(b)), RMP_E_ALIGN, "rmp_graph_norm: 16-byte alignment");
+    RMP_REQUIRE(B <= 65535, RMP_E_SHAPE, "rmp_graph_norm: B=%d exceeds 65535 structures per call", B);
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaError_t e = cudaMemsetAsync(stats_ws, 0, (size_t)B * 257 * sizeof(double), st);
+    if (e != cudaSuccess) { set_error("rmp_graph_norm: memset: %s", cudaGetErrorString(e)); return (int)e; }
+    graph_norm_stats_kernel<<<dim3(ceil_div(N, kGnRows), B), 128, 0, st>>>(a, b, mask, N, stats_ws);
+    const size_t rows = (size_t)B * N;
+    graph_norm_apply_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(a, b, mask, N, n_total, stats_ws, scale, shift,
+                                                                         zero_b, rows, out);
+    return check_launch("rmp_graph_norm", 2);
+}
+
+extern "C" int rmp_res_attention(const float* qkv, const float* mask, int B, int N, int E, int heads, float* out,
+                                 void* stream) {
+    RMP_REQUIRE(qkv && mask && out, RMP_E_ARG, "rmp_res_attention: null pointer");
+    RMP_REQUIRE(B > 0 && N > 0 && heads > 0 && E > 0 && E % heads == 0, RMP_E_ARG, "rmp_res_attention: bad sizes");
+    RMP_REQUIRE(aligned16(qkv) && aligned16(out), RMP_E_ALIGN, "rmp_res_attention: 16-byte alignment");
+    RMP_REQUIRE(B <= 65535 && heads <= 65535, RMP_E_SHAPE, "rmp_res_attention: grid too large");
+    const int hd = E / heads;
+    dim3 grid(ceil_div(N, kAttnTile), heads, B);
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (hd) {
+        case 8: res_attention_kernel<8><<<grid, kAttnTile, 0, st>>>(qkv, mask, N, E, out); break;
+        case 16: res_attention_kernel<16><<<grid, kAttnTile, 0, st>>>(qkv, mask, N, E, out); break;
+        case 32: res_attention_kernel<32><<<grid, kAttnTile, 0, st>>>(qkv, mask, N, E, out); break;
+        default:
+            set_error("rmp_res_attention: head dim %d not in {8,16,32}", hd);
+            return RMP_E_SHAPE;
+    }
+    return check_launch("rmp_res_attention");
+}
+
+extern "C" int rmp_scale_rows(float* x, const float* w, int64_t rows, int width, void* stream) {
+    RMP_REQUIRE(x && w && rows >= 0 && width > 0, RMP_E_ARG, "rmp_scale_rows: bad arguments");
+    if (rows == 0) return RMP_OK;
+    const size_t total = (size_t)rows * width;
+    scale_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(x, w, (size_t)rows, width);
+    return check_launch("rmp_scale_rows");
+}

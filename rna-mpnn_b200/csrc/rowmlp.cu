@@ -175,7 +175,7 @@ __global__ void __launch_bounds__(kThreads) row_mlp_kernel(const rmp_mlp_desc d,
                     run = 0.f;
                     cur = sg;
                 }
-                run += fin[(size_t)t * RS + r];
+                run += d.row_scale ? fin[(size_t)t * RS + r] * __ldg(d.row_scale + r0 + r) : fin[(size_t)t * RS + r];
             }
             atomicAdd(d.out + (size_t)cur * 128 + t, run * d.alpha);
         }
@@ -185,7 +185,13 @@ __global__ void __launch_bounds__(kThreads) row_mlp_kernel(const rmp_mlp_desc d,
     for (int r = w; r < rv; r += kThreads / 32) {
         float* orow = d.out + (size_t)(r0 + r) * n;
         if (d.epilogue == RMP_EPI_STORE) {
-            for (int c = lane; c < n; c += 32) orow[c] = fin[(size_t)c * RS + r];
+            const float rs = d.row_scale ? __ldg(d.row_scale + r0 + r) : 1.f;
+            for (int c = lane; c < n; c += 32) orow[c] = d.row_scale ? fin[(size_t)c * RS + r] * rs : fin[(size_t)c * RS + r];
+            continue;
+        }
+        if (d.epilogue == RMP_EPI_RESID_ADD) {
+            const float* rrow = d.resid + (size_t)(r0 + r) * n;
+            for (int c = lane; c < n; c += 32) orow[c] = rrow[c] + fin[(size_t)c * RS + r];
             continue;
         }
         // NORMALIZE / RESID_LN operate on n == 128 channels: 4 per lane
@@ -266,7 +272,8 @@ __global__ void __launch_bounds__(256) readout_head_kernel(const float* __restri
                                                           const float* __restrict__ W, const float* __restrict__ b,
                                                           float temperature, uint64_t seed,
                                                           const int32_t* __restrict__ rows_dev, int rows_slot,
-                                                          int rows_cap, float* __restrict__ logits,
+                                                          int rows_cap, const float* __restrict__ row_mask,
+                                                          float* __restrict__ logits,
                                                           float* __restrict__ probs, int64_t* __restrict__ samples) {
     const int nrows = rows_dev ? min(rows_dev[rows_slot], rows_cap) : rows_cap;
     const int r = blockIdx.x * 8 + (threadIdx.x >> 5);
@@ -281,6 +288,11 @@ __global__ void __launch_bounds__(256) readout_head_kernel(const float* __restri
 #pragma unroll
     for (int o = 0; o < 4; ++o) acc[o] = warp_sum(acc[o]) + __ldg(b + o);
     if (lane != 0) return;
+    if (row_mask) {                                            // logits *= mask (rnampnn/model/functional.py:88)
+        const float mk = row_mask[r];
+#pragma unroll
+        for (int o = 0; o < 4; ++o) acc[o] *= mk;
+    }
     float p[4];
     const float m = fmaxf(fmaxf(acc[0], acc[1]), fmaxf(acc[2], acc[3]));
     float z = 0.f;
@@ -372,11 +384,11 @@ extern "C" int rmp_row_mlp(const rmp_mlp_desc* dp, void* stream) {
         wmax = wmax > d.n_out[s] ? wmax : d.n_out[s];
     }
     const int n_last = d.n_out[d.num_stages - 1];
-    if (d.epilogue != RMP_EPI_STORE)
+    if (d.epilogue != RMP_EPI_STORE && d.epilogue != RMP_EPI_RESID_ADD)
         RMP_REQUIRE(n_last == 128, RMP_E_SHAPE, "rmp_row_mlp: epilogue %d needs 128 output channels", d.epilogue);
     if (d.epilogue == RMP_EPI_NORMALIZE || d.epilogue == RMP_EPI_RESID_LN)
         RMP_REQUIRE(d.gain && d.beta, RMP_E_ARG, "rmp_row_mlp: gain/beta missing");
-    if (d.epilogue == RMP_EPI_RESID_LN) RMP_REQUIRE(d.resid, RMP_E_ARG, "rmp_row_mlp: resid missing");
+    if (d.epilogue == RMP_EPI_RESID_LN || d.epilogue == RMP_EPI_RESID_ADD) RMP_REQUIRE(d.resid, RMP_E_ARG, "rmp_row_mlp: resid missing");
     if (d.epilogue == RMP_EPI_SEGSUM) RMP_REQUIRE(d.seg_id, RMP_E_ARG, "rmp_row_mlp: seg_id missing");
     if (cap1 == 0) cap1 = kNB;
     cudaStream_t st = (cudaStream_t)stream;
@@ -417,8 +429,20 @@ extern "C" int rmp_readout_head(const float* h, int k_in, const float* W, const 
                 "rmp_readout_head: logits/probs must be 16-byte aligned");
     if (rows_cap <= 0) return RMP_OK;
     readout_head_kernel<<<ceil_div(rows_cap, 8), 256, 0, (cudaStream_t)stream>>>(
-        h, k_in, W, b, temperature, seed, rows_dev, rows_slot, rows_cap, logits, probs, samples);
+        h, k_in, W, b, temperature, seed, rows_dev, rows_slot, rows_cap, nullptr, logits, probs, samples);
     return check_launch("rmp_readout_head");
+}
+
+extern "C" int rmp_readout_head_masked(const float* h, int k_in, const float* W, const float* b, const float* row_mask,
+                                       float temperature, uint64_t seed, int rows, float* logits, float* probs,
+                                       int64_t* samples, void* stream) {
+    RMP_REQUIRE(h && W && b && row_mask && k_in > 0, RMP_E_ARG, "rmp_readout_head_masked: null pointer");
+    RMP_REQUIRE((!logits || aligned16(logits)) && (!probs || aligned16(probs)), RMP_E_ALIGN,
+                "rmp_readout_head_masked: logits/probs must be 16-byte aligned");
+    if (rows <= 0) return RMP_OK;
+    readout_head_kernel<<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(
+        h, k_in, W, b, temperature, seed, nullptr, 0, rows, row_mask, logits, probs, samples);
+    return check_launch("rmp_readout_head_masked");
 }
 
 extern "C" int rmp_cast_bf16(const float* src, void* dst, int64_t n, void* stream) {

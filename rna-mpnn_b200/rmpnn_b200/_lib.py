@@ -7,9 +7,9 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB = None
 
-MAX_STAGES = 4
+MAX_STAGES = 6
 MAX_SEGS = 3
-EPI_STORE, EPI_NORMALIZE, EPI_RESID_LN, EPI_SEGSUM = 0, 1, 2, 3
+EPI_STORE, EPI_NORMALIZE, EPI_RESID_LN, EPI_SEGSUM, EPI_RESID_ADD = 0, 1, 2, 3, 4
 PREC_FP32, PREC_BF16 = 0, 1
 
 
@@ -36,6 +36,7 @@ class MlpDesc(C.Structure):
         ("resid", C.c_void_p),
         ("seg_id", C.c_void_p),
         ("alpha", C.c_float),
+        ("row_scale", C.c_void_p),
         ("out", C.c_void_p),
         ("rows_dev", C.c_void_p),
         ("rows_slot", C.c_int32),
@@ -57,6 +58,13 @@ SIGNATURES = {
     "rmp_add_layernorm": [P, P, P, P, F, P, I, I, I, I, P, P],
     "rmp_readout_head": [P, I, P, P, F, U64, P, I, I, P, P, P, P],
     "rmp_cast_bf16": [P, P, I64, P],
+    "rmp_res_graph": [P, P, I, I, I, I, P, P, P],
+    "rmp_res_edge_rows": [P, P, I, I, I, P, P, P, P, P],
+    "rmp_res_raw_features": [P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P],
+    "rmp_graph_norm": [P, P, P, I, I, I, P, P, I, P, P, P],
+    "rmp_res_attention": [P, P, I, I, I, I, P, P],
+    "rmp_scale_rows": [P, P, I64, I, P],
+    "rmp_readout_head_masked": [P, I, P, P, P, F, U64, I, P, P, P, P],
     "rmp_edge_embed_bf16": [P, P, P, P, P, I, P, P, P, P, P, P, P],
     "rmp_node_mlp_bf16": [P, P, I, P, P, I, P, P, P, P, P, P, P, P, P, P, P, I, P],
     "rmp_edge_mlp_bf16": [P, P, I, P, P, P, P, P, P, I, F, P, P, P],

@@ -1,0 +1,231 @@
+"""Forward engine of the secondary (rnampnn) path: sequences the C-ABI kernels over a padded batch.
+
+``RNAMPNNEngine`` is what the drop-in ``rnampnn.model.rnampnn.RNAMPNN`` and ``bench.py --model rnampnn``
+call.  It owns the packed (kernel-layout) parameters; activations are torch-allocated per call.  The
+reference keeps the padded [B,N,..] layout end to end, so rows here are dense residues b*N+i and edges are
+(row, slot k); padded rows are carried as zeros exactly like the reference carries them.
+
+Reference call sites: ``RNAMPNN.forward`` / ``embedding`` rnampnn/model/rnampnn.py:161-185,269-278,
+``ResFeature.forward`` rnampnn/model/feature.py:573-592, ``ResMPNN.forward`` rnampnn/model/mpnn.py:267-294,
+``RNABert.forward`` rnampnn/model/functional.py:161-172, ``RawFFN`` :191-202, ``Readout`` :76-90.
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass, field
+from typing import Dict, List, Mapping, Optional, Tuple
+
+import torch
+
+from . import ops
+
+
+def _indexed(p: Mapping[str, torch.Tensor], prefix: str):
+    ids = sorted({int(k[len(prefix):].split(".")[0]) for k in p if k.startswith(prefix)
+                  and k[len(prefix):].split(".")[0].isdigit()})
+    return [(p[f"{prefix}{i}.weight"], p[f"{prefix}{i}.bias"]) for i in ids]
+
+
+def _stack(p, prefix, last_bare: bool):
+    """[(PackedLinear, gelu)] of an nn.Sequential of Linear/GELU/Dropout under ``prefix``."""
+    lin = _indexed(p, prefix)
+    return [(ops.pack_linear(w, b), not (last_bare and n == len(lin) - 1)) for n, (w, b) in enumerate(lin)]
+
+
+@dataclass
+class BertWeights:
+    """``RNABert`` (rnampnn/model/functional.py:93-127)."""
+    attn: List[Tuple[ops.PackedLinear, ops.PackedLinear]] = field(default_factory=list)   # (in_proj, out_proj)
+    norms: List[Tuple[torch.Tensor, torch.Tensor]] = field(default_factory=list)
+    ffn: List[Tuple[ops.PackedLinear, bool]] = field(default_factory=list)
+
+    @staticmethod
+    def load(p, prefix):
+        bw = BertWeights()
+        n_attn = len([k for k in p if k.startswith(prefix + "bi_attention_layers.") and k.endswith("in_proj_weight")])
+        for l in range(n_attn):
+            a = f"{prefix}bi_attention_layers.{l}."
+            bw.attn.append((ops.pack_linear(p[a + "in_proj_weight"], p[a + "in_proj_bias"]),
+                            ops.pack_linear(p[a + "out_proj.weight"], p[a + "out_proj.bias"])))
+            g = f"{prefix}graph_norm_layers.{l}."
+            bw.norms.append((p[g + "scale"].reshape(-1).contiguous(), p[g + "shift"].reshape(-1).contiguous()))
+        bw.ffn = _stack(p, prefix + "ffn_layers.", last_bare=True)
+        return bw
+
+
+@dataclass
+class ResLayerWeights:
+    message: List[Tuple[ops.PackedLinear, bool]]
+    edge: List[Tuple[ops.PackedLinear, bool]]
+    gn: Tuple[torch.Tensor, torch.Tensor]
+
+
+class RNAMPNNWeights:
+    """Kernel-layout copy of an ``RNAMPNN`` state_dict (same key names as the reference)."""
+
+    def __init__(self, params: Mapping[str, torch.Tensor], device):
+        p = {k: v.detach().to(device=device, dtype=torch.float32).contiguous() for k, v in params.items()
+             if torch.is_tensor(v)}
+        self.device = torch.device(device)
+        H = p["res_feature.raw_project.weight"].shape[0]
+        if H != ops.HIDDEN:
+            raise ValueError("rmpnn_b200 kernels are specialised for res_embedding_dim = 128")
+        gn = lambda k: (p[k + ".scale"].reshape(-1).contiguous(), p[k + ".shift"].reshape(-1).contiguous())
+        self.raw_project = ops.pack_linear(p["res_feature.raw_project.weight"], p["res_feature.raw_project.bias"])
+        self.embed_bert = BertWeights.load(p, "res_feature.res_embedding.")
+        self.embed_gn = gn("res_feature.graph_norm")
+        self.edge_embed = _stack(p, "res_feature.res_edge_embedding_layers.", last_bare=False)
+        n_layers = 1 + max(int(k.split(".")[1]) for k in p if k.startswith("res_mpnn_layers."))
+        self.layers = [ResLayerWeights(_stack(p, f"res_mpnn_layers.{l}.message_layers.", False),
+                                       _stack(p, f"res_mpnn_layers.{l}.edge_layers.", False),
+                                       gn(f"res_mpnn_layers.{l}.graph_norm")) for l in range(n_layers)]
+        self.post_fusion = BertWeights.load(p, "post_fusion.")
+        self.raw_ffn = _stack(p, "raw_embedding.raw_ffn.", last_bare=True)
+        self.raw_gn = gn("raw_embedding.graph_norm")
+        ro = _indexed(p, "readout.readout_layers.")
+        self.readout_hidden = [(ops.pack_linear(w, b), True) for w, b in ro[:-1]]
+        self.readout_w, self.readout_b = ro[-1]
+
+
+class RNAMPNNEngine:
+    """graph + raw features -> embeddings -> ResMPNN layers -> attention fusion -> readout, on the C-ABI kernels."""
+
+    def __init__(self, params: Mapping[str, torch.Tensor], num_neighbours: int = 3, inside=(7, 6, 6), cross=(7, 6, 6),
+                 embed_heads: int = 8, fusion_heads: int = 8, padding_len: int = 4500, device="cuda"):
+        if not torch.cuda.is_available():
+            raise RuntimeError("rmpnn_b200 needs a CUDA device (sm_100a); there is no CPU path")
+        self.w = RNAMPNNWeights(params, device)
+        self.K = int(num_neighbours)
+        self.inside, self.cross = tuple(inside), tuple(cross)
+        self.embed_heads, self.fusion_heads = int(embed_heads), int(fusion_heads)
+        self.padding_len = int(padding_len)
+        self.kernel_timer = None
+
+    @classmethod
+    def from_config(cls, params, cfg, device="cuda"):
+        """``cfg``: any object with the ``RNAMPNN`` constructor's field names (rnampnn/model/rnampnn.py:19-54)."""
+        return cls(params, cfg.num_res_neighbours,
+                   (cfg.num_inside_dist_atoms, cfg.num_inside_angle_atoms, cfg.num_inside_dihedral_atoms),
+                   (cfg.num_cross_dist_atoms, cfg.num_cross_angle_atoms, cfg.num_cross_dihedral_atoms),
+                   cfg.num_embedding_heads, cfg.num_post_fusion_heads, cfg.padding_len, device)
+
+    # ---- building blocks ----------------------------------------------------------
+    @staticmethod
+    def _mlp(segments, stages, rows, row_scale=None):
+        out = torch.empty(rows, stages[-1][0].n_out, dtype=torch.float32, device=segments[0][0].device)
+        for s0 in range(0, len(stages), ops._lib.MAX_STAGES):
+            chunk = stages[s0:s0 + ops._lib.MAX_STAGES]
+            last = s0 + ops._lib.MAX_STAGES >= len(stages)
+            y = out if last else torch.empty(rows, chunk[-1][0].n_out, dtype=torch.float32, device=out.device)
+            ops.row_mlp(segments, chunk, ops.EPI_STORE, y, rows, row_scale=row_scale if last else None)
+            segments = [(y, None)]
+        return out
+
+    def bert(self, bw: BertWeights, x, mask_flat, B, N, heads, pre: Optional[list] = None):
+        """``RNABert.forward`` on the N real rows (the 4500-row padding only enters GraphNorm's variance).
+        ``pre``: Linear stages applied before the FFN when there is no attention layer (raw_project)."""
+        rows = B * N
+        stages = list(bw.ffn)
+        if pre:
+            if bw.attn:
+                x = self._mlp([(x, None)], pre, rows)
+            else:
+                stages = pre + stages
+        if len(bw.attn) and self.padding_len < N:
+            raise ValueError(f"padding_len={self.padding_len} is shorter than the batch (N={N})")
+        for (in_proj, out_proj), (scale, shift) in zip(bw.attn, bw.norms):
+            qkv = self._mlp([(x, None)], [(in_proj, False)], rows)
+            att = ops.res_attention(qkv, mask_flat, B, N, heads)
+            y = self._mlp([(att, None)], [(out_proj, False)], rows)
+            x = ops.graph_norm(x, y, mask_flat, B, N, scale, shift, n_total=self.padding_len)
+        return self._mlp([(x, None)], stages, rows, row_scale=mask_flat)
+
+    def features(self, coords, mask, edge_index=None):
+        """``ResFeature.forward`` -> (raw [B*N,28], h [B*N,128], e [B*N*K,128], ResGraph)."""
+        B, N = mask.shape
+        mask_flat = mask.reshape(-1)
+        if edge_index is None:
+            edge_index = ops.res_graph(coords, mask, self.K)
+        g = ops.res_edge_rows(edge_index, mask)
+        raw, edge_raw = ops.res_raw_features(coords, mask, edge_index, self.inside, self.cross)
+        e = self._mlp([(edge_raw, None)], self.w.edge_embed, B * N * g.K, row_scale=g.edge_keep)
+        x = self.bert(self.w.embed_bert, raw, mask_flat, B, N, self.embed_heads, pre=[(self.w.raw_project, False)])
+        h = ops.graph_norm(x, None, mask_flat, B, N, *self.w.embed_gn)
+        return raw, h, e, g
+
+    def layer(self, l: int, h, e, g: ops.ResGraph, mask_flat, agg=None):
+        """``ResMPNN.forward`` (rnampnn/model/mpnn.py:267-294); ``e`` is updated in place like the reference."""
+        lw = self.w.layers[l]
+        rows, edges = g.B * g.N, g.B * g.N * g.K
+        if agg is None:
+            agg = torch.zeros_like(h)
+        if self.kernel_timer is not None:
+            ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
+            ev[0].record(torch.cuda.current_stream())
+        seg = [(h, g.ctr_row), (h, g.nbr_row), (e, None)]
+        # masked mean of the messages: sum_k valid_k * m_k / max(#valid, 1)  (mpnn.py:191-192, :212-219)
+        ops.row_mlp(seg, lw.message, ops.EPI_SEGSUM, agg, edges, seg_id=g.ctr_row, alpha=1.0, row_scale=g.edge_w)
+        h = ops.graph_norm(h, agg, mask_flat, g.B, g.N, *lw.gn, zero_b=True)
+        # e += MLP([h_i | h_j | e]) with the UPDATED h, on every slot (mpnn.py:229-265)
+        ops.row_mlp([(h, g.ctr_row), (h, g.nbr_row), (e, None)], lw.edge, ops.EPI_RESID_ADD, e, edges, resid=e)
+        if self.kernel_timer is not None:
+            ev[1].record(torch.cuda.current_stream())
+            self.kernel_timer.append(ev)
+        return h, e
+
+    def encode(self, coords, mask, edge_index=None, return_layers=False):
+        B, N = mask.shape
+        mask_flat = mask.reshape(-1)
+        raw, h, e, g = self.features(coords, mask, edge_index)
+        out = {"raw": raw, "graph": g}
+        if return_layers:
+            out["h0"], out["e0"], out["layers"] = h, e.clone(), []
+        agg = torch.zeros_like(h)
+        for l in range(len(self.w.layers)):
+            h, e = self.layer(l, h, e, g, mask_flat, agg)
+            if return_layers:
+                out["layers"].append(h)
+        fused = self.bert(self.w.post_fusion, h, mask_flat, B, N, self.fusion_heads)
+        remb = self._mlp([(raw, None)], self.w.raw_ffn, B * N)
+        remb = ops.graph_norm(remb, None, mask_flat, B, N, *self.w.raw_gn)
+        out.update(h=h, e=e, fused=fused, raw_embedding=remb)
+        return out
+
+    def readout(self, fused, remb, mask_flat, temperature: float = 0.0, seed: int = 0):
+        """``Readout(cat[res | raw])`` + softmax/argmax (rnampnn/model/functional.py:76-90, rnampnn.py:201-207)."""
+        rows = fused.shape[0]
+        if self.w.readout_hidden:
+            x = self._mlp([(fused, None), (remb, None)], self.w.readout_hidden, rows)
+        else:
+            x = torch.cat([fused, remb], -1)
+        return ops.readout_head_masked(x, self.w.readout_w, self.w.readout_b, mask_flat, temperature, seed)
+
+    @torch.no_grad()
+    def forward(self, coords, mask, edge_index=None, temperature: float = 0.0, seed: int = 0,
+                return_layers: bool = False) -> Dict[str, torch.Tensor]:
+        """All tensors keep the reference's padded layout, flattened over (b, i): logits [B*N,4] etc."""
+        ops._need_cuda(coords, mask)
+        coords, mask = ops._f32c(coords), ops._f32c(mask)
+        out = self.encode(coords, mask, edge_index, return_layers)
+        logits, probs, samples = self.readout(out["fused"], out["raw_embedding"], mask.reshape(-1), temperature, seed)
+        out.update(logits=logits, probs=probs, samples=samples)
+        return out
+
+    @torch.no_grad()
+    def capture(self, coords, mask, temperature: float = 0.0, seed: int = 0):
+        """Capture one forward for fixed shapes into a CUDA graph: ``(replay, static)`` like ``RDesignEngine.capture``
+        (no host read-back exists on this path, so no sizes are needed)."""
+        static = {"coords": coords.clone(), "mask": mask.clone()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self.forward(static["coords"], static["mask"], None, temperature, seed)
+        torch.cuda.current_stream().wait_stream(side)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self.forward(static["coords"], static["mask"], None, temperature, seed)
+
+        def replay():
+            graph.replay()
+            return out
+        return replay, static

@@ -13,7 +13,7 @@ from typing import Optional, Sequence
 import torch
 
 from . import _lib
-from ._lib import EPI_NORMALIZE, EPI_RESID_LN, EPI_SEGSUM, EPI_STORE, MlpDesc, check, lib
+from ._lib import EPI_NORMALIZE, EPI_RESID_ADD, EPI_RESID_LN, EPI_SEGSUM, EPI_STORE, MlpDesc, check, lib
 
 HIDDEN = 128
 NODE_RAW = 101
@@ -173,7 +173,7 @@ def pack_linear(weight: torch.Tensor, bias: Optional[torch.Tensor]) -> PackedLin
 
 def row_mlp(segments: Sequence, stages: Sequence, epilogue: int, out: torch.Tensor, rows: int,
             gain=None, beta=None, resid=None, seg_id=None, alpha: float = 1.0,
-            rows_dev: Optional[torch.Tensor] = None, rows_slot: int = 0):
+            rows_dev: Optional[torch.Tensor] = None, rows_slot: int = 0, row_scale=None):
     """One fused launch: concat(gathered segments) -> chained Linear(+GELU) -> epilogue.
 
     segments: [(src [*, width] fp32, idx int32 [rows] or None), ...]
@@ -181,7 +181,7 @@ def row_mlp(segments: Sequence, stages: Sequence, epilogue: int, out: torch.Tens
     """
     d = MlpDesc()
     if not 1 <= len(segments) <= _lib.MAX_SEGS or not 1 <= len(stages) <= _lib.MAX_STAGES:
-        raise ValueError("row_mlp: 1..3 input segments and 1..4 stages per launch")
+        raise ValueError(f"row_mlp: 1..{_lib.MAX_SEGS} input segments and 1..{_lib.MAX_STAGES} stages per launch")
     keep = []
     for s, (src, idx) in enumerate(segments):
         _need_cuda(src, idx)
@@ -194,9 +194,11 @@ def row_mlp(segments: Sequence, stages: Sequence, epilogue: int, out: torch.Tens
         d.Wt[s], d.bias[s], d.k_in[s], d.n_out[s], d.gelu[s] = _ptr(pl.Wt), _ptr(pl.bias), pl.k_in, pl.n_out, int(gelu)
     d.num_stages = len(stages)
     d.epilogue = epilogue
-    _need_cuda(out, gain, beta, resid, seg_id, rows_dev)
+    _need_cuda(out, gain, beta, resid, seg_id, rows_dev, row_scale)
     d.gain, d.beta, d.resid, d.seg_id = _ptr(gain), _ptr(beta), _ptr(resid), _ptr(seg_id)
     d.alpha = float(alpha)
+    assert row_scale is None or (row_scale.dtype == torch.float32 and row_scale.is_contiguous())
+    d.row_scale = _ptr(row_scale)
     d.out = _ptr(out)
     d.rows_dev, d.rows_slot, d.rows_cap = _ptr(rows_dev), rows_slot, int(rows)
     check(lib().rmp_row_mlp(C.byref(d), _stream()), "rmp_row_mlp")
@@ -283,6 +285,118 @@ def cast_bf16(src: torch.Tensor) -> torch.Tensor:
     return dst
 
 
-__all__ = ["Graph", "PackedLinear", "edge_embed_bf16", "pack_edge_embedding", "edge_mlp_bf16", "node_mlp_bf16", "knn", "build_graph", "raw_features", "pack_linear", "row_mlp",
+# =========================================================================== rnampnn (secondary path)
+@dataclass
+class ResGraph:
+    """Dense (padded-layout) residue graph of the rnampnn path and its per-edge bookkeeping."""
+    B: int
+    N: int
+    K: int
+    edge_index: torch.Tensor   # [B,N,K] int64, -1 sentinel
+    ctr_row: torch.Tensor      # [B*N*K] int32 dense row of the centre
+    nbr_row: torch.Tensor      # [B*N*K] int32 dense row of the neighbour (-1 -> row b*N)
+    edge_keep: torch.Tensor    # [B*N*K] fp32 (edge_index != -1) * mask_i
+    edge_w: torch.Tensor       # [B*N*K] fp32 (edge_index != -1) / max(#valid, 1)
+
+
+def res_graph(coords: torch.Tensor, mask: torch.Tensor, num_neighbours: int, want_dist: bool = False):
+    """``ResFeature._get_res_graph`` (rnampnn/model/feature.py:205-256) -> edge_index [B,N,K] int64."""
+    _need_cuda(coords, mask)
+    coords, mask = _f32c(coords), _f32c(mask)
+    B, N, A, _ = coords.shape
+    K = int(num_neighbours)
+    ei = torch.empty(B, N, K, dtype=torch.int64, device=coords.device)
+    D = torch.empty(B, N, K, dtype=torch.float32, device=coords.device) if want_dist else None
+    check(lib().rmp_res_graph(_ptr(coords), _ptr(mask), B, N, A, K, _ptr(ei), _ptr(D), _stream()), "rmp_res_graph")
+    return (ei, D) if want_dist else ei
+
+
+def res_edge_rows(edge_index: torch.Tensor, mask: torch.Tensor) -> ResGraph:
+    _need_cuda(edge_index, mask)
+    edge_index = edge_index.detach().to(torch.int64).contiguous()
+    mask = _f32c(mask)
+    B, N, K = edge_index.shape
+    dev = edge_index.device
+    ctr = torch.empty(B * N * K, dtype=torch.int32, device=dev)
+    nbr = torch.empty(B * N * K, dtype=torch.int32, device=dev)
+    keep = torch.empty(B * N * K, dtype=torch.float32, device=dev)
+    w = torch.empty(B * N * K, dtype=torch.float32, device=dev)
+    check(lib().rmp_res_edge_rows(_ptr(edge_index), _ptr(mask), B, N, K, _ptr(ctr), _ptr(nbr), _ptr(keep), _ptr(w),
+                                  _stream()), "rmp_res_edge_rows")
+    return ResGraph(B, N, K, edge_index, ctr, nbr, keep, w)
+
+
+def res_raw_features(coords, mask, edge_index, inside=(7, 6, 6), cross=(7, 6, 6), want_raw=True, want_edges=True):
+    """raw [B*N, raw_dim], edge_raw [B*N*K, edge_dim]   (rnampnn/model/feature.py:298-517)."""
+    _need_cuda(coords, mask, edge_index)
+    coords, mask = _f32c(coords), _f32c(mask)
+    B, N, A, _ = coords.shape
+    dev = coords.device
+    nd, na, nh = (int(v) for v in inside)
+    cd, ca, ch = (int(v) for v in cross)
+    raw = torch.empty(B * N, nd * (nd - 1) // 2 + na - 2 + nh - 3, dtype=torch.float32, device=dev) if want_raw else None
+    K = 0
+    edge_raw = None
+    if want_edges:
+        edge_index = edge_index.detach().to(torch.int64).contiguous()
+        K = edge_index.shape[-1]
+        edge_raw = torch.empty(B * N * K, cd * cd + (ca - 1) ** 2 + (ch - 2) ** 2, dtype=torch.float32, device=dev)
+    check(lib().rmp_res_raw_features(_ptr(coords), _ptr(mask), _ptr(edge_index) if want_edges else None, B, N, A, K,
+                                     nd, na, nh, cd, ca, ch, _ptr(raw), _ptr(edge_raw), _stream()),
+          "rmp_res_raw_features")
+    return raw, edge_raw
+
+
+def graph_norm(a, b, mask, B: int, N: int, scale, shift, n_total: Optional[int] = None, zero_b: bool = False,
+               out=None, stats_ws=None):
+    """``GraphNormalization`` (rnampnn/model/functional.py:18-48) of x = a (+ b) over rows [B*N, 128]."""
+    _need_cuda(a, b, mask, scale, shift, out, stats_ws)
+    assert a.dtype == torch.float32 and a.is_contiguous() and a.shape[-1] == HIDDEN
+    if out is None:
+        out = torch.empty_like(a)
+    if stats_ws is None:
+        stats_ws = torch.empty(B * 257, dtype=torch.float64, device=a.device)
+    check(lib().rmp_graph_norm(_ptr(a), _ptr(b), _ptr(mask), B, N, int(N if n_total is None else n_total),
+                               _ptr(scale), _ptr(shift), int(zero_b), _ptr(stats_ws), _ptr(out), _stream()),
+          "rmp_graph_norm")
+    return out
+
+
+def res_attention(qkv, mask, B: int, N: int, heads: int, out=None):
+    """softmax(q k^T / sqrt(hd)) v over the valid keys of every structure (rnampnn/model/functional.py:165-168)."""
+    _need_cuda(qkv, mask, out)
+    E = qkv.shape[-1] // 3
+    assert qkv.dtype == torch.float32 and qkv.is_contiguous()
+    if out is None:
+        out = torch.empty(B * N, E, dtype=torch.float32, device=qkv.device)
+    check(lib().rmp_res_attention(_ptr(qkv), _ptr(mask), B, N, E, int(heads), _ptr(out), _stream()), "rmp_res_attention")
+    return out
+
+
+def scale_rows(x, w):
+    """x[r,:] *= w[r] in place."""
+    _need_cuda(x, w)
+    assert x.is_contiguous() and x.dtype == torch.float32 and w.dtype == torch.float32
+    check(lib().rmp_scale_rows(_ptr(x), _ptr(w), x.shape[0], x.shape[1], _stream()), "rmp_scale_rows")
+    return x
+
+
+def readout_head_masked(h, weight, bias, row_mask, temperature: float = 0.0, seed: int = 0, want_probs=True,
+                        want_samples=True):
+    """Final Linear(->4), logits *= mask, softmax, argmax / sampling (rnampnn/model/functional.py:86-88)."""
+    _need_cuda(h, weight, bias, row_mask)
+    rows, k_in = h.shape
+    dev = h.device
+    logits = torch.empty(rows, 4, dtype=torch.float32, device=dev)
+    probs = torch.empty(rows, 4, dtype=torch.float32, device=dev) if want_probs else None
+    samples = torch.empty(rows, dtype=torch.int64, device=dev) if want_samples else None
+    check(lib().rmp_readout_head_masked(_ptr(h), k_in, _ptr(weight), _ptr(bias), _ptr(row_mask), float(temperature),
+                                        int(seed), rows, _ptr(logits), _ptr(probs), _ptr(samples), _stream()),
+          "rmp_readout_head_masked")
+    return logits, probs, samples
+
+
+__all__ = ["ResGraph", "res_graph", "res_edge_rows", "res_raw_features", "graph_norm", "res_attention", "scale_rows",
+           "readout_head_masked", "EPI_RESID_ADD", "Graph", "PackedLinear", "edge_embed_bf16", "pack_edge_embedding", "edge_mlp_bf16", "node_mlp_bf16", "knn", "build_graph", "raw_features", "pack_linear", "row_mlp",
            "add_layernorm", "readout_head", "cast_bf16", "EPI_STORE", "EPI_NORMALIZE", "EPI_RESID_LN",
            "EPI_SEGSUM", "HIDDEN", "NODE_RAW", "EDGE_RAW", "MAX_K"]

@@ -1,0 +1,263 @@
+"""Drop-in ``rnampnn.model.rnampnn.RNAMPNN`` (reference: rnampnn/model/rnampnn.py:18-352).
+
+Same constructor arguments, hyper-parameter names, ``state_dict`` keys and method signatures as the reference
+LightningModule, so reference checkpoints load with ``strict=True``.  ``forward`` / ``embedding`` run the B200
+path (``rmpnn_b200.engine_rnampnn.RNAMPNNEngine``): centroid kNN, fused feature / message / edge kernels, a
+two-launch GraphNorm and self-attention over the valid rows only (the reference pads every structure to 4500
+rows).  In ``train()`` mode with autograd the sub-modules compose the same math from differentiable torch-CUDA
+ops.  The training / logging / checkpoint / XGBoost plumbing is host orchestration outside the hot path.
+"""
+from __future__ import annotations
+
+import csv
+import os
+import pickle
+import types
+from typing import Any
+
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from rmpnn_b200.engine_rnampnn import RNAMPNNEngine
+from ..config.glob import DEFAULT_HIDDEN_DIM, DEFAULT_SEED, NUM_MAIN_SEQ_ATOMS, NUM_RES_TYPES, OUTPUT_PATH, REVERSE_VOCAB
+from ..utils.data import separate
+from .feature import ResFeature
+from .functional import RawFFN, Readout, RNABert, _kernel_path
+from .mpnn import ResMPNN
+
+try:
+    import pytorch_lightning as pl
+    _Base = pl.LightningModule
+except ImportError:                                          # image without Lightning
+    class _Base(nn.Module):
+        """The handful of LightningModule facilities RNAMPNN relies on."""
+
+        def save_hyperparameters(self, *_, **__):
+            import inspect
+            loc = inspect.currentframe().f_back.f_locals
+            self.hparams = types.SimpleNamespace(**{k: v for k, v in loc.items()
+                                                    if k not in ("self", "__class__") and not k.startswith("_")})
+
+        def log(self, *_, **__):
+            pass
+
+        @property
+        def device(self):
+            return next(self.parameters()).device
+
+        def on_load_checkpoint(self, checkpoint):
+            pass
+
+try:
+    import xgboost as xgb
+except ImportError:
+    xgb = None
+
+
+def _make_xgb(hp):
+    if xgb is None:
+        return None
+    return xgb.XGBClassifier(objective='multi:softmax', num_class=NUM_RES_TYPES, n_estimators=hp.n_estimators,
+                             max_depth=hp.xgb_max_depth, learning_rate=hp.xgb_learning_rate,
+                             subsample=hp.xgb_subsample, colsample_bytree=hp.xgb_colsample_bytree,
+                             random_state=DEFAULT_SEED)
+
+
+class RNAMPNN(_Base):
+    def __init__(self,
+                 num_res_neighbours: int = 3,
+                 num_inside_dist_atoms: int = NUM_MAIN_SEQ_ATOMS,
+                 num_inside_angle_atoms: int = NUM_MAIN_SEQ_ATOMS - 1,
+                 num_inside_dihedral_atoms: int = NUM_MAIN_SEQ_ATOMS - 1,
+                 num_cross_dist_atoms: int = NUM_MAIN_SEQ_ATOMS,
+                 num_cross_angle_atoms: int = NUM_MAIN_SEQ_ATOMS - 1,
+                 num_cross_dihedral_atoms: int = NUM_MAIN_SEQ_ATOMS - 1,
+                 res_embedding_dim: int = DEFAULT_HIDDEN_DIM,
+                 num_embedding_attn_layers: int = 0,
+                 num_embedding_heads: int = 8,
+                 embedding_ffn_dim: int = 512,
+                 num_embedding_ffn_layers: int = 3,
+                 res_edge_embedding_dim: int = DEFAULT_HIDDEN_DIM,
+                 depth_res_edge_feature: int = 2,
+                 num_res_mpnn_layers: int = 10,
+                 depth_res_mpnn: int = 2,
+                 num_mpnn_edge_layers: int = 2,
+                 padding_len: int = 4500,
+                 num_post_fusion_attn_layers: int = 2,
+                 num_post_fusion_heads: int = 8,
+                 post_fusion_ffn_dim: int = 512,
+                 num_post_fusion_ffn_layers: int = 3,
+                 num_raw_ffn_dim: int = 512,
+                 num_raw_ffn_layers: int = 3,
+                 raw_embedding_dim: int = DEFAULT_HIDDEN_DIM,
+                 readout_hidden_dim: int = 512,
+                 num_readout_layers: int = 2,
+                 dropout: float = 0.4,
+                 lr: float = 2e-3,
+                 weight_decay: float = 0.0002,
+                 n_estimators: int = 150,
+                 xgb_max_depth: int = 8,
+                 xgb_learning_rate: float = 0.1,
+                 xgb_subsample: float = 0.8,
+                 xgb_colsample_bytree: float = 0.8, ):
+        super().__init__()
+        self.name, self.version = 'RNAMPNN-X', 0
+        self.save_hyperparameters()
+        self.res_feature = ResFeature(num_neighbours=num_res_neighbours,
+                                      num_inside_dist_atoms=num_inside_dist_atoms,
+                                      num_inside_angle_atoms=num_inside_angle_atoms,
+                                      num_inside_dihedral_atoms=num_inside_dihedral_atoms,
+                                      num_cross_dist_atoms=num_cross_dist_atoms,
+                                      num_cross_angle_atoms=num_cross_angle_atoms,
+                                      num_cross_dihedral_atoms=num_cross_dihedral_atoms,
+                                      res_embedding_dim=res_embedding_dim, padding_len=padding_len,
+                                      num_attn_layers=num_embedding_attn_layers, num_heads=num_embedding_heads,
+                                      ffn_dim=embedding_ffn_dim, num_ffn_layers=num_embedding_ffn_layers,
+                                      res_edge_embedding_dim=res_edge_embedding_dim,
+                                      num_edge_layers=depth_res_edge_feature, dropout=dropout)
+        self.res_mpnn_layers = nn.ModuleList([
+            ResMPNN(res_embedding_dim=res_embedding_dim, res_edge_embedding_dim=res_edge_embedding_dim,
+                    depth_res_mpnn=depth_res_mpnn, num_edge_layers=num_mpnn_edge_layers, dropout=dropout)
+            for _ in range(num_res_mpnn_layers)])
+        self.post_fusion = RNABert(padding_len=padding_len, res_embedding_dim=res_embedding_dim,
+                                   num_attn_layers=num_post_fusion_attn_layers, num_heads=num_post_fusion_heads,
+                                   ffn_dim=post_fusion_ffn_dim, num_ffn_layers=num_post_fusion_ffn_layers,
+                                   dropout=dropout)
+        self.raw_embedding = RawFFN(raw_dim=self.res_feature.raw_dim, num_raw_ffn_layers=num_raw_ffn_layers,
+                                    num_raw_ffn_dim=num_raw_ffn_dim, raw_embedding_dim=raw_embedding_dim,
+                                    dropout=dropout)
+        self.readout = Readout(embedding_dim=raw_embedding_dim + res_embedding_dim,
+                               readout_hidden_dim=readout_hidden_dim, num_layers=num_readout_layers, dropout=dropout)
+        self.xgb_readout = _make_xgb(self.hparams)
+        self.loss_fn = self.mix_loss
+        self.val_step_outputs = {'val_loss': [], 'correct': [], 'len': [], 'recovery_rates': []}
+        self.test_step_outputs = {'test_loss': [], 'correct': [], 'len': [], 'recovery_rates': []}
+        self._engine = None
+        self._engine_key = None
+
+    @staticmethod
+    def mix_loss(valid_probs, valid_sequences):
+        return F.cross_entropy(valid_probs, valid_sequences.argmax(dim=-1), reduction='mean')
+
+    def configure_optimizers(self):
+        optimizer = torch.optim.Adam(self.parameters(), lr=self.hparams.lr, weight_decay=self.hparams.weight_decay)
+        scheduler = torch.optim.lr_scheduler.StepLR(optimizer, step_size=15, gamma=0.8)
+        return [optimizer], [scheduler]
+
+    # ------------------------------------------------------------------ fused engine
+    def engine(self) -> RNAMPNNEngine:
+        """Kernel-layout weights, rebuilt whenever a parameter changed or moved."""
+        params = list(self.parameters())
+        key = tuple((p.data_ptr(), p._version) for p in params)
+        if self._engine is None or key != self._engine_key:
+            self._engine = RNAMPNNEngine.from_config(self.state_dict(), self.hparams, device=params[0].device)
+            self._engine_key = key
+        return self._engine
+
+    def _fused(self, coords, mask) -> bool:
+        hp = self.hparams
+        dims_ok = (hp.res_embedding_dim == 128 and hp.res_edge_embedding_dim == 128 and hp.raw_embedding_dim == 128
+                   and all(w % 128 == 0 for w in (hp.embedding_ffn_dim, hp.post_fusion_ffn_dim, hp.num_raw_ffn_dim,
+                                                  hp.readout_hidden_dim))
+                   and (hp.num_embedding_attn_layers == 0 or 128 // hp.num_embedding_heads in (8, 16, 32))
+                   and (hp.num_post_fusion_attn_layers == 0 or 128 // hp.num_post_fusion_heads in (8, 16, 32))
+                   and hp.depth_res_mpnn > 0 and hp.num_mpnn_edge_layers > 0 and hp.depth_res_edge_feature > 0)
+        return _kernel_path(coords, mask, *self.parameters(), training=self.training) and dims_ok \
+            and not (self.training and hp.dropout > 0)
+
+    def forward(self, coords: torch.Tensor, mask: torch.Tensor, is_predict: bool = False) -> torch.Tensor:
+        """logits [B,N,4], zero on padded rows (reference: rnampnn.py:161-185)."""
+        if self._fused(coords, mask):
+            out = self.engine().forward(coords, mask)
+            return out["logits"].reshape(*mask.shape, NUM_RES_TYPES)
+        raw, res_embedding, res_edge_embedding, edge_index = self.res_feature(coords, mask)
+        for layer in self.res_mpnn_layers:
+            res_embedding, res_edge_embedding = layer(res_embedding, res_edge_embedding, edge_index, mask)
+        res_embedding = self.post_fusion(res_embedding, mask)
+        raw_embedding = self.raw_embedding(raw, mask)
+        return self.readout(torch.cat((res_embedding, raw_embedding), dim=-1), mask)
+
+    def embedding(self, coords: torch.Tensor, mask: torch.Tensor, is_predict: bool = False) -> torch.Tensor:
+        """[B,N,256] = post-fusion residue embedding | raw embedding (reference: rnampnn.py:269-278)."""
+        if self._fused(coords, mask):
+            from rmpnn_b200 import ops
+            out = self.engine().encode(ops._f32c(coords), ops._f32c(mask))
+            return torch.cat((out["fused"], out["raw_embedding"]), dim=-1).reshape(*mask.shape, -1)
+        raw, res_embedding, res_edge_embedding, edge_index = self.res_feature(coords, mask)
+        for layer in self.res_mpnn_layers:
+            res_embedding, _ = layer(res_embedding, res_edge_embedding, edge_index, mask)
+        res_embedding = self.post_fusion(res_embedding, mask)
+        return torch.cat((res_embedding, self.raw_embedding(raw, mask)), dim=-1)
+
+    # ------------------------------------------------------------------ steps (host orchestration)
+    def _step(self, batch):
+        sequences, coords, mask, _ = batch
+        dev = self.device
+        sequences, coords, mask = sequences.to(dev), coords.to(dev), mask.to(dev)
+        probs = F.softmax(self(coords, mask), dim=-1)            # the reference feeds probabilities to
+        valid_probs, valid_sequences = probs[mask.bool()], sequences[mask.bool()]   # cross_entropy (:200-203)
+        return self.loss_fn(valid_probs, valid_sequences), valid_probs, valid_sequences, mask
+
+    def training_step(self, batch):
+        loss, _, _, _ = self._step(batch)
+        self.log('train_loss', loss, prog_bar=True, sync_dist=True)
+        return loss
+
+    def _eval_step(self, batch, store, loss_key, name):
+        loss, valid_probs, valid_sequences, mask = self._step(batch)
+        correct = (valid_probs.argmax(dim=-1) == valid_sequences.argmax(dim=-1)).to(dtype=torch.float32)
+        lengths = torch.sum(mask, dim=-1)
+        sep = separate(correct, lengths).to(device=self.device)
+        rates = (sep.sum(dim=-1) / lengths).tolist()
+        store[loss_key].append(loss * correct.shape[0])
+        store['correct'].append(correct.sum(dim=-1).item())
+        store['len'].append(correct.shape[0])
+        store['recovery_rates'] += rates
+        return {name: loss, 'recovery_rates': rates}
+
+    def validation_step(self, batch):
+        return self._eval_step(batch, self.val_step_outputs, 'val_loss', 'validation loss')
+
+    def test_step(self, batch):
+        return self._eval_step(batch, self.test_step_outputs, 'test_loss', 'test loss')
+
+    # ------------------------------------------------------------------ inference
+    def predict(self, batch, batch_id, output_dir, filename):
+        self.eval()
+        _, coords, mask, pdb_id = batch
+        coords, mask = coords.to(self.device), mask.to(self.device)
+        with torch.no_grad():
+            predictions = None
+            if self.xgb_readout is not None:
+                try:
+                    emb = self.embedding(coords, mask).reshape(mask.numel(), -1).cpu().numpy()
+                    predictions = torch.as_tensor(self.xgb_readout.predict(emb)).reshape(mask.shape)
+                except Exception as e:                        # NotFittedError: fall back to the MLP head
+                    if type(e).__name__ != 'NotFittedError':
+                        raise
+            if predictions is None:
+                predictions = self(coords, mask).argmax(dim=-1).cpu()
+        os.makedirs(output_dir, exist_ok=True)
+        with open(os.path.join(output_dir, filename), mode="a", newline="") as f:
+            writer = csv.writer(f)
+            if batch_id == 0:
+                writer.writerow(["pdb_id", "seq"])
+            for i, pdb in enumerate(pdb_id):
+                keep = (mask[i] == 1).cpu()
+                writer.writerow([pdb, "".join(REVERSE_VOCAB[int(v)] for v in predictions[i][keep].tolist())])
+
+    # ------------------------------------------------------------------ checkpoint hooks
+    def on_save_checkpoint(self, checkpoint: dict) -> None:
+        checkpoint['name'], checkpoint['version'] = self.name, self.version
+
+    def on_load_checkpoint(self, checkpoint: dict[str, Any]) -> None:
+        super().on_load_checkpoint(checkpoint)
+        self.name = checkpoint.get('name', 'RNAMPNN-X')
+        self.version = checkpoint.get('version', 0)
+        self.xgb_readout = _make_xgb(self.hparams)
+        try:
+            with open(f"{OUTPUT_PATH}/checkpoints/{self.name}/XGB-V{self.version}.pkl", 'rb') as f:
+                self.xgb_readout = pickle.load(f)
+        except FileNotFoundError:
+            print("=========  XGBoost model not found. Please train the model first.  =========")

@@ -1,0 +1,213 @@
+"""GPU parity tests of the secondary (rnampnn) path, SURVEY.md section 8a rows a-10..a-16: the CUDA kernels
+(through the C ABI) against the CPU oracle and the golden vectors of the unmodified reference.
+Run on the B200 box: pytest -m gpu.
+
+Tolerances: edge_index bit-exact under the documented (distance, index) tie-break; raw features 2e-5;
+fp32 logits within 1e-4 abs; identical argmax sequences.
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import rnampnn_oracle as O
+from oracle.weights import RNAMPNNConfig, make_rnampnn_state_dict, synthetic_backbones
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 1e-4
+RAW_TOL = 2e-5
+SMALL = ("rnampnn_toy", "rnampnn_tiny")        # GraphNorm over 2..5 nodes amplifies rounding noise
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from rmpnn_b200 import ops as _ops
+    return _ops
+
+
+def _engine(params, cfg):
+    from rmpnn_b200.engine_rnampnn import RNAMPNNEngine
+    return RNAMPNNEngine.from_config(params, cfg, device="cuda")
+
+
+def _valid_prefix_distances(coords, mask, K):
+    """Sorted adjusted distances of the oracle (for the D_neighbors output)."""
+    D = torch.sort(O.centroid_distance(coords, mask), -1, stable=True).values
+    N = D.shape[-1]
+    return D[..., :min(K, N)]
+
+
+# --------------------------------------------------------------------------- a-10
+def test_res_graph_bit_exact_on_golden_inputs(rgolden, ops):
+    coords, mask, cfg = rgolden["coords"], rgolden["mask"], rgolden["config"]
+    K = cfg.num_res_neighbours
+    want = O.res_graph(coords, mask, K)
+    got, D = ops.res_graph(coords.cuda(), mask.cuda(), K, want_dist=True)
+    assert got.dtype == torch.int64 and got.shape == want.shape
+    assert torch.equal(got.cpu(), want)
+    Dw = _valid_prefix_distances(coords, mask, K)
+    valid_rows = mask.bool()
+    assert torch.equal(D.cpu()[..., :Dw.shape[-1]][valid_rows], Dw[valid_rows])
+
+
+@pytest.mark.parametrize("B,N,K,lengths", [
+    (4, 256, 3, None), (3, 300, 5, [300, 77, 4]), (2, 1000, 3, [1000, 999]), (5, 33, 40, [33, 32, 31, 2, 1]),
+    (1, 1, 3, None), (2, 130, 128, [130, 129]), (2, 2, 7, [2, 1]), (1, 1500, 30, None),
+])
+def test_res_graph_bit_exact_random(ops, B, N, K, lengths):
+    coords, _, mask = synthetic_backbones(B, N, 4000 + N + K, lengths=lengths, atoms=7)
+    want = O.res_graph(coords, mask, K)
+    got = ops.res_graph(coords.cuda(), mask.cuda(), K)
+    assert torch.equal(got.cpu(), want)
+
+
+def test_res_graph_ties_and_holes(ops):
+    """Integer lattice (many exact ties) and a mask with holes (non-prefix): the canonical (distance, index)
+    order, including the reference's slot == valid_neighbours quirk for padded residues with a lower index."""
+    g = torch.Generator().manual_seed(5)
+    coords = torch.randint(0, 3, (3, 40, 7, 3), generator=g).float()
+    mask = (torch.rand(3, 40, generator=g) > 0.3).float()
+    mask[2] = 0
+    mask[2, 7] = 1                                          # a structure with one valid residue in the middle
+    for K in (3, 12, 45):
+        want = O.res_graph(coords, mask, K)
+        got = ops.res_graph(coords.cuda(), mask.cuda(), K)
+        assert torch.equal(got.cpu(), want), K
+
+
+def test_res_graph_long_structure_global_memory_path(ops):
+    """N > 8192: the structure is not staged in shared memory."""
+    coords, _, mask = synthetic_backbones(1, 8300, 4242, lengths=[8211], atoms=7)
+    want = O.res_graph(coords, mask, 3)
+    got = ops.res_graph(coords.cuda(), mask.cuda(), 3)
+    assert torch.equal(got.cpu(), want)
+
+
+# --------------------------------------------------------------------------- a-11 / a-12
+def test_raw_features_match_oracle_and_reference(rgolden, ops):
+    coords, mask, cfg = rgolden["coords"], rgolden["mask"], rgolden["config"]
+    ei = torch.from_numpy(rgolden["edge_index"])
+    inside = (cfg.num_inside_dist_atoms, cfg.num_inside_angle_atoms, cfg.num_inside_dihedral_atoms)
+    cross = (cfg.num_cross_dist_atoms, cfg.num_cross_angle_atoms, cfg.num_cross_dihedral_atoms)
+    raw, er = ops.res_raw_features(coords.cuda(), mask.cuda(), ei.cuda(), inside, cross)
+    raw_o = O.inside_features(coords, mask, *inside)
+    er_o = O.cross_features(coords, mask, ei, *cross)
+    np.testing.assert_allclose(raw.cpu().numpy(), raw_o.reshape(raw.shape).numpy(), atol=RAW_TOL, rtol=1e-6)
+    np.testing.assert_allclose(er.cpu().numpy(), er_o.reshape(er.shape).numpy(), atol=RAW_TOL, rtol=1e-6)
+    st = int(rgolden["edge_stride"])
+    np.testing.assert_allclose(raw.cpu().numpy(), rgolden["raw"].reshape(raw.shape), atol=RAW_TOL, rtol=1e-6)
+    np.testing.assert_allclose(er.cpu().numpy()[::st], rgolden["edge_raw"], atol=RAW_TOL, rtol=1e-6)
+
+
+# --------------------------------------------------------------------------- a-13
+@pytest.mark.parametrize("n_total", [None, 4500])
+def test_graph_norm_matches_oracle(ops, n_total):
+    g = torch.Generator().manual_seed(9)
+    B, N = 5, 150
+    x = torch.randn(B, N, 128, generator=g) * 2 + torch.randn(1, 1, 128, generator=g) * 3
+    y = torch.randn(B, N, 128, generator=g)
+    mask = (torch.rand(B, N, generator=g) > 0.25).float()
+    mask[3] = 0                                             # empty structure: n_valid clamps to 1, output 0
+    mask[4, 1:] = 0                                         # single residue
+    scale = 1 + 0.1 * torch.randn(128, generator=g)
+    shift = 0.1 * torch.randn(128, generator=g)
+    want = O.graph_norm(x + y, mask, scale, shift, n_total=n_total)
+    b = y.reshape(-1, 128).contiguous().cuda()
+    got = ops.graph_norm(x.reshape(-1, 128).contiguous().cuda(), b, mask.reshape(-1).cuda(), B, N, scale.cuda(),
+                         shift.cuda(), n_total=n_total, zero_b=True)
+    np.testing.assert_allclose(got.cpu().numpy(), want.reshape(-1, 128).numpy(), atol=2e-5, rtol=1e-5)
+    assert float(b.abs().max()) == 0.0                      # the segmented-sum buffer is re-armed
+
+
+# --------------------------------------------------------------------------- a-15
+@pytest.mark.parametrize("heads", [4, 8, 16])
+def test_attention_matches_oracle(ops, heads):
+    g = torch.Generator().manual_seed(21 + heads)
+    B, N, E = 3, 200, 128
+    x = torch.randn(B, N, E, generator=g)
+    mask = torch.ones(B, N)
+    mask[1, 131:] = 0
+    mask[2, 1:] = 0
+    in_w = torch.randn(3 * E, E, generator=g) / E ** 0.5 * 2
+    in_b = torch.randn(3 * E, generator=g) * 0.1
+    out_w, out_b = torch.eye(E), torch.zeros(E)
+    want = O.attention(x, mask, in_w, in_b, out_w, out_b, heads) * mask[..., None]
+    qkv = torch.nn.functional.linear(x, in_w, in_b).reshape(B * N, 3 * E).contiguous().cuda()
+    got = ops.res_attention(qkv, mask.reshape(-1).cuda(), B, N, heads)
+    np.testing.assert_allclose(got.cpu().numpy(), want.reshape(B * N, E).numpy(), atol=2e-5, rtol=1e-5)
+
+
+# --------------------------------------------------------------------------- whole path
+def test_forward_matches_oracle_and_reference(rgolden):
+    """Engine on the reference's own graph: every stage against the oracle, logits against the reference."""
+    coords, mask, cfg = rgolden["coords"], rgolden["mask"], rgolden["config"]
+    ei = torch.from_numpy(rgolden["edge_index"])
+    ref = O.forward(rgolden["params"], coords, mask, cfg, edge_index=ei, return_layers=True)
+    eng = _engine(rgolden["params"], cfg)
+    out = eng.forward(coords.cuda(), mask.cuda(), edge_index=ei.cuda(), return_layers=True)
+    torch.cuda.synchronize()
+    B, N = mask.shape
+    small = rgolden["name"] in SMALL
+    tol = dict(atol=5e-4 if small else 5e-5, rtol=1e-5)
+    flat = lambda t: t.reshape(-1, t.shape[-1]).numpy()
+    np.testing.assert_allclose(out["h0"].cpu().numpy(), flat(ref["h0"]), **tol)
+    np.testing.assert_allclose(out["e0"].cpu().numpy(), flat(ref["e0"]), **tol)
+    for l, h in enumerate(out["layers"]):
+        np.testing.assert_allclose(h.cpu().numpy(), flat(ref["layers"][l][0]), **tol)
+    np.testing.assert_allclose(out["e"].cpu().numpy(), flat(ref["e"]), atol=tol["atol"] * 2, rtol=1e-5)
+    np.testing.assert_allclose(out["fused"].cpu().numpy(), flat(ref["fused"]), atol=tol["atol"] * 2, rtol=1e-5)
+    np.testing.assert_allclose(out["raw_embedding"].cpu().numpy(), flat(ref["raw_embedding"]), **tol)
+    logit_tol = 1e-3 if small else LOGIT_TOL
+    assert (out["logits"].cpu() - ref["logits"].reshape(-1, 4)).abs().max() < logit_tol
+    # the unmodified reference's own outputs
+    assert np.abs(out["logits"].cpu().numpy() - rgolden["logits"].reshape(-1, 4)).max() < logit_tol
+    valid = mask.reshape(-1).bool().numpy()
+    if not small:
+        assert np.array_equal(out["samples"].cpu().numpy()[valid], rgolden["samples"].reshape(-1)[valid])
+    assert np.array_equal(out["samples"].cpu().numpy()[~valid], np.zeros((~valid).sum(), np.int64))
+
+
+def test_forward_from_coordinates(rgolden):
+    """End to end from coordinates (own graph): identical graph to the oracle, logits within 1e-4, same argmax."""
+    coords, mask, cfg = rgolden["coords"], rgolden["mask"], rgolden["config"]
+    ref = O.forward(rgolden["params"], coords, mask, cfg)
+    eng = _engine(rgolden["params"], cfg)
+    out = eng.forward(coords.cuda(), mask.cuda())
+    assert torch.equal(out["graph"].edge_index.cpu(), ref["edge_index"])
+    small = rgolden["name"] in SMALL
+    assert (out["logits"].cpu() - ref["logits"].reshape(-1, 4)).abs().max() < (1e-3 if small else LOGIT_TOL)
+    if not small:
+        valid = mask.reshape(-1).bool()
+        assert torch.equal(out["samples"].cpu()[valid], ref["samples"].reshape(-1)[valid])
+
+
+def test_forward_ragged_batch_with_holes():
+    """Masks with holes and empty structures: padded rows stay exactly zero, valid rows match the oracle."""
+    cfg = RNAMPNNConfig(num_res_mpnn_layers=3)
+    params = make_rnampnn_state_dict(cfg, 31)
+    coords, _, mask = synthetic_backbones(4, 70, 4100, lengths=[70, 41, 9, 0], atoms=7)
+    mask[0, 10:14] = 0
+    mask[1, 0] = 0
+    ref = O.forward(params, coords, mask, cfg)
+    out = _engine(params, cfg).forward(coords.cuda(), mask.cuda())
+    assert torch.equal(out["graph"].edge_index.cpu(), ref["edge_index"])
+    assert (out["logits"].cpu() - ref["logits"].reshape(-1, 4)).abs().max() < LOGIT_TOL
+    dead = ~mask.reshape(-1).bool()
+    assert float(out["logits"].cpu()[dead].abs().max()) == 0.0
+    assert float(out["fused"].cpu()[dead].abs().max()) == 0.0
+
+
+def test_cuda_graph_replay_matches_eager():
+    cfg = RNAMPNNConfig(num_res_mpnn_layers=2)
+    params = make_rnampnn_state_dict(cfg, 33)
+    coords, _, mask = synthetic_backbones(3, 64, 4200, lengths=[64, 50, 12], atoms=7)
+    eng = _engine(params, cfg)
+    eager = eng.forward(coords.cuda(), mask.cuda())["logits"].clone()
+    replay, static = eng.capture(coords.cuda(), mask.cuda())
+    coords2, _, mask2 = synthetic_backbones(3, 64, 4201, lengths=[30, 64, 64], atoms=7)
+    static["coords"].copy_(coords2.cuda()); static["mask"].copy_(mask2.cuda())
+    replay()
+    static["coords"].copy_(coords.cuda()); static["mask"].copy_(mask.cuda())
+    got = replay()["logits"]
+    torch.cuda.synchronize()
+    assert torch.equal(got, eager)
