@@ -92,7 +92,7 @@ class Readout(nn.Module):
             return self.readout_layers(res_embedding) * mask.unsqueeze(-1)
         x = _flat(res_embedding)
         if len(lin) > 1:
-            x = RNAMPNNEngine._mlp([(x, None)], _packed(self.readout_layers, last_bare=True)[:-1], x.shape[0])
+            x = RNAMPNNEngine._mlp([(x, None)], [(ops.pack_linear(m.weight, m.bias), True) for m in lin[:-1]], x.shape[0])
         logits, _, _ = ops.readout_head_masked(x, lin[-1].weight.detach().contiguous(), lin[-1].bias.detach().contiguous(),
                                                mask.to(torch.float32).reshape(-1).contiguous(), want_probs=False,
                                                want_samples=False)

@@ -11,6 +11,7 @@ import torch
 
 from oracle import rnampnn_oracle as O
 from oracle.weights import RNAMPNNConfig, make_rnampnn_state_dict, synthetic_backbones
+from conftest import assert_close_fp32, to_fp64
 
 pytestmark = pytest.mark.gpu
 
@@ -32,7 +33,7 @@ def _engine(params, cfg):
 
 def _valid_prefix_distances(coords, mask, K):
     """Sorted adjusted distances of the oracle (for the D_neighbors output)."""
-    D = torch.sort(O.centroid_distance(coords, mask), -1, stable=True).values
+    D = torch.sort(O.centroid_distance(coords, mask), dim=-1, stable=True).values
     N = D.shape[-1]
     return D[..., :min(K, N)]
 
@@ -143,20 +144,17 @@ def test_forward_matches_oracle_and_reference(rgolden):
     coords, mask, cfg = rgolden["coords"], rgolden["mask"], rgolden["config"]
     ei = torch.from_numpy(rgolden["edge_index"])
     ref = O.forward(rgolden["params"], coords, mask, cfg, edge_index=ei, return_layers=True)
+    ref64 = O.forward(to_fp64(rgolden["params"]), coords.double(), mask.double(), cfg, edge_index=ei, return_layers=True)
     eng = _engine(rgolden["params"], cfg)
     out = eng.forward(coords.cuda(), mask.cuda(), edge_index=ei.cuda(), return_layers=True)
     torch.cuda.synchronize()
     B, N = mask.shape
     small = rgolden["name"] in SMALL
-    tol = dict(atol=5e-4 if small else 5e-5, rtol=1e-5)
-    flat = lambda t: t.reshape(-1, t.shape[-1]).numpy()
-    np.testing.assert_allclose(out["h0"].cpu().numpy(), flat(ref["h0"]), **tol)
-    np.testing.assert_allclose(out["e0"].cpu().numpy(), flat(ref["e0"]), **tol)
+    atol = 5e-4 if small else 5e-5
+    for key in ("h0", "e0", "e", "fused", "raw_embedding"):
+        assert_close_fp32(out[key], ref[key], ref64[key], atol, key)
     for l, h in enumerate(out["layers"]):
-        np.testing.assert_allclose(h.cpu().numpy(), flat(ref["layers"][l][0]), **tol)
-    np.testing.assert_allclose(out["e"].cpu().numpy(), flat(ref["e"]), atol=tol["atol"] * 2, rtol=1e-5)
-    np.testing.assert_allclose(out["fused"].cpu().numpy(), flat(ref["fused"]), atol=tol["atol"] * 2, rtol=1e-5)
-    np.testing.assert_allclose(out["raw_embedding"].cpu().numpy(), flat(ref["raw_embedding"]), **tol)
+        assert_close_fp32(h, ref["layers"][l][0], ref64["layers"][l][0], atol, f"layer {l}")
     logit_tol = 1e-3 if small else LOGIT_TOL
     assert (out["logits"].cpu() - ref["logits"].reshape(-1, 4)).abs().max() < logit_tol
     # the unmodified reference's own outputs
@@ -210,4 +208,4 @@ def test_cuda_graph_replay_matches_eager():
     static["coords"].copy_(coords.cuda()); static["mask"].copy_(mask.cuda())
     got = replay()["logits"]
     torch.cuda.synchronize()
-    assert torch.equal(got, eager)
+    assert (got - eager).abs().max() < 1e-5        # fp64 atomics of the GraphNorm statistics are order-free only to ~1e-16

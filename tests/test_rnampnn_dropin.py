@@ -10,6 +10,7 @@ import torch
 
 from oracle import rnampnn_oracle as O
 from oracle.weights import RNAMPNNConfig, make_rnampnn_state_dict, synthetic_backbones
+from conftest import assert_close_fp32, to_fp64
 
 
 def _model(cfg, seed, device=None):
@@ -98,9 +99,10 @@ def test_model_forward_matches_reference(rgolden):
         emb = m.embedding(coords.cuda(), mask.cuda())
     assert logits.shape == (*mask.shape, 4) and emb.shape == (*mask.shape, 256)
     ref = O.forward(rgolden["params"], coords, mask, cfg)
+    ref64 = O.forward(to_fp64(rgolden["params"]), coords.double(), mask.double(), cfg, edge_index=ref["edge_index"])
     tol = 1e-3 if rgolden["name"] in SMALL else 1e-4
     assert (logits.cpu() - ref["logits"]).abs().max() < tol
-    assert (emb.cpu() - ref["embedding"]).abs().max() < tol * 2
+    assert_close_fp32(emb, ref["embedding"], ref64["embedding"], tol, "embedding")
     if torch.equal(ref["edge_index"], torch.from_numpy(rgolden["edge_index"])):
         assert np.abs(logits.cpu().numpy() - rgolden["logits"]).max() < tol
 
@@ -115,10 +117,11 @@ def test_res_feature_module(rgolden):
         raw, h0, e0, ei = m.res_feature(coords.cuda(), mask.cuda())
     want = O.res_feature(rgolden["params"], coords, mask, cfg)
     assert torch.equal(ei.cpu(), want[3]) and ei.dtype == torch.int64
-    tol = dict(atol=5e-4 if rgolden["name"] in SMALL else 5e-5, rtol=1e-5)
+    want64 = O.res_feature(to_fp64(rgolden["params"]), coords.double(), mask.double(), cfg, edge_index=want[3])
+    atol = 5e-4 if rgolden["name"] in SMALL else 5e-5
     np.testing.assert_allclose(raw.cpu().numpy(), want[0].numpy(), atol=2e-5, rtol=1e-6)
-    np.testing.assert_allclose(h0.cpu().numpy(), want[1].numpy(), **tol)
-    np.testing.assert_allclose(e0.cpu().numpy(), want[2].numpy(), **tol)
+    assert_close_fp32(h0, want[1], want64[1], atol, "res_embedding")
+    assert_close_fp32(e0, want[2], want64[2], atol, "res_edge_embedding")
     assert torch.equal(m.res_feature._get_res_graph(coords.cuda(), mask.cuda()).cpu(), want[3])
 
 
@@ -195,7 +198,10 @@ def test_training_mode_composes_the_same_math_and_differentiates():
     assert out.requires_grad
     assert (out - ref).abs().max() < 2e-4
     out.square().sum().backward()
-    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in m.parameters())
+    for name, p in m.named_parameters():
+        if name.startswith("res_mpnn_layers.1.edge_layers."):
+            continue                                    # the last layer's edge update never reaches the logits
+        assert p.grad is not None and torch.isfinite(p.grad).all(), name
 
 
 @gpu
