@@ -238,6 +238,23 @@ int rmp_readout_head_masked(const float* h, int k_in, const float* W, const floa
                             float temperature, uint64_t seed, int rows, float* logits, float* probs,
                             int64_t* samples, void* stream);
 
+/* Tensor-core arm of rmp_row_mlp (tcgen05 / TMEM / TMA): same descriptor, with the weights passed separately as
+ * bf16 in nn.Linear layout, W_bf16[s] = [n_out[s]][k_in[s]] (desc->Wt is ignored).  Operands are rounded to bf16,
+ * accumulation is fp32, GELU is the tanh form; 2e-2 logit budget like RMP_PREC_BF16.
+ * Restrictions: every segment width a multiple of 128; k_in % 64 == 0, n_out % 128 == 0, both <= 512; bias required;
+ * epilogues RMP_EPI_STORE / RMP_EPI_SEGSUM / RMP_EPI_RESID_ADD; rows given on the host (rows_dev == NULL).
+ * Replaces the Linear/GELU stacks of rnampnn/model/mpnn.py:131-152 (message / edge MLPs) and
+ * rnampnn/model/functional.py:62-74, :105-127, :179-187 (Readout hidden layer, RNABert FFN + projections, RawFFN). */
+int rmp_row_mlp_bf16(const rmp_mlp_desc* desc, const void* const* W_bf16, void* stream);
+
+/* Same kernel with a choice of 16-bit operand format.  RMP_OPERAND_FP16 (weights passed as IEEE fp16) keeps 11
+ * significant bits instead of 8; conversions saturate to +-65504, so finite inputs never produce inf / NaN.  The
+ * rnampnn engine uses it for the two stacks that consume raw geometry and feed a GraphNorm directly (embedding FFN,
+ * RawFFN), where bf16 rounding is amplified beyond the 2e-2 budget on badly scaled inputs. */
+#define RMP_OPERAND_BF16 0
+#define RMP_OPERAND_FP16 1
+int rmp_row_mlp_tc(const rmp_mlp_desc* desc, const void* const* W_16, int operand_format, void* stream);
+
 /* ------------------------------------------------------------------ bf16 tensor-core layer path
  * (tcgen05 / TMEM / TMA).  Declared here, implemented in layer_tc.cu.
  */

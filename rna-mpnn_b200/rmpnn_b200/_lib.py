@@ -11,6 +11,7 @@ MAX_STAGES = 6
 MAX_SEGS = 3
 EPI_STORE, EPI_NORMALIZE, EPI_RESID_LN, EPI_SEGSUM, EPI_RESID_ADD = 0, 1, 2, 3, 4
 PREC_FP32, PREC_BF16 = 0, 1
+OPERAND_BF16, OPERAND_FP16 = 0, 1
 
 
 class LibraryMissing(RuntimeError):
@@ -55,6 +56,8 @@ SIGNATURES = {
     "rmp_edge_list": [P, P, P, P, P, P, I, I, I, I, P, P, P, P],
     "rmp_rdesign_raw_features": [P, I, I, P, P, P, P, I, I, P, P, P, P, P],
     "rmp_row_mlp": [C.POINTER(MlpDesc), P],
+    "rmp_row_mlp_bf16": [C.POINTER(MlpDesc), P, P],
+    "rmp_row_mlp_tc": [C.POINTER(MlpDesc), P, I, P],
     "rmp_add_layernorm": [P, P, P, P, F, P, I, I, I, I, P, P],
     "rmp_readout_head": [P, I, P, P, F, U64, P, I, I, P, P, P, P],
     "rmp_cast_bf16": [P, P, I64, P],

@@ -17,6 +17,7 @@ from typing import Dict, List, Mapping, Optional, Tuple
 import torch
 
 from . import ops
+from ._lib import PREC_BF16, PREC_FP32
 
 
 def _indexed(p: Mapping[str, torch.Tensor], prefix: str):
@@ -90,7 +91,8 @@ class RNAMPNNEngine:
     """graph + raw features -> embeddings -> ResMPNN layers -> attention fusion -> readout, on the C-ABI kernels."""
 
     def __init__(self, params: Mapping[str, torch.Tensor], num_neighbours: int = 3, inside=(7, 6, 6), cross=(7, 6, 6),
-                 embed_heads: int = 8, fusion_heads: int = 8, padding_len: int = 4500, device="cuda"):
+                 embed_heads: int = 8, fusion_heads: int = 8, padding_len: int = 4500, device="cuda",
+                 precision: int = PREC_FP32):
         if not torch.cuda.is_available():
             raise RuntimeError("rmpnn_b200 needs a CUDA device (sm_100a); there is no CPU path")
         self.w = RNAMPNNWeights(params, device)
@@ -99,45 +101,73 @@ class RNAMPNNEngine:
         self.embed_heads, self.fusion_heads = int(embed_heads), int(fusion_heads)
         self.padding_len = int(padding_len)
         self.kernel_timer = None
+        if precision not in (PREC_FP32, PREC_BF16):
+            raise ValueError("precision must be RMP_PREC_FP32 or RMP_PREC_BF16")
+        # RMP_PREC_BF16: every Linear stack runs on the tcgen05 row-MLP kernel (bf16 operands, fp32 accumulate),
+        # except a first stage fed by raw geometry (28 / 90 unbounded distances), which stays in fp32
+        self.precision = precision
+        # the two stacks that consume raw geometry (embedding FFN, RawFFN) feed a GraphNorm directly; on badly scaled
+        # inputs (atoms parked at the origin) their operand rounding is what the GraphNorm amplifies.  They run with
+        # fp16 operands (11 significant bits, saturating conversions) instead of bf16; "fp32" keeps them on the
+        # CUDA-core kernel, "bf16" treats them like every other stack.
+        self.raw_stacks = "fp16"
 
     @classmethod
-    def from_config(cls, params, cfg, device="cuda"):
+    def from_config(cls, params, cfg, device="cuda", precision: int = PREC_FP32):
         """``cfg``: any object with the ``RNAMPNN`` constructor's field names (rnampnn/model/rnampnn.py:19-54)."""
         return cls(params, cfg.num_res_neighbours,
                    (cfg.num_inside_dist_atoms, cfg.num_inside_angle_atoms, cfg.num_inside_dihedral_atoms),
                    (cfg.num_cross_dist_atoms, cfg.num_cross_angle_atoms, cfg.num_cross_dihedral_atoms),
-                   cfg.num_embedding_heads, cfg.num_post_fusion_heads, cfg.padding_len, device)
+                   cfg.num_embedding_heads, cfg.num_post_fusion_heads, cfg.padding_len, device, precision)
 
     # ---- building blocks ----------------------------------------------------------
     @staticmethod
-    def _mlp(segments, stages, rows, row_scale=None):
-        out = torch.empty(rows, stages[-1][0].n_out, dtype=torch.float32, device=segments[0][0].device)
-        for s0 in range(0, len(stages), ops._lib.MAX_STAGES):
-            chunk = stages[s0:s0 + ops._lib.MAX_STAGES]
-            last = s0 + ops._lib.MAX_STAGES >= len(stages)
-            y = out if last else torch.empty(rows, chunk[-1][0].n_out, dtype=torch.float32, device=out.device)
-            ops.row_mlp(segments, chunk, ops.EPI_STORE, y, rows, row_scale=row_scale if last else None)
-            segments = [(y, None)]
+    def _mlp(segments, stages, rows, row_scale=None, tensor_core: bool = False, fp16: bool = False):
+        """Chained Linear(+GELU) stages -> fp32 [rows, n_out], result rows times ``row_scale``.  With ``tensor_core``
+        the stages the tcgen05 kernel can take run on it; a leading stage it cannot take (raw geometry, K = 28 / 90)
+        runs on the fp32 kernel first."""
+        dev = segments[0][0].device
+        groups = [(stages, False)]                    # [(stages, tensor_core)]
+        if tensor_core:
+            if ops.tc_eligible(segments, stages):
+                groups = [(stages, True)]
+            elif len(stages) > 1 and stages[0][0].n_out % 128 == 0 and ops.tc_eligible([], stages[1:]):
+                groups = [(stages[:1], False), (stages[1:], True)]
+        out = None
+        for gi, (group, tc) in enumerate(groups):
+            for s0 in range(0, len(group), ops._lib.MAX_STAGES):
+                chunk = group[s0:s0 + ops._lib.MAX_STAGES]
+                last = gi == len(groups) - 1 and s0 + ops._lib.MAX_STAGES >= len(group)
+                out = torch.empty(rows, chunk[-1][0].n_out, dtype=torch.float32, device=dev)
+                ops.row_mlp(segments, chunk, ops.EPI_STORE, out, rows, row_scale=row_scale if last else None,
+                            tensor_core=tc, fp16=fp16)
+                segments = [(out, None)]
         return out
 
-    def bert(self, bw: BertWeights, x, mask_flat, B, N, heads, pre: Optional[list] = None):
+    @property
+    def tc(self) -> bool:
+        return getattr(self, "precision", PREC_FP32) == PREC_BF16
+
+    def bert(self, bw: BertWeights, x, mask_flat, B, N, heads, pre: Optional[list] = None, tc: Optional[bool] = None,
+             fp16: bool = False):
         """``RNABert.forward`` on the N real rows (the 4500-row padding only enters GraphNorm's variance).
         ``pre``: Linear stages applied before the FFN when there is no attention layer (raw_project)."""
         rows = B * N
+        tc = self.tc if tc is None else tc
         stages = list(bw.ffn)
         if pre:
             if bw.attn:
-                x = self._mlp([(x, None)], pre, rows)
+                x = self._mlp([(x, None)], pre, rows, tensor_core=tc, fp16=fp16)
             else:
                 stages = pre + stages
         if len(bw.attn) and self.padding_len < N:
             raise ValueError(f"padding_len={self.padding_len} is shorter than the batch (N={N})")
         for (in_proj, out_proj), (scale, shift) in zip(bw.attn, bw.norms):
-            qkv = self._mlp([(x, None)], [(in_proj, False)], rows)
+            qkv = self._mlp([(x, None)], [(in_proj, False)], rows, tensor_core=tc, fp16=fp16)
             att = ops.res_attention(qkv, mask_flat, B, N, heads)
-            y = self._mlp([(att, None)], [(out_proj, False)], rows)
+            y = self._mlp([(att, None)], [(out_proj, False)], rows, tensor_core=tc, fp16=fp16)
             x = ops.graph_norm(x, y, mask_flat, B, N, scale, shift, n_total=self.padding_len)
-        return self._mlp([(x, None)], stages, rows, row_scale=mask_flat)
+        return self._mlp([(x, None)], stages, rows, row_scale=mask_flat, tensor_core=tc, fp16=fp16)
 
     def features(self, coords, mask, edge_index=None):
         """``ResFeature.forward`` -> (raw [B*N,28], h [B*N,128], e [B*N*K,128], ResGraph)."""
@@ -147,8 +177,9 @@ class RNAMPNNEngine:
             edge_index = ops.res_graph(coords, mask, self.K)
         g = ops.res_edge_rows(edge_index, mask)
         raw, edge_raw = ops.res_raw_features(coords, mask, edge_index, self.inside, self.cross)
-        e = self._mlp([(edge_raw, None)], self.w.edge_embed, B * N * g.K, row_scale=g.edge_keep)
-        x = self.bert(self.w.embed_bert, raw, mask_flat, B, N, self.embed_heads, pre=[(self.w.raw_project, False)])
+        e = self._mlp([(edge_raw, None)], self.w.edge_embed, B * N * g.K, row_scale=g.edge_keep, tensor_core=self.tc)
+        x = self.bert(self.w.embed_bert, raw, mask_flat, B, N, self.embed_heads, pre=[(self.w.raw_project, False)],
+                      tc=self.tc and self.raw_stacks != "fp32", fp16=self.raw_stacks == "fp16")
         h = ops.graph_norm(x, None, mask_flat, B, N, *self.w.embed_gn)
         return raw, h, e, g
 
@@ -163,10 +194,13 @@ class RNAMPNNEngine:
             ev[0].record(torch.cuda.current_stream())
         seg = [(h, g.ctr_row), (h, g.nbr_row), (e, None)]
         # masked mean of the messages: sum_k valid_k * m_k / max(#valid, 1)  (mpnn.py:191-192, :212-219)
-        ops.row_mlp(seg, lw.message, ops.EPI_SEGSUM, agg, edges, seg_id=g.ctr_row, alpha=1.0, row_scale=g.edge_w)
+        tc = self.tc and ops.tc_eligible(seg, lw.message) and ops.tc_eligible(seg, lw.edge)
+        ops.row_mlp(seg, lw.message, ops.EPI_SEGSUM, agg, edges, seg_id=g.ctr_row, alpha=1.0, row_scale=g.edge_w,
+                    tensor_core=tc)
         h = ops.graph_norm(h, agg, mask_flat, g.B, g.N, *lw.gn, zero_b=True)
         # e += MLP([h_i | h_j | e]) with the UPDATED h, on every slot (mpnn.py:229-265)
-        ops.row_mlp([(h, g.ctr_row), (h, g.nbr_row), (e, None)], lw.edge, ops.EPI_RESID_ADD, e, edges, resid=e)
+        ops.row_mlp([(h, g.ctr_row), (h, g.nbr_row), (e, None)], lw.edge, ops.EPI_RESID_ADD, e, edges, resid=e,
+                    tensor_core=tc)
         if self.kernel_timer is not None:
             ev[1].record(torch.cuda.current_stream())
             self.kernel_timer.append(ev)
@@ -185,7 +219,8 @@ class RNAMPNNEngine:
             if return_layers:
                 out["layers"].append(h)
         fused = self.bert(self.w.post_fusion, h, mask_flat, B, N, self.fusion_heads)
-        remb = self._mlp([(raw, None)], self.w.raw_ffn, B * N)
+        remb = self._mlp([(raw, None)], self.w.raw_ffn, B * N, tensor_core=self.tc and self.raw_stacks != "fp32",
+                         fp16=self.raw_stacks == "fp16")
         remb = ops.graph_norm(remb, None, mask_flat, B, N, *self.w.raw_gn)
         out.update(h=h, e=e, fused=fused, raw_embedding=remb)
         return out
@@ -194,7 +229,7 @@ class RNAMPNNEngine:
         """``Readout(cat[res | raw])`` + softmax/argmax (rnampnn/model/functional.py:76-90, rnampnn.py:201-207)."""
         rows = fused.shape[0]
         if self.w.readout_hidden:
-            x = self._mlp([(fused, None), (remb, None)], self.w.readout_hidden, rows)
+            x = self._mlp([(fused, None), (remb, None)], self.w.readout_hidden, rows, tensor_core=self.tc)
         else:
             x = torch.cat([fused, remb], -1)
         return ops.readout_head_masked(x, self.w.readout_w, self.w.readout_b, mask_flat, temperature, seed)

@@ -158,6 +158,8 @@ class PackedLinear:
     bias: Optional[torch.Tensor]
     k_in: int
     n_out: int
+    W16: Optional[torch.Tensor] = None      # bf16 [n_out, k_in] (nn.Linear layout) for the tensor-core arm
+    W16h: Optional[torch.Tensor] = None     # the same as IEEE fp16 (RMP_OPERAND_FP16)
 
 
 def pack_linear(weight: torch.Tensor, bias: Optional[torch.Tensor]) -> PackedLinear:
@@ -168,12 +170,21 @@ def pack_linear(weight: torch.Tensor, bias: Optional[torch.Tensor]) -> PackedLin
     k_pad = (k_in + 31) // 32 * 32
     Wt = torch.zeros(k_pad, n_out, dtype=torch.float32, device=weight.device)
     Wt[:k_in] = weight.detach().to(torch.float32).t()
-    return PackedLinear(Wt.contiguous(), None if bias is None else _f32c(bias), k_in, n_out)
+    return PackedLinear(Wt.contiguous(), None if bias is None else _f32c(bias), k_in, n_out,
+                        weight.detach().to(torch.bfloat16).contiguous(),
+                        weight.detach().to(torch.float32).clamp(-65504.0, 65504.0).to(torch.float16).contiguous())
+
+
+def tc_eligible(segments: Sequence, stages: Sequence) -> bool:
+    """Shapes the tcgen05 row-MLP kernel (rmp_row_mlp_bf16) takes."""
+    return (all(src.shape[-1] % 128 == 0 for src, _ in segments)
+            and all(pl.k_in % 64 == 0 and pl.k_in <= 512 and pl.n_out % 128 == 0 and pl.n_out <= 512
+                    and pl.bias is not None and pl.W16 is not None for pl, _ in stages))
 
 
 def row_mlp(segments: Sequence, stages: Sequence, epilogue: int, out: torch.Tensor, rows: int,
             gain=None, beta=None, resid=None, seg_id=None, alpha: float = 1.0,
-            rows_dev: Optional[torch.Tensor] = None, rows_slot: int = 0, row_scale=None):
+            rows_dev: Optional[torch.Tensor] = None, rows_slot: int = 0, row_scale=None, tensor_core: bool = False, fp16: bool = False):
     """One fused launch: concat(gathered segments) -> chained Linear(+GELU) -> epilogue.
 
     segments: [(src [*, width] fp32, idx int32 [rows] or None), ...]
@@ -201,7 +212,11 @@ def row_mlp(segments: Sequence, stages: Sequence, epilogue: int, out: torch.Tens
     d.row_scale = _ptr(row_scale)
     d.out = _ptr(out)
     d.rows_dev, d.rows_slot, d.rows_cap = _ptr(rows_dev), rows_slot, int(rows)
-    check(lib().rmp_row_mlp(C.byref(d), _stream()), "rmp_row_mlp")
+    if tensor_core:
+        w16 = (C.c_void_p * len(stages))(*[_ptr(pl.W16h if fp16 else pl.W16) for pl, _ in stages])
+        check(lib().rmp_row_mlp_tc(C.byref(d), C.cast(w16, C.c_void_p), int(fp16), _stream()), "rmp_row_mlp_tc")
+    else:
+        check(lib().rmp_row_mlp(C.byref(d), _stream()), "rmp_row_mlp")
     return out
 
 
@@ -396,7 +411,7 @@ def readout_head_masked(h, weight, bias, row_mask, temperature: float = 0.0, see
     return logits, probs, samples
 
 
-__all__ = ["ResGraph", "res_graph", "res_edge_rows", "res_raw_features", "graph_norm", "res_attention", "scale_rows",
+__all__ = ["tc_eligible", "ResGraph", "res_graph", "res_edge_rows", "res_raw_features", "graph_norm", "res_attention", "scale_rows",
            "readout_head_masked", "EPI_RESID_ADD", "Graph", "PackedLinear", "edge_embed_bf16", "pack_edge_embedding", "edge_mlp_bf16", "node_mlp_bf16", "knn", "build_graph", "raw_features", "pack_linear", "row_mlp",
            "add_layernorm", "readout_head", "cast_bf16", "EPI_STORE", "EPI_NORMALIZE", "EPI_RESID_LN",
            "EPI_SEGSUM", "HIDDEN", "NODE_RAW", "EDGE_RAW", "MAX_K"]

@@ -135,6 +135,8 @@ class RNAMPNN(_Base):
         self.test_step_outputs = {'test_loss': [], 'correct': [], 'len': [], 'recovery_rates': []}
         self._engine = None
         self._engine_key = None
+        # "fp32": CUDA-core kernels, 1e-4 logit parity; "bf16": Linear stacks on tcgen05 tensor cores, 2e-2 budget
+        self.precision_mode = os.environ.get("RMPNN_PRECISION", "fp32")
 
     @staticmethod
     def mix_loss(valid_probs, valid_sequences):
@@ -148,10 +150,13 @@ class RNAMPNN(_Base):
     # ------------------------------------------------------------------ fused engine
     def engine(self) -> RNAMPNNEngine:
         """Kernel-layout weights, rebuilt whenever a parameter changed or moved."""
+        from rmpnn_b200 import _lib
         params = list(self.parameters())
-        key = tuple((p.data_ptr(), p._version) for p in params)
+        key = (tuple((p.data_ptr(), p._version) for p in params), self.precision_mode)
         if self._engine is None or key != self._engine_key:
-            self._engine = RNAMPNNEngine.from_config(self.state_dict(), self.hparams, device=params[0].device)
+            prec = _lib.PREC_BF16 if self.precision_mode == "bf16" else _lib.PREC_FP32
+            self._engine = RNAMPNNEngine.from_config(self.state_dict(), self.hparams, device=params[0].device,
+                                                     precision=prec)
             self._engine_key = key
         return self._engine
 

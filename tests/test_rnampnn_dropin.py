@@ -108,6 +108,19 @@ def test_model_forward_matches_reference(rgolden):
 
 
 @gpu
+def test_model_bf16_mode_within_budget():
+    """RNAMPNN with precision_mode = "bf16" (RMPNN_PRECISION=bf16): tensor-core Linear stacks, 2e-2 logit budget."""
+    cfg = RNAMPNNConfig()
+    coords, _, mask = synthetic_backbones(3, 90, 91, lengths=[90, 61, 7], atoms=7)
+    m = _model(cfg, 42, "cuda").eval()
+    m.precision_mode = "bf16"
+    with torch.no_grad():
+        logits = m(coords.cuda(), mask.cuda())
+    ref = O.forward(make_rnampnn_state_dict(cfg, 42), coords, mask, cfg)
+    assert (logits.cpu() - ref["logits"]).abs().max() < 2e-2
+
+
+@gpu
 def test_res_feature_module(rgolden):
     from rnampnn.model.feature import ResFeature
     coords, mask, cfg = rgolden["coords"], rgolden["mask"], rgolden["config"]
