@@ -134,6 +134,8 @@ typedef struct rmp_mlp_desc {
     const float*   seg_src[RMP_MAX_SEGS];
     const int32_t* seg_idx[RMP_MAX_SEGS];
     int32_t        seg_width[RMP_MAX_SEGS];
+    int32_t        seg_bf16[RMP_MAX_SEGS];  /* tensor-core arm only: segment rows are bf16 (a side copy written by
+                                               out_bf16 / rmp_graph_norm), gathered with 256-bit loads, no conversion */
     int32_t        num_segs;
     /* stages */
     const float*   Wt[RMP_MAX_STAGES];      /* [k_pad][n_out] */
@@ -152,6 +154,7 @@ typedef struct rmp_mlp_desc {
     const float*   row_scale;               /* optional [rows]: STORE / SEGSUM multiply row r's result by it
                                                (row masks, 1/valid-neighbour-count; rnampnn/model/mpnn.py:192,219) */
     float*         out;
+    void*          out_bf16;                /* tensor-core arm, STORE / RESID_ADD: optional bf16 copy of the result rows */
     /* rows: device count (rows_dev[rows_slot]) bounded by rows_cap */
     const int32_t* rows_dev;
     int32_t        rows_slot;
@@ -222,7 +225,8 @@ int rmp_res_raw_features(const float* coords, const float* mask, const int64_t* 
  *   zero_b != 0 re-zeroes b after it is read (b doubles as the segmented-sum buffer of the message kernel).
  *   stats_ws: caller workspace of B*257 doubles. */
 int rmp_graph_norm(const float* a, float* b, const float* mask, int B, int N, int n_total,
-                   const float* scale, const float* shift, int zero_b, double* stats_ws, float* out, void* stream);
+                   const float* scale, const float* shift, int zero_b, double* stats_ws, float* out,
+                   void* out_bf16 /* optional bf16 copy of out for the tensor-core gathers, or NULL */, void* stream);
 
 /* a-15.  Replaces nn.MultiheadAttention(query=key=value=x, key_padding_mask=~mask) inside RNABert.forward,
  * rnampnn/model/functional.py:161-168, between in_proj and out_proj (both run on rmp_row_mlp).
@@ -254,6 +258,9 @@ int rmp_row_mlp_bf16(const rmp_mlp_desc* desc, const void* const* W_bf16, void* 
 #define RMP_OPERAND_BF16 0
 #define RMP_OPERAND_FP16 1
 int rmp_row_mlp_tc(const rmp_mlp_desc* desc, const void* const* W_16, int operand_format, void* stream);
+/* tuning aid: int64 [500] device buffer receiving (tag, clock64) pairs of CTA 0's first epilogue thread of every
+ * following rmp_row_mlp_tc launch (scripts/rowmlp_tc_timeline.py); NULL disables it */
+void rmp_set_row_tc_timeline(void* buf);
 
 /* ------------------------------------------------------------------ bf16 tensor-core layer path
  * (tcgen05 / TMEM / TMA).  Declared here, implemented in layer_tc.cu.

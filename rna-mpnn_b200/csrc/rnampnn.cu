@@ -7,6 +7,8 @@
 // The Linear stacks run on the fused row-MLP kernel (rowmlp.cu); this file holds what is not a Linear.
 #include "geom.cuh"
 
+#include <cuda_bf16.h>
+
 namespace rmp {
 
 constexpr int kMaxAtoms = 7;
@@ -168,70 +170,112 @@ __global__ void __launch_bounds__(kEdgeTile) res_cross_kernel(const float* __res
 //           out = ((x - mean)/sqrt(var + 1e-6) * scale + shift) * mask
 // x = a + b fuses the residual adds that precede every GraphNorm in the reference (mpnn.py:222, functional.py:165).
 // --------------------------------------------------------------------------------
-constexpr int kGnRows = 64;       // rows per stats block
+constexpr int kGnRows = 32;       // rows per block (both kernels)
 
-__global__ void __launch_bounds__(128) graph_norm_stats_kernel(const float* __restrict__ a, const float* __restrict__ b,
+__global__ void __launch_bounds__(256) graph_norm_stats_kernel(const float* __restrict__ a, const float* __restrict__ b,
                                                               const float* __restrict__ mask, int N,
                                                               double* __restrict__ stats) {
-    const int g = blockIdx.y, c = threadIdx.x;
-    const int r0 = blockIdx.x * kGnRows;
-    const int r1 = min(N, r0 + kGnRows);
-    double s1 = 0.0, s2 = 0.0;
-    int n = 0;
-    for (int r = r0; r < r1; ++r) {
-        const size_t row = (size_t)g * N + r;
-        if (mask[row] == 0.0f) continue;
-        float x = a[row * 128 + c];
-        if (b) x += b[row * 128 + c];
-        s1 += (double)x;
-        s2 += (double)x * (double)x;
-        ++n;
+    __shared__ double s_part[2][128];
+    __shared__ int s_cnt;
+    const int g = blockIdx.y, c = threadIdx.x & 127, rh = threadIdx.x >> 7;
+    const int r0 = blockIdx.x * kGnRows + rh * 16;
+    const size_t base = (size_t)g * N;
+    // 16 rows per thread, every load issued before the first use
+    float x[16];
+    unsigned ok = 0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        const int r = r0 + q;
+        x[q] = 0.f;
+        if (r < N && mask[base + r] != 0.0f) {
+            ok |= 1u << q;
+            x[q] = a[(base + r) * 128 + c];
+        }
     }
-    if (n == 0) return;
-    double* st = stats + (size_t)g * 257;
-    atomicAdd(st + c, s1);
-    atomicAdd(st + 128 + c, s2);
-    if (c == 0) atomicAdd(st + 256, (double)n);
+    if (b) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q)
+            if (ok >> q & 1) x[q] += b[(base + r0 + q) * 128 + c];
+    }
+    double s1 = 0.0, s2 = 0.0;
+#pragma unroll
+    for (int q = 0; q < 16; ++q) {
+        s1 += (double)x[q];                                   // masked rows hold exact zeros
+        s2 += (double)x[q] * (double)x[q];
+    }
+    if (rh == 1) { s_part[0][c] = s1; s_part[1][c] = s2; }
+    if (threadIdx.x == 128) s_cnt = __popc(ok);
+    __syncthreads();
+    if (rh == 0) {
+        s1 += s_part[0][c];
+        s2 += s_part[1][c];
+        const int n = __popc(ok) + s_cnt;
+        if (n == 0) return;
+        double* st = stats + (size_t)g * 257;
+        atomicAdd(st + c, s1);
+        atomicAdd(st + 128 + c, s2);
+        if (c == 0) atomicAdd(st + 256, (double)n);
+    }
 }
 
 __global__ void __launch_bounds__(256) graph_norm_apply_kernel(const float* __restrict__ a, float* __restrict__ b,
                                                               const float* __restrict__ mask, int N, int n_total,
                                                               const double* __restrict__ stats,
                                                               const float* __restrict__ scale,
-                                                              const float* __restrict__ shift, int zero_b, size_t rows,
-                                                              float* __restrict__ out) {
-    const size_t row = (size_t)blockIdx.x * 8 + (threadIdx.x >> 5);
-    if (row >= rows) return;
-    const int lane = threadIdx.x & 31;
-    const int g = (int)(row / N);
-    float4* op = reinterpret_cast<float4*>(out + row * 128) + lane;
-    float4* bp = b ? reinterpret_cast<float4*>(b + row * 128) + lane : nullptr;
-    if (mask[row] == 0.0f) {
-        *op = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (bp && zero_b) *bp = make_float4(0.f, 0.f, 0.f, 0.f);
-        return;
+                                                              const float* __restrict__ shift, int zero_b,
+                                                              float* __restrict__ out, uint2* __restrict__ out16) {
+    __shared__ __align__(16) float s_mean[128], s_mul[128];     // mean, standard deviation
+    const int g = blockIdx.y;
+    if (threadIdx.x < 128) {                                   // per-channel statistics of this graph, once per block
+        const int c = threadIdx.x;
+        const double* st = stats + (size_t)g * 257;
+        const double cnt = st[256];
+        const double n = cnt > 0.0 ? cnt : 1.0;
+        const double mean = st[c] / n;
+        double var = (st[128 + c] - n * mean * mean + ((double)n_total - cnt) * mean * mean) / n;
+        var = var > 0.0 ? var : 0.0;
+        const float sd = sqrtf((float)var + 1e-6f);
+        s_mean[c] = (float)mean;
+        s_mul[c] = sd;
     }
-    float4 x = reinterpret_cast<const float4*>(a + row * 128)[lane];
-    if (bp) {
-        const float4 y = *bp;
-        x.x += y.x; x.y += y.y; x.z += y.z; x.w += y.w;
-        if (zero_b) *bp = make_float4(0.f, 0.f, 0.f, 0.f);
-    }
-    const double* st = stats + (size_t)g * 257;
-    const double n = st[256] > 0.0 ? st[256] : 1.0;
-    const double n_pad = (double)n_total - st[256];
-    float xs[4] = {x.x, x.y, x.z, x.w}, ys[4];
+    __syncthreads();
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const float4 mu = reinterpret_cast<const float4*>(s_mean)[lane];
+    const float4 iv = reinterpret_cast<const float4*>(s_mul)[lane];
+    const float4 sc = __ldg(reinterpret_cast<const float4*>(scale) + lane);
+    const float4 sh = __ldg(reinterpret_cast<const float4*>(shift) + lane);
+    const size_t base = (size_t)g * N;
+    float4 x[4], y[4];
+    bool live[4], inside[4];
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const int c = lane * 4 + q;
-        const double mean = st[c] / n;
-        double var = (st[128 + c] - n * mean * mean + n_pad * mean * mean) / n;
-        var = var > 0.0 ? var : 0.0;
-        const float mf = (float)mean;
-        const float sd = sqrtf((float)var + 1e-6f);
-        ys[q] = (xs[q] - mf) / sd * __ldg(scale + c) + __ldg(shift + c);
+        const int r = blockIdx.x * kGnRows + w * 4 + q;
+        inside[q] = r < N;
+        live[q] = inside[q] && mask[base + r] != 0.0f;
+        x[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+        y[q] = x[q];
+        if (live[q]) x[q] = reinterpret_cast<const float4*>(a + (base + r) * 128)[lane];
+        if (live[q] && b) y[q] = reinterpret_cast<const float4*>(b + (base + r) * 128)[lane];
     }
-    *op = make_float4(ys[0], ys[1], ys[2], ys[3]);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        if (!inside[q]) continue;
+        const size_t row = base + blockIdx.x * kGnRows + w * 4 + q;
+        float4 o = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (live[q]) {
+            // (x - mean) / sd * scale + shift, the division as in the reference (functional.py:42-43)
+            o.x = (x[q].x + y[q].x - mu.x) / iv.x * sc.x + sh.x;
+            o.y = (x[q].y + y[q].y - mu.y) / iv.y * sc.y + sh.y;
+            o.z = (x[q].z + y[q].z - mu.z) / iv.z * sc.z + sh.z;
+            o.w = (x[q].w + y[q].w - mu.w) / iv.w * sc.w + sh.w;
+        }
+        reinterpret_cast<float4*>(out + row * 128)[lane] = o;
+        if (out16) {
+            const __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
+            out16[row * 32 + lane] = make_uint2(*reinterpret_cast<const unsigned*>(&lo), *reinterpret_cast<const unsigned*>(&hi));
+        }
+        if (b && zero_b) reinterpret_cast<float4*>(b + row * 128)[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
 }
 
 // --------------------------------------------------------------------------------
@@ -383,7 +427,7 @@ extern "C" int rmp_res_raw_features(const float* coords, const float* mask, cons
 
 extern "C" int rmp_graph_norm(const float* a, float* b, const float* mask, int B, int N, int n_total,
                               const float* scale, const float* shift, int zero_b, double* stats_ws, float* out,
-                              void* stream) {
+                              void* out_bf16, void* stream) {
     RMP_REQUIRE(a && mask && scale && shift && stats_ws && out, RMP_E_ARG, "rmp_graph_norm: null pointer");
     RMP_REQUIRE(B > 0 && N > 0 && n_total >= N, RMP_E_ARG, "rmp_graph_norm: bad sizes (n_total must be >= N)");
     RMP_REQUIRE(aligned16(a) && aligned16(out) && (!b || aligned16(b)), RMP_E_ALIGN, "rmp_graph_norm: 16-byte alignment");
@@ -391,10 +435,9 @@ extern "C" int rmp_graph_norm(const float* a, float* b, const float* mask, int B
     cudaStream_t st = (cudaStream_t)stream;
     cudaError_t e = cudaMemsetAsync(stats_ws, 0, (size_t)B * 257 * sizeof(double), st);
     if (e != cudaSuccess) { set_error("rmp_graph_norm: memset: %s", cudaGetErrorString(e)); return (int)e; }
-    graph_norm_stats_kernel<<<dim3(ceil_div(N, kGnRows), B), 128, 0, st>>>(a, b, mask, N, stats_ws);
-    const size_t rows = (size_t)B * N;
-    graph_norm_apply_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(a, b, mask, N, n_total, stats_ws, scale, shift,
-                                                                         zero_b, rows, out);
+    graph_norm_stats_kernel<<<dim3(ceil_div(N, kGnRows), B), 256, 0, st>>>(a, b, mask, N, stats_ws);
+    graph_norm_apply_kernel<<<dim3(ceil_div(N, kGnRows), B), 256, 0, st>>>(a, b, mask, N, n_total, stats_ws, scale, shift,
+                                                                            zero_b, out, reinterpret_cast<uint2*>(out_bf16));
     return check_launch("rmp_graph_norm", 2);
 }
 

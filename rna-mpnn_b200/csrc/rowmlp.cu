@@ -367,6 +367,7 @@ extern "C" int rmp_row_mlp(const rmp_mlp_desc* dp, void* stream) {
     int k0 = 0;
     for (int s = 0; s < d.num_segs; ++s) {
         RMP_REQUIRE(d.seg_src[s] && d.seg_width[s] > 0, RMP_E_ARG, "rmp_row_mlp: segment %d", s);
+        RMP_REQUIRE(!d.seg_bf16[s], RMP_E_ARG, "rmp_row_mlp: bf16 segments are a tensor-core arm feature");
         RMP_REQUIRE((d.seg_width[s] & 3) != 0 || aligned16(d.seg_src[s]), RMP_E_ALIGN,
                     "rmp_row_mlp: segment %d not 16-byte aligned", s);
         k0 += d.seg_width[s];

@@ -71,6 +71,14 @@ struct RowParams {
     float* out;
     int n_rows;
     int a_kblocks;                                // K-blocks of the activation buffer (max K over stages / 64)
+    // the input as 128-wide pieces (a segment of width w contributes w/128 of them); used when there are <= 3
+    long long* timeline;                          // optional clock64 trace of CTA 0's first epilogue thread (tuning aid)
+    int a_pieces;
+    const float* piece_src[3];
+    const int32_t* piece_idx[3];
+    int piece_stride[3];
+    int all_bf16;                                 // every piece is a bf16 side copy: 256-bit gathers, no conversion
+    uint16_t* out16;                              // optional bf16 copy of the STORE / RESID_ADD result
     uint32_t tmem_cols;
 };
 struct alignas(8) RowBarriers {
@@ -158,6 +166,12 @@ row_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
         const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
         const int ew = warp - 2;                                   // 8 warps x 16 rows in the prologue
         uint32_t ph_acc = 0;
+        int tl_n = 0;
+        const bool tl_on = p.timeline != nullptr && blockIdx.x == 0 && threadIdx.x == 64;
+        auto stamp = [&](int tag) {
+            if (tl_on && tl_n < 200) { p.timeline[tl_n * 2] = tag; p.timeline[tl_n * 2 + 1] = clock64(); ++tl_n; }
+        };
+        stamp(1);
 
         for (int i = 0; i < my_tiles; ++i) {
             const int tile = blockIdx.x + i * gridDim.x;
@@ -165,6 +179,78 @@ row_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
             const bool valid = r < p.n_rows;
             // ---- prologue: gather + concat + bf16 -> swizzled A operand.  One warp per row, a lane holds 4 consecutive
             //      channels of every 128-wide piece; the loads of 8 rows are issued before the first use ----
+            if (p.all_bf16) {
+                // bf16 side copies (h16 / e16): a 256-byte row is 8 lanes x 32 bytes, one LDG.256 instruction brings 4
+                // rows; the 6 loads of 8 rows x 3 pieces are all in flight before the first use (two such batches)
+                const int sub = lane >> 3, part = lane & 7;           // row inside the group of 4, 32-byte part of the row
+                for (int g0 = 0; g0 < 4; g0 += 2) {
+                uint32_t xr[3][2][8];
+#pragma unroll
+                for (int pc = 0; pc < 3; ++pc) {
+                    if (pc < p.a_pieces) {
+                        const uint16_t* src = reinterpret_cast<const uint16_t*>(p.piece_src[pc]);
+                        const int32_t* idx = p.piece_idx[pc];
+#pragma unroll
+                        for (int gq = 0; gq < 2; ++gq) {
+                            const int rg = tile * kTileM + ew * 16 + (g0 + gq) * 4 + sub;
+#pragma unroll
+                            for (int q = 0; q < 8; ++q) xr[pc][gq][q] = 0u;
+                            if (rg < p.n_rows)
+                                ldg256(src + (size_t)(idx ? __ldg(idx + rg) : rg) * 128 + part * 16, xr[pc][gq]);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int pc = 0; pc < 3; ++pc) {
+                    if (pc < p.a_pieces) {
+#pragma unroll
+                        for (int gq = 0; gq < 2; ++gq) {
+                            const int rl = ew * 16 + (g0 + gq) * 4 + sub;
+                            uint8_t* kb = sA + (2 * pc + (part >> 2)) * kKBlockBytes;
+                            const int j = (2 * part) & 7;
+                            *reinterpret_cast<uint4*>(kb + sw128_chunk(rl, j)) =
+                                make_uint4(xr[pc][gq][0], xr[pc][gq][1], xr[pc][gq][2], xr[pc][gq][3]);
+                            *reinterpret_cast<uint4*>(kb + sw128_chunk(rl, j + 1)) =
+                                make_uint4(xr[pc][gq][4], xr[pc][gq][5], xr[pc][gq][6], xr[pc][gq][7]);
+                        }
+                    }
+                }
+                }
+            } else if (p.a_pieces <= 3) {
+                // up to three 128-wide pieces (the gathered [h_i | h_j | e] input): all 12 row loads of a 4-row batch
+                // are in flight before the first use, so a batch costs one L2 round trip instead of one per piece
+                for (int r0 = 0; r0 < 16; r0 += 4) {
+                    float4 xs[3][4];
+#pragma unroll
+                    for (int pc = 0; pc < 3; ++pc) {
+                        if (pc < p.a_pieces) {
+                            const float* src = p.piece_src[pc];
+                            const int32_t* idx = p.piece_idx[pc];
+                            const int wdt = p.piece_stride[pc];
+#pragma unroll
+                            for (int rr = 0; rr < 4; ++rr) {
+                                const int rg = tile * kTileM + ew * 16 + r0 + rr;
+                                xs[pc][rr] = make_float4(0.f, 0.f, 0.f, 0.f);
+                                if (rg < p.n_rows)
+                                    xs[pc][rr] = __ldg(reinterpret_cast<const float4*>(
+                                                           src + (size_t)(idx ? __ldg(idx + rg) : rg) * wdt) + lane);
+                            }
+                        }
+                    }
+#pragma unroll
+                    for (int pc = 0; pc < 3; ++pc) {
+                        if (pc < p.a_pieces) {
+#pragma unroll
+                            for (int rr = 0; rr < 4; ++rr) {
+                                const int rl = ew * 16 + r0 + rr;
+                                *reinterpret_cast<uint2*>(sA + (2 * pc + (lane >> 4)) * kKBlockBytes +
+                                                          sw128_chunk(rl, (lane & 15) >> 1) + (lane & 1) * 8) =
+                                    make_uint2(pack16<F16>(xs[pc][rr].x, xs[pc][rr].y), pack16<F16>(xs[pc][rr].z, xs[pc][rr].w));
+                            }
+                        }
+                    }
+                }
+            } else {
             for (int r0 = 0; r0 < 16; r0 += 8) {
                 int kb0 = 0;
                 for (int sg = 0; sg < p.num_segs; ++sg) {
@@ -196,6 +282,8 @@ row_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
                     kb0 += wdt >> 6;
                 }
             }
+            }
+            stamp(2);
             tc_fence_before();
             fence_proxy_async();
             mbar_arrive(&bars->act_ready);
@@ -214,6 +302,7 @@ row_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
                 }
                 mbar_wait(&bars->acc_full, ph_acc); ph_acc ^= 1;
                 tc_fence_after();
+                stamp(10 + s);
                 for (int ch = 0; ch < ncols / 32; ++ch) {
                     const int col0 = cb + ch * 32;
                     float v[32];
@@ -256,15 +345,25 @@ row_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
                         }
 #pragma unroll
                         for (int q = 0; q < 4; ++q) stg256f(dst + 8 * q, &v[8 * q]);
+                        if (p.out16) {
+                            uint32_t pk[16];
+#pragma unroll
+                            for (int q = 0; q < 16; ++q) pk[q] = pack_bf16(v[2 * q], v[2 * q + 1]);
+                            stg256u(p.out16 + (size_t)r * stg.N + col0, &pk[0]);
+                            stg256u(p.out16 + (size_t)r * stg.N + col0 + 16, &pk[8]);
+                        }
                     }
                 }
                 tc_fence_before();
+                stamp(20 + s);
                 if (!last) {
                     fence_proxy_async();
                     mbar_arrive(&bars->act_ready);
                 }
             }
         }
+        stamp(3);
+        if (tl_on) p.timeline[499] = tl_n;
     }
     tc_fence_before();
     __syncthreads();
@@ -275,6 +374,9 @@ row_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
 }  // namespace rmp
 
 using namespace rmp;
+
+static void* g_row_tc_timeline = nullptr;
+extern "C" void rmp_set_row_tc_timeline(void* buf) { g_row_tc_timeline = buf; }
 
 extern "C" int rmp_row_mlp_tc(const rmp_mlp_desc* dp, const void* const* W_bf16, int operand_format, void* stream) {
     RMP_REQUIRE(dp && W_bf16, RMP_E_ARG, "rmp_row_mlp_bf16: null descriptor");
@@ -291,7 +393,10 @@ extern "C" int rmp_row_mlp_tc(const rmp_mlp_desc* dp, const void* const* W_bf16,
     tc::RowParams p;
     memset(&p, 0, sizeof(p));
     int k0 = 0;
+    int n_bf16 = 0;
     for (int s = 0; s < d.num_segs; ++s) {
+        n_bf16 += d.seg_bf16[s] != 0;
+        RMP_REQUIRE(!d.seg_bf16[s] || d.seg_width[s] == 128, RMP_E_SHAPE, "rmp_row_mlp_bf16: bf16 segment %d must be 128 wide", s);
         RMP_REQUIRE(d.seg_src[s] && d.seg_width[s] > 0 && d.seg_width[s] % 128 == 0, RMP_E_SHAPE,
                     "rmp_row_mlp_bf16: segment %d width %d must be a multiple of 128", s, d.seg_width[s]);
         RMP_REQUIRE(aligned16(d.seg_src[s]), RMP_E_ALIGN, "rmp_row_mlp_bf16: segment %d not 16-byte aligned", s);
@@ -299,6 +404,20 @@ extern "C" int rmp_row_mlp_tc(const rmp_mlp_desc* dp, const void* const* W_bf16,
         k0 += d.seg_width[s];
     }
     p.num_segs = d.num_segs;
+    p.a_pieces = k0 / 128;
+    RMP_REQUIRE(n_bf16 == 0 || (n_bf16 == d.num_segs && p.a_pieces <= 3 && operand_format == RMP_OPERAND_BF16), RMP_E_SHAPE,
+                "rmp_row_mlp_bf16: bf16 segments need all (<= 3) segments bf16 and bf16 operands");
+    p.all_bf16 = n_bf16 > 0;
+    p.out16 = reinterpret_cast<uint16_t*>(d.out_bf16);
+    RMP_REQUIRE(!d.out_bf16 || (d.epilogue != RMP_EPI_SEGSUM && aligned16(d.out_bf16)), RMP_E_ARG,
+                "rmp_row_mlp_bf16: out_bf16 goes with STORE / RESID_ADD and must be 16-byte aligned");
+    if (p.a_pieces <= 3) {
+        int pc = 0;
+        for (int s = 0; s < d.num_segs; ++s)
+            for (int o = 0; o < d.seg_width[s]; o += 128, ++pc) {
+                p.piece_src[pc] = d.seg_src[s] + o; p.piece_idx[pc] = d.seg_idx[s]; p.piece_stride[pc] = d.seg_width[s];
+            }
+    }
     RMP_REQUIRE(k0 == d.k_in[0], RMP_E_SHAPE, "rmp_row_mlp_bf16: segments give %d inputs, stage 0 expects %d", k0, d.k_in[0]);
     int kmax = 0, nmax = 0;
     CUtensorMap maps[tc::kRowMaxStages];
@@ -326,6 +445,7 @@ extern "C" int rmp_row_mlp_tc(const rmp_mlp_desc* dp, const void* const* W_bf16,
     RMP_REQUIRE(aligned16(d.out), RMP_E_ALIGN, "rmp_row_mlp_bf16: out not 16-byte aligned");
     p.resid = d.resid; p.seg_id = d.seg_id; p.row_scale = d.row_scale; p.alpha = d.alpha; p.out = d.out;
     p.n_rows = d.rows_cap;
+    p.timeline = reinterpret_cast<long long*>(g_row_tc_timeline);
     p.a_kblocks = kmax / 64;
     p.tmem_cols = nmax <= 128 ? 128u : (nmax <= 256 ? 256u : 512u);
     const size_t smem = 1024 + (size_t)p.a_kblocks * tc::kKBlockBytes + (size_t)tc::kRowRing * tc::kRowSlotBytes +

@@ -24,6 +24,7 @@ class MlpDesc(C.Structure):
         ("seg_src", C.c_void_p * MAX_SEGS),
         ("seg_idx", C.c_void_p * MAX_SEGS),
         ("seg_width", C.c_int32 * MAX_SEGS),
+        ("seg_bf16", C.c_int32 * MAX_SEGS),
         ("num_segs", C.c_int32),
         ("Wt", C.c_void_p * MAX_STAGES),
         ("bias", C.c_void_p * MAX_STAGES),
@@ -39,6 +40,7 @@ class MlpDesc(C.Structure):
         ("alpha", C.c_float),
         ("row_scale", C.c_void_p),
         ("out", C.c_void_p),
+        ("out_bf16", C.c_void_p),
         ("rows_dev", C.c_void_p),
         ("rows_slot", C.c_int32),
         ("rows_cap", C.c_int32),
@@ -64,7 +66,7 @@ SIGNATURES = {
     "rmp_res_graph": [P, P, I, I, I, I, P, P, P],
     "rmp_res_edge_rows": [P, P, I, I, I, P, P, P, P, P],
     "rmp_res_raw_features": [P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P],
-    "rmp_graph_norm": [P, P, P, I, I, I, P, P, I, P, P, P],
+    "rmp_graph_norm": [P, P, P, I, I, I, P, P, I, P, P, P, P],
     "rmp_res_attention": [P, P, I, I, I, I, P, P],
     "rmp_scale_rows": [P, P, I64, I, P],
     "rmp_readout_head_masked": [P, I, P, P, P, F, U64, I, P, P, P, P],

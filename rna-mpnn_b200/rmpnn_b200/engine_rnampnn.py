@@ -122,7 +122,7 @@ class RNAMPNNEngine:
 
     # ---- building blocks ----------------------------------------------------------
     @staticmethod
-    def _mlp(segments, stages, rows, row_scale=None, tensor_core: bool = False, fp16: bool = False):
+    def _mlp(segments, stages, rows, row_scale=None, tensor_core: bool = False, fp16: bool = False, out_bf16=None):
         """Chained Linear(+GELU) stages -> fp32 [rows, n_out], result rows times ``row_scale``.  With ``tensor_core``
         the stages the tcgen05 kernel can take run on it; a leading stage it cannot take (raw geometry, K = 28 / 90)
         runs on the fp32 kernel first."""
@@ -140,7 +140,7 @@ class RNAMPNNEngine:
                 last = gi == len(groups) - 1 and s0 + ops._lib.MAX_STAGES >= len(group)
                 out = torch.empty(rows, chunk[-1][0].n_out, dtype=torch.float32, device=dev)
                 ops.row_mlp(segments, chunk, ops.EPI_STORE, out, rows, row_scale=row_scale if last else None,
-                            tensor_core=tc, fp16=fp16)
+                            tensor_core=tc, fp16=fp16, out_bf16=out_bf16 if (last and tc) else None)
                 segments = [(out, None)]
         return out
 
@@ -177,10 +177,15 @@ class RNAMPNNEngine:
             edge_index = ops.res_graph(coords, mask, self.K)
         g = ops.res_edge_rows(edge_index, mask)
         raw, edge_raw = ops.res_raw_features(coords, mask, edge_index, self.inside, self.cross)
-        e = self._mlp([(edge_raw, None)], self.w.edge_embed, B * N * g.K, row_scale=g.edge_keep, tensor_core=self.tc)
+        # bf16 arm: h and e carry bf16 side copies (written by the producing kernels' epilogues) that the message /
+        # edge kernels gather with 256-bit loads; the fp32 tensors stay the masters (residuals, GraphNorm)
+        self._e16 = torch.empty(B * N * g.K, ops.HIDDEN, dtype=torch.bfloat16, device=raw.device) if self.tc else None
+        e = self._mlp([(edge_raw, None)], self.w.edge_embed, B * N * g.K, row_scale=g.edge_keep, tensor_core=self.tc,
+                      out_bf16=self._e16)
         x = self.bert(self.w.embed_bert, raw, mask_flat, B, N, self.embed_heads, pre=[(self.w.raw_project, False)],
                       tc=self.tc and self.raw_stacks != "fp32", fp16=self.raw_stacks == "fp16")
-        h = ops.graph_norm(x, None, mask_flat, B, N, *self.w.embed_gn)
+        self._h16 = torch.empty(B * N, ops.HIDDEN, dtype=torch.bfloat16, device=raw.device) if self.tc else None
+        h = ops.graph_norm(x, None, mask_flat, B, N, *self.w.embed_gn, out_bf16=self._h16)
         return raw, h, e, g
 
     def layer(self, l: int, h, e, g: ops.ResGraph, mask_flat, agg=None):
@@ -193,14 +198,19 @@ class RNAMPNNEngine:
             ev = (torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True))
             ev[0].record(torch.cuda.current_stream())
         seg = [(h, g.ctr_row), (h, g.nbr_row), (e, None)]
-        # masked mean of the messages: sum_k valid_k * m_k / max(#valid, 1)  (mpnn.py:191-192, :212-219)
         tc = self.tc and ops.tc_eligible(seg, lw.message) and ops.tc_eligible(seg, lw.edge)
+        h16 = getattr(self, "_h16", None) if tc else None
+        e16 = getattr(self, "_e16", None) if tc else None
+        side = h16 is not None and e16 is not None and h16.shape[0] == h.shape[0] and e16.shape[0] == e.shape[0]
+        if side:
+            seg = [(h16, g.ctr_row), (h16, g.nbr_row), (e16, None)]
+        # masked mean of the messages: sum_k valid_k * m_k / max(#valid, 1)  (mpnn.py:191-192, :212-219)
         ops.row_mlp(seg, lw.message, ops.EPI_SEGSUM, agg, edges, seg_id=g.ctr_row, alpha=1.0, row_scale=g.edge_w,
                     tensor_core=tc)
-        h = ops.graph_norm(h, agg, mask_flat, g.B, g.N, *lw.gn, zero_b=True)
+        h = ops.graph_norm(h, agg, mask_flat, g.B, g.N, *lw.gn, zero_b=True, out_bf16=h16 if side else None)
         # e += MLP([h_i | h_j | e]) with the UPDATED h, on every slot (mpnn.py:229-265)
-        ops.row_mlp([(h, g.ctr_row), (h, g.nbr_row), (e, None)], lw.edge, ops.EPI_RESID_ADD, e, edges, resid=e,
-                    tensor_core=tc)
+        seg = [(h16, g.ctr_row), (h16, g.nbr_row), (e16, None)] if side else [(h, g.ctr_row), (h, g.nbr_row), (e, None)]
+        ops.row_mlp(seg, lw.edge, ops.EPI_RESID_ADD, e, edges, resid=e, tensor_core=tc, out_bf16=e16 if side else None)
         if self.kernel_timer is not None:
             ev[1].record(torch.cuda.current_stream())
             self.kernel_timer.append(ev)

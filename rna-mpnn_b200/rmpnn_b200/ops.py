@@ -177,14 +177,14 @@ def pack_linear(weight: torch.Tensor, bias: Optional[torch.Tensor]) -> PackedLin
 
 def tc_eligible(segments: Sequence, stages: Sequence) -> bool:
     """Shapes the tcgen05 row-MLP kernel (rmp_row_mlp_bf16) takes."""
-    return (all(src.shape[-1] % 128 == 0 for src, _ in segments)
+    return (all(src.shape[-1] % 128 == 0 for src, _ in segments) and len({src.dtype for src, _ in segments}) <= 1
             and all(pl.k_in % 64 == 0 and pl.k_in <= 512 and pl.n_out % 128 == 0 and pl.n_out <= 512
                     and pl.bias is not None and pl.W16 is not None for pl, _ in stages))
 
 
 def row_mlp(segments: Sequence, stages: Sequence, epilogue: int, out: torch.Tensor, rows: int,
             gain=None, beta=None, resid=None, seg_id=None, alpha: float = 1.0,
-            rows_dev: Optional[torch.Tensor] = None, rows_slot: int = 0, row_scale=None, tensor_core: bool = False, fp16: bool = False):
+            rows_dev: Optional[torch.Tensor] = None, rows_slot: int = 0, row_scale=None, tensor_core: bool = False, fp16: bool = False, out_bf16=None):
     """One fused launch: concat(gathered segments) -> chained Linear(+GELU) -> epilogue.
 
     segments: [(src [*, width] fp32, idx int32 [rows] or None), ...]
@@ -196,9 +196,10 @@ def row_mlp(segments: Sequence, stages: Sequence, epilogue: int, out: torch.Tens
     keep = []
     for s, (src, idx) in enumerate(segments):
         _need_cuda(src, idx)
-        assert src.dtype == torch.float32 and src.is_contiguous()
+        assert src.dtype in (torch.float32, torch.bfloat16) and src.is_contiguous()
         assert idx is None or (idx.dtype == torch.int32 and idx.is_contiguous())
         d.seg_src[s], d.seg_idx[s], d.seg_width[s] = _ptr(src), _ptr(idx), src.shape[-1]
+        d.seg_bf16[s] = int(src.dtype == torch.bfloat16)
         keep.append((src, idx))
     d.num_segs = len(segments)
     for s, (pl, gelu) in enumerate(stages):
@@ -210,6 +211,9 @@ def row_mlp(segments: Sequence, stages: Sequence, epilogue: int, out: torch.Tens
     d.alpha = float(alpha)
     assert row_scale is None or (row_scale.dtype == torch.float32 and row_scale.is_contiguous())
     d.row_scale = _ptr(row_scale)
+    _need_cuda(out_bf16)
+    assert out_bf16 is None or (out_bf16.dtype == torch.bfloat16 and out_bf16.is_contiguous())
+    d.out_bf16 = _ptr(out_bf16)
     d.out = _ptr(out)
     d.rows_dev, d.rows_slot, d.rows_cap = _ptr(rows_dev), rows_slot, int(rows)
     if tensor_core:
@@ -363,7 +367,7 @@ def res_raw_features(coords, mask, edge_index, inside=(7, 6, 6), cross=(7, 6, 6)
 
 
 def graph_norm(a, b, mask, B: int, N: int, scale, shift, n_total: Optional[int] = None, zero_b: bool = False,
-               out=None, stats_ws=None):
+               out=None, stats_ws=None, out_bf16=None):
     """``GraphNormalization`` (rnampnn/model/functional.py:18-48) of x = a (+ b) over rows [B*N, 128]."""
     _need_cuda(a, b, mask, scale, shift, out, stats_ws)
     assert a.dtype == torch.float32 and a.is_contiguous() and a.shape[-1] == HIDDEN
@@ -372,7 +376,7 @@ def graph_norm(a, b, mask, B: int, N: int, scale, shift, n_total: Optional[int] 
     if stats_ws is None:
         stats_ws = torch.empty(B * 257, dtype=torch.float64, device=a.device)
     check(lib().rmp_graph_norm(_ptr(a), _ptr(b), _ptr(mask), B, N, int(N if n_total is None else n_total),
-                               _ptr(scale), _ptr(shift), int(zero_b), _ptr(stats_ws), _ptr(out), _stream()),
+                               _ptr(scale), _ptr(shift), int(zero_b), _ptr(stats_ws), _ptr(out), _ptr(out_bf16), _stream()),
           "rmp_graph_norm")
     return out
 
