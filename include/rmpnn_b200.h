@@ -187,6 +187,14 @@ int rmp_readout_head(const float* h, int k_in, const float* W, const float* b,
                      const int32_t* rows_dev, int rows_slot, int rows_cap,
                      float* logits, float* probs, int64_t* samples, void* stream);
 
+/* ------------------------------------------------------------------ device-side collate (section 8f)
+ * Replaces the host collate loops rdesign/utils/data.py:84-119 and rnampnn/utils/data.py:110-142.
+ *   packed    [sum L, A_in, 3] fp32 or fp64 (packed_is_f64): the residues of all structures back to back
+ *   row_start [B] int64: first packed row of each structure of this batch; lengths [B] int32
+ *   X [B,N,A_out,3] fp32: the first A_out atoms, NaN -> 0, zero padded;  mask [B,N] fp32 prefix mask.  N >= max length. */
+int rmp_collate(const void* packed, int packed_is_f64, const int64_t* row_start, const int32_t* lengths,
+                int B, int N, int A_in, int A_out, float* X, float* mask, void* stream);
+
 /* ================================================================== secondary path: rnampnn (a-10 .. a-16)
  * The reference keeps the padded layout end to end: rows are dense residues b*N+i, edges are (row, slot k),
  * edge_index [B,N,K] int64 holds the neighbour's index INSIDE its structure or -1.  The Linear stacks of this

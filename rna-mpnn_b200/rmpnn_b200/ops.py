@@ -304,6 +304,20 @@ def cast_bf16(src: torch.Tensor) -> torch.Tensor:
     return dst
 
 
+def collate(packed: torch.Tensor, row_start: torch.Tensor, lengths: torch.Tensor, N: int, atoms_out: int = 6):
+    """Device-side ``featurize`` (rdesign/utils/data.py:84-119): packed [sum L, A, 3] (fp32 / fp64) + per-structure
+    (row_start int64 [B], lengths int32 [B]) -> X [B,N,atoms_out,3] fp32 (NaN -> 0, zero padded), mask [B,N]."""
+    _need_cuda(packed, row_start, lengths)
+    assert packed.dtype in (torch.float32, torch.float64) and packed.is_contiguous() and packed.dim() == 3
+    assert row_start.dtype == torch.int64 and lengths.dtype == torch.int32
+    B = lengths.shape[0]
+    X = torch.empty(B, N, atoms_out, 3, dtype=torch.float32, device=packed.device)
+    mask = torch.empty(B, N, dtype=torch.float32, device=packed.device)
+    check(lib().rmp_collate(_ptr(packed), int(packed.dtype == torch.float64), _ptr(row_start), _ptr(lengths), B, int(N),
+                            packed.shape[1], int(atoms_out), _ptr(X), _ptr(mask), _stream()), "rmp_collate")
+    return X, mask
+
+
 # =========================================================================== rnampnn (secondary path)
 @dataclass
 class ResGraph:
@@ -415,7 +429,7 @@ def readout_head_masked(h, weight, bias, row_mask, temperature: float = 0.0, see
     return logits, probs, samples
 
 
-__all__ = ["tc_eligible", "ResGraph", "res_graph", "res_edge_rows", "res_raw_features", "graph_norm", "res_attention", "scale_rows",
+__all__ = ["collate", "tc_eligible", "ResGraph", "res_graph", "res_edge_rows", "res_raw_features", "graph_norm", "res_attention", "scale_rows",
            "readout_head_masked", "EPI_RESID_ADD", "Graph", "PackedLinear", "edge_embed_bf16", "pack_edge_embedding", "edge_mlp_bf16", "node_mlp_bf16", "knn", "build_graph", "raw_features", "pack_linear", "row_mlp",
            "add_layernorm", "readout_head", "cast_bf16", "EPI_STORE", "EPI_NORMALIZE", "EPI_RESID_LN",
            "EPI_SEGSUM", "HIDDEN", "NODE_RAW", "EDGE_RAW", "MAX_K"]

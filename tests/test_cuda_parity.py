@@ -283,3 +283,33 @@ def test_error_paths(ops):
     X, S, mask = synthetic_backbones(1, 200, 1)
     with pytest.raises(RuntimeError, match="RMP_MAX_K|exceeds"):
         ops.knn(X.cuda(), mask.cuda(), 150)
+
+
+# --------------------------------------------------------------------------- device-side collate (section 8f)
+@pytest.mark.parametrize("dtype,atoms_out", [(torch.float64, 6), (torch.float32, 7)])
+def test_device_collate_matches_host_featurize(ops, dtype, atoms_out):
+    """rmp_collate against the host collate of the reference (rdesign/utils/data.py:84-119): bit-exact."""
+    from rdesign.utils.data import ATOMS, featurize
+    rng = np.random.default_rng(3)
+    lengths = [17, 1, 40, 23, 40]
+    structs = []
+    for L in lengths:
+        c = rng.normal(size=(L, 7, 3)) * 30
+        c[rng.random((L, 7)) < 0.05] = np.nan                      # missing atoms
+        structs.append(c.astype(np.float64 if dtype == torch.float64 else np.float32))
+    packed = torch.from_numpy(np.concatenate(structs, 0)).cuda()
+    starts = np.concatenate([[0], np.cumsum(lengths)[:-1]])
+    order = [3, 0, 4, 1]                                            # a batch is any subset, in any order
+    X, mask = ops.collate(packed, torch.tensor(starts[order], dtype=torch.int64).cuda(),
+                          torch.tensor([lengths[i] for i in order], dtype=torch.int32).cuda(), 40, atoms_out)
+    if atoms_out == 6:
+        batch = [{"name": str(i), "seq": "A" * lengths[i],
+                  "coords": {a: structs[i][:, k, :] for k, a in enumerate(ATOMS)}} for i in order]
+        Xh, _, mh, _, _ = featurize(batch)
+    else:
+        Xh = torch.zeros(len(order), 40, 7, 3)
+        mh = torch.zeros(len(order), 40)
+        for j, i in enumerate(order):
+            Xh[j, :lengths[i]] = torch.from_numpy(np.nan_to_num(structs[i], nan=0.0)).float()
+            mh[j, :lengths[i]] = 1
+    assert torch.equal(X.cpu(), Xh) and torch.equal(mask.cpu(), mh)
