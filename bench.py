@@ -60,16 +60,40 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    """SM clocks / throttle reasons sampled during the timed region: NVML (nvidia_ml_py) polled every few
+    milliseconds from a thread, `nvidia-smi -lms` as the fallback when the module is missing."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
 
-    def __init__(self, index):
-        self.index, self.lines, self.proc = index, [], None
+    def __init__(self, index, period_s=0.004):
+        self.index, self.period = index, period_s
+        self.lines, self.proc, self.samples, self.stop = [], None, [], threading.Event()
+        self.nvml = None
+
+    def _physical_index(self):
+        vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+        if vis:
+            ids = [v.strip() for v in vis.split(",") if v.strip()]
+            if self.index < len(ids) and ids[self.index].isdigit():
+                return int(ids[self.index])
+        return self.index
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+            import pynvml
+            pynvml.nvmlInit()
+            self.nvml = pynvml
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(self._physical_index())
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.handle, pynvml.NVML_CLOCK_SM))
+            self._poll_once()
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self.nvml = None
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self._physical_index()}", f"--query-gpu={self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
@@ -78,19 +102,49 @@ class ClockSampler:
             self.proc = None
         return self
 
+    def _poll_once(self):
+        n = self.nvml
+        mhz = float(n.nvmlDeviceGetClockInfo(self.handle, n.NVML_CLOCK_SM))
+        try:
+            bits = int(n.nvmlDeviceGetCurrentClocksEventReasons(self.handle))
+        except Exception:
+            bits = int(n.nvmlDeviceGetCurrentClocksThrottleReasons(self.handle))
+        self.samples.append((mhz, bits))
+
+    def _poll(self):
+        while not self.stop.is_set():
+            try:
+                self._poll_once()
+            except Exception:
+                break
+            self.stop.wait(self.period)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def __exit__(self, *a):
+        if self.nvml is not None:
+            self.stop.set()
+            self.thread.join(timeout=2)
+            return
         if self.proc is not None:
             time.sleep(0.15)
             self.proc.terminate()
             self.thread.join(timeout=2)
 
     def summary(self):
+        if self.nvml is not None and self.samples:
+            n = self.nvml
+            flags = {"hw_slowdown": getattr(n, "nvmlClocksEventReasonHwSlowdown", 0x8),
+                     "hw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonHwThermalSlowdown", 0x40),
+                     "sw_thermal_slowdown": getattr(n, "nvmlClocksEventReasonSwThermalSlowdown", 0x20),
+                     "sw_power_cap": getattr(n, "nvmlClocksEventReasonSwPowerCap", 0x4)}
+            sm = sorted(m for m, _ in self.samples)
+            reasons = sorted(k for k, f in flags.items() if any(b & f for _, b in self.samples))
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": reasons,
+                    "samples": len(sm), "source": "nvml"}
         sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for l in self.lines:
             f = [x.strip() for x in l.split(",")]
             if len(f) < 6:
@@ -99,13 +153,14 @@ class ClockSampler:
                 sm.append(float(f[0])); mx.append(float(f[1]))
             except ValueError:
                 continue
-            for n, v in zip(names, f[2:6]):
+            for n, v in zip(self.NAMES, f[2:6]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0, "source": "nvidia-smi"}
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi"}
 
 
 def model_and_inputs(workload, rank=0):
