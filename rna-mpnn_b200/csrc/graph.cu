@@ -308,7 +308,8 @@ static int launch_knn(const float* X, const float* mask, int B, int N, int A, in
     if (N <= kKnnSmemPoints) {
         const size_t smem = (size_t)N * sizeof(float4);
         auto k = knn_kernel<R, true, MODE>;
-        if (smem > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        // the kernel also holds ~4 KB of static shared memory (candidate rings): opt in before the sum reaches 48 KB
+        if (smem + 8 * 1024 > 48 * 1024) cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         k<<<grid, kKnnWarps * 32, smem, st>>>(X, mask, N, A, atom, K, rpw, E_idx, D);
     } else {
         knn_kernel<R, false, MODE><<<grid, kKnnWarps * 32, 0, st>>>(X, mask, N, A, atom, K, rpw, E_idx, D);

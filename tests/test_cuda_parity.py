@@ -313,3 +313,12 @@ def test_device_collate_matches_host_featurize(ops, dtype, atoms_out):
             Xh[j, :lengths[i]] = torch.from_numpy(np.nan_to_num(structs[i], nan=0.0)).float()
             mh[j, :lengths[i]] = 1
     assert torch.equal(X.cpu(), Xh) and torch.equal(mask.cpu(), mh)
+
+
+def test_knn_shared_memory_opt_in_boundary(ops):
+    """N just below 3072: 48 KB of staged points plus the kernel's static rings crosses the 48 KB default limit
+    (found on the 3065-nt chain of the reference's validation set)."""
+    X, _, mask = synthetic_backbones(1, 3065, 77)
+    D_o, I_o = O.knn(X[:, :, 0, :], mask, 25)
+    D_c, I_c = ops.knn(X.cuda(), mask.cuda(), 25)
+    assert torch.equal(I_c.cpu(), I_o) and torch.equal(D_c.cpu(), D_o)
