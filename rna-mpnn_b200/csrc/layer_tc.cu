@@ -560,6 +560,14 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
 constexpr int kNodeMaxStages = 5;
 constexpr int kRing = 4;                          // weight ring slots of 32 KB ([256 rows][64 k])
 constexpr int kSlotBytes = 256 * 128;
+// 16 prologue / epilogue warps: thread = row x quarter of the stage's columns.  With 8 warps (two per SM
+// sub-partition) the tcgen05.ld -> GELU -> st.shared chain of a 256-wide stage ran 128 columns deep per thread and its
+// latency was exposed (4.3-7.3 k cycles per stage, profiles/r1_node_timeline.txt); four warps per sub-partition halve
+// the per-thread chain and cover each other's TMEM / L2 latencies.
+constexpr int kNodeParts = 4;
+constexpr int kNodeEpiThreads = 128 * kNodeParts;            // 512
+constexpr int kNodeThreads = 64 + kNodeEpiThreads;           // 576
+__device__ __forceinline__ void node_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(kNodeEpiThreads) : "memory"); }
 
 struct NodeStage {
     int K, N, kind;
@@ -584,7 +592,7 @@ struct alignas(8) NodeBarriers {
     uint64_t w_full[kRing], w_empty[kRing], acc_full, act_ready;
 };
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kNodeThreads, 1)
 node_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant__ CUtensorMap tm1,
                    const __grid_constant__ CUtensorMap tm2, const __grid_constant__ CUtensorMap tm3,
                    const __grid_constant__ CUtensorMap tm4, const NodeParams p) {
@@ -594,7 +602,7 @@ node_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
     uint8_t* sW = sA + 4 * kKBlockBytes;                 // weight ring
     NodeBarriers* bars = reinterpret_cast<NodeBarriers*>(sW + kRing * kSlotBytes);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 1);
-    float* s_red = reinterpret_cast<float*>(s_tmem + 4);  // [2 stats][2 halves][128 rows]
+    float* s_red = reinterpret_cast<float*>(s_tmem + 4);  // [2 stats][4 column parts][128 rows]
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = (p.n_rows + kTileM - 1) / kTileM;
@@ -604,7 +612,7 @@ node_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
     if (threadIdx.x == 0) {
         for (int i = 0; i < kRing; ++i) { mbar_init(&bars->w_full[i], 1); mbar_init(&bars->w_empty[i], 1); }
         mbar_init(&bars->acc_full, 1);
-        mbar_init(&bars->act_ready, kEpiThreads);
+        mbar_init(&bars->act_ready, kNodeEpiThreads);
         fence_barrier_init();
     }
     if (warp == 1) tmem_alloc(s_tmem, kTmemCols);
@@ -656,12 +664,12 @@ node_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
         __syncwarp();
     } else {
         // ===================== prologue / epilogue warps =====================
-        const int half = (warp - 2) >> 2;
+        const int part = (warp - 2) >> 2;           // quarter of the stage's columns
         const int lane_grp = warp & 3;
         const int row = lane_grp * 32 + lane;
         const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
-        float* red_sum = s_red;                    // [2][128]
-        float* red_sq = s_red + 2 * kTileM;        // [2][128]
+        float* red_sum = s_red;                            // [4][128]
+        float* red_sq = s_red + kNodeParts * kTileM;       // [4][128]
         uint32_t ph_acc = 0;
         int tl_n = 0;
         const bool tl_on = p.timeline != nullptr && blockIdx.x == 0 && threadIdx.x == 64;
@@ -670,39 +678,29 @@ node_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
         };
         stamp(1);
 
-        // LayerNorm over the 128 channels of a row held as 64 + 64 by the two column halves
-        auto layer_norm64 = [&](float (&x)[64], const float* gamma, const float* beta, int c0) {
+        // LayerNorm over the 128 channels of a row held as 4 x 32 by the four column parts
+        auto layer_norm32 = [&](float (&x)[32], const float* gamma, const float* beta, int c0) {
             float sm = 0.f;
 #pragma unroll
-            for (int q = 0; q < 64; ++q) sm += x[q];
-            red_sum[half * kTileM + row] = sm;
-            epi_bar_sync();
-            const float mu = (sm + red_sum[(half ^ 1) * kTileM + row]) * (1.f / 128.f);
+            for (int q = 0; q < 32; ++q) sm += x[q];
+            red_sum[part * kTileM + row] = sm;
+            node_bar_sync();
+            const float mu = ((red_sum[row] + red_sum[kTileM + row]) + (red_sum[2 * kTileM + row] + red_sum[3 * kTileM + row])) *
+                             (1.f / 128.f);
             float sq = 0.f;
 #pragma unroll
-            for (int q = 0; q < 64; ++q) { x[q] -= mu; sq = fmaf(x[q], x[q], sq); }
-            red_sq[half * kTileM + row] = sq;
-            epi_bar_sync();
-            const float inv = 1.f / sqrtf((sq + red_sq[(half ^ 1) * kTileM + row]) * (1.f / 128.f) + 1e-5f);
+            for (int q = 0; q < 32; ++q) { x[q] -= mu; sq = fmaf(x[q], x[q], sq); }
+            red_sq[part * kTileM + row] = sq;
+            node_bar_sync();
+            const float var = ((red_sq[row] + red_sq[kTileM + row]) + (red_sq[2 * kTileM + row] + red_sq[3 * kTileM + row])) *
+                              (1.f / 128.f);
+            const float inv = 1.f / sqrtf(var + 1e-5f);
 #pragma unroll
-            for (int q = 0; q < 16; ++q) {
+            for (int q = 0; q < 8; ++q) {
                 const float4 g = __ldg(reinterpret_cast<const float4*>(gamma + c0) + q);
                 const float4 b = __ldg(reinterpret_cast<const float4*>(beta + c0) + q);
                 x[4 * q + 0] = fmaf(x[4 * q + 0] * inv, g.x, b.x); x[4 * q + 1] = fmaf(x[4 * q + 1] * inv, g.y, b.y);
                 x[4 * q + 2] = fmaf(x[4 * q + 2] * inv, g.z, b.z); x[4 * q + 3] = fmaf(x[4 * q + 3] * inv, g.w, b.w);
-            }
-        };
-        auto store_row64 = [&](float* dst, const float (&x)[64]) {      // 8 full 32-byte sectors per thread
-#pragma unroll
-            for (int q = 0; q < 8; ++q) stg256f(dst + 8 * q, &x[8 * q]);
-        };
-        auto to_operand64 = [&](const float (&x)[64], int c0) {
-#pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-                float v[32];
-#pragma unroll
-                for (int q = 0; q < 32; ++q) v[q] = x[ch * 32 + q];
-                store_act_chunk(sA, row, c0 + ch * 32, v);
             }
         };
 
@@ -710,128 +708,125 @@ node_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
             const int tile = blockIdx.x + i * gridDim.x;
             const int r = tile * kTileM + row;
             const bool valid = r < p.n_rows;
-            const int c0 = half * 64;
             // ---- prologue: x1 = LN1(h + agg) (or h).  One warp per row, lanes across the 128 channels: fully
-            //      coalesced 512-byte row accesses, LayerNorm by warp shuffles, bf16 copy -> swizzled A operand ----
+            //      coalesced 512-byte row accesses, LayerNorm by warp shuffles, bf16 copy -> swizzled A operand.
+            //      16 warps x 8 rows: every load of the tile is in flight at once ----
             {
-                const int ew = warp - 2;                               // 8 warps x 16 rows
+                const int ew = warp - 2;
                 float4 g1 = make_float4(1.f, 1.f, 1.f, 1.f), b1 = make_float4(0.f, 0.f, 0.f, 0.f);
                 if (p.prologue_ln) {
                     g1 = __ldg(reinterpret_cast<const float4*>(p.ln1_g) + lane);
                     b1 = __ldg(reinterpret_cast<const float4*>(p.ln1_b) + lane);
                 }
-                for (int r0 = 0; r0 < 16; r0 += 8) {                  // 8 rows per batch: 16 independent loads in flight
-                    float4 xs[8];
+                float4 xs[8], as[8];
+                const bool with_agg = p.prologue_ln && p.agg;
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) {
+                    const int rg = tile * kTileM + ew * 8 + rr;
+                    xs[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    as[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (rg < p.n_rows) {
+                        xs[rr] = __ldg(reinterpret_cast<const float4*>(p.h_in + (size_t)rg * 128) + lane);
+                        if (with_agg) as[rr] = reinterpret_cast<const float4*>(p.agg + (size_t)rg * 128)[lane];
+                    }
+                }
+                stamp(100);
+                if (with_agg) {
 #pragma unroll
                     for (int rr = 0; rr < 8; ++rr) {
-                        const int rg = tile * kTileM + ew * 16 + r0 + rr;
-                        xs[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (rg < p.n_rows) xs[rr] = __ldg(reinterpret_cast<const float4*>(p.h_in + (size_t)rg * 128) + lane);
+                        const int rg = tile * kTileM + ew * 8 + rr;
+                        xs[rr].x += as[rr].x; xs[rr].y += as[rr].y; xs[rr].z += as[rr].z; xs[rr].w += as[rr].w;
+                        if (rg < p.n_rows)                         // re-arm the neighbour-sum buffer
+                            reinterpret_cast<float4*>(p.agg + (size_t)rg * 128)[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
                     }
-                    stamp(100 + r0);
-                    if (p.prologue_ln && p.agg) {
-                        float4 as[8];
+                }
+                stamp(110);
+                if (p.prologue_ln) {
+                    // LayerNorm of the 8 rows at once: the 8 butterfly reductions of a step are independent
+                    // shuffles, so their latencies overlap instead of adding up row after row
+                    float sm[8], sq[8];
 #pragma unroll
-                        for (int rr = 0; rr < 8; ++rr) {
-                            const int rg = tile * kTileM + ew * 16 + r0 + rr;
-                            as[rr] = make_float4(0.f, 0.f, 0.f, 0.f);
-                            if (rg < p.n_rows) as[rr] = reinterpret_cast<const float4*>(p.agg + (size_t)rg * 128)[lane];
-                        }
+                    for (int rr = 0; rr < 8; ++rr) sm[rr] = (xs[rr].x + xs[rr].y) + (xs[rr].z + xs[rr].w);
 #pragma unroll
-                        for (int rr = 0; rr < 8; ++rr) {
-                            const int rg = tile * kTileM + ew * 16 + r0 + rr;
-                            xs[rr].x += as[rr].x; xs[rr].y += as[rr].y; xs[rr].z += as[rr].z; xs[rr].w += as[rr].w;
-                            if (rg < p.n_rows)                         // re-arm the neighbour-sum buffer
-                                reinterpret_cast<float4*>(p.agg + (size_t)rg * 128)[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-                        }
-                    }
-                    stamp(110 + r0);
-                    if (p.prologue_ln) {
-                        // LayerNorm of the 8 rows at once: the 8 butterfly reductions of a step are independent
-                        // shuffles, so their latencies overlap instead of adding up row after row
-                        float sm[8], sq[8];
+                    for (int o = 16; o > 0; o >>= 1) {
 #pragma unroll
-                        for (int rr = 0; rr < 8; ++rr) sm[rr] = (xs[rr].x + xs[rr].y) + (xs[rr].z + xs[rr].w);
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                            for (int rr = 0; rr < 8; ++rr) sm[rr] += __shfl_xor_sync(0xffffffffu, sm[rr], o);
-                        }
-#pragma unroll
-                        for (int rr = 0; rr < 8; ++rr) {
-                            const float mu = sm[rr] * (1.f / 128.f);
-                            xs[rr].x -= mu; xs[rr].y -= mu; xs[rr].z -= mu; xs[rr].w -= mu;
-                            sq[rr] = (xs[rr].x * xs[rr].x + xs[rr].y * xs[rr].y) + (xs[rr].z * xs[rr].z + xs[rr].w * xs[rr].w);
-                        }
-#pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                            for (int rr = 0; rr < 8; ++rr) sq[rr] += __shfl_xor_sync(0xffffffffu, sq[rr], o);
-                        }
-#pragma unroll
-                        for (int rr = 0; rr < 8; ++rr) {
-                            const int rg = tile * kTileM + ew * 16 + r0 + rr;
-                            const float inv = 1.f / sqrtf(sq[rr] * (1.f / 128.f) + 1e-5f);
-                            float4& x = xs[rr];
-                            x.x = fmaf(x.x * inv, g1.x, b1.x); x.y = fmaf(x.y * inv, g1.y, b1.y);
-                            x.z = fmaf(x.z * inv, g1.z, b1.z); x.w = fmaf(x.w * inv, g1.w, b1.w);
-                            if (rg < p.n_rows && p.x1) reinterpret_cast<float4*>(p.x1 + (size_t)rg * 128)[lane] = x;
-                        }
+                        for (int rr = 0; rr < 8; ++rr) sm[rr] += __shfl_xor_sync(0xffffffffu, sm[rr], o);
                     }
 #pragma unroll
                     for (int rr = 0; rr < 8; ++rr) {
-                        const int rl = ew * 16 + r0 + rr;              // row inside the tile
-                        const float4 x = xs[rr];
-                        // columns 4*lane .. 4*lane+3 -> K-block lane/16, 16-byte chunk (lane%16)/2, 8-byte half lane%2
-                        *reinterpret_cast<uint2*>(sA + (lane >> 4) * kKBlockBytes + sw128_chunk(rl, (lane & 15) >> 1) + (lane & 1) * 8) =
-                            make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
+                        const float mu = sm[rr] * (1.f / 128.f);
+                        xs[rr].x -= mu; xs[rr].y -= mu; xs[rr].z -= mu; xs[rr].w -= mu;
+                        sq[rr] = (xs[rr].x * xs[rr].x + xs[rr].y * xs[rr].y) + (xs[rr].z * xs[rr].z + xs[rr].w * xs[rr].w);
                     }
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                        for (int rr = 0; rr < 8; ++rr) sq[rr] += __shfl_xor_sync(0xffffffffu, sq[rr], o);
+                    }
+#pragma unroll
+                    for (int rr = 0; rr < 8; ++rr) {
+                        const int rg = tile * kTileM + ew * 8 + rr;
+                        const float inv = 1.f / sqrtf(sq[rr] * (1.f / 128.f) + 1e-5f);
+                        float4& x = xs[rr];
+                        x.x = fmaf(x.x * inv, g1.x, b1.x); x.y = fmaf(x.y * inv, g1.y, b1.y);
+                        x.z = fmaf(x.z * inv, g1.z, b1.z); x.w = fmaf(x.w * inv, g1.w, b1.w);
+                        if (rg < p.n_rows && p.x1) reinterpret_cast<float4*>(p.x1 + (size_t)rg * 128)[lane] = x;
+                    }
+                }
+#pragma unroll
+                for (int rr = 0; rr < 8; ++rr) {
+                    const int rl = ew * 8 + rr;                    // row inside the tile
+                    const float4 x = xs[rr];
+                    // columns 4*lane .. 4*lane+3 -> K-block lane/16, 16-byte chunk (lane%16)/2, 8-byte half lane%2
+                    *reinterpret_cast<uint2*>(sA + (lane >> 4) * kKBlockBytes + sw128_chunk(rl, (lane & 15) >> 1) + (lane & 1) * 8) =
+                        make_uint2(pack_bf16(x.x, x.y), pack_bf16(x.z, x.w));
                 }
                 stamp(3);
                 tc_fence_before();
                 fence_proxy_async();
                 mbar_arrive(&bars->act_ready);
-                epi_bar_sync();                                        // x1 rows written above are re-read by other warps
+                node_bar_sync();                                       // x1 rows written above are re-read by other warps
                 stamp(4);
             }
             // ---- stage epilogues ----
             for (int s = 0; s < S; ++s) {
                 const NodeStage stg = p.st[s];
-                const int ncols = stg.N >> 1;                 // columns of this half
-                const int cb = half * ncols;
-                float x[64];
-                if (stg.kind == 1) {
+                const int ncols = stg.N >> 2;                 // columns of this part: 32 (N = 128) or 64 (N = 256)
+                const int cb = part * ncols;
+                if (stg.kind == 1) {                          // N == 128: bias + residual + LN2 -> h_out (+ operand)
+                    float x[32];
                     // residual x1 (written by this CTA's prologue, L2): requested before the accumulator wait
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
+                    for (int q = 0; q < 4; ++q) {
                         float rsd[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
                         if (valid) ldg256f(p.x1 + (size_t)r * 128 + cb + 8 * q, rsd);
 #pragma unroll
                         for (int k = 0; k < 8; ++k) x[8 * q + k] = rsd[k];
                     }
-                }
-                mbar_wait(&bars->acc_full, ph_acc); ph_acc ^= 1;
-                tc_fence_after();
-                stamp(10 + s);
-                if (stg.kind == 1) {                          // N == 128: bias + residual + LN2 -> h_out (+ operand)
-#pragma unroll
-                    for (int ch = 0; ch < 2; ++ch) {
+                    mbar_wait(&bars->acc_full, ph_acc); ph_acc ^= 1;
+                    tc_fence_after();
+                    stamp(10 + s);
+                    {
                         float v[32];
-                        tmem_ld32(t_row + (uint32_t)(cb + ch * 32), v);
+                        tmem_ld32(t_row + (uint32_t)cb, v);
 #pragma unroll
-                        for (int q = 0; q < 32; ++q) x[ch * 32 + q] += v[q];
+                        for (int q = 0; q < 32; ++q) x[q] += v[q];
                     }
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
-                        const float4 ba = __ldg(reinterpret_cast<const float4*>(stg.bias + cb) + 2 * q);
-                        const float4 bb = __ldg(reinterpret_cast<const float4*>(stg.bias + cb) + 2 * q + 1);
-                        x[8 * q + 0] += ba.x; x[8 * q + 1] += ba.y; x[8 * q + 2] += ba.z; x[8 * q + 3] += ba.w;
-                        x[8 * q + 4] += bb.x; x[8 * q + 5] += bb.y; x[8 * q + 6] += bb.z; x[8 * q + 7] += bb.w;
+                        const float4 ba = __ldg(reinterpret_cast<const float4*>(stg.bias + cb) + q);
+                        x[4 * q + 0] += ba.x; x[4 * q + 1] += ba.y; x[4 * q + 2] += ba.z; x[4 * q + 3] += ba.w;
                     }
-                    layer_norm64(x, p.ln2_g, p.ln2_b, cb);
-                    if (valid) store_row64(p.h_out + (size_t)r * 128 + cb, x);
-                    if (s + 1 < S) to_operand64(x, cb);
+                    layer_norm32(x, p.ln2_g, p.ln2_b, cb);
+                    if (valid) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) stg256f(p.h_out + (size_t)r * 128 + cb + 8 * q, &x[8 * q]);
+                    }
+                    if (s + 1 < S) store_act_chunk(sA, row, cb, x);
                 } else {
+                    mbar_wait(&bars->acc_full, ph_acc); ph_acc ^= 1;
+                    tc_fence_after();
+                    stamp(10 + s);
                     for (int ch = 0; ch < ncols / 32; ++ch) {
                         const int col0 = cb + ch * 32;
                         float v[32];
@@ -863,7 +858,7 @@ node_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
                     fence_proxy_async();
                     mbar_arrive(&bars->act_ready);
                 } else {
-                    epi_bar_sync();          // every TMEM read of this tile is done before the next prologue arrives
+                    node_bar_sync();         // every TMEM read of this tile is done before the next prologue arrives
                 }
             }
         }
@@ -972,11 +967,11 @@ extern "C" int rmp_node_mlp_bf16(const float* h_in, float* agg, int prologue_ln,
     p.S = num_stages; p.n_rows = n_rows;
     p.timeline = reinterpret_cast<long long*>(getenv("RMP_NODE_TIMELINE") ? g_node_timeline : nullptr);
     const size_t smem = 1024 + 4 * tc::kKBlockBytes + tc::kRing * tc::kSlotBytes + sizeof(tc::NodeBarriers) + 16 +
-                        4 * tc::kTileM * sizeof(float);
+                        2 * tc::kNodeParts * tc::kTileM * sizeof(float);
     cudaFuncSetAttribute(tc::node_mlp_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int n_tiles = ceil_div(n_rows, tc::kTileM);
     const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
-    tc::node_mlp_tc_kernel<<<grid, tc::kThreads, smem, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3],
-                                                                              maps[4], p);
+    tc::node_mlp_tc_kernel<<<grid, tc::kNodeThreads, smem, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3],
+                                                                                  maps[4], p);
     return check_launch("rmp_node_mlp_bf16");
 }

@@ -58,5 +58,47 @@ def full(src, dst):
     print(open(dst).read())
 
 
+def table(src, dst):
+    """One row per kernel (mean over its launches in the capture): time, DRAM bytes and GB/s against the measured
+    HBM peak, tensor / FMA / XU pipe activity.  The per-kernel roofline table of a whole forward pass."""
+    import json, os
+    out = subprocess.run(["ncu", "-i", src, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    col = {m: hdr.index(m) for m in FULL_METRICS if m in hdr}
+    peaks_path = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
+    hbm = json.load(open(peaks_path))["hbm_gbs"] if os.path.exists(peaks_path) else 6650.0
+
+    def val(r, m):
+        v = float(r[col[m]].replace(",", ""))
+        u = units[col[m]]
+        scale = {"ns": 1e-3, "us": 1.0, "ms": 1e3, "s": 1e6, "byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(u, 1.0)
+        return v * scale
+    agg = defaultdict(lambda: defaultdict(float))
+    for r in rows[2:]:
+        name = r[hdr.index("Kernel Name")].split("(")[0].replace("void ", "")
+        a = agg[name]
+        a["n"] += 1
+        a["us"] += val(r, "gpu__time_duration.sum")
+        a["bytes"] += val(r, "dram__bytes_read.sum") + val(r, "dram__bytes_write.sum")
+        for k, m in (("tensor", "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"),
+                     ("fma", "sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active"),
+                     ("xu", "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active"),
+                     ("issue", "smsp__issue_active.avg.pct_of_peak_sustained_active")):
+            if m in col:
+                a[k] += val(r, m)
+    with open(dst, "w") as f:
+        f.write(f"# ncu --set full --clock-control none, one forward pass; source {src}\n")
+        f.write(f"# per kernel, mean over its launches (cold-cache, serialised).  HBM peak {hbm:.0f} GB/s (MEASURED_PEAKS.json)\n")
+        f.write(f"{'launches':>8} {'us':>9} {'DRAM MB':>9} {'GB/s':>8} {'of HBM':>7} {'tensor%':>8} {'fma%':>6} {'xu%':>6} {'issue%':>7}  kernel\n")
+        for name, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
+            n = a["n"]
+            us, mb = a["us"] / n, a["bytes"] / n / 1e6
+            gbs = a["bytes"] / n / (us * 1e-6) / 1e9 if us > 0 else 0.0
+            f.write(f"{int(n):8d} {us:9.1f} {mb:9.2f} {gbs:8.0f} {gbs / hbm:7.1%} {a['tensor'] / n:8.1f} {a['fma'] / n:6.1f} "
+                    f"{a['xu'] / n:6.1f} {a['issue'] / n:7.1f}  {name}\n")
+    print(open(dst).read())
+
+
 if __name__ == "__main__":
-    {"launches": launches, "full": full}[sys.argv[1]](sys.argv[2], sys.argv[3])
+    {"launches": launches, "full": full, "table": table}[sys.argv[1]](sys.argv[2], sys.argv[3])
