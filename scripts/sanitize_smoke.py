@@ -1,0 +1,28 @@
+"""Small end-to-end invocation of every kernel family for compute-sanitizer (memcheck): rdesign fp32 / bf16 forward,
+rnampnn fp32 / bf16 forward, device collate.  Kept tiny: the sanitizer slows kernels down by 10-100x."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "rna-mpnn_b200")):
+    sys.path.insert(0, p)
+import torch
+from oracle.weights import (RDesignConfig, RNAMPNNConfig, make_rnampnn_state_dict, make_state_dict, synthetic_backbones)
+from rmpnn_b200 import _lib, ops
+from rmpnn_b200.engine import RDesignEngine
+from rmpnn_b200.engine_rnampnn import RNAMPNNEngine
+
+cfg = RDesignConfig(k_neighbors=8, num_mpnn_layers=2)
+X, S, mask = synthetic_backbones(3, 70, 7, lengths=[70, 33, 5])
+for prec in (_lib.PREC_FP32, _lib.PREC_BF16):
+    out = RDesignEngine(make_state_dict(cfg, 1), 8, 30.0, device="cuda", precision=prec).forward(X.cuda(), mask.cuda())
+    torch.cuda.synchronize()
+    print("rdesign", prec, float(out["logits"].abs().max()))
+rcfg = RNAMPNNConfig(num_res_mpnn_layers=2, num_post_fusion_attn_layers=1)
+coords, _, rmask = synthetic_backbones(3, 150, 8, lengths=[150, 77, 2], atoms=7)
+for prec in (_lib.PREC_FP32, _lib.PREC_BF16):
+    out = RNAMPNNEngine.from_config(make_rnampnn_state_dict(rcfg, 1), rcfg, device="cuda", precision=prec).forward(coords.cuda(), rmask.cuda())
+    torch.cuda.synchronize()
+    print("rnampnn", prec, float(out["logits"].abs().max()))
+packed = torch.randn(100, 7, 3, dtype=torch.float64).cuda()
+Xc, mc = ops.collate(packed, torch.tensor([0, 60], dtype=torch.int64).cuda(), torch.tensor([60, 40], dtype=torch.int32).cuda(), 64, 6)
+torch.cuda.synchronize()
+print("collate", tuple(Xc.shape), float(mc.sum()))
