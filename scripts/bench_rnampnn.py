@@ -24,7 +24,7 @@ import torch  # noqa: E402
 
 from bench import ClockSampler, peaks  # noqa: E402
 
-WORKLOADS = {"r2": (64, 256, 1012), "r3": (8, 4096, 1013)}     # (B, L, seed); K = 3 (reference default)
+WORKLOADS = {"r2": (64, 256, 1012), "r3": (8, 4096, 1013), "r4": (256, 256, 1014)}     # (B, L, seed); K = 3 (reference default)
 UNIT = "nt/s"
 
 
