@@ -132,37 +132,57 @@ edge_embed_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const EmbedParams
                 const float* xi = p.X + (size_t)si * 18;
                 const float* xj = p.X + (size_t)sj * 18;
                 const V3 pj = ld3(xj);
+                // The two column halves of a row split the feature work evenly (the slower one gates the tile):
+                //   half 0: RBF of atoms P, O5', C5', C4' (chunks 0..7) + the frame quaternion (first half of chunk 12)
+                //   half 1: RBF of atoms C3', O3' (chunks 8..11) + the five local-frame directions (chunks 12..14)
+                // Normalisations use MUFU.RSQ (v * rsqrt(|v|^2), 0 for a zero vector): the results are rounded to bf16
+                // right away, so the fp32 arm's IEEE sqrt + divisions (geom.cuh) are not reproduced here.
                 if (half == 0) {
-                    // RBF of |atom a (centre) - P (neighbour)|, a = P, O5', C5', C4'  -> chunks 0..7
 #pragma unroll
                     for (int a = 0; a < 4; ++a) rbf16_bf16(eps_dist(ld3(xi + a * 3), pj), p.mu, sA, row, 2 * a);
-                } else {
-                    // a = C3', O3' -> chunks 8..11; quaternion + direction -> chunks 12..14; zero pad
-#pragma unroll
-                    for (int a = 4; a < 6; ++a) rbf16_bf16(eps_dist(ld3(xi + a * 3), pj), p.mu, sA, row, 2 * a);
                     float Qi[9], Qj[9];
 #pragma unroll
                     for (int c = 0; c < 9; ++c) { Qi[c] = __ldg(p.frames + (size_t)si * 9 + c); Qj[c] = __ldg(p.frames + (size_t)sj * 9 + c); }
-                    float f[24];
-                    {
-                        float q[4];
-                        frame_quaternion(Qi, Qj, q);
-                        f[0] = q[0]; f[1] = q[1]; f[2] = q[2]; f[3] = q[3];
-                    }
+                    float R[3][3];
+#pragma unroll
+                    for (int r = 0; r < 3; ++r)
+#pragma unroll
+                        for (int c = 0; c < 3; ++c) R[r][c] = fmaf(Qi[6 + r], Qj[6 + c], fmaf(Qi[3 + r], Qj[3 + c], Qi[r] * Qj[c]));
+                    const float Rxx = R[0][0], Ryy = R[1][1], Rzz = R[2][2];
+                    const float qx = sign_of(R[2][1] - R[1][2]) * (0.5f * sqrtf(fabsf(1.f + (Rxx - Ryy - Rzz))));
+                    const float qy = sign_of(R[0][2] - R[2][0]) * (0.5f * sqrtf(fabsf(1.f + (-Rxx + Ryy - Rzz))));
+                    const float qz = sign_of(R[1][0] - R[0][1]) * (0.5f * sqrtf(fabsf(1.f + (-Rxx - Ryy + Rzz))));
+                    const float qw = 0.5f * sqrtf(fmaxf(1.f + (Rxx + Ryy + Rzz), 0.f));
+                    const float n2 = fmaf(qw, qw, fmaf(qz, qz, fmaf(qy, qy, qx * qx)));
+                    const float inv = rsqrtf(fmaxf(n2, 1e-24f));               // F.normalize: / max(|q|, 1e-12)
+                    *reinterpret_cast<uint2*>(sA + kKBlockBytes + sw128_chunk(row, 4)) =
+                        make_uint2(pack_bf16(qx * inv, qy * inv), pack_bf16(qz * inv, qw * inv));
+                } else {
+#pragma unroll
+                    for (int a = 4; a < 6; ++a) rbf16_bf16(eps_dist(ld3(xi + a * 3), pj), p.mu, sA, row, 2 * a);
+                    float Qi[9];
+#pragma unroll
+                    for (int c = 0; c < 9; ++c) Qi[c] = __ldg(p.frames + (size_t)si * 9 + c);
+                    float f[20];
                     const V3 c3 = ld3(xi + 12);
                     const int atoms[5] = {0, 1, 2, 3, 5};
 #pragma unroll
                     for (int a = 0; a < 5; ++a) {
-                        const V3 d = unit_nan0(rotate(Qi, ld3(xj + atoms[a] * 3) - c3));
-                        f[4 + a * 3 + 0] = d.x; f[4 + a * 3 + 1] = d.y; f[4 + a * 3 + 2] = d.z;
+                        const V3 d = rotate(Qi, ld3(xj + atoms[a] * 3) - c3);
+                        const float n2 = fmaf(d.z, d.z, fmaf(d.y, d.y, d.x * d.x));
+                        const float inv = n2 > 0.f ? rsqrtf(n2) : 0.f;            // 0/0 -> 0 (rdesign/utils/data.py:164-171)
+                        f[a * 3 + 0] = d.x * inv; f[a * 3 + 1] = d.y * inv; f[a * 3 + 2] = d.z * inv;
                     }
 #pragma unroll
-                    for (int c = 19; c < 24; ++c) f[c] = 0.f;
+                    for (int c = 15; c < 20; ++c) f[c] = 0.f;
+                    // directions 0..3 complete chunk 12 behind the quaternion, 4..11 -> chunk 13, 12..14 + zeros -> chunk 14
+                    *reinterpret_cast<uint2*>(sA + kKBlockBytes + sw128_chunk(row, 4) + 8) =
+                        make_uint2(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]));
 #pragma unroll
-                    for (int j = 0; j < 3; ++j)
-                        *reinterpret_cast<uint4*>(sA + kKBlockBytes + sw128_chunk(row, 4 + j)) =
-                            make_uint4(pack_bf16(f[8 * j + 0], f[8 * j + 1]), pack_bf16(f[8 * j + 2], f[8 * j + 3]),
-                                       pack_bf16(f[8 * j + 4], f[8 * j + 5]), pack_bf16(f[8 * j + 6], f[8 * j + 7]));
+                    for (int j = 0; j < 2; ++j)
+                        *reinterpret_cast<uint4*>(sA + kKBlockBytes + sw128_chunk(row, 5 + j)) =
+                            make_uint4(pack_bf16(f[4 + 8 * j + 0], f[4 + 8 * j + 1]), pack_bf16(f[4 + 8 * j + 2], f[4 + 8 * j + 3]),
+                                       pack_bf16(f[4 + 8 * j + 4], f[4 + 8 * j + 5]), pack_bf16(f[4 + 8 * j + 6], f[4 + 8 * j + 7]));
                     *reinterpret_cast<uint4*>(sA + kKBlockBytes + sw128_chunk(row, 7)) = make_uint4(0u, 0u, 0u, 0u);
                 }
             } else {
