@@ -251,7 +251,18 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(const float* __rest
         for (int r = 0; r < R; ++r) slot[r] = kKeyMax;
         u64 thresh = kKeyMax;
         int head = 0, cnt = 0;                               // ring state (warp-uniform)
-        for (int base = 0; base < N; base += 32) {
+        // Candidate blocks are visited outward from the query's own position (i/32, then +1, -1, +2, ...): along a chain
+        // the sequence neighbours are the likely spatial neighbours, so the running K-th key tightens within the first
+        // few blocks and almost nothing passes it afterwards.  Scanning j = 0..N-1 instead approaches the query
+        // monotonically -- nearly every candidate below i beats the current K-th key and pays for a sort / merge
+        // (measured 0.8 ms at 8 x 4096, K = 48).  The (distance, index) order is total, so the result is the same.
+        const int nblk = (N + 31) >> 5;
+        int blk_lo = i >> 5, blk_hi = (i >> 5) + 1;
+        for (int tb = 0; tb < nblk; ++tb) {
+            int blk;
+            if ((((tb & 1) == 0) && blk_lo >= 0) || blk_hi >= nblk) blk = blk_lo--;
+            else blk = blk_hi++;
+            const int base = blk << 5;
             const int j = base + lane;
             u64 key = kKeyMax;
             if (j < N) {
