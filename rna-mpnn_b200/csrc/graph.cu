@@ -258,21 +258,28 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(const float* __rest
         // (measured 0.8 ms at 8 x 4096, K = 48).  The (distance, index) order is total, so the result is the same.
         const int nblk = (N + 31) >> 5;
         int blk_lo = i >> 5, blk_hi = (i >> 5) + 1;
-        for (int tb = 0; tb < nblk; ++tb) {
-            int blk;
-            if ((((tb & 1) == 0) && blk_lo >= 0) || blk_hi >= nblk) blk = blk_lo--;
-            else blk = blk_hi++;
-            const int base = blk << 5;
-            const int j = base + lane;
-            u64 key = kKeyMax;
-            if (j < N) {
-                const float4 pj = SMEM ? s_pts[j] : load_point(j);
-                const float d = MODE == 0 ? ref_pair_distance(pi, pj) : res_pair_distance(pi, pj, j == i);
-                key = ((u64)__float_as_uint(d) << 32) | (unsigned)j;
-            }
+        // squared prefilter: a valid pair with s > T^2 (1 + 2^-20) has sqrt.rn(s) > T = the current K-th distance and
+        // can never enter the list, so its IEEE square root is skipped (the margin is 16x the rounding of T*T and of
+        // sqrt.rn: every candidate that could tie or beat T still takes the exact path)
+        float s_thr = INFINITY;
+        auto next_block = [&](int tb) -> int {
+            if ((((tb & 1) == 0) && blk_lo >= 0) || blk_hi >= nblk) return blk_lo--;
+            return blk_hi++;
+        };
+        auto make_key = [&](int j) -> u64 {
+            if (j >= N) return kKeyMax;
+            const float4 pj = SMEM ? s_pts[j] : load_point(j);
+            if (pi.w == 0.0f || pj.w == 0.0f || (MODE == 1 && j == i))
+                return ((u64)__float_as_uint(MODE == 0 ? 20001.0f : 1e6f) << 32) | (unsigned)j;
+            const float dx = __fsub_rn(pj.x, pi.x), dy = __fsub_rn(pj.y, pi.y), dz = __fsub_rn(pj.z, pi.z);
+            const float sq = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)), 1e-6f);
+            if (sq > s_thr) return kKeyMax;
+            return ((u64)__float_as_uint(__fsqrt_rn(sq)) << 32) | (unsigned)j;
+        };
+        auto offer = [&](u64 key) {                            // warp-uniform control flow
             const bool pass = key < thresh;
             const unsigned m = __ballot_sync(0xffffffffu, pass);
-            if (m == 0) continue;
+            if (m == 0) return;
             if (pass) ring[(head + cnt + __popc(m & lt_mask)) & (kKnnRing - 1)] = key;
             cnt += __popc(m);
             if (cnt >= 32) {
@@ -283,7 +290,20 @@ __global__ void __launch_bounds__(kKnnWarps * 32) knn_kernel(const float* __rest
                 cnt -= 32;
                 warp_merge_batch<R>(slot, cand, lane);
                 thresh = warp_slot_read<R>(slot, K - 1);
+                if (thresh != kKeyMax) {
+                    const float T = __uint_as_float((unsigned)(thresh >> 32));
+                    s_thr = __fmul_rn(__fmul_rn(T, T), 1.0000009537f);          // 1 + 2^-20
+                }
             }
+        };
+        // two candidate blocks per iteration: their distance chains are independent and hide each other's latency
+        for (int tb = 0; tb < nblk; tb += 2) {
+            const int blk_a = next_block(tb);
+            const int blk_b = tb + 1 < nblk ? next_block(tb + 1) : -1;
+            const u64 key_a = make_key((blk_a << 5) + lane);
+            const u64 key_b = blk_b >= 0 ? make_key((blk_b << 5) + lane) : kKeyMax;
+            offer(key_a);
+            offer(key_b);
         }
         if (cnt > 0) {                                       // the last, partial batch
             __syncwarp();
