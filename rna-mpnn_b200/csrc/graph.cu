@@ -120,7 +120,7 @@ typedef unsigned long long u64;
 constexpr u64 kKeyMax = ~0ull;
 // rows handled by one warp: more rows amortise staging the structure in shared memory
 __host__ __device__ inline int knn_rows_per_warp(int N) { return N <= 1024 ? 1 : (N <= 4096 ? 2 : 8); }
-constexpr int kKnnWarps = 8;
+constexpr int kKnnWarps = 16;
 constexpr int kKnnSmemPoints = 8192;      // structures up to this length are staged in smem
 constexpr int kKnnRing = 64;              // candidate ring entries per warp
 
