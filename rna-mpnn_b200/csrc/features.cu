@@ -53,7 +53,12 @@ __device__ __forceinline__ float dihedral_angle(const float* __restrict__ Xb, in
     return sign_of(dot(u[0], nb)) * acosf(c);
 }
 
-__global__ void __launch_bounds__(kNodeTile) node_raw_kernel(const float* __restrict__ X, int N,
+// Four threads per node, each computing a quarter of the 101 features (same per-feature arithmetic as one thread per
+// node, so the values are unchanged): with one thread per node the whole batch was 110 threads per SM of long serial
+// work (80 expf, 6 acosf per thread) and the kernel took as long as a message-passing layer's node update.
+constexpr int kNodeParts = 4;
+
+__global__ void __launch_bounds__(kNodeTile * kNodeParts) node_raw_kernel(const float* __restrict__ X, int N,
                                                             const int32_t* __restrict__ node_src,
                                                             const int32_t* __restrict__ counts, int nv_cap,
                                                             RbfMu mu, const float* __restrict__ frames,
@@ -62,41 +67,47 @@ __global__ void __launch_bounds__(kNodeTile) node_raw_kernel(const float* __rest
     const int nv = min(counts[0], nv_cap);
     const int v0 = blockIdx.x * kNodeTile;
     if (v0 >= nv) return;
-    const int t = threadIdx.x, v = v0 + t;
+    const int t = threadIdx.x % kNodeTile, part = threadIdx.x / kNodeTile, v = v0 + t;
     if (v < nv) {
         float* f = tile + t * RMP_NODE_RAW;
         const int src = node_src[v];
         const int b = src / N, i = src - b * N;
         const float* Xb = X + (size_t)b * N * 18;
         const float* xi = Xb + (size_t)i * 18;
-        // angle: cos | sin of the six slots
+        if (part < 2) {
+            // angle: cos | sin of the six slots (three per thread)
 #pragma unroll
-        for (int a = 0; a < 6; ++a) {
-            const float ang = dihedral_angle(Xb, N, 6 * i + a);
-            f[a] = cosf(ang);
-            f[6 + a] = sinf(ang);
-        }
-        // distance: atoms O5',C5',C4',C3',O3' to own P
-        const V3 p = ld3(xi);
+            for (int a3 = 0; a3 < 3; ++a3) {
+                const int a = part * 3 + a3;
+                const float ang = dihedral_angle(Xb, N, 6 * i + a);
+                f[a] = cosf(ang);
+                f[6 + a] = sinf(ang);
+            }
+        } else {
+            // distance: atoms O5',C5',C4' (part 2) / C3',O3' (part 3) to own P
+            const V3 p = ld3(xi);
+            const int a_lo = part == 2 ? 1 : 4, a_hi = part == 2 ? 4 : 6;
+            for (int a = a_lo; a < a_hi; ++a) {
+                float* dst = f + 12 + (a - 1) * 16;
+                rbf16(eps_dist(ld3(xi + a * 3), p), mu, [&](int r, float val) { dst[r] = val; });
+            }
+            if (part == 3) {
+                // direction: frame_i * (P, C5', C4' - C3')
+                const float* q = frames + (size_t)src * 9;
+                const V3 c3 = ld3(xi + 12);
+                const int atoms[3] = {0, 2, 3};
 #pragma unroll
-        for (int a = 1; a < 6; ++a) {
-            float* dst = f + 12 + (a - 1) * 16;
-            rbf16(eps_dist(ld3(xi + a * 3), p), mu, [&](int r, float val) { dst[r] = val; });
-        }
-        // direction: frame_i * (P, C5', C4' - C3')
-        const float* q = frames + (size_t)src * 9;
-        const V3 c3 = ld3(xi + 12);
-        const int atoms[3] = {0, 2, 3};
-#pragma unroll
-        for (int a = 0; a < 3; ++a) {
-            const V3 d = unit_nan0(rotate(q, ld3(xi + atoms[a] * 3) - c3));
-            f[92 + a * 3 + 0] = d.x; f[92 + a * 3 + 1] = d.y; f[92 + a * 3 + 2] = d.z;
+                for (int a = 0; a < 3; ++a) {
+                    const V3 d = unit_nan0(rotate(q, ld3(xi + atoms[a] * 3) - c3));
+                    f[92 + a * 3 + 0] = d.x; f[92 + a * 3 + 1] = d.y; f[92 + a * 3 + 2] = d.z;
+                }
+            }
         }
     }
     __syncthreads();
     const int rows = min(kNodeTile, nv - v0);
     float* out = node_raw + (size_t)v0 * RMP_NODE_RAW;
-    for (int o = t; o < rows * RMP_NODE_RAW; o += kNodeTile) out[o] = tile[o];
+    for (int o = threadIdx.x; o < rows * RMP_NODE_RAW; o += kNodeTile * kNodeParts) out[o] = tile[o];
 }
 
 // --------------------------------------------------------------------------------
@@ -170,7 +181,7 @@ extern "C" int rmp_rdesign_raw_features(const float* X, int B, int N, const int3
     const size_t total = (size_t)B * N;
     frames_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(X, B, N, frames);
     if (node_raw && nv_cap > 0)
-        node_raw_kernel<<<ceil_div(nv_cap, kNodeTile), kNodeTile, 0, st>>>(X, N, node_src, counts, nv_cap, mu, frames,
+        node_raw_kernel<<<ceil_div(nv_cap, kNodeTile), kNodeTile * kNodeParts, 0, st>>>(X, N, node_src, counts, nv_cap, mu, frames,
                                                                            node_raw);
     if (edge_raw && ne_cap > 0) {
         const int smem = kEdgeTile * RMP_EDGE_RAW * (int)sizeof(float);
