@@ -287,6 +287,43 @@ __global__ void __launch_bounds__(256) graph_norm_apply_kernel(const float* __re
 // --------------------------------------------------------------------------------
 constexpr int kAttnTile = 128;
 
+// packed fp32x2 arithmetic (FFMA2 / FMUL2 on sm_100): one instruction per two channels
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{\n\t"
+        ".reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rb, {%4, %5};\n\t"
+        "mov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t"
+        "}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+__device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
+    float2 d;
+    asm("{\n\t"
+        ".reg .b64 ra, rb, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rb, {%4, %5};\n\t"
+        "mul.rn.f32x2 rd, ra, rb;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t"
+        "}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y));
+    return d;
+}
+__device__ __forceinline__ float ex2_fast(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+
+// Scores are kept in the log2 domain (q is pre-scaled by log2(e)/sqrt(HD)), so the softmax needs one MUFU.EX2 per key
+// instead of a full expf; dot products and the P.V update run on packed fp32x2 FMAs.  ex2.approx is accurate to 2^-22
+// relative, far inside the 1e-4 logit tolerance of the fp32 arm.
 template <int HD>
 __global__ void __launch_bounds__(kAttnTile) res_attention_kernel(const float* __restrict__ qkv,
                                                                  const float* __restrict__ mask, int N, int E,
@@ -298,16 +335,17 @@ __global__ void __launch_bounds__(kAttnTile) res_attention_kernel(const float* _
     const int qi = blockIdx.x * kAttnTile + t;
     const size_t base = (size_t)b * N;
     const bool q_ok = qi < N && mask[base + qi] != 0.0f;
-    float q[HD], acc[HD];
-    const float qs = 1.0f / sqrtf((float)HD);
+    float2 q[HD / 2], acc[HD / 2];
+    const float qs = 1.4426950408889634f / sqrtf((float)HD);
 #pragma unroll
-    for (int d = 0; d < HD; ++d) { q[d] = 0.f; acc[d] = 0.f; }
+    for (int d = 0; d < HD / 2; ++d) { q[d] = make_float2(0.f, 0.f); acc[d] = make_float2(0.f, 0.f); }
     if (q_ok) {
         const float4* qp = reinterpret_cast<const float4*>(qkv + (base + qi) * 3 * E + h * HD);
 #pragma unroll
         for (int d4 = 0; d4 < HD / 4; ++d4) {
             const float4 v = qp[d4];
-            q[d4 * 4 + 0] = v.x * qs; q[d4 * 4 + 1] = v.y * qs; q[d4 * 4 + 2] = v.z * qs; q[d4 * 4 + 3] = v.w * qs;
+            q[2 * d4] = make_float2(v.x * qs, v.y * qs);
+            q[2 * d4 + 1] = make_float2(v.z * qs, v.w * qs);
         }
     }
     float m = -INFINITY, l = 0.f;
@@ -337,26 +375,37 @@ __global__ void __launch_bounds__(kAttnTile) res_attention_kernel(const float* _
                 const int kk = c0 + u;
                 s[u] = -INFINITY;
                 if (kk < kn && s_ok[kk] != 0.f) {               // uniform across the block
-                    float d0 = 0.f;
+                    float2 da = make_float2(0.f, 0.f), db = make_float2(0.f, 0.f);
 #pragma unroll
-                    for (int d = 0; d < HD; ++d) d0 = fmaf(q[d], s_k[kk][d], d0);
+                    for (int d4 = 0; d4 < HD / 4; ++d4) {
+                        const float4 kv = reinterpret_cast<const float4*>(s_k[kk])[d4];
+                        da = ffma2(q[2 * d4], make_float2(kv.x, kv.y), da);
+                        db = ffma2(q[2 * d4 + 1], make_float2(kv.z, kv.w), db);
+                    }
+                    const float d0 = (da.x + da.y) + (db.x + db.y);
                     s[u] = d0;
                     cmax = fmaxf(cmax, d0);
                 }
             }
             if (cmax == -INFINITY) continue;
             const float m_new = fmaxf(m, cmax);
-            const float corr = expf(m - m_new);                 // exp(-inf) = 0 on the first chunk
+            const float corr = ex2_fast(m - m_new);             // 2^-inf = 0 on the first chunk
             l *= corr;
+            const float2 c2 = make_float2(corr, corr);
 #pragma unroll
-            for (int d = 0; d < HD; ++d) acc[d] *= corr;
+            for (int d = 0; d < HD / 2; ++d) acc[d] = fmul2(acc[d], c2);
 #pragma unroll
             for (int u = 0; u < 8; ++u) {
                 if (s[u] == -INFINITY) continue;
-                const float p = expf(s[u] - m_new);
+                const float p = ex2_fast(s[u] - m_new);
                 l += p;
+                const float2 p2 = make_float2(p, p);
 #pragma unroll
-                for (int d = 0; d < HD; ++d) acc[d] = fmaf(p, s_v[c0 + u][d], acc[d]);
+                for (int d4 = 0; d4 < HD / 4; ++d4) {
+                    const float4 vv = reinterpret_cast<const float4*>(s_v[c0 + u])[d4];
+                    acc[2 * d4] = ffma2(p2, make_float2(vv.x, vv.y), acc[2 * d4]);
+                    acc[2 * d4 + 1] = ffma2(p2, make_float2(vv.z, vv.w), acc[2 * d4 + 1]);
+                }
             }
             m = m_new;
         }
@@ -366,7 +415,7 @@ __global__ void __launch_bounds__(kAttnTile) res_attention_kernel(const float* _
         const float inv = (q_ok && l > 0.f) ? 1.0f / l : 0.f;
 #pragma unroll
         for (int d4 = 0; d4 < HD / 4; ++d4)
-            op[d4] = make_float4(acc[d4 * 4] * inv, acc[d4 * 4 + 1] * inv, acc[d4 * 4 + 2] * inv, acc[d4 * 4 + 3] * inv);
+            op[d4] = make_float4(acc[2 * d4].x * inv, acc[2 * d4].y * inv, acc[2 * d4 + 1].x * inv, acc[2 * d4 + 1].y * inv);
     }
 }
 
