@@ -43,6 +43,22 @@ __device__ __forceinline__ float warp_sum(float v) {
     return v;
 }
 
+// packed fp32x2 FMA (FFMA2 on sm_100): d = a * b + c on two lanes of a 64-bit register pair, each rounded like fmaf
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+    float2 d;
+    asm("{\n\t"
+        ".reg .b64 ra, rb, rc, rd;\n\t"
+        "mov.b64 ra, {%2, %3};\n\t"
+        "mov.b64 rb, {%4, %5};\n\t"
+        "mov.b64 rc, {%6, %7};\n\t"
+        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
+        "mov.b64 {%0, %1}, rd;\n\t"
+        "}"
+        : "=f"(d.x), "=f"(d.y)
+        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
+    return d;
+}
+
 // exact (erf) GELU, nn.GELU() default (rdesign/model/mpnn.py:17)
 __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));

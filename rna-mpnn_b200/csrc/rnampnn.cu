@@ -288,20 +288,6 @@ __global__ void __launch_bounds__(256) graph_norm_apply_kernel(const float* __re
 constexpr int kAttnTile = 128;
 
 // packed fp32x2 arithmetic (FFMA2 / FMUL2 on sm_100): one instruction per two channels
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
-    float2 d;
-    asm("{\n\t"
-        ".reg .b64 ra, rb, rc, rd;\n\t"
-        "mov.b64 ra, {%2, %3};\n\t"
-        "mov.b64 rb, {%4, %5};\n\t"
-        "mov.b64 rc, {%6, %7};\n\t"
-        "fma.rn.f32x2 rd, ra, rb, rc;\n\t"
-        "mov.b64 {%0, %1}, rd;\n\t"
-        "}"
-        : "=f"(d.x), "=f"(d.y)
-        : "f"(a.x), "f"(a.y), "f"(b.x), "f"(b.y), "f"(c.x), "f"(c.y));
-    return d;
-}
 __device__ __forceinline__ float2 fmul2(float2 a, float2 b) {
     float2 d;
     asm("{\n\t"

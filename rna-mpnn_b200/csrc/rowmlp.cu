@@ -92,11 +92,13 @@ __global__ void __launch_bounds__(kThreads) row_mlp_kernel(const rmp_mlp_desc d,
         const float* __restrict__ Wt = d.Wt[s];
         const int nchunks = kpad / kKC;
         for (int nb = 0; nb < nout; nb += kNB) {
-            float acc[TR][8];
+            // accumulators as fp32 pairs: the inner product runs on packed fma.rn.f32x2 (same rounding as fmaf, half the
+            // issue slots -- the loop is issue-bound, not FMA-pipe-bound)
+            float2 acc2[TR][4];
 #pragma unroll
             for (int i = 0; i < TR; ++i)
 #pragma unroll
-                for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
+                for (int j = 0; j < 4; ++j) acc2[i][j] = make_float2(0.f, 0.f);
 
             auto prefetch = [&](int chunk, int stage) {
                 float* dst = wbuf + stage * kKC * kNB;
@@ -132,11 +134,14 @@ __global__ void __launch_bounds__(kThreads) row_mlp_kernel(const rmp_mlp_desc d,
                     }
                     const float4 b0 = *reinterpret_cast<const float4*>(w + kk * kNB + tx * 4);
                     const float4 b1 = *reinterpret_cast<const float4*>(w + kk * kNB + 64 + tx * 4);
-                    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                    const float2 bv[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y),
+                                          make_float2(b1.z, b1.w)};
 #pragma unroll
-                    for (int i = 0; i < TR; ++i)
+                    for (int i = 0; i < TR; ++i) {
+                        const float2 aa = make_float2(a[i], a[i]);
 #pragma unroll
-                        for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], bv[j], acc[i][j]);
+                        for (int j = 0; j < 4; ++j) acc2[i][j] = ffma2(aa, bv[j], acc2[i][j]);
+                    }
                 }
                 __syncthreads();
             }
@@ -149,7 +154,7 @@ __global__ void __launch_bounds__(kThreads) row_mlp_kernel(const rmp_mlp_desc d,
                 float v[TR];
 #pragma unroll
                 for (int i = 0; i < TR; ++i) {
-                    v[i] = acc[i][j] + bj;
+                    v[i] = ((j & 1) ? acc2[i][j >> 1].y : acc2[i][j >> 1].x) + bj;
                     if (d.gelu[s]) v[i] = gelu_erf(v[i]);
                 }
                 float* dst = out + (size_t)col * RS + ty * TR;
