@@ -176,22 +176,11 @@ __device__ __forceinline__ u64 warp_slot_read(const u64 (&slot)[R], int s) {
     return out;
 }
 
-// adjusted distance of the reference: exact rounding sequence, no contraction.
-__device__ __forceinline__ float ref_pair_distance(float4 a, float4 b) {
-    if (a.w == 0.0f || b.w == 0.0f) return 20001.0f;       // 10000 + (rowmax 10000 + 1)
-    const float dx = __fsub_rn(b.x, a.x), dy = __fsub_rn(b.y, a.y), dz = __fsub_rn(b.z, a.z);
-    const float s = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-    return __fsqrt_rn(__fadd_rn(s, 1e-6f));
-}
-
-// rnampnn variant (MODE 1, rnampnn/model/feature.py:218-227): pairs with a padded end and the diagonal sit at
-// exactly 1e6 (1e-3 + 1e6 rounds to 1e6 in fp32) and take part in the ordering like any other candidate.
-__device__ __forceinline__ float res_pair_distance(float4 a, float4 b, bool same) {
-    if (same || a.w == 0.0f || b.w == 0.0f) return 1e6f;
-    const float dx = __fsub_rn(b.x, a.x), dy = __fsub_rn(b.y, a.y), dz = __fsub_rn(b.z, a.z);
-    const float s = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
-    return __fsqrt_rn(__fadd_rn(s, 1e-6f));
-}
+// Adjusted distances (make_key below), exact rounding sequence, no contraction:
+//   MODE 0 (rdesign/model/feature.py:42-48): sqrt.rn(((dx*dx + dy*dy) + dz*dz) + 1e-6); a pair with a masked end is
+//           20001 = 10000 + (rowmax 10000 + 1).
+//   MODE 1 (rnampnn/model/feature.py:218-227): the same on centroids; pairs with a padded end and the diagonal sit at
+//           exactly 1e6 (1e-3 + 1e6 rounds to 1e6 in fp32) and take part in the ordering like any other candidate.
 
 // MODE 0: rdesign (one atom per residue, self included, E_idx [B,N,K] with K <= N).
 // MODE 1: rnampnn (centroid of the A atoms, self excluded, -1 sentinels, K may exceed N).
