@@ -164,7 +164,7 @@ class ClockSampler:
 
 
 def model_and_inputs(workload, rank=0):
-    from oracle.weights import RDesignConfig, make_state_dict, synthetic_backbones
+    from rmpnn_b200.synthetic import RDesignConfig, make_state_dict, synthetic_backbones
     B, L, K, seed = WORKLOADS[workload]
     cfg = RDesignConfig(k_neighbors=K)
     params = make_state_dict(cfg, 42)

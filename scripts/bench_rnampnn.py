@@ -52,7 +52,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"])
     args = ap.parse_args()
 
-    from oracle.weights import RNAMPNNConfig, make_rnampnn_state_dict, synthetic_backbones
+    from rmpnn_b200.synthetic import RNAMPNNConfig, make_rnampnn_state_dict, synthetic_backbones
     from rmpnn_b200 import _lib
     from rmpnn_b200.engine_rnampnn import RNAMPNNEngine
 

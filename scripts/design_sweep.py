@@ -42,7 +42,7 @@ def main():
     args = ap.parse_args()
 
     import torch.distributed as dist
-    from oracle.weights import RDesignConfig, make_state_dict
+    from rmpnn_b200.synthetic import RDesignConfig, make_state_dict
     from rmpnn_b200 import _lib, ops, shard
     from rmpnn_b200.engine import RDesignEngine
 

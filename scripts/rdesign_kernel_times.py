@@ -5,7 +5,7 @@ for p in (ROOT, os.path.join(ROOT, "rna-mpnn_b200")):
     sys.path.insert(0, p)
 import torch
 from torch.profiler import profile, ProfilerActivity
-from oracle.weights import RDesignConfig, make_state_dict, synthetic_backbones
+from rmpnn_b200.synthetic import RDesignConfig, make_state_dict, synthetic_backbones
 from rmpnn_b200 import _lib
 from rmpnn_b200.engine import RDesignEngine
 

@@ -7,7 +7,7 @@ for p in (ROOT, os.path.join(ROOT, "rna-mpnn_b200"), os.path.join(ROOT, "tests")
 import torch
 from conftest import load_rnampnn_golden, RNAMPNN_GOLDEN_CASES
 from oracle import rnampnn_oracle as O
-from oracle.weights import RNAMPNNConfig, make_rnampnn_state_dict, synthetic_backbones
+from rmpnn_b200.synthetic import RNAMPNNConfig, make_rnampnn_state_dict, synthetic_backbones
 from rmpnn_b200 import _lib
 from rmpnn_b200.engine_rnampnn import RNAMPNNEngine
 

@@ -5,7 +5,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 for p in (ROOT, os.path.join(ROOT, "rna-mpnn_b200")):
     sys.path.insert(0, p)
 import torch
-from oracle.weights import (RDesignConfig, RNAMPNNConfig, make_rnampnn_state_dict, make_state_dict, synthetic_backbones)
+from rmpnn_b200.synthetic import (RDesignConfig, RNAMPNNConfig, make_rnampnn_state_dict, make_state_dict, synthetic_backbones)
 from rmpnn_b200 import _lib, ops
 from rmpnn_b200.engine import RDesignEngine
 from rmpnn_b200.engine_rnampnn import RNAMPNNEngine

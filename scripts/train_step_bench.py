@@ -39,7 +39,7 @@ def main():
 
     import torch.distributed as dist
     import torch.nn.functional as F
-    from oracle.weights import RDesignConfig, make_state_dict, synthetic_backbones
+    from rmpnn_b200.synthetic import RDesignConfig, make_state_dict, synthetic_backbones
     from rdesign.model.rdesign import RNAModel
     from rmpnn_b200 import _lib
 
