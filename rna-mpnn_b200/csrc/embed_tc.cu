@@ -220,14 +220,18 @@ edge_embed_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const EmbedParams
             const float sigma = sqrtf((sq + red_sq[(half ^ 1) * kTileM + row]) * (1.f / 127.f) + 1e-6f);
             const float inv = 1.f / (sigma + 1e-6f);
             if (valid) {
-                uint4* dst = reinterpret_cast<uint4*>(p.h_E + (size_t)e * 128 + c0);
+                // 32-byte stores: every instruction writes full sectors (16-byte stores left each sector half written)
+                uint16_t* dst = p.h_E + (size_t)e * 128 + c0;
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                    float y[8];
+                for (int j = 0; j < 4; ++j) {
+                    uint32_t pk[8];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        y[q] = fmaf(s_par[128 + c0 + 8 * j + q], x[8 * j + q] * inv, s_par[256 + c0 + 8 * j + q]);
-                    dst[j] = make_uint4(pack_bf16(y[0], y[1]), pack_bf16(y[2], y[3]), pack_bf16(y[4], y[5]), pack_bf16(y[6], y[7]));
+                    for (int q = 0; q < 8; ++q) {
+                        const int c = 16 * j + 2 * q;
+                        pk[q] = pack_bf16(fmaf(s_par[128 + c0 + c], x[c] * inv, s_par[256 + c0 + c]),
+                                          fmaf(s_par[128 + c0 + c + 1], x[c + 1] * inv, s_par[256 + c0 + c + 1]));
+                    }
+                    stg256u(dst + 16 * j, pk);
                 }
             }
             tc_fence_before();
