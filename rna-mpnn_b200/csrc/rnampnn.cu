@@ -397,11 +397,17 @@ __global__ void __launch_bounds__(kAttnTile) res_attention_kernel(const float* _
         }
     }
     if (qi < N) {
-        float4* op = reinterpret_cast<float4*>(out + (base + qi) * E + h * HD);
+        float* op = out + (base + qi) * E + h * HD;
         const float inv = (q_ok && l > 0.f) ? 1.0f / l : 0.f;
+        // 32-byte stores: full sectors per instruction (a thread's head slice is HD * 4 = 32..128 contiguous bytes)
 #pragma unroll
-        for (int d4 = 0; d4 < HD / 4; ++d4)
-            op[d4] = make_float4(acc[2 * d4].x * inv, acc[2 * d4].y * inv, acc[2 * d4 + 1].x * inv, acc[2 * d4 + 1].y * inv);
+        for (int d8 = 0; d8 < HD / 8; ++d8) {
+            const float2 a0 = acc[4 * d8], a1 = acc[4 * d8 + 1], a2 = acc[4 * d8 + 2], a3 = acc[4 * d8 + 3];
+            asm volatile("st.global.v8.f32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(op + 8 * d8), "f"(a0.x * inv),
+                         "f"(a0.y * inv), "f"(a1.x * inv), "f"(a1.y * inv), "f"(a2.x * inv), "f"(a2.y * inv),
+                         "f"(a3.x * inv), "f"(a3.y * inv)
+                         : "memory");
+        }
     }
 }
 
