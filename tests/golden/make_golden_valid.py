@@ -1,6 +1,6 @@
 """Generate tests/golden/valid_set.npz: the reference's own held-out structures (data/valid_data.csv; data/test_data.csv
 is empty) run one by one (batch 1, the reference's inference setting) through the UNMODIFIED
-reference RNAModel on CPU with the seeded default weights.  Stores the packed coordinates (NaNs kept: NaN -> 0 is part of
+reference RNAModel on CPU with the seeded default weights (all 234 structures).  Stores the packed coordinates (NaNs kept: NaN -> 0 is part of
 the collate under test), the true sequences, and the reference's logits / argmax sequences.
 
     python tests/golden/make_golden_valid.py
@@ -27,11 +27,7 @@ def main():
     import pandas as pd
     torch.set_num_threads(8)
     df = pd.read_csv(os.path.join(REF, "data", "valid_data.csv"))
-    L = df["seq"].str.len()
-    keep = list(df.index[L <= 600])
-    for target in (1000, 1500, 4000):                     # three long chains: ~1000, ~1500 nt and the longest one
-        rest = [i for i in df.index if i not in keep]
-        keep.append(min(rest, key=lambda i: abs(L[i] - target)))
+    keep = list(df.index)                                 # all 234 held-out structures (123,781 nt, L 2..3065)
     model = load_reference_model(RDesignConfig(), 42)
     coords, lengths, seqs, logits, names = [], [], [], [], []
     for i in keep:

@@ -1,5 +1,5 @@
 """Sequence-recovery parity on the reference's own held-out structures (data/valid_data.csv; its test_data.csv is
-empty): 178 real RNA backbones run one by one through the unmodified reference on CPU (tests/golden/valid_set.npz,
+empty): all 234 real RNA backbones (123,781 nt) run one by one through the unmodified reference on CPU (tests/golden/valid_set.npz,
 made by tests/golden/make_golden_valid.py).  The B200 path has to return the same argmax sequence for every structure,
 hence the same recovery rate (BASELINE.json north_star: "parity with the reference on its own test_data.csv recovery")."""
 import os
@@ -41,7 +41,7 @@ def test_oracle_reproduces_reference_sequences(valid_set):
 @pytest.mark.gpu
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
 def test_recovery_parity_on_reference_validation_set(valid_set, precision):
-    """GPU: device-side collate from the packed coordinates (NaN -> 0) + engine forward at batch 1, all 178 structures.
+    """GPU: device-side collate from the packed coordinates (NaN -> 0) + engine forward at batch 1, all 234 structures.
     fp32 arm: logits within 1e-4 and IDENTICAL argmax sequences (identical recovery).  bf16 arm: logits within 2e-2,
     >= 99 % of the nucleotides agree, recovery within 0.5 points."""
     from rmpnn_b200 import _lib, ops
