@@ -31,6 +31,8 @@ inline int check_launch(const char* what, int kernels = 1) {
     } while (0)
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+// pointers touched by 256-bit vector accesses (ld/st.global.v8)
+inline bool aligned32(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 31u) == 0; }
 
 constexpr int kNumSMs = 148;   // B200: 2 dies x 74 SMs
 

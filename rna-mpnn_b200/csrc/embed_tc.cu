@@ -253,7 +253,7 @@ extern "C" int rmp_edge_embed_bf16(const float* X, const float* frames, const in
                                    void* stream) {
     RMP_REQUIRE(X && frames && node_src && ctr && nbr && rbf_mu_host && W_perm_bf16 && bias && gain && beta && h_E_bf16,
                 RMP_E_ARG, "rmp_edge_embed_bf16: null pointer");
-    RMP_REQUIRE(aligned16(W_perm_bf16) && aligned16(h_E_bf16), RMP_E_ALIGN, "rmp_edge_embed_bf16: unaligned pointer");
+    RMP_REQUIRE(aligned16(W_perm_bf16) && aligned32(h_E_bf16), RMP_E_ALIGN, "rmp_edge_embed_bf16: W must be 16-byte, h_E 32-byte aligned (256-bit stores)");
     if (n_edges <= 0) return RMP_OK;
     CUtensorMap tm_w;
     int rc = tc::make_map_bf16_rows128(&tm_w, W_perm_bf16, 128);

@@ -896,8 +896,8 @@ extern "C" int rmp_edge_mlp_bf16_traced(const void* h_E_bf16, const void* W_bf16
     RMP_REQUIRE(h_E_bf16 && W_bf16 && Pc && Pn && ctr && nbr && agg && bias, RMP_E_ARG, "rmp_edge_mlp_bf16: null pointer");
     RMP_REQUIRE(num_stages >= 1 && num_stages <= tc::kMaxStages, RMP_E_SHAPE, "rmp_edge_mlp_bf16: 1..4 message layers");
     RMP_REQUIRE(n_edges >= 0, RMP_E_ARG, "rmp_edge_mlp_bf16: bad sizes");
-    RMP_REQUIRE(aligned16(h_E_bf16) && aligned16(W_bf16) && aligned16(Pc) && aligned16(Pn), RMP_E_ALIGN,
-                "rmp_edge_mlp_bf16: pointers must be 16-byte aligned");
+    RMP_REQUIRE(aligned16(h_E_bf16) && aligned16(W_bf16) && aligned32(Pc) && aligned32(Pn), RMP_E_ALIGN,
+                "rmp_edge_mlp_bf16: h_E / W must be 16-byte aligned, Pc / Pn 32-byte aligned (256-bit gathers)");
     if (n_edges == 0) return RMP_OK;
     CUtensorMap tm_e, tm_w;
     int rc = tc::make_map_bf16_rows128(&tm_e, h_E_bf16, (uint64_t)n_edges);
@@ -942,6 +942,9 @@ extern "C" int rmp_node_mlp_bf16(const float* h_in, float* agg, int prologue_ln,
     RMP_REQUIRE(num_stages >= 1 && num_stages <= tc::kNodeMaxStages, RMP_E_SHAPE, "rmp_node_mlp_bf16: 1..5 stages");
     RMP_REQUIRE(!prologue_ln || (ln1_g && ln1_b), RMP_E_ARG, "rmp_node_mlp_bf16: LayerNorm-1 parameters missing");
     if (n_rows <= 0) return RMP_OK;
+    RMP_REQUIRE(aligned16(h_in) && (!agg || aligned16(agg)) && (!x1_scratch || aligned32(x1_scratch)) &&
+                (!h_out || aligned32(h_out)) && (!p_out || aligned32(p_out)) && (!pn_out_bf16 || aligned32(pn_out_bf16)),
+                RMP_E_ALIGN, "rmp_node_mlp_bf16: h_in / agg must be 16-byte aligned, x1 / h_out / p_out / pn_out 32-byte aligned");
     tc::NodeParams p{};
     CUtensorMap maps[tc::kNodeMaxStages];
     memset(maps, 0, sizeof(maps));

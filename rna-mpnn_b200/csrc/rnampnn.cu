@@ -486,7 +486,7 @@ extern "C" int rmp_res_attention(const float* qkv, const float* mask, int B, int
                                  void* stream) {
     RMP_REQUIRE(qkv && mask && out, RMP_E_ARG, "rmp_res_attention: null pointer");
     RMP_REQUIRE(B > 0 && N > 0 && heads > 0 && E > 0 && E % heads == 0, RMP_E_ARG, "rmp_res_attention: bad sizes");
-    RMP_REQUIRE(aligned16(qkv) && aligned16(out), RMP_E_ALIGN, "rmp_res_attention: 16-byte alignment");
+    RMP_REQUIRE(aligned16(qkv) && aligned32(out), RMP_E_ALIGN, "rmp_res_attention: qkv 16-byte, out 32-byte alignment (256-bit stores)");
     RMP_REQUIRE(B <= 65535 && heads <= 65535, RMP_E_SHAPE, "rmp_res_attention: grid too large");
     const int hd = E / heads;
     dim3 grid(ceil_div(N, kAttnTile), heads, B);

@@ -399,7 +399,8 @@ extern "C" int rmp_row_mlp_tc(const rmp_mlp_desc* dp, const void* const* W_bf16,
         RMP_REQUIRE(!d.seg_bf16[s] || d.seg_width[s] == 128, RMP_E_SHAPE, "rmp_row_mlp_bf16: bf16 segment %d must be 128 wide", s);
         RMP_REQUIRE(d.seg_src[s] && d.seg_width[s] > 0 && d.seg_width[s] % 128 == 0, RMP_E_SHAPE,
                     "rmp_row_mlp_bf16: segment %d width %d must be a multiple of 128", s, d.seg_width[s]);
-        RMP_REQUIRE(aligned16(d.seg_src[s]), RMP_E_ALIGN, "rmp_row_mlp_bf16: segment %d not 16-byte aligned", s);
+        RMP_REQUIRE(d.seg_bf16[s] ? aligned32(d.seg_src[s]) : aligned16(d.seg_src[s]), RMP_E_ALIGN,
+                    "rmp_row_mlp_bf16: segment %d unaligned (fp32 rows 16 bytes, bf16 rows 32 bytes: 256-bit gathers)", s);
         p.seg_src[s] = d.seg_src[s]; p.seg_idx[s] = d.seg_idx[s]; p.seg_width[s] = d.seg_width[s];
         k0 += d.seg_width[s];
     }
@@ -409,7 +410,7 @@ extern "C" int rmp_row_mlp_tc(const rmp_mlp_desc* dp, const void* const* W_bf16,
                 "rmp_row_mlp_bf16: bf16 segments need all (<= 3) segments bf16 and bf16 operands");
     p.all_bf16 = n_bf16 > 0;
     p.out16 = reinterpret_cast<uint16_t*>(d.out_bf16);
-    RMP_REQUIRE(!d.out_bf16 || (d.epilogue != RMP_EPI_SEGSUM && aligned16(d.out_bf16)), RMP_E_ARG,
+    RMP_REQUIRE(!d.out_bf16 || (d.epilogue != RMP_EPI_SEGSUM && aligned32(d.out_bf16)), RMP_E_ARG,
                 "rmp_row_mlp_bf16: out_bf16 goes with STORE / RESID_ADD and must be 16-byte aligned");
     if (p.a_pieces <= 3) {
         int pc = 0;
@@ -440,9 +441,9 @@ extern "C" int rmp_row_mlp_tc(const rmp_mlp_desc* dp, const void* const* W_bf16,
     for (int s = 0; s + 1 < d.num_stages; ++s) kmax = d.n_out[s] > kmax ? d.n_out[s] : kmax;
     p.S = d.num_stages;
     p.epilogue = d.epilogue;
-    if (d.epilogue == RMP_EPI_RESID_ADD) RMP_REQUIRE(d.resid && aligned16(d.resid), RMP_E_ARG, "rmp_row_mlp_bf16: resid missing");
+    if (d.epilogue == RMP_EPI_RESID_ADD) RMP_REQUIRE(d.resid && aligned32(d.resid), RMP_E_ARG, "rmp_row_mlp_bf16: resid missing or not 32-byte aligned");
     if (d.epilogue == RMP_EPI_SEGSUM) RMP_REQUIRE(d.seg_id, RMP_E_ARG, "rmp_row_mlp_bf16: seg_id missing");
-    RMP_REQUIRE(aligned16(d.out), RMP_E_ALIGN, "rmp_row_mlp_bf16: out not 16-byte aligned");
+    RMP_REQUIRE(aligned32(d.out), RMP_E_ALIGN, "rmp_row_mlp_bf16: out not 32-byte aligned (256-bit stores)");
     p.resid = d.resid; p.seg_id = d.seg_id; p.row_scale = d.row_scale; p.alpha = d.alpha; p.out = d.out;
     p.n_rows = d.rows_cap;
     p.timeline = reinterpret_cast<long long*>(g_row_tc_timeline);
@@ -451,13 +452,10 @@ extern "C" int rmp_row_mlp_tc(const rmp_mlp_desc* dp, const void* const* W_bf16,
     const size_t smem = 1024 + (size_t)p.a_kblocks * tc::kKBlockBytes + (size_t)tc::kRowRing * tc::kRowSlotBytes +
                         sizeof(tc::RowBarriers) + 64;
     RMP_REQUIRE(smem <= 227 * 1024, RMP_E_SHAPE, "rmp_row_mlp_bf16: needs %zu B of shared memory", smem);
-    static int max_set[2] = {0, 0};
     const int f = operand_format == RMP_OPERAND_FP16 ? 1 : 0;
     auto kern = f ? tc::row_mlp_tc_kernel<true> : tc::row_mlp_tc_kernel<false>;
-    if ((int)smem > max_set[f]) {
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        max_set[f] = (int)smem;
-    }
+    // per device and not cached: the opt-in is a per-device function attribute (a process may drive several GPUs)
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int n_tiles = ceil_div(d.rows_cap, tc::kTileM);
     const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
     kern<<<grid, tc::kThreads, smem, (cudaStream_t)stream>>>(maps[0], maps[1], maps[2], maps[3], maps[4], maps[5], p);

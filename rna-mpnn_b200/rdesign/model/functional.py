@@ -22,13 +22,21 @@ from rmpnn_b200 import ops
 def _kernel_path(*tensors, training: bool = True) -> bool:
     """True -> run the C-ABI kernels; False -> differentiable torch-CUDA composition.
 
-    The composition is taken only by a module in ``train()`` mode with autograd enabled
-    and something to differentiate; ``eval()`` mode and ``torch.no_grad()`` always run
-    the kernels (their outputs carry no autograd graph)."""
+    ``train()`` mode with autograd enabled and something to differentiate takes the composition.  In ``eval()``
+    mode the kernels run (their outputs carry no autograd graph) unless autograd is on and either a non-parameter
+    input requires grad (saliency / gradient checks through an eval-mode model) or ``RMPNN_EVAL_AUTOGRAD=1`` is set
+    (fine-tuning with dropout off).  Parameters alone do not switch an eval-mode model to the composition: the
+    reference's ``predict()`` (rdesign/model/rdesign.py:144-172) runs without ``torch.no_grad()`` and must stay on
+    the kernels."""
+    import os
     for t in tensors:
         if not t.is_cuda:
             raise RuntimeError("rdesign (B200 build) runs on CUDA tensors only; there is no CPU path")
-    return not (training and torch.is_grad_enabled() and any(t.requires_grad for t in tensors))
+    if not torch.is_grad_enabled():
+        return True
+    if training or os.environ.get("RMPNN_EVAL_AUTOGRAD", "0") == "1":
+        return not any(t.requires_grad for t in tensors)
+    return not any(t.requires_grad and not isinstance(t, nn.Parameter) for t in tensors)
 
 
 def scatter_sum(src: torch.Tensor, index: torch.Tensor, dim: int = -1, out: Optional[torch.Tensor] = None,

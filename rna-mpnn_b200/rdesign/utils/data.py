@@ -101,6 +101,8 @@ def featurize(batch):
 
 
 class RNADataModule(LightningDataModule):
+    num_workers = 19                                   # the reference's loader setting; tests set 0
+
     @classmethod
     def from_defaults(cls, batch_size=16, split_ratio=SPLIT_RATIO):
         split_dataset(gen_dataframe(), split_ratio=split_ratio)
@@ -122,8 +124,8 @@ class RNADataModule(LightningDataModule):
             self.test_dataset = RNADataset(*self.paths['test'])
 
     def _loader(self, ds, shuffle):
-        return torch.utils.data.DataLoader(ds, batch_size=self.batch_size, num_workers=19, shuffle=shuffle,
-                                           persistent_workers=True, collate_fn=featurize)
+        return torch.utils.data.DataLoader(ds, batch_size=self.batch_size, num_workers=self.num_workers, shuffle=shuffle,
+                                           persistent_workers=self.num_workers > 0, collate_fn=featurize)
 
     def train_dataloader(self):
         return self._loader(self.train_dataset, True)

@@ -433,3 +433,44 @@ __all__ = ["collate", "tc_eligible", "ResGraph", "res_graph", "res_edge_rows", "
            "readout_head_masked", "EPI_RESID_ADD", "Graph", "PackedLinear", "edge_embed_bf16", "pack_edge_embedding", "edge_mlp_bf16", "node_mlp_bf16", "knn", "build_graph", "raw_features", "pack_linear", "row_mlp",
            "add_layernorm", "readout_head", "cast_bf16", "EPI_STORE", "EPI_NORMALIZE", "EPI_RESID_LN",
            "EPI_SEGSUM", "HIDDEN", "NODE_RAW", "EDGE_RAW", "MAX_K"]
+
+
+# --------------------------------------------------------------------------- device guard
+def _cuda_device_of(objs, depth=0):
+    """Device of the first CUDA tensor found in ``objs`` (tensors, Graph / ResGraph / PackedLinear, short sequences)."""
+    for o in objs:
+        if torch.is_tensor(o):
+            if o.is_cuda:
+                return o.device
+        elif isinstance(o, (Graph, ResGraph, PackedLinear)):
+            d = _cuda_device_of(vars(o).values(), depth + 1)
+            if d is not None:
+                return d
+        elif isinstance(o, (list, tuple)) and depth < 3:
+            d = _cuda_device_of(o, depth + 1)
+            if d is not None:
+                return d
+    return None
+
+
+def _on_tensor_device(fn):
+    """Run ``fn`` with the CUDA device of its tensor arguments current: kernels, function attributes and
+    ``torch.cuda.current_stream()`` then all refer to the GPU that owns the memory (a model on cuda:1 while
+    cuda:0 is current would otherwise enqueue device-1 pointers on device 0)."""
+    import functools
+
+    @functools.wraps(fn)
+    def guarded(*args, **kwargs):
+        dev = _cuda_device_of(list(args) + list(kwargs.values()))
+        if dev is None or dev.index == torch.cuda.current_device():
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+    return guarded
+
+
+for _name, _fn in list(globals().items()):
+    if callable(_fn) and not _name.startswith("_") and getattr(_fn, "__module__", None) == __name__ \
+            and not isinstance(_fn, type):
+        globals()[_name] = _on_tensor_device(_fn)
+del _name, _fn

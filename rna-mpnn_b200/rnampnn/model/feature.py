@@ -6,8 +6,10 @@ warp-level top-K (no [B,N,N] tensor), per-residue / per-edge feature kernels tha
 distances from coordinates, and the fused row-MLP for the Linear stacks.
 
 Neighbour order: ascending centroid distance, exact ties broken by the lower residue index (the reference's
-``torch.topk`` leaves tie order unspecified).  ``AtomFeature`` / ``to_atom_format`` of the reference file are
-never reached from ``RNAMPNN.forward`` and are not provided.
+``torch.topk`` leaves tie order unspecified).
+
+``AtomFeature`` / ``to_atom_format`` (reference :10-130) are never reached from ``RNAMPNN.forward``; they are kept as
+plain-PyTorch passthroughs (any device) so that ``test.py::test_atom_*`` and user code importing them keep working.
 """
 from __future__ import annotations
 
@@ -16,8 +18,56 @@ from torch import nn
 
 from rmpnn_b200 import ops
 from rmpnn_b200.engine_rnampnn import RNAMPNNEngine
-from ..config.glob import DEFAULT_HIDDEN_DIM, NUM_MAIN_SEQ_ATOMS
+from ..config.glob import DEFAULT_HIDDEN_DIM, LEPS, NUM_MAIN_SEQ_ATOMS, SEPS
 from .functional import GraphNormalization, RNABert, _dropout_active, _flat, _kernel_path, _packed, _widths_ok
+
+
+def to_atom_format(coords: torch.Tensor, mask: torch.Tensor):
+    """Residue layout -> atom layout: coords [B,N,A,3] -> [B,N*A,3], mask [B,N] -> [B,N*7] (every residue's flag
+    repeated for its seven atoms)."""
+    B = coords.shape[0]
+    return coords.reshape(B, -1, coords.shape[3]), mask.repeat_interleave(NUM_MAIN_SEQ_ATOMS, dim=1)
+
+
+class AtomFeature(nn.Module):
+    """Atom-level graph and type embedding (passthrough, plain PyTorch; O(M^2) in the number of atoms like the
+    reference).  Neighbours = the ``num_atom_neighbours`` nearest atoms by sqrt(|d|^2 + 1e-6); the atom itself and
+    pairs with a padded atom sit at 1e6; the self slot becomes -1, and a padded atom's whole row is -1 / 1e6."""
+
+    def __init__(self, num_atom_neighbours: int, atom_embedding_dim: int = DEFAULT_HIDDEN_DIM):
+        super().__init__()
+        self.num_atom_neighbours = num_atom_neighbours
+        self.atom_embedding_dim = atom_embedding_dim
+        self.embedding = nn.Embedding(num_embeddings=NUM_MAIN_SEQ_ATOMS, embedding_dim=atom_embedding_dim)
+        self.graph_norm = GraphNormalization(embedding_dim=atom_embedding_dim)
+
+    def _get_atom_graph(self, atom_coords: torch.Tensor, atom_mask: torch.Tensor):
+        B, M, _ = atom_coords.shape
+        K = self.num_atom_neighbours
+        m = atom_mask.to(atom_coords.dtype)
+        delta = atom_coords[:, None, :, :] - atom_coords[:, :, None, :]
+        dist = torch.sqrt(delta.square().sum(dim=-1) + SEPS)
+        dist = dist + LEPS * torch.eye(M, device=dist.device, dtype=dist.dtype)
+        both = m[:, None, :] * m[:, :, None]
+        dist = dist * both + (1.0 - both) * LEPS
+        near_d, near_i = torch.topk(dist, min(K, M), dim=-1, largest=False)
+        if K > M:                                              # fewer atoms than requested neighbours
+            near_d = torch.cat([near_d, near_d.new_full((B, M, K - M), LEPS)], dim=-1)
+            near_i = torch.cat([near_i, near_i.new_full((B, M, K - M), -1)], dim=-1)
+        own = torch.arange(M, device=near_i.device)[None, :, None]
+        near_i = torch.where(near_i == own, torch.full_like(near_i, -1), near_i)
+        padded = (atom_mask == 0)[:, :, None]
+        return near_d.masked_fill(padded, LEPS), near_i.masked_fill(padded, -1)
+
+    def _atom_embedding(self, atom_mask: torch.Tensor) -> torch.Tensor:
+        B, M = atom_mask.shape
+        kinds = (torch.arange(M, device=atom_mask.device) % NUM_MAIN_SEQ_ATOMS)[None, :].expand(B, -1)
+        return self.graph_norm.compose(self.embedding(kinds) * atom_mask[:, :, None], atom_mask)
+
+    def forward(self, atom_coords: torch.Tensor, atom_mask: torch.Tensor):
+        """-> (atom_embedding [B,M,D], atom_cross_dists [B,M,K], atom_edge_index [B,M,K])."""
+        dists, index = self._get_atom_graph(atom_coords, atom_mask)
+        return self._atom_embedding(atom_mask), dists, index
 
 
 class ResFeature(nn.Module):

@@ -20,11 +20,18 @@ from ..config.glob import NUM_RES_TYPES, SEPS
 
 
 def _kernel_path(*tensors, training: bool = True) -> bool:
-    """True -> C-ABI kernels; False -> differentiable torch-CUDA composition (train() + autograd only)."""
+    """True -> C-ABI kernels; False -> differentiable torch-CUDA composition.  Same rule as the rdesign mirror:
+    train() + autograd -> composition; eval() -> kernels, unless a non-parameter input requires grad or
+    ``RMPNN_EVAL_AUTOGRAD=1`` asks for gradients through an eval-mode model."""
+    import os
     for t in tensors:
         if not t.is_cuda:
             raise RuntimeError("rnampnn (B200 build) runs on CUDA tensors only; there is no CPU path")
-    return not (training and torch.is_grad_enabled() and any(t.requires_grad for t in tensors))
+    if not torch.is_grad_enabled():
+        return True
+    if training or os.environ.get("RMPNN_EVAL_AUTOGRAD", "0") == "1":
+        return not any(t.requires_grad for t in tensors)
+    return not any(t.requires_grad and not isinstance(t, nn.Parameter) for t in tensors)
 
 
 def _dropout_active(module: nn.Module) -> bool:
@@ -64,6 +71,11 @@ class GraphNormalization(nn.Module):
             out = ops.graph_norm(_flat(features), None, mask.to(torch.float32).reshape(-1).contiguous(), B, N,
                                  self.scale.detach().reshape(-1).contiguous(), self.shift.detach().reshape(-1).contiguous())
             return out.reshape(features.shape)
+        return self.compose(features, mask)
+
+    def compose(self, features: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+        """The same normalisation from differentiable torch ops (any device): the train()-mode path, and what the
+        plain-PyTorch passthrough modules (AtomFeature, AtomMPNN) call."""
         m = mask.unsqueeze(-1).to(features.dtype)
         xm = features * m
         n = m.sum(dim=1, keepdim=True)

@@ -3,7 +3,8 @@
 ``forward`` runs three launches on the sm_100a kernels: the fused message MLP (the kernel gathers
 ``h[centre] | h[neighbour] | e`` itself, applies the two Linear+GELU stages and accumulates the masked mean per
 centre), the two-launch GraphNorm with the residual add fused in, and the fused edge MLP with its in-place
-``e +=`` epilogue.  ``AtomMPNN`` of the reference file is never reached from ``RNAMPNN.forward`` and is not provided.
+``e +=`` epilogue.  ``AtomMPNN`` (reference :7-112) is never reached from ``RNAMPNN.forward``; it is kept as a
+plain-PyTorch passthrough so that ``test.py::test_atom_mpnn`` and user code importing it keep working.
 """
 from __future__ import annotations
 
@@ -14,6 +15,38 @@ from torch import nn
 
 from rmpnn_b200 import ops
 from .functional import GraphNormalization, _dropout_active, _flat, _kernel_path, _packed
+
+
+class AtomMPNN(nn.Module):
+    """Atom-level message passing (passthrough, plain PyTorch): message MLP on [h_neighbour | h_atom | distance],
+    mean over the valid neighbour slots, residual, GraphNormalization."""
+
+    def __init__(self, atom_embedding_dim: int, depth_atom_mpnn: int, dropout: float = 0.1):
+        super().__init__()
+        self.graph_norm = GraphNormalization(embedding_dim=atom_embedding_dim)
+        layers, width = [], 2 * atom_embedding_dim + 1
+        for _ in range(depth_atom_mpnn):
+            layers += [nn.Linear(width, atom_embedding_dim), nn.GELU(), nn.Dropout(dropout)]
+            width = atom_embedding_dim
+        self.message_layers = nn.Sequential(*layers)
+
+    def message(self, atom_embedding, atom_cross_dists, atom_edge_index, atom_mask):
+        """[B,M,K,D] messages; slots holding -1 are zero."""
+        B, M, K = atom_edge_index.shape
+        h = atom_embedding * atom_mask[:, :, None]
+        rows = atom_edge_index.clamp(min=0)                    # -1 reads atom 0; the slot is zeroed below
+        nbr = torch.gather(h, 1, rows.reshape(B, M * K, 1).expand(-1, -1, h.shape[-1])).reshape(B, M, K, -1)
+        pair = torch.cat([nbr, h[:, :, None, :].expand(-1, -1, K, -1), atom_cross_dists[..., None]], dim=-1)
+        return self.message_layers(pair) * (atom_edge_index != -1)[..., None].float()
+
+    @staticmethod
+    def aggregation(atom_embedding, messages, atom_edge_index, atom_mask):
+        count = (atom_edge_index != -1).sum(dim=-1, keepdim=True).float().clamp(min=1.0)
+        return (atom_embedding + messages.sum(dim=2) / count) * atom_mask[:, :, None]
+
+    def forward(self, atom_embedding, atom_cross_dists, atom_edge_index, atom_mask):
+        messages = self.message(atom_embedding, atom_cross_dists, atom_edge_index, atom_mask)
+        return self.graph_norm.compose(self.aggregation(atom_embedding, messages, atom_edge_index, atom_mask), atom_mask)
 
 
 class ResMPNN(nn.Module):

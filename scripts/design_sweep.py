@@ -38,7 +38,8 @@ def main():
     ap.add_argument("--token-budget", type=int, default=32768)
     ap.add_argument("--k", type=int, default=30)
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"])
-    ap.add_argument("--check", action="store_true", help="T=0 argmax of the first batches against the CPU oracle")
+    ap.add_argument("--check", action="store_true", help="T=0 argmax of ~200 structures against the CPU oracle")
+    ap.add_argument("--check-structures", type=int, default=200)
     args = ap.parse_args()
 
     import torch.distributed as dist
@@ -128,17 +129,26 @@ def main():
         dist.all_reduce(nt)
     ok = None
     if args.check and rank == 0:
+        # T = 0 argmax against the CPU oracle on ~200 structures spread over this rank's batches (short and long).
+        # The oracle sees the same padded rows (a structure's result depends on its batch's N).
         from oracle import rdesign_oracle as O
-        sweep(0.0, False, limit=2)
-        torch.cuda.synchronize()
-        got = seqs.cpu()
-        s0, n, N, Nv, Ne = plan[0]
-        X, mask = ops.collate(packed, starts_d[s0:s0 + n], len_d[s0:s0 + n], N, 6)
-        sub = slice(0, min(n, 4))
-        ref = O.forward(make_state_dict(cfg, 42), X[sub].cpu(), torch.zeros(X[sub].shape[:2], dtype=torch.long), mask[sub].cpu(),
-                        args.k, cfg.scale)
-        m = ref["samples"].shape[0]
-        ok = float((got[:m].long() == ref["samples"]).float().mean())
+        params = make_state_dict(cfg, 42)
+        want, per_batch = args.check_structures, 8
+        picks = sorted({int(round(j * (len(plan) - 1) / max(1, want // per_batch - 1))) for j in range(max(1, want // per_batch))})
+        same = seen = n_struct = 0
+        worst = 0.0
+        for bi in picks:
+            s0, n, N, Nv, Ne = plan[bi]
+            X, mask = ops.collate(packed, starts_d[s0:s0 + n], len_d[s0:s0 + n], N, 6)
+            out = eng.forward(X, mask, sizes=(Nv, Ne), temperature=0.0)
+            m = min(n, per_batch)
+            ref = O.forward(params, X[:m].cpu(), torch.zeros(m, N, dtype=torch.long), mask[:m].cpu(), args.k, cfg.scale)
+            k = ref["samples"].shape[0]
+            same += int((out["samples"][:k].cpu() == ref["samples"]).sum())
+            worst = max(worst, float((out["logits"][:k].cpu() - ref["logits"]).abs().max()))
+            seen += k
+            n_struct += m
+        ok = {"structures": n_struct, "nucleotides": seen, "agreement": same / max(1, seen), "max_abs_dlogit": worst}
     if rank == 0:
         resident_ms, e2e_ms = t.tolist()
         total_nt, total_structs = nt.tolist()
