@@ -28,6 +28,18 @@ def pytest_collection_modifyitems(config, items):
             item.add_marker(skip)
 
 
+@pytest.fixture(autouse=True)
+def _restore_global_torch_state():
+    """The reference's ``seeding()`` (mirrored by the drop-in) sets ``float32_matmul_precision('medium')`` and cuDNN
+    flags process-wide; on hosts with bf16 matmul units that changes the CPU oracle's fp32 results.  Tests that call
+    it must not leak the setting into the parity tests that follow."""
+    prec = torch.get_float32_matmul_precision()
+    det, bench = torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark
+    yield
+    torch.set_float32_matmul_precision(prec)
+    torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark = det, bench
+
+
 def load_golden(name):
     """Golden vectors produced by the unmodified reference (tests/golden/make_golden.py)."""
     from oracle.weights import RDesignConfig, make_state_dict
