@@ -2,12 +2,15 @@
 """bench.py -- RNA nucleotides/s of the structure-to-sequence forward path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--precision fp32|bf16] [--workload c2|c3]
+                    [--precision fp32|bf16] [--workload c2|c3|c5]
 
 One "step" = one pass of the hot path (kNN + featurizer -> 9 message-passing layers ->
 readout head with softmax/argmax) over one synthetic padded batch.  The N=1 workload is
 BASELINE.json configs[1]: synthetic RNA backbones L=256, K=30, batch 64, default model.
-N>1 shards whole structures across ranks (no data-path collective), weak scaling.
+N>1 shards whole structures across ranks (no data-path collective), weak scaling; the line then also carries a
+"pool" block: a mixed-length pool (L~U[50,1000], N x 131,072 nt) partitioned with rmpnn_b200.shard.partition and run
+eagerly per batch, with every rank's busy time (the limiter of real sharded inference: partition balance and launches).
+`--workload c5` runs BASELINE configs[4] itself (100 k structures, temperature sampling, scripts/design_sweep.py).
 
 `--impl reference` times the CPU arm on the host cores: the reference's own RNAModel from the staged copy
 oracle/_ref (written by oracle/make_ref.py; kind "reference", the whole batch per step), or, when no copy of the
@@ -232,9 +235,33 @@ def cpu_forward_rate(workload, budget_s, min_reps=1, sample_B=None):
             "sample": f"{what}: {sB} of {B} structures (L={L}, K={K}), {reps} forward passes in {el:.1f} s"}, el / reps
 
 
+def sweep_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("design_sweep", os.path.join(ROOT, "scripts", "design_sweep.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def run_c5(args):
+    """BASELINE configs[4]: batched design sweep, strong scaling over the ranks (one sweep = one step)."""
+    import torch.distributed as dist
+    ds = sweep_module()
+    sa = ds.parse_args(["--precision", args.precision] + (["--structures", str(args.structures)] if args.structures else []))
+    res = ds.run(sa)
+    if res is not None:
+        res.update({"steps": 1, "warmup": 1, "ms_per_step": res["sweep_ms"], "vs_baseline": None})
+        print(json.dumps(res), flush=True)
+    if dist.is_initialized():
+        dist.destroy_process_group()
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        return
+    if args.workload not in WORKLOADS:
+        print(json.dumps({"impl": "reference", "unavailable": f"the CPU arm times workloads {sorted(WORKLOADS)}"}))
         return
     B, L, K, _ = WORKLOADS[args.workload]
     # one step = one forward over the bounded sample (budget 0 -> exactly one pass)
@@ -368,6 +395,18 @@ def run_ours(args):
     value = nt_all / (total_ms * 1e-3)
     e2e = nt_all / (e2e_ms * 1e-3)
 
+    pool = None
+    if world > 1 and not args.no_pool:
+        # sharded mixed-length pool (what real multi-GPU inference looks like): world x 8 x 16,384 nt (eight C2 steps per rank), LPT partition,
+        # eager per-batch launches, per-rank busy time.  Reported next to the replica timing above, not instead of it.
+        ds = sweep_module()
+        sa = ds.parse_args(["--precision", args.precision, "--total-nt", str(8 * 16384 * world), "--temperature", "0.0",
+                            "--token-budget", "16384"])
+        pr = ds.run(sa, init_dist=False)
+        if pr is not None:
+            pool = {"workload": pr["config"]["workload"], "value": pr["value"], "unit": pr["unit"], "sweep_ms": pr["sweep_ms"],
+                    "per_rank": pr["per_rank"], "gpu_launches_rank0": pr["gpu_launches"]}
+
     if rank == 0:
         pk = peaks()
         k_ms = sum(ktimes) / max(1, len(ktimes))
@@ -397,6 +436,8 @@ def run_ours(args):
                 "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": Xp.numel() * 4 + mp.numel() * 4,
                         "d2h_bytes_per_step": samples_host.numel() * 8},
                 "gpu_launches": int(launches), "clocks": clocks.summary()}
+        if pool is not None:
+            line["pool"] = pool
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -409,13 +450,17 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default=os.environ.get("RMPNN_PRECISION", "bf16"), choices=["fp32", "bf16"])
-    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS))
+    ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c5"])
+    ap.add_argument("--structures", type=int, default=0, help="c5: number of structures (default 100000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pool", action="store_true", help="N>1: skip the sharded mixed-length pool pass")
     ap.add_argument("--graph", dest="graph", action="store_true", default=True, help="replay the forward as a CUDA graph")
     ap.add_argument("--no-graph", dest="graph", action="store_false")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "c5":
+        run_c5(args)
     else:
         run_ours(args)
 

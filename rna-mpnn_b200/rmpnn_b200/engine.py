@@ -140,9 +140,12 @@ class RDesignEngine:
                 raise ValueError("bf16 layer kernels need message layers of shape 384->128->128..")
             # per-node projections of W_0's centre / neighbour column blocks: emitted by the previous
             # layer's node kernel, or computed here for the first layer
-            P = getattr(self, "_next_P", None)
+            tagged = getattr(self, "_next_P", None)
             self._next_P = None
-            if P is None or P[0].shape[0] != g.Nv:
+            P = None
+            if tagged is not None and tagged[0] == (l, h_V.data_ptr(), g.Nv):
+                P = tagged[1]              # emitted by the previous layer's node kernel for exactly this h_V
+            if P is None:
                 P = self._proj_buffers(g.Nv, h_V.device)
                 ops.node_mlp_bf16(h_V, [(*lw.proj16, 2)], g.Nv, p_out=P[0], pn_out=P[1])
             if self.kernel_timer is not None:
@@ -175,7 +178,7 @@ class RDesignEngine:
         x1 = torch.empty_like(h_V)
         ops.node_mlp_bf16(h_V, stages, g.Nv, agg=agg, ln1=(lw.norm1_w, lw.norm1_b), ln2=(lw.norm2_w, lw.norm2_b),
                           x1=x1, h_out=out, p_out=pc, pn_out=pn)
-        self._next_P = (pc, pn) if pc is not None else None
+        self._next_P = ((l + 1, out.data_ptr(), g.Nv), (pc, pn)) if pc is not None else None
         return out
 
     @staticmethod

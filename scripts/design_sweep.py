@@ -29,7 +29,7 @@ for p in (ROOT, os.path.join(ROOT, "rna-mpnn_b200")):
 import torch  # noqa: E402
 
 
-def main():
+def parse_args(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--structures", type=int, default=100000)
     ap.add_argument("--min-len", type=int, default=50)
@@ -40,7 +40,13 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"])
     ap.add_argument("--check", action="store_true", help="T=0 argmax of ~200 structures against the CPU oracle")
     ap.add_argument("--check-structures", type=int, default=200)
-    args = ap.parse_args()
+    ap.add_argument("--total-nt", type=int, default=0,
+                    help="draw structures until this many nucleotides are reached (overrides --structures)")
+    return ap.parse_args(argv)
+
+
+def run(args, init_dist=True):
+    """Runs the sweep on this rank; returns the result dict on rank 0 (None elsewhere)."""
 
     import torch.distributed as dist
     from rmpnn_b200.synthetic import RDesignConfig, make_state_dict
@@ -54,11 +60,17 @@ def main():
         raise SystemExit("design_sweep.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    if world > 1 and init_dist and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=dev)
 
     g = torch.Generator().manual_seed(1005)
     lengths = torch.randint(args.min_len, args.max_len + 1, (args.structures,), generator=g).tolist()
+    if args.total_nt:
+        acc, n = 0, 0
+        while n < len(lengths) and acc < args.total_nt:
+            acc += lengths[n]
+            n += 1
+        lengths = lengths[:n]
     parts = shard.partition(lengths, world, top_k=args.k, token_budget=args.token_budget)
     mine = parts[rank]
     own = [i for b in mine for i in b]
@@ -124,9 +136,16 @@ def main():
     barrier()
     t = torch.tensor([e[0].elapsed_time(e[1]), e[2].elapsed_time(e[3])], dtype=torch.float64, device=dev)
     nt = torch.tensor([float(done), float(len(own))], dtype=torch.float64, device=dev)
+    # per-rank busy time and load (nucleotides, launches): shows whether the limiter is the partition or the launches
+    mine_stats = torch.tensor([e[0].elapsed_time(e[1]), float(done), float(launches), float(len(plan))],
+                              dtype=torch.float64, device=dev)
+    all_stats = [torch.zeros_like(mine_stats) for _ in range(world)]
     if world > 1:
+        dist.all_gather(all_stats, mine_stats)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         dist.all_reduce(nt)
+    else:
+        all_stats = [mine_stats]
     ok = None
     if args.check and rank == 0:
         # T = 0 argmax against the CPU oracle on ~200 structures spread over this rank's batches (short and long).
@@ -149,24 +168,38 @@ def main():
             seen += k
             n_struct += m
         ok = {"structures": n_struct, "nucleotides": seen, "agreement": same / max(1, seen), "max_abs_dlogit": worst}
+    result = None
     if rank == 0:
+        busy = [float(a[0]) for a in all_stats]
+        per_rank = {"busy_ms": busy, "nucleotides": [int(a[1]) for a in all_stats],
+                    "launches": [int(a[2]) for a in all_stats], "batches": [int(a[3]) for a in all_stats],
+                    "worst_over_mean_busy": max(busy) / (sum(busy) / len(busy)),
+                    "worst_over_mean_nt": max(float(a[1]) for a in all_stats) / (sum(float(a[1]) for a in all_stats) / world)}
         resident_ms, e2e_ms = t.tolist()
         total_nt, total_structs = nt.tolist()
         pad = sum(n * N for _, n, N, _, _ in plan) / max(1, sum(Nv for *_, Nv, _ in plan))
-        print(json.dumps({
+        result = {
             "metric": "RNA nucleotides/sec (design sweep, temperature sampling)", "value": total_nt / (resident_ms * 1e-3),
             "unit": "nt/s", "structures_per_s": total_structs / (resident_ms * 1e-3), "n_gpus": world,
             "sweep_ms": resident_ms, "higher_is_better": True, "scaling": "strong",
             "dtype": "bf16" if prec == _lib.PREC_BF16 else "f32", "data": "synthetic",
-            "config": {"workload": f"c5: {args.structures} synthetic structures L~U[{args.min_len},{args.max_len}], K={args.k}, "
+            "config": {"workload": f"c5: {len(lengths)} synthetic structures L~U[{args.min_len},{args.max_len}], K={args.k}, "
                                    f"T={args.temperature}, RNAModel default", "token_budget": args.token_budget,
                        "batches_rank0": len(plan), "padding_overhead_rank0": pad,
                        "sharding": "whole structures, length-sorted token-budget batches, LPT over ranks; no collective",
                        "launch": "eager (shapes change per batch)"},
             "e2e": {"value": total_nt / (e2e_ms * 1e-3), "unit": "nt/s", "h2d_bytes": int(total_nt) * 72,
                     "d2h_bytes": int(total_nt)},
-            "gpu_launches": int(launches), "argmax_agreement_with_oracle_T0": ok}), flush=True)
-    if world > 1:
+            "gpu_launches": int(launches), "per_rank": per_rank, "argmax_agreement_with_oracle_T0": ok}
+    return result
+
+
+def main():
+    import torch.distributed as dist
+    res = run(parse_args())
+    if res is not None:
+        print(json.dumps(res), flush=True)
+    if dist.is_initialized():
         dist.destroy_process_group()
 
 

@@ -44,7 +44,7 @@ def _row_ptr(ctr, Nv):
 
 
 @pytest.mark.parametrize("Nv,deg,S", [(4, 32, 3), (129, 30, 3), (1600, 25, 3), (300, 2, 3), (500, 1, 2), (37, 48, 2),
-                                      (3, 128, 3)])
+                                      (3, 128, 3), (16384, 30, 3), (2000, 7, 3), (700, 9, 2)])
 def test_edge_mlp_tc_matches_fp32_reference(Nv, deg, S):
     from rmpnn_b200 import ops
     g = torch.Generator().manual_seed(Nv * 7 + deg)
