@@ -297,6 +297,30 @@ int rmp_edge_mlp_bf16_traced(const void* h_E_bf16, const void* W_bf16, int num_s
                              const int32_t* row_ptr, int n_edges, float alpha, float* agg, float* debug,
                              long long* timeline, void* stream);
 
+/* ------------------------------------------------------------------ training path (section 8f rank 1, configs[3])
+ * Per-edge backward of MPNNLayer's message MLP (rdesign/model/mpnn.py:15-19, :33-34), decomposed into HBM-bound passes
+ * over bf16 [rows,128] tensors and tcgen05 GEMMs; the Linear stages themselves run on rmp_row_mlp_tc (forward with the
+ * weight, backward-data with the transposed weight).  Dropout masks are never stored: both directions regenerate them
+ * from Philox-4x32-10(seed, element group, stream_id).
+ *
+ * a = Dropout_p(GELU_erf(z)) (nn.GELU + nn.Dropout, mpnn.py:17-18); z, a bf16 [rows,width], width % 8 == 0 */
+int rmp_act_fwd_bf16(const void* z_bf16, void* a_bf16, int64_t rows, int width, float p_drop, uint64_t seed,
+                     uint32_t stream_id, void* stream);
+/* dz = da * mask/(1-p) * GELU'(z) for 128-wide rows; da is either a bf16 [rows,128] tensor or, for the last message
+ * stage, gathered on the fly as dagg[ctr[r],:] * alpha (the backward of scatter_sum / scale, mpnn.py:34).
+ * db [128] fp32 (may be NULL) accumulates the column sums of dz = the bias gradient. */
+int rmp_act_bwd_bf16(const void* z_bf16, const void* da_bf16, const float* dagg, const int32_t* ctr, float alpha,
+                     void* dz_bf16, float* db, int rows, float p_drop, uint64_t seed, uint32_t stream_id, void* stream);
+/* out[idx[r],:] += x[r,:]   x bf16 [rows,128], out fp32: backward of the h_V[E_idx] gathers (rdesign.py:85) */
+int rmp_scatter_add_rows(const void* x_bf16, const int32_t* idx, float* out, int rows, void* stream);
+/* dW[n,k] += sum_r dZ[r,n] X[r,k]   dZ, X bf16 [rows,128], dW fp32 [128,128]: weight gradient of a 128->128 Linear
+ * (tcgen05, both operands read MN-major from their row-major tiles, per-CTA TMEM accumulator, one red.global pass) */
+int rmp_gemm_dw_bf16(const void* dZ_bf16, const void* X_bf16, float* dW, int rows, void* stream);
+/* torch.optim.Adam step (no weight decay, no amsgrad) over flat fp32 buffers of n elements (n % 4 == 0);
+ * grad is multiplied by grad_scale first (1 / world size after the all-reduce; rdesign.py:90-93) */
+int rmp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float grad_scale,
+                  float lr, float beta1, float beta2, float eps, int step, void* stream);
+
 /* Fused node-update kernel on 128-node tiles (tcgen05, weights streamed by TMA):
  *   x1 = prologue_ln ? LayerNorm1(h_in + agg) : h_in      (agg rows are re-zeroed after being read)
  *   then num_stages chained Linear stages, stage s: K[s] -> N[s] (N in {128,256}), W_bf16[s] = nn.Linear

@@ -343,8 +343,10 @@ row_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
 #pragma unroll
                             for (int q = 0; q < 32; ++q) v[q] = rs == 0.f ? 0.f : v[q] * rs;
                         }
+                        if (p.out) {
 #pragma unroll
-                        for (int q = 0; q < 4; ++q) stg256f(dst + 8 * q, &v[8 * q]);
+                            for (int q = 0; q < 4; ++q) stg256f(dst + 8 * q, &v[8 * q]);
+                        }
                         if (p.out16) {
                             uint32_t pk[16];
 #pragma unroll
@@ -386,7 +388,8 @@ extern "C" int rmp_row_mlp_tc(const rmp_mlp_desc* dp, const void* const* W_bf16,
     RMP_REQUIRE(d.num_segs >= 1 && d.num_segs <= RMP_MAX_SEGS, RMP_E_ARG, "rmp_row_mlp_bf16: num_segs=%d", d.num_segs);
     RMP_REQUIRE(d.num_stages >= 1 && d.num_stages <= RMP_MAX_STAGES, RMP_E_ARG, "rmp_row_mlp_bf16: num_stages=%d",
                 d.num_stages);
-    RMP_REQUIRE(d.out && d.rows_cap >= 0 && !d.rows_dev, RMP_E_ARG, "rmp_row_mlp_bf16: bad output / rows (host row count only)");
+    RMP_REQUIRE((d.out || (d.out_bf16 && d.epilogue == RMP_EPI_STORE)) && d.rows_cap >= 0 && !d.rows_dev, RMP_E_ARG,
+                "rmp_row_mlp_bf16: bad output / rows (host row count only; out may be NULL only for STORE with out_bf16)");
     RMP_REQUIRE(d.epilogue == RMP_EPI_STORE || d.epilogue == RMP_EPI_SEGSUM || d.epilogue == RMP_EPI_RESID_ADD, RMP_E_SHAPE,
                 "rmp_row_mlp_bf16: epilogue %d not supported on the tensor-core arm", d.epilogue);
     if (d.rows_cap == 0) return RMP_OK;

@@ -1,0 +1,317 @@
+// Training-path kernels of the rdesign message MLP (BASELINE configs[3]).
+//
+// The per-edge part of MPNNLayer's backward (rdesign/model/mpnn.py:15-19, :33-34: three Linear + GELU + Dropout on
+// [h_E | h_V[ctr] | h_V[nbr]], scatter_sum / scale) is 96 % of the training step's flops and bytes.  It is
+// decomposed into a few HBM-bound passes over bf16 [Ne,128] tensors and tcgen05 GEMMs:
+//   forward   z_s = a_{s-1} W_s^T + b_s            rmp_row_mlp_tc (pre-activations kept as bf16 for the backward)
+//             a_s = Dropout(GELU(z_s))             rmp_act_fwd_bf16        (Philox mask from (seed, stream, element))
+//   backward  dz_s = da_s * mask/(1-p) * GELU'(z_s)  rmp_act_bwd_bf16      (mask regenerated, + column sums = db_s;
+//                                                     the last stage gathers da from d(agg)[ctr] * alpha itself)
+//             da_{s-1} = dz_s W_s                  rmp_row_mlp_tc with the transposed weight
+//             dW_s += dz_s^T a_{s-1}               rmp_gemm_dw_bf16        (tcgen05, both operands MN-major from smem)
+//             d(Pc) = segment sums of dz_0 by centre / neighbour: rmp_scatter_add_rows
+// plus rmp_adam_step, a fused Adam update over the flat parameter / gradient buffers.
+#include "tc_common.cuh"
+
+namespace rmp {
+namespace train {
+
+// Philox-4x32-10: four 32-bit words per (seed, counter, stream)
+__device__ __forceinline__ uint4 philox4(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t stream) {
+    uint32_t c[4] = {c0, c1, stream, 0u};
+    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+    for (int round = 0; round < 10; ++round) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+        const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return make_uint4(c[0], c[1], c[2], c[3]);
+}
+// keep-mask of the 8 elements of group g (16-bit lanes of the four words): bit j set = element j survives
+__device__ __forceinline__ uint32_t keep_mask8(uint64_t seed, uint64_t g, uint32_t stream, uint32_t thresh16) {
+    if (thresh16 == 0) return 0xffu;
+    const uint4 r = philox4(seed, (uint32_t)g, (uint32_t)(g >> 32), stream);
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    uint32_t m = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) m |= (uint32_t)(((w[j >> 1] >> ((j & 1) * 16)) & 0xffffu) >= thresh16) << j;
+    return m;
+}
+__device__ __forceinline__ float gelu_erf_grad(float x) {
+    // d/dx [x Phi(x)] = Phi(x) + x phi(x)
+    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+    return cdf + x * 0.39894228040143267794f * __expf(-0.5f * x * x);
+}
+__device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
+__device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
+
+// a = Dropout(GELU(z)); one thread per 8 consecutive elements (16 bytes)
+__global__ void __launch_bounds__(256) act_fwd_kernel(const uint4* __restrict__ z, uint4* __restrict__ a, size_t n_groups,
+                                                      uint32_t thresh16, float keep_scale, uint64_t seed, uint32_t stream) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n_groups) return;
+    const uint4 zi = z[g];
+    const uint32_t zw[4] = {zi.x, zi.y, zi.z, zi.w};
+    const uint32_t keep = keep_mask8(seed, g, stream, thresh16);
+    uint32_t o[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const float lo = (keep >> (2 * j)) & 1u ? gelu_erf(bf_lo(zw[j])) * keep_scale : 0.f;
+        const float hi = (keep >> (2 * j + 1)) & 1u ? gelu_erf(bf_hi(zw[j])) * keep_scale : 0.f;
+        o[j] = tc::pack_bf16(lo, hi);
+    }
+    a[g] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+
+// dz = da * mask/(1-p) * GELU'(z), da either a bf16 tensor or gathered from dagg[ctr[row]] * alpha (fp32 rows);
+// column sums of dz are accumulated into db.  Block = 256 threads = 16 rows x 16 column groups of 8 (width 128).
+__global__ void __launch_bounds__(256) act_bwd_kernel(const uint4* __restrict__ z, const uint4* __restrict__ da,
+                                                      const float* __restrict__ dagg, const int32_t* __restrict__ ctr,
+                                                      float alpha, uint4* __restrict__ dz, float* __restrict__ db,
+                                                      int rows, int rows_per_block, uint32_t thresh16, float keep_scale,
+                                                      uint64_t seed, uint32_t stream) {
+    __shared__ float s_db[16][128];
+    const int cg = threadIdx.x & 15, rl = threadIdx.x >> 4;          // column group (8 columns), row lane
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const int r0 = blockIdx.x * rows_per_block;
+    const int r1 = min(rows, r0 + rows_per_block);
+    for (int r = r0 + rl; r < r1; r += 16) {
+        const size_t g = (size_t)r * 16 + cg;
+        const uint4 zi = z[g];
+        const uint32_t zw[4] = {zi.x, zi.y, zi.z, zi.w};
+        float d[8];
+        if (da) {
+            const uint4 di = da[g];
+            const uint32_t dw[4] = {di.x, di.y, di.z, di.w};
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { d[2 * j] = bf_lo(dw[j]); d[2 * j + 1] = bf_hi(dw[j]); }
+        } else {
+            const float4* src = reinterpret_cast<const float4*>(dagg + (size_t)__ldg(ctr + r) * 128 + cg * 8);
+            const float4 x = __ldg(src), y = __ldg(src + 1);
+            d[0] = x.x * alpha; d[1] = x.y * alpha; d[2] = x.z * alpha; d[3] = x.w * alpha;
+            d[4] = y.x * alpha; d[5] = y.y * alpha; d[6] = y.z * alpha; d[7] = y.w * alpha;
+        }
+        const uint32_t keep = keep_mask8(seed, g, stream, thresh16);
+        uint32_t o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float lo = (keep >> (2 * j)) & 1u ? d[2 * j] * keep_scale * gelu_erf_grad(bf_lo(zw[j])) : 0.f;
+            const float hi = (keep >> (2 * j + 1)) & 1u ? d[2 * j + 1] * keep_scale * gelu_erf_grad(bf_hi(zw[j])) : 0.f;
+            o[j] = tc::pack_bf16(lo, hi);
+            acc[2 * j] += bf_lo(o[j]); acc[2 * j + 1] += bf_hi(o[j]);      // the bias gradient sums what the GEMMs will see
+        }
+        dz[g] = make_uint4(o[0], o[1], o[2], o[3]);
+    }
+    if (db) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) s_db[rl][cg * 8 + j] = acc[j];
+        __syncthreads();
+        if (threadIdx.x < 128) {
+            float t = 0.f;
+#pragma unroll
+            for (int k = 0; k < 16; ++k) t += s_db[k][threadIdx.x];
+            atomicAdd(db + threadIdx.x, t);
+        }
+    }
+}
+
+// out[idx[r], :] += x[r, :]  (x bf16 [rows,128], out fp32): one thread per 8 columns, red.global.v4
+__global__ void __launch_bounds__(256) scatter_add_kernel(const uint4* __restrict__ x, const int32_t* __restrict__ idx,
+                                                          float* __restrict__ out, int rows) {
+    const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= (size_t)rows * 16) return;
+    const int r = (int)(g >> 4), cg = (int)(g & 15);
+    const uint4 xi = x[g];
+    float* dst = out + (size_t)__ldg(idx + r) * 128 + cg * 8;
+    tc::red_add_v4(dst, bf_lo(xi.x), bf_hi(xi.x), bf_lo(xi.y), bf_hi(xi.y));
+    tc::red_add_v4(dst + 4, bf_lo(xi.z), bf_hi(xi.z), bf_lo(xi.w), bf_hi(xi.w));
+}
+
+// Adam (torch.optim.Adam semantics, no weight decay / amsgrad): p -= lr * m_hat / (sqrt(v_hat) + eps)
+__global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
+                                                   float4* __restrict__ v, size_t n4, float grad_scale, float lr, float b1,
+                                                   float b2, float eps, float bc1, float bc2_sqrt) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n4) return;
+    float4 pi = p[i], mi = m[i], vi = v[i];
+    const float4 gi = g[i];
+    const float step = lr / bc1;
+    auto upd = [&](float& pp, float gg, float& mm, float& vv) {
+        gg *= grad_scale;
+        mm = b1 * mm + (1.f - b1) * gg;
+        vv = b2 * vv + (1.f - b2) * gg * gg;
+        pp -= step * mm / (sqrtf(vv) / bc2_sqrt + eps);
+    };
+    upd(pi.x, gi.x, mi.x, vi.x); upd(pi.y, gi.y, mi.y, vi.y); upd(pi.z, gi.z, mi.z, vi.z); upd(pi.w, gi.w, mi.w, vi.w);
+    p[i] = pi; m[i] = mi; v[i] = vi;
+}
+
+// ------------------------------------------------------------------------------------------------------------------
+// dW[n][k] += sum_r dZ[r][n] X[r][k]   (dZ, X bf16 [rows,128]; dW fp32 [128,128])
+// The contraction runs over the rows, so both operand tiles are read MN-major from their natural row-major
+// [128 rows][128 cols] layout (two 128-byte-swizzled [128][64] blocks per tile, exactly what TMA delivers):
+// A = dZ^T (M = n), B = X^T (N = k), K = 16 rows per tcgen05.mma.  One persistent CTA per SM accumulates its row
+// tiles in TMEM and adds its 128x128 partial to dW with red.global at the end.
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kDwStages = 3;
+constexpr int kDwThreads = 192;                   // warp 0 TMA, warp 1 MMA, warps 2..5 drain (one TMEM lane quadrant each)
+struct alignas(8) DwBarriers { uint64_t full[kDwStages], empty[kDwStages], done; };
+
+__global__ void __launch_bounds__(kDwThreads, 1)
+gemm_dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant__ CUtensorMap tm_x, float* __restrict__ dW,
+               int rows) {
+    using namespace tc;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sA = smem;                                    // [stages][2][128][64] dZ tiles
+    uint8_t* sB = sA + kDwStages * kTileBytes;             // [stages][2][128][64] X tiles
+    DwBarriers* bars = reinterpret_cast<DwBarriers*>(sB + kDwStages * kTileBytes);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = (rows + kTileM - 1) / kTileM;
+    const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kDwStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+        mbar_init(&bars->done, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(s_tmem, 128);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tm_dz); tma_prefetch_desc(&tm_x);
+            for (int i = 0; i < my_tiles; ++i) {
+                const int st = i % kDwStages;
+                const int tile = blockIdx.x + i * gridDim.x;
+                mbar_wait(&bars->empty[st], ((i / kDwStages) & 1) ^ 1);
+                mbar_expect_tx(&bars->full[st], 2 * kTileBytes);      // rows past the end are zero-filled by TMA
+                for (int kb = 0; kb < 2; ++kb) {
+                    tma_load_2d(sA + (size_t)st * kTileBytes + kb * kKBlockBytes, &tm_dz, &bars->full[st], kb * 64, tile * kTileM);
+                    tma_load_2d(sB + (size_t)st * kTileBytes + kb * kKBlockBytes, &tm_x, &bars->full[st], kb * 64, tile * kTileM);
+                }
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = instr_desc_bf16(128, 128, 1) | (1u << 15);     // A and B MN-major
+            for (int i = 0; i < my_tiles; ++i) {
+                const int st = i % kDwStages;
+                mbar_wait(&bars->full[st], (i / kDwStages) & 1);
+                tc_fence_after();
+                const uint64_t d_a = smem_desc_sw128(smem_u32(sA + (size_t)st * kTileBytes), kKBlockBytes, 1024);
+                const uint64_t d_b = smem_desc_sw128(smem_u32(sB + (size_t)st * kTileBytes), kKBlockBytes, 1024);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {                      // 128 rows = 8 x UMMA_K(16); 16 rows = 2048 B
+                    const uint64_t off = (uint64_t)((k * 2048) >> 4);
+                    umma_bf16(tmem_base, d_a + off, d_b + off, idesc, (uint32_t)((i | k) > 0));
+                }
+                umma_commit(&bars->empty[st]);
+            }
+            umma_commit(&bars->done);
+        }
+        __syncwarp();
+    } else if (my_tiles > 0) {
+        // drain: thread = output row n (TMEM lane), 128 columns k in four chunks
+        const int lane_grp = warp & 3;
+        const int n = lane_grp * 32 + lane;
+        mbar_wait(&bars->done, 0);
+        tc_fence_after();
+        const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            float v[32];
+            tmem_ld32(t_row + (uint32_t)(c * 32), v);
+            float* dst = dW + (size_t)n * 128 + c * 32;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) red_add_v4(dst + 4 * q, v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 128);
+}
+
+}  // namespace train
+}  // namespace rmp
+
+using namespace rmp;
+
+static uint32_t drop_threshold(float p) { return p <= 0.f ? 0u : (uint32_t)(p * 65536.0f + 0.5f); }
+
+extern "C" int rmp_act_fwd_bf16(const void* z_bf16, void* a_bf16, int64_t rows, int width, float p_drop, uint64_t seed,
+                                uint32_t stream_id, void* stream) {
+    RMP_REQUIRE(z_bf16 && a_bf16 && rows >= 0 && width > 0 && width % 8 == 0, RMP_E_ARG, "rmp_act_fwd_bf16: bad arguments");
+    RMP_REQUIRE(aligned16(z_bf16) && aligned16(a_bf16), RMP_E_ALIGN, "rmp_act_fwd_bf16: 16-byte alignment");
+    RMP_REQUIRE(p_drop >= 0.f && p_drop < 1.f, RMP_E_ARG, "rmp_act_fwd_bf16: dropout probability in [0,1)");
+    const size_t groups = (size_t)rows * width / 8;
+    if (groups == 0) return RMP_OK;
+    train::act_fwd_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(z_bf16), reinterpret_cast<uint4*>(a_bf16), groups, drop_threshold(p_drop),
+        1.0f / (1.0f - p_drop), seed, stream_id);
+    return check_launch("rmp_act_fwd_bf16");
+}
+
+extern "C" int rmp_act_bwd_bf16(const void* z_bf16, const void* da_bf16, const float* dagg, const int32_t* ctr, float alpha,
+                                void* dz_bf16, float* db, int rows, float p_drop, uint64_t seed, uint32_t stream_id,
+                                void* stream) {
+    RMP_REQUIRE(z_bf16 && dz_bf16 && rows >= 0, RMP_E_ARG, "rmp_act_bwd_bf16: null pointer");
+    RMP_REQUIRE((da_bf16 != nullptr) != (dagg != nullptr && ctr != nullptr), RMP_E_ARG,
+                "rmp_act_bwd_bf16: give either da_bf16 or (dagg, ctr)");
+    RMP_REQUIRE(aligned16(z_bf16) && aligned16(dz_bf16) && (!da_bf16 || aligned16(da_bf16)) && (!dagg || aligned16(dagg)),
+                RMP_E_ALIGN, "rmp_act_bwd_bf16: 16-byte alignment");
+    if (rows == 0) return RMP_OK;
+    const int rows_per_block = 128;
+    train::act_bwd_kernel<<<ceil_div(rows, rows_per_block), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(z_bf16), reinterpret_cast<const uint4*>(da_bf16), dagg, ctr, alpha,
+        reinterpret_cast<uint4*>(dz_bf16), db, rows, rows_per_block, drop_threshold(p_drop), 1.0f / (1.0f - p_drop), seed,
+        stream_id);
+    return check_launch("rmp_act_bwd_bf16");
+}
+
+extern "C" int rmp_scatter_add_rows(const void* x_bf16, const int32_t* idx, float* out, int rows, void* stream) {
+    RMP_REQUIRE(x_bf16 && idx && out && rows >= 0, RMP_E_ARG, "rmp_scatter_add_rows: null pointer");
+    RMP_REQUIRE(aligned16(x_bf16) && aligned16(out), RMP_E_ALIGN, "rmp_scatter_add_rows: 16-byte alignment");
+    if (rows == 0) return RMP_OK;
+    const size_t groups = (size_t)rows * 16;
+    train::scatter_add_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(x_bf16), idx, out, rows);
+    return check_launch("rmp_scatter_add_rows");
+}
+
+extern "C" int rmp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float grad_scale,
+                             float lr, float beta1, float beta2, float eps, int step, void* stream) {
+    RMP_REQUIRE(param && grad && exp_avg && exp_avg_sq && n >= 0 && step >= 1, RMP_E_ARG, "rmp_adam_step: bad arguments");
+    RMP_REQUIRE(n % 4 == 0 && aligned16(param) && aligned16(grad) && aligned16(exp_avg) && aligned16(exp_avg_sq), RMP_E_ALIGN,
+                "rmp_adam_step: buffers must be 16-byte aligned and a multiple of 4 elements (pad the flat buffer)");
+    if (n == 0) return RMP_OK;
+    const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
+    const size_t n4 = (size_t)n / 4;
+    train::adam_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<float4*>(param), reinterpret_cast<const float4*>(grad), reinterpret_cast<float4*>(exp_avg),
+        reinterpret_cast<float4*>(exp_avg_sq), n4, grad_scale, lr, beta1, beta2, eps, bc1, sqrtf(bc2));
+    return check_launch("rmp_adam_step");
+}
+
+extern "C" int rmp_gemm_dw_bf16(const void* dZ_bf16, const void* X_bf16, float* dW, int rows, void* stream) {
+    RMP_REQUIRE(dZ_bf16 && X_bf16 && dW && rows >= 0, RMP_E_ARG, "rmp_gemm_dw_bf16: null pointer");
+    RMP_REQUIRE(aligned16(dZ_bf16) && aligned16(X_bf16) && aligned16(dW), RMP_E_ALIGN, "rmp_gemm_dw_bf16: 16-byte alignment");
+    if (rows == 0) return RMP_OK;
+    CUtensorMap tm_dz, tm_x;
+    int rc = tc::make_map_bf16_rows128(&tm_dz, dZ_bf16, (uint64_t)rows);
+    if (rc) return rc;
+    rc = tc::make_map_bf16_rows128(&tm_x, X_bf16, (uint64_t)rows);
+    if (rc) return rc;
+    const size_t smem = 1024 + 2 * (size_t)train::kDwStages * tc::kTileBytes + sizeof(train::DwBarriers) + 16;
+    cudaFuncSetAttribute(train::gemm_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int n_tiles = ceil_div(rows, tc::kTileM);
+    const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
+    train::gemm_dw_kernel<<<grid, train::kDwThreads, smem, (cudaStream_t)stream>>>(tm_dz, tm_x, dW, rows);
+    return check_launch("rmp_gemm_dw_bf16");
+}

@@ -435,6 +435,50 @@ __all__ = ["collate", "tc_eligible", "ResGraph", "res_graph", "res_edge_rows", "
            "EPI_SEGSUM", "HIDDEN", "NODE_RAW", "EDGE_RAW", "MAX_K"]
 
 
+# --------------------------------------------------------------------------- training path
+def act_fwd(z16: torch.Tensor, p_drop: float, seed: int, stream_id: int) -> torch.Tensor:
+    """a = Dropout(GELU(z)) on bf16 rows (rmp_act_fwd_bf16)."""
+    _need_cuda(z16)
+    assert z16.dtype == torch.bfloat16 and z16.is_contiguous()
+    a = torch.empty_like(z16)
+    check(lib().rmp_act_fwd_bf16(_ptr(z16), _ptr(a), z16.shape[0], z16.shape[1], float(p_drop), int(seed), int(stream_id),
+                                 _stream()), "rmp_act_fwd_bf16")
+    return a
+
+
+def act_bwd(z16, p_drop: float, seed: int, stream_id: int, da16=None, dagg=None, ctr=None, alpha: float = 1.0, db=None):
+    """dz = da * mask/(1-p) * GELU'(z); da bf16, or gathered from dagg[ctr] * alpha; db [128] += column sums."""
+    _need_cuda(z16, da16, dagg, ctr, db)
+    assert z16.dtype == torch.bfloat16 and z16.is_contiguous() and z16.shape[1] == 128
+    dz = torch.empty_like(z16)
+    check(lib().rmp_act_bwd_bf16(_ptr(z16), _ptr(da16), _ptr(dagg), _ptr(ctr), float(alpha), _ptr(dz), _ptr(db),
+                                 z16.shape[0], float(p_drop), int(seed), int(stream_id), _stream()), "rmp_act_bwd_bf16")
+    return dz
+
+
+def scatter_add_rows(x16, idx, out):
+    _need_cuda(x16, idx, out)
+    assert x16.dtype == torch.bfloat16 and x16.is_contiguous() and x16.shape[1] == 128 and out.dtype == torch.float32
+    check(lib().rmp_scatter_add_rows(_ptr(x16), _ptr(idx), _ptr(out), x16.shape[0], _stream()), "rmp_scatter_add_rows")
+    return out
+
+
+def gemm_dw(dz16, x16, dW):
+    """dW [128,128] fp32 += dz16^T @ x16 (both bf16 [rows,128])."""
+    _need_cuda(dz16, x16, dW)
+    assert dz16.dtype == x16.dtype == torch.bfloat16 and dz16.shape == x16.shape and dz16.shape[1] == 128
+    assert dz16.is_contiguous() and x16.is_contiguous() and dW.dtype == torch.float32 and dW.is_contiguous()
+    check(lib().rmp_gemm_dw_bf16(_ptr(dz16), _ptr(x16), _ptr(dW), dz16.shape[0], _stream()), "rmp_gemm_dw_bf16")
+    return dW
+
+
+def adam_step(param, grad, exp_avg, exp_avg_sq, step: int, lr: float, grad_scale: float = 1.0, betas=(0.9, 0.999),
+              eps: float = 1e-8):
+    _need_cuda(param, grad, exp_avg, exp_avg_sq)
+    check(lib().rmp_adam_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), float(grad_scale),
+                              float(lr), float(betas[0]), float(betas[1]), float(eps), int(step), _stream()), "rmp_adam_step")
+
+
 # --------------------------------------------------------------------------- device guard
 def _cuda_device_of(objs, depth=0):
     """Device of the first CUDA tensor found in ``objs`` (tensors, Graph / ResGraph / PackedLinear, short sequences)."""

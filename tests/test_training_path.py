@@ -1,0 +1,141 @@
+"""Training-path kernels (csrc/train.cu) and the native training step (rmpnn_b200/train_engine.py) against PyTorch:
+BASELINE configs[3] / SURVEY.md section 8f rank 1.  Reference: training_step rdesign/model/rdesign.py:95-104,
+optimizer :90-93, message MLP with Dropout after every GELU rdesign/model/mpnn.py:15-19."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf(x):
+    return x.to(torch.bfloat16).to(torch.float32)
+
+
+@pytest.mark.parametrize("rows", [1, 127, 128, 1000, 40001])
+def test_gemm_dw_matches_torch(rows):
+    from rmpnn_b200 import ops
+    g = torch.Generator().manual_seed(rows)
+    dz = torch.randn(rows, 128, generator=g).cuda().to(torch.bfloat16)
+    x = torch.randn(rows, 128, generator=g).cuda().to(torch.bfloat16)
+    dW = torch.full((128, 128), 0.5, device="cuda")
+    ops.gemm_dw(dz, x, dW)
+    ref = 0.5 + dz.float().t() @ x.float()
+    err = (dW - ref).abs().max().item()
+    assert err < 2e-3 * max(1.0, rows ** 0.5), err          # fp32 accumulation of bf16 products, order differs
+
+
+def test_act_fwd_bwd_no_dropout_match_torch_gelu():
+    from rmpnn_b200 import ops
+    g = torch.Generator().manual_seed(0)
+    z = (2 * torch.randn(3000, 128, generator=g)).cuda().to(torch.bfloat16)
+    da = torch.randn(3000, 128, generator=g).cuda().to(torch.bfloat16)
+    a = ops.act_fwd(z, 0.0, 7, 3)
+    zf = z.float().requires_grad_(True)
+    ref = F.gelu(zf)
+    np.testing.assert_allclose(a.float().cpu().numpy(), _bf(ref.detach()).cpu().numpy(), atol=1e-2, rtol=1e-2)
+    db = torch.zeros(128, device="cuda")
+    dz = ops.act_bwd(z, 0.0, 7, 3, da16=da, db=db)
+    (ref * da.float()).sum().backward()
+    np.testing.assert_allclose(dz.float().cpu().numpy(), _bf(zf.grad).cpu().numpy(), atol=2e-2, rtol=2e-2)
+    np.testing.assert_allclose(db.cpu().numpy(), dz.float().sum(0).cpu().numpy(), atol=2e-2, rtol=1e-3)
+
+
+def test_dropout_mask_is_regenerated_identically_and_has_the_right_rate():
+    from rmpnn_b200 import ops
+    z = torch.ones(20000, 128, device="cuda", dtype=torch.bfloat16)
+    a = ops.act_fwd(z, 0.1, 11, 5)
+    keep = a != 0
+    assert abs(keep.float().mean().item() - 0.9) < 2e-3
+    kept_val = a[keep].float().unique()
+    assert kept_val.numel() == 1 and abs(kept_val.item() - F.gelu(torch.tensor(1.0)).item() / 0.9) < 1e-2
+    dz = ops.act_bwd(z, 0.1, 11, 5, da16=torch.ones_like(z))
+    assert torch.equal(dz != 0, keep)                                   # same mask in both directions
+    assert not torch.equal(ops.act_fwd(z, 0.1, 11, 6) != 0, keep)       # another stream id, another mask
+    assert not torch.equal(ops.act_fwd(z, 0.1, 12, 5) != 0, keep)       # another seed, another mask
+
+
+def test_act_bwd_gathers_the_scatter_sum_gradient():
+    from rmpnn_b200 import ops
+    g = torch.Generator().manual_seed(2)
+    Nv, deg = 300, 7
+    ctr = torch.repeat_interleave(torch.arange(Nv), deg).to(torch.int32).cuda()
+    z = torch.randn(Nv * deg, 128, generator=g).cuda().to(torch.bfloat16)
+    dagg = torch.randn(Nv, 128, generator=g).cuda()
+    dz = ops.act_bwd(z, 0.0, 1, 0, dagg=dagg, ctr=ctr, alpha=1 / 30)
+    zf = z.float().requires_grad_(True)
+    agg = torch.zeros(Nv, 128, device="cuda").index_add_(0, ctr.long(), F.gelu(zf)) / 30
+    (agg * dagg).sum().backward()
+    np.testing.assert_allclose(dz.float().cpu().numpy(), _bf(zf.grad).cpu().numpy(), atol=2e-3, rtol=2e-2)
+
+
+def test_scatter_add_and_adam():
+    from rmpnn_b200 import ops
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(5000, 128, generator=g).cuda().to(torch.bfloat16)
+    idx = torch.randint(0, 97, (5000,), generator=g, dtype=torch.int32).cuda()
+    out = torch.zeros(97, 128, device="cuda")
+    ops.scatter_add_rows(x, idx, out)
+    ref = torch.zeros(97, 128, device="cuda").index_add_(0, idx.long(), x.float())
+    np.testing.assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), atol=1e-3, rtol=1e-4)
+    p = torch.randn(4096, generator=g).cuda()
+    p_ref = p.clone().requires_grad_(True)
+    opt = torch.optim.Adam([p_ref], lr=2e-3)
+    m, v = torch.zeros_like(p), torch.zeros_like(p)
+    for step in range(1, 4):
+        grad = torch.randn(4096, generator=g).cuda()
+        p_ref.grad = grad.clone() / 2
+        opt.step()
+        ops.adam_step(p, grad, m, v, step, 2e-3, grad_scale=0.5)
+        np.testing.assert_allclose(p.cpu().numpy(), p_ref.detach().cpu().numpy(), atol=2e-6, rtol=1e-5)
+
+
+def test_native_training_step_gradients_match_autograd():
+    """Whole training step with dropout off: every parameter gradient of the native path (bf16 tensor-core GEMMs)
+    against fp32 autograd through the drop-in's differentiable composition, which itself matches the oracle."""
+    from oracle.weights import RDesignConfig, make_state_dict, synthetic_backbones
+    from rdesign.model.rdesign import RNAModel
+    from rmpnn_b200.train_engine import RDesignTrainer
+    cfg = RDesignConfig(k_neighbors=12, num_mpnn_layers=3)
+    X, S, mask = synthetic_backbones(3, 60, 9, lengths=[60, 41, 23])
+    X, S, mask = X.cuda(), S.cuda(), mask.cuda()
+
+    ref = RNAModel(**cfg.as_kwargs(), dropout=0.0).cuda().train()
+    ref.load_state_dict(make_state_dict(cfg, 42), strict=True)
+    h_V, S_v = ref(X, S, mask)
+    loss_ref = F.cross_entropy(ref.readout(h_V), S_v)
+    loss_ref.backward()
+    ref_grads = {n: p.grad.clone() for n, p in ref.named_parameters()}
+
+    model = RNAModel(**cfg.as_kwargs(), dropout=0.0).cuda().train()
+    model.load_state_dict(make_state_dict(cfg, 42), strict=True)
+    tr = RDesignTrainer(model, autocast=False)
+    loss = tr.loss_and_grads(X, S, mask, seed=1)
+    assert abs(loss.item() - loss_ref.item()) < 2e-2, (loss.item(), loss_ref.item())
+    worst = 0.0
+    for n, p in model.named_parameters():
+        a, b = p.grad.float(), ref_grads[n].float()
+        rel = ((a - b).norm() / (b.norm() + 1e-12)).item()
+        worst = max(worst, rel)
+        assert rel < 6e-2 or (a - b).abs().max().item() < 1e-5, (n, rel, b.norm().item())
+    print(f"native training step: loss {loss.item():.5f} vs {loss_ref.item():.5f}, worst relative gradient error {worst:.3e}")
+    # one optimizer step moves the parameters like torch.optim.Adam on the reference gradients would
+    before = tr.flat_p.clone()
+    tr.apply_gradients()
+    delta = (tr.flat_p - before)[:tr.n_params]
+    assert torch.isfinite(delta).all() and (delta.abs() <= model.hparams.lr * 1.001).all() and delta.abs().max() > 0
+
+
+def test_training_loss_decreases_with_dropout_on():
+    from oracle.weights import RDesignConfig, make_state_dict, synthetic_backbones
+    from rdesign.model.rdesign import RNAModel
+    from rmpnn_b200.train_engine import RDesignTrainer
+    cfg = RDesignConfig(k_neighbors=10, num_mpnn_layers=2)
+    X, S, mask = synthetic_backbones(4, 50, 5)
+    X, S, mask = X.cuda(), S.cuda(), mask.cuda()
+    model = RNAModel(**cfg.as_kwargs()).cuda().train()
+    model.load_state_dict(make_state_dict(cfg, 42), strict=True)
+    tr = RDesignTrainer(model)
+    losses = [tr.step(X, S, mask).item() for _ in range(25)]
+    assert np.isfinite(losses).all() and np.mean(losses[-5:]) < np.mean(losses[:5]) - 0.05, losses
