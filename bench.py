@@ -291,21 +291,38 @@ def run_c4(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for _ in range(max(3, args.warmup)):
-        loss = tr.step(Xd, Sd, md)
-    barrier()
+    lengths = mask.sum(1).long()
+    sizes = (Nv, int((lengths * torch.clamp(lengths, max=min(cfg.k_neighbors, L))).sum().item()))
     n0 = L_.rmp_launch_count()
+    tr.step(Xd, Sd, md, sizes=sizes)                         # one eager step: counts the library's launches per step
+    launches = L_.rmp_launch_count() - n0
+    replay = static = None
+    if args.graph:                                           # the whole step (fwd, bwd, all-reduce, Adam) as one CUDA graph
+        replay, static = tr.capture(Xd, Sd, md, sizes)
+
+    def step_resident():
+        return replay() if replay else tr.step(Xd, Sd, md, sizes=sizes)
+
+    def step_e2e():
+        if replay:
+            static["X"].copy_(Xp, non_blocking=True); static["S"].copy_(Sp, non_blocking=True)
+            static["mask"].copy_(mp, non_blocking=True)
+            return replay()
+        return tr.step(Xp.to(dev, non_blocking=True), Sp.to(dev, non_blocking=True), mp.to(dev, non_blocking=True), sizes=sizes)
+
+    for _ in range(max(3, args.warmup)):
+        loss = step_resident()
+    barrier()
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
-    with ClockSampler(local) as clocks:
+    with ClockSampler(local, period_s=0.05) as clocks:      # an eager step loop is Python-heavy: poll NVML rarely (GIL)
         ev[0].record(stream)
         for _ in range(args.steps):
-            loss = tr.step(Xd, Sd, md)
+            loss = step_resident()
         ev[1].record(stream)
         barrier()
-    launches = (L_.rmp_launch_count() - n0) // args.steps
     ev[2].record(stream)
     for _ in range(args.steps):                              # end to end: batch from pinned host memory, loss read back
-        loss = tr.step(Xp.to(dev, non_blocking=True), Sp.to(dev, non_blocking=True), mp.to(dev, non_blocking=True))
+        loss = step_e2e()
         loss_host = float(loss)
     ev[3].record(stream)
     barrier()
@@ -323,7 +340,8 @@ def run_c4(args):
                        "path": "per-edge forward/backward on the sm_100a kernels (tcgen05 row GEMMs, rmp_gemm_dw_bf16, "
                                "csrc/train.cu), per-node remainder torch under bf16 autocast",
                        "collective": f"one NCCL all-reduce of a flat fp32 gradient buffer, {tr.n_params * 4 / 1e6:.1f} MB, "
-                                     "side stream, then rmp_adam_step"},
+                                     "side stream, then rmp_adam_step",
+                       "launch": "CUDA graph replay of the whole step" if replay else "eager"},
             "e2e": {"value": Nv * world / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": Xp.numel() * 4 + Sp.numel() * 8 + mp.numel() * 4, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "clocks": clocks.summary()}), flush=True)

@@ -301,25 +301,36 @@ int rmp_edge_mlp_bf16_traced(const void* h_E_bf16, const void* W_bf16, int num_s
  * Per-edge backward of MPNNLayer's message MLP (rdesign/model/mpnn.py:15-19, :33-34), decomposed into HBM-bound passes
  * over bf16 [rows,128] tensors and tcgen05 GEMMs; the Linear stages themselves run on rmp_row_mlp_tc (forward with the
  * weight, backward-data with the transposed weight).  Dropout masks are never stored: both directions regenerate them
- * from Philox-4x32-10(seed, element group, stream_id).
+ * from a counter-based hash of (seed + *seed_dev, element group, stream_id); seed_dev / step_dev are optional device
+ * words so that a CUDA-graph replay of the step sees a new seed / step number without new kernel arguments.
  *
  * a = Dropout_p(GELU_erf(z)) (nn.GELU + nn.Dropout, mpnn.py:17-18); z, a bf16 [rows,width], width % 8 == 0 */
 int rmp_act_fwd_bf16(const void* z_bf16, void* a_bf16, int64_t rows, int width, float p_drop, uint64_t seed,
-                     uint32_t stream_id, void* stream);
+                     const uint64_t* seed_dev, uint32_t stream_id, void* stream);
 /* dz = da * mask/(1-p) * GELU'(z) for 128-wide rows; da is either a bf16 [rows,128] tensor or, for the last message
  * stage, gathered on the fly as dagg[ctr[r],:] * alpha (the backward of scatter_sum / scale, mpnn.py:34).
  * db [128] fp32 (may be NULL) accumulates the column sums of dz = the bias gradient. */
 int rmp_act_bwd_bf16(const void* z_bf16, const void* da_bf16, const float* dagg, const int32_t* ctr, float alpha,
-                     void* dz_bf16, float* db, int rows, float p_drop, uint64_t seed, uint32_t stream_id, void* stream);
+                     void* dz_bf16, float* db, int rows, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                     uint32_t stream_id, void* stream);
 /* out[idx[r],:] += x[r,:]   x bf16 [rows,128], out fp32: backward of the h_V[E_idx] gathers (rdesign.py:85) */
 int rmp_scatter_add_rows(const void* x_bf16, const int32_t* idx, float* out, int rows, void* stream);
 /* dW[n,k] += sum_r dZ[r,n] X[r,k]   dZ, X bf16 [rows,128], dW fp32 [128,128]: weight gradient of a 128->128 Linear
  * (tcgen05, both operands read MN-major from their row-major tiles, per-CTA TMEM accumulator, one red.global pass) */
 int rmp_gemm_dw_bf16(const void* dZ_bf16, const void* X_bf16, float* dW, int rows, void* stream);
+/* One 128 -> 128 Linear stage over bf16 rows as a lean HBM-bound tcgen05 GEMM with fused epilogues:
+ *   Z = A W^T (+ bias) (+ Pc[ctr[r]] + Pn[nbr[r]]);   A bf16 [rows,128], W bf16 [128,128] (nn.Linear layout)
+ *   z_bf16 <- Z;  a_bf16 <- Dropout_p(GELU(Z)) (same mask as rmp_act_fwd/bwd_bf16 for (seed, stream_id));
+ *   acc32 += Z (fp32, gradient accumulation).  Any subset of the three outputs; Pc/Pn fp32 [Nv,128] optional. */
+int rmp_gemm_rows_bf16(const void* A_bf16, const void* W_bf16, const float* bias, const float* Pc, const float* Pn,
+                       const int32_t* ctr, const int32_t* nbr, void* z_bf16, void* a_bf16, float* acc32, int rows,
+                       int w_ld /* elements per row of the matrix W is a 128x128 window of; 0 = 128 */,
+                       int w_transposed /* Z = A W instead of A W^T: backward-data without a transposed copy */,
+                       float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t stream_id, void* stream);
 /* torch.optim.Adam step (no weight decay, no amsgrad) over flat fp32 buffers of n elements (n % 4 == 0);
  * grad is multiplied by grad_scale first (1 / world size after the all-reduce; rdesign.py:90-93) */
 int rmp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float grad_scale,
-                  float lr, float beta1, float beta2, float eps, int step, void* stream);
+                  float lr, float beta1, float beta2, float eps, int step, const int* step_dev, void* stream);
 
 /* Fused node-update kernel on 128-node tiles (tcgen05, weights streamed by TMA):
  *   x1 = prologue_ln ? LayerNorm1(h_in + agg) : h_in      (agg rows are re-zeroed after being read)

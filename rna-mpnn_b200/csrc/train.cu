@@ -16,51 +16,59 @@
 namespace rmp {
 namespace train {
 
-// Philox-4x32-10: four 32-bit words per (seed, counter, stream)
-__device__ __forceinline__ uint4 philox4(uint64_t seed, uint32_t c0, uint32_t c1, uint32_t stream) {
-    uint32_t c[4] = {c0, c1, stream, 0u};
-    uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
-#pragma unroll
-    for (int round = 0; round < 10; ++round) {
-        const uint32_t hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
-        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
-        const uint32_t n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
-        c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
-        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
-    }
-    return make_uint4(c[0], c[1], c[2], c[3]);
+// Counter-based mask generator: 128 bits per (seed, element group, stream) from two rounds of the 64-bit murmur3 /
+// splitmix finalizer (stateless, so the backward regenerates exactly the forward's mask; ~25 integer instructions per
+// 8 elements where Philox-4x32-10 needs ~80, which made the activation passes instruction-bound).
+__device__ __forceinline__ uint64_t mix64(uint64_t x) {
+    x ^= x >> 33; x *= 0xff51afd7ed558ccdull;
+    x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull;
+    x ^= x >> 33;
+    return x;
 }
-// keep-mask of the 8 elements of group g (16-bit lanes of the four words): bit j set = element j survives
+// keep-mask of the 8 elements of group g (16-bit lanes): bit j set = element j survives
 __device__ __forceinline__ uint32_t keep_mask8(uint64_t seed, uint64_t g, uint32_t stream, uint32_t thresh16) {
     if (thresh16 == 0) return 0xffu;
-    const uint4 r = philox4(seed, (uint32_t)g, (uint32_t)(g >> 32), stream);
-    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    const uint64_t k = seed + 0x9E3779B97F4A7C15ull * (g + 1) + ((uint64_t)stream << 40);
+    const uint64_t h0 = mix64(k), h1 = mix64(k ^ 0xD6E8FEB86659FD93ull);
     uint32_t m = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) m |= (uint32_t)(((w[j >> 1] >> ((j & 1) * 16)) & 0xffffu) >= thresh16) << j;
+    for (int j = 0; j < 4; ++j) {
+        m |= (uint32_t)(((h0 >> (16 * j)) & 0xffffu) >= thresh16) << j;
+        m |= (uint32_t)(((h1 >> (16 * j)) & 0xffffu) >= thresh16) << (4 + j);
+    }
     return m;
 }
-__device__ __forceinline__ float gelu_erf_grad(float x) {
-    // d/dx [x Phi(x)] = Phi(x) + x phi(x)
-    const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
-    return cdf + x * 0.39894228040143267794f * __expf(-0.5f * x * x);
+// GELU (tanh form, MUFU.TANH) and its derivative; the same pair is used in both directions, so the backward is the
+// exact derivative of what the forward computed (|tanh form - erf form| <= 5e-4, below the bf16 rounding of a)
+__device__ __forceinline__ void gelu_tanh_both(float x, float& y, float& dy) {
+    const float x2 = x * x;
+    const float u = x * fmaf(x2, 0.0356774081f, 0.7978845608f);
+    float t;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(u));
+    const float hx = 0.5f * x;
+    y = fmaf(hx, t, hx);
+    // d/dx: 0.5 (1 + t) + 0.5 x (1 - t^2) (c0 + 3 c1 x^2)
+    dy = fmaf(hx * (1.f - t * t), fmaf(x2, 0.1070322243f, 0.7978845608f), 0.5f + 0.5f * t);
 }
+__device__ __forceinline__ float gelu_tanh_y(float x) { float y, d; gelu_tanh_both(x, y, d); return y; }
+__device__ __forceinline__ float gelu_tanh_dy(float x) { float y, d; gelu_tanh_both(x, y, d); return d; }
 __device__ __forceinline__ float bf_lo(uint32_t w) { return __uint_as_float(w << 16); }
 __device__ __forceinline__ float bf_hi(uint32_t w) { return __uint_as_float(w & 0xffff0000u); }
 
 // a = Dropout(GELU(z)); one thread per 8 consecutive elements (16 bytes)
 __global__ void __launch_bounds__(256) act_fwd_kernel(const uint4* __restrict__ z, uint4* __restrict__ a, size_t n_groups,
-                                                      uint32_t thresh16, float keep_scale, uint64_t seed, uint32_t stream) {
+                                                      uint32_t thresh16, float keep_scale, uint64_t seed, const uint64_t* __restrict__ seed_dev, uint32_t stream) {
     const size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n_groups) return;
+    if (seed_dev) seed += __ldg(seed_dev);
     const uint4 zi = z[g];
     const uint32_t zw[4] = {zi.x, zi.y, zi.z, zi.w};
     const uint32_t keep = keep_mask8(seed, g, stream, thresh16);
     uint32_t o[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        const float lo = (keep >> (2 * j)) & 1u ? gelu_erf(bf_lo(zw[j])) * keep_scale : 0.f;
-        const float hi = (keep >> (2 * j + 1)) & 1u ? gelu_erf(bf_hi(zw[j])) * keep_scale : 0.f;
+        const float lo = (keep >> (2 * j)) & 1u ? gelu_tanh_y(bf_lo(zw[j])) * keep_scale : 0.f;
+        const float hi = (keep >> (2 * j + 1)) & 1u ? gelu_tanh_y(bf_hi(zw[j])) * keep_scale : 0.f;
         o[j] = tc::pack_bf16(lo, hi);
     }
     a[g] = make_uint4(o[0], o[1], o[2], o[3]);
@@ -72,8 +80,9 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const uint4* __restrict__ 
                                                       const float* __restrict__ dagg, const int32_t* __restrict__ ctr,
                                                       float alpha, uint4* __restrict__ dz, float* __restrict__ db,
                                                       int rows, int rows_per_block, uint32_t thresh16, float keep_scale,
-                                                      uint64_t seed, uint32_t stream) {
+                                                      uint64_t seed, const uint64_t* __restrict__ seed_dev, uint32_t stream) {
     __shared__ float s_db[16][128];
+    if (seed_dev) seed += __ldg(seed_dev);
     const int cg = threadIdx.x & 15, rl = threadIdx.x >> 4;          // column group (8 columns), row lane
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const int r0 = blockIdx.x * rows_per_block;
@@ -98,8 +107,8 @@ __global__ void __launch_bounds__(256) act_bwd_kernel(const uint4* __restrict__ 
         uint32_t o[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-            const float lo = (keep >> (2 * j)) & 1u ? d[2 * j] * keep_scale * gelu_erf_grad(bf_lo(zw[j])) : 0.f;
-            const float hi = (keep >> (2 * j + 1)) & 1u ? d[2 * j + 1] * keep_scale * gelu_erf_grad(bf_hi(zw[j])) : 0.f;
+            const float lo = (keep >> (2 * j)) & 1u ? d[2 * j] * keep_scale * gelu_tanh_dy(bf_lo(zw[j])) : 0.f;
+            const float hi = (keep >> (2 * j + 1)) & 1u ? d[2 * j + 1] * keep_scale * gelu_tanh_dy(bf_hi(zw[j])) : 0.f;
             o[j] = tc::pack_bf16(lo, hi);
             acc[2 * j] += bf_lo(o[j]); acc[2 * j + 1] += bf_hi(o[j]);      // the bias gradient sums what the GEMMs will see
         }
@@ -133,9 +142,15 @@ __global__ void __launch_bounds__(256) scatter_add_kernel(const uint4* __restric
 // Adam (torch.optim.Adam semantics, no weight decay / amsgrad): p -= lr * m_hat / (sqrt(v_hat) + eps)
 __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
                                                    float4* __restrict__ v, size_t n4, float grad_scale, float lr, float b1,
-                                                   float b2, float eps, float bc1, float bc2_sqrt) {
+                                                   float b2, float eps, float bc1, float bc2_sqrt,
+                                                   const int* __restrict__ step_dev) {
     const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n4) return;
+    if (step_dev) {                 // graph replay: the step number lives on the device
+        const float t = (float)__ldg(step_dev);
+        bc1 = 1.0f - powf(b1, t);
+        bc2_sqrt = sqrtf(1.0f - powf(b2, t));
+    }
     float4 pi = p[i], mi = m[i], vi = v[i];
     const float4 gi = g[i];
     const float step = lr / bc1;
@@ -238,6 +253,175 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant_
     if (warp == 1) tmem_dealloc(tmem_base, 128);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Z[r][n] = sum_k A[r][k] W[n][k] (+ bias[n]) (+ Pc[ctr[r]][n] + Pn[nbr[r]][n])      A bf16 [rows,128], W bf16 [128,128]
+// One Linear stage of the training path as a lean, HBM-bound GEMM: A tiles by TMA through a 4-slot ring, W resident,
+// one tcgen05 128x128x128 GEMM per tile into one of two TMEM accumulators, 8 epilogue warps (thread = row x 64
+// columns) that overlap the next tile's GEMM.  Epilogue outputs (any subset):
+//   z16   bf16 [rows,128]   the pre-activation (kept for the backward)
+//   a16   bf16 [rows,128]   Dropout(GELU(z16)): the activation pass fused in (forward)
+//   acc32 fp32 [rows,128]   += Z: gradient accumulation over the layers (d h_E)
+// ------------------------------------------------------------------------------------------------------------------
+constexpr int kGrStages = 4;
+constexpr int kGrEpiWarps = 8;
+constexpr int kGrThreads = 64 + 32 * kGrEpiWarps;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+struct alignas(8) GrBarriers { uint64_t w_full, full[kGrStages], empty[kGrStages], acc_full[2], acc_empty[2]; };
+struct GrParams {
+    const float* bias;
+    const float* Pc; const float* Pn; const int32_t* ctr; const int32_t* nbr;
+    uint16_t* z16; uint16_t* a16; float* acc32;
+    int rows;
+    uint32_t thresh16; float keep_scale; uint64_t seed; const uint64_t* seed_dev; uint32_t stream;
+    int w_mn_major;                 // 1: W is used transposed (Z = A W): read MN-major, no transposed copy needed
+};
+
+__global__ void __launch_bounds__(kGrThreads, 1)
+gemm_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const GrParams p) {
+    using namespace tc;
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+    uint8_t* sW = smem;                                    // [2][128][64] bf16
+    uint8_t* sA = sW + kTileBytes;                         // [stages][2][128][64]
+    GrBarriers* bars = reinterpret_cast<GrBarriers*>(sA + kGrStages * kTileBytes);
+    uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int n_tiles = (p.rows + kTileM - 1) / kTileM;
+    const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&bars->w_full, 1);
+        for (int i = 0; i < kGrStages; ++i) { mbar_init(&bars->full[i], 1); mbar_init(&bars->empty[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&bars->acc_full[i], 1); mbar_init(&bars->acc_empty[i], 32 * kGrEpiWarps); }
+        fence_barrier_init();
+    }
+    if (warp == 1) tmem_alloc(s_tmem, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *s_tmem;
+    if (warp == 0) {
+        if (lane == 0) {
+            tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_w);
+            mbar_expect_tx(&bars->w_full, kTileBytes);
+            for (int kb = 0; kb < 2; ++kb) tma_load_2d(sW + kb * kKBlockBytes, &tm_w, &bars->w_full, kb * 64, 0);
+            for (int i = 0; i < my_tiles; ++i) {
+                const int st = i % kGrStages;
+                const int tile = blockIdx.x + i * gridDim.x;
+                mbar_wait(&bars->empty[st], ((i / kGrStages) & 1) ^ 1);
+                mbar_expect_tx(&bars->full[st], kTileBytes);
+                for (int kb = 0; kb < 2; ++kb)
+                    tma_load_2d(sA + (size_t)st * kTileBytes + kb * kKBlockBytes, &tm_a, &bars->full[st], kb * 64, tile * kTileM);
+            }
+        }
+        __syncwarp();
+    } else if (warp == 1) {
+        if (lane == 0) {
+            const uint32_t idesc = instr_desc_bf16(128, 128, p.w_mn_major);
+            mbar_wait(&bars->w_full, 0);
+            for (int i = 0; i < my_tiles; ++i) {
+                const int st = i % kGrStages, ab = i & 1;
+                mbar_wait(&bars->acc_empty[ab], ((i >> 1) & 1) ^ 1);
+                mbar_wait(&bars->full[st], (i / kGrStages) & 1);
+                tc_fence_after();
+                const uint32_t a_addr = smem_u32(sA + (size_t)st * kTileBytes), w_addr = smem_u32(sW);
+#pragma unroll
+                for (int k = 0; k < 8; ++k) {
+                    const uint32_t off = (uint32_t)((k >> 2) * kKBlockBytes + (k & 3) * 32);
+                    // W as stored is [n][k] (Z = A W^T, K-major B); for Z = A W the same bytes are B = W read MN-major:
+                    // rows of the tile are the contraction index, 16 of them (2048 B) per MMA
+                    const uint64_t d_w = p.w_mn_major ? smem_desc_sw128(w_addr + (uint32_t)(k * 2048), kKBlockBytes, 1024)
+                                                      : smem_desc_sw128(w_addr + off, 16, 1024);
+                    umma_bf16(tmem_base + (uint32_t)(ab * 128), smem_desc_sw128(a_addr + off, 16, 1024), d_w, idesc, (uint32_t)(k > 0));
+                }
+                umma_commit(&bars->empty[st]);
+                umma_commit(&bars->acc_full[ab]);
+            }
+        }
+        __syncwarp();
+    } else {
+        const int ew = warp - 2;
+        const int lane_grp = warp & 3;
+        const int row = lane_grp * 32 + lane;
+        const int cb = (ew >> 2) * 64;                     // this thread's 64 columns
+        const uint64_t seed = p.seed + (p.seed_dev ? __ldg(p.seed_dev) : 0ull);
+        const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+        for (int i = 0; i < my_tiles; ++i) {
+            const int ab = i & 1;
+            const int tile = blockIdx.x + i * gridDim.x;
+            const int r = tile * kTileM + row;
+            const bool valid = r < p.rows;
+            int c = 0, nb = 0;
+            if (p.Pc && valid) { c = __ldg(p.ctr + r); nb = __ldg(p.nbr + r); }
+            mbar_wait(&bars->acc_full[ab], (i >> 1) & 1);
+            tc_fence_after();
+#pragma unroll
+            for (int ch = 0; ch < 2; ++ch) {
+                const int col0 = cb + ch * 32;
+                float v[32];
+                tmem_ld32(t_row + (uint32_t)(ab * 128 + col0), v);
+                if (ch == 1) {                             // both chunks are in registers: the accumulator is free again
+                    tc_fence_before();
+                    mbar_arrive(&bars->acc_empty[ab]);
+                }
+                if (!valid) continue;
+                if (p.bias) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + q);
+                        v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+                    }
+                }
+                if (p.Pc) {                                // gathered per-node projections (the h_V[E_idx] part of W1)
+                    const float4* pc = reinterpret_cast<const float4*>(p.Pc + (size_t)c * 128 + col0);
+                    const float4* pn = reinterpret_cast<const float4*>(p.Pn + (size_t)nb * 128 + col0);
+#pragma unroll
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 x = __ldg(pc + q), y = __ldg(pn + q);
+                        v[4 * q] += x.x + y.x; v[4 * q + 1] += x.y + y.y; v[4 * q + 2] += x.z + y.z; v[4 * q + 3] += x.w + y.w;
+                    }
+                }
+                if (p.acc32) {
+                    float* dst = p.acc32 + (size_t)r * 128 + col0;
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        float t[8];
+                        ldg256f(dst + 8 * q, t);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) t[k] += v[8 * q + k];
+                        stg256f(dst + 8 * q, t);
+                    }
+                }
+                uint32_t zp[16];
+#pragma unroll
+                for (int q = 0; q < 16; ++q) zp[q] = pack_bf16(v[2 * q], v[2 * q + 1]);
+                if (p.z16) {
+                    stg256u(p.z16 + (size_t)r * 128 + col0, &zp[0]);
+                    stg256u(p.z16 + (size_t)r * 128 + col0 + 16, &zp[8]);
+                }
+                if (p.a16) {                               // a = Dropout(GELU(bf16(z))): what rmp_act_fwd_bf16 would write
+                    uint32_t ap[16];
+#pragma unroll
+                    for (int g8 = 0; g8 < 4; ++g8) {
+                        const uint32_t keep = keep_mask8(seed, (uint64_t)r * 16 + (uint64_t)(col0 / 8 + g8), p.stream, p.thresh16);
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const uint32_t w = zp[4 * g8 + j];
+                            const float lo = (keep >> (2 * j)) & 1u ? gelu_tanh_y(bf_lo(w)) * p.keep_scale : 0.f;
+                            const float hi = (keep >> (2 * j + 1)) & 1u ? gelu_tanh_y(bf_hi(w)) * p.keep_scale : 0.f;
+                            ap[4 * g8 + j] = pack_bf16(lo, hi);
+                        }
+                    }
+                    stg256u(p.a16 + (size_t)r * 128 + col0, &ap[0]);
+                    stg256u(p.a16 + (size_t)r * 128 + col0 + 16, &ap[8]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, 256);
+}
+
 }  // namespace train
 }  // namespace rmp
 
@@ -246,7 +430,7 @@ using namespace rmp;
 static uint32_t drop_threshold(float p) { return p <= 0.f ? 0u : (uint32_t)(p * 65536.0f + 0.5f); }
 
 extern "C" int rmp_act_fwd_bf16(const void* z_bf16, void* a_bf16, int64_t rows, int width, float p_drop, uint64_t seed,
-                                uint32_t stream_id, void* stream) {
+                                const uint64_t* seed_dev, uint32_t stream_id, void* stream) {
     RMP_REQUIRE(z_bf16 && a_bf16 && rows >= 0 && width > 0 && width % 8 == 0, RMP_E_ARG, "rmp_act_fwd_bf16: bad arguments");
     RMP_REQUIRE(aligned16(z_bf16) && aligned16(a_bf16), RMP_E_ALIGN, "rmp_act_fwd_bf16: 16-byte alignment");
     RMP_REQUIRE(p_drop >= 0.f && p_drop < 1.f, RMP_E_ARG, "rmp_act_fwd_bf16: dropout probability in [0,1)");
@@ -254,13 +438,13 @@ extern "C" int rmp_act_fwd_bf16(const void* z_bf16, void* a_bf16, int64_t rows, 
     if (groups == 0) return RMP_OK;
     train::act_fwd_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const uint4*>(z_bf16), reinterpret_cast<uint4*>(a_bf16), groups, drop_threshold(p_drop),
-        1.0f / (1.0f - p_drop), seed, stream_id);
+        1.0f / (1.0f - p_drop), seed, seed_dev, stream_id);
     return check_launch("rmp_act_fwd_bf16");
 }
 
 extern "C" int rmp_act_bwd_bf16(const void* z_bf16, const void* da_bf16, const float* dagg, const int32_t* ctr, float alpha,
-                                void* dz_bf16, float* db, int rows, float p_drop, uint64_t seed, uint32_t stream_id,
-                                void* stream) {
+                                void* dz_bf16, float* db, int rows, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                                uint32_t stream_id, void* stream) {
     RMP_REQUIRE(z_bf16 && dz_bf16 && rows >= 0, RMP_E_ARG, "rmp_act_bwd_bf16: null pointer");
     RMP_REQUIRE((da_bf16 != nullptr) != (dagg != nullptr && ctr != nullptr), RMP_E_ARG,
                 "rmp_act_bwd_bf16: give either da_bf16 or (dagg, ctr)");
@@ -271,7 +455,7 @@ extern "C" int rmp_act_bwd_bf16(const void* z_bf16, const void* da_bf16, const f
     train::act_bwd_kernel<<<ceil_div(rows, rows_per_block), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const uint4*>(z_bf16), reinterpret_cast<const uint4*>(da_bf16), dagg, ctr, alpha,
         reinterpret_cast<uint4*>(dz_bf16), db, rows, rows_per_block, drop_threshold(p_drop), 1.0f / (1.0f - p_drop), seed,
-        stream_id);
+        seed_dev, stream_id);
     return check_launch("rmp_act_bwd_bf16");
 }
 
@@ -286,16 +470,16 @@ extern "C" int rmp_scatter_add_rows(const void* x_bf16, const int32_t* idx, floa
 }
 
 extern "C" int rmp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float grad_scale,
-                             float lr, float beta1, float beta2, float eps, int step, void* stream) {
-    RMP_REQUIRE(param && grad && exp_avg && exp_avg_sq && n >= 0 && step >= 1, RMP_E_ARG, "rmp_adam_step: bad arguments");
+                             float lr, float beta1, float beta2, float eps, int step, const int* step_dev, void* stream) {
+    RMP_REQUIRE(param && grad && exp_avg && exp_avg_sq && n >= 0 && (step >= 1 || step_dev), RMP_E_ARG, "rmp_adam_step: bad arguments");
     RMP_REQUIRE(n % 4 == 0 && aligned16(param) && aligned16(grad) && aligned16(exp_avg) && aligned16(exp_avg_sq), RMP_E_ALIGN,
                 "rmp_adam_step: buffers must be 16-byte aligned and a multiple of 4 elements (pad the flat buffer)");
     if (n == 0) return RMP_OK;
-    const float bc1 = 1.0f - powf(beta1, (float)step), bc2 = 1.0f - powf(beta2, (float)step);
+    const float bc1 = 1.0f - powf(beta1, (float)(step < 1 ? 1 : step)), bc2 = 1.0f - powf(beta2, (float)(step < 1 ? 1 : step));
     const size_t n4 = (size_t)n / 4;
     train::adam_kernel<<<(unsigned)((n4 + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<float4*>(param), reinterpret_cast<const float4*>(grad), reinterpret_cast<float4*>(exp_avg),
-        reinterpret_cast<float4*>(exp_avg_sq), n4, grad_scale, lr, beta1, beta2, eps, bc1, sqrtf(bc2));
+        reinterpret_cast<float4*>(exp_avg_sq), n4, grad_scale, lr, beta1, beta2, eps, bc1, sqrtf(bc2), step_dev);
     return check_launch("rmp_adam_step");
 }
 
@@ -314,4 +498,45 @@ extern "C" int rmp_gemm_dw_bf16(const void* dZ_bf16, const void* X_bf16, float* 
     const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
     train::gemm_dw_kernel<<<grid, train::kDwThreads, smem, (cudaStream_t)stream>>>(tm_dz, tm_x, dW, rows);
     return check_launch("rmp_gemm_dw_bf16");
+}
+
+extern "C" int rmp_gemm_rows_bf16(const void* A_bf16, const void* W_bf16, const float* bias, const float* Pc, const float* Pn,
+                                  const int32_t* ctr, const int32_t* nbr, void* z_bf16, void* a_bf16, float* acc32, int rows,
+                                  int w_ld, int w_transposed, float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t stream_id,
+                                  void* stream) {
+    RMP_REQUIRE(A_bf16 && W_bf16 && rows >= 0 && (z_bf16 || a_bf16 || acc32), RMP_E_ARG, "rmp_gemm_rows_bf16: null pointer / no output");
+    RMP_REQUIRE((Pc == nullptr) == (Pn == nullptr) && (!Pc || (ctr && nbr)), RMP_E_ARG, "rmp_gemm_rows_bf16: Pc, Pn, ctr, nbr go together");
+    RMP_REQUIRE(aligned16(A_bf16) && aligned16(W_bf16) && (!bias || aligned16(bias)) && (!Pc || (aligned16(Pc) && aligned16(Pn))) &&
+                (!z_bf16 || aligned32(z_bf16)) && (!a_bf16 || aligned32(a_bf16)) && (!acc32 || aligned32(acc32)), RMP_E_ALIGN,
+                "rmp_gemm_rows_bf16: inputs 16-byte, outputs 32-byte aligned");
+    RMP_REQUIRE(p_drop >= 0.f && p_drop < 1.f, RMP_E_ARG, "rmp_gemm_rows_bf16: dropout probability in [0,1)");
+    if (rows == 0) return RMP_OK;
+    CUtensorMap tm_a, tm_w;
+    int rc = tc::make_map_bf16_rows128(&tm_a, A_bf16, (uint64_t)rows);
+    if (rc) return rc;
+    {   // W: 128 x 128 window of a row-major matrix with w_ld elements per row (a column block of a wider weight)
+        tc::EncodeTiledFn fn = tc::encode_fn();
+        RMP_REQUIRE(fn != nullptr, RMP_E_ARCH, "cuTensorMapEncodeTiled entry point not found");
+        const int ld = w_ld > 0 ? w_ld : 128;
+        RMP_REQUIRE(ld >= 128 && ld % 8 == 0, RMP_E_SHAPE, "rmp_gemm_rows_bf16: w_ld must be >= 128 and a multiple of 8");
+        const cuuint64_t dims[2] = {128, 128};
+        const cuuint64_t strides[1] = {(cuuint64_t)ld * 2};
+        const cuuint32_t box[2] = {64, 128};
+        const cuuint32_t estr[2] = {1, 1};
+        CUresult r = fn(&tm_w, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(W_bf16), dims, strides, box, estr,
+                        CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        RMP_REQUIRE(r == CUDA_SUCCESS, RMP_E_ARG, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+    }
+    train::GrParams p{};
+    p.bias = bias; p.Pc = Pc; p.Pn = Pn; p.ctr = ctr; p.nbr = nbr;
+    p.z16 = reinterpret_cast<uint16_t*>(z_bf16); p.a16 = reinterpret_cast<uint16_t*>(a_bf16); p.acc32 = acc32; p.rows = rows;
+    p.thresh16 = drop_threshold(p_drop); p.keep_scale = 1.0f / (1.0f - p_drop); p.seed = seed; p.seed_dev = seed_dev;
+    p.stream = stream_id; p.w_mn_major = w_transposed ? 1 : 0;
+    const size_t smem = 1024 + (size_t)(1 + train::kGrStages) * tc::kTileBytes + sizeof(train::GrBarriers) + 16;
+    cudaFuncSetAttribute(train::gemm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int n_tiles = ceil_div(rows, tc::kTileM);
+    const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
+    train::gemm_rows_kernel<<<grid, train::kGrThreads, smem, (cudaStream_t)stream>>>(tm_a, tm_w, p);
+    return check_launch("rmp_gemm_rows_bf16");
 }

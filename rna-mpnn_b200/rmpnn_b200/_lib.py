@@ -75,11 +75,12 @@ SIGNATURES = {
     "rmp_node_mlp_bf16": [P, P, I, P, P, I, P, P, P, P, P, P, P, P, P, P, P, I, P],
     "rmp_edge_mlp_bf16": [P, P, I, P, P, P, P, P, P, I, F, P, P, P],
     "rmp_edge_mlp_bf16_traced": [P, P, I, P, P, P, P, P, P, I, F, P, P, P, P],
-    "rmp_act_fwd_bf16": [P, P, I64, I, F, U64, C.c_uint32, P],
-    "rmp_act_bwd_bf16": [P, P, P, P, F, P, P, I, F, U64, C.c_uint32, P],
+    "rmp_act_fwd_bf16": [P, P, I64, I, F, U64, P, C.c_uint32, P],
+    "rmp_act_bwd_bf16": [P, P, P, P, F, P, P, I, F, U64, P, C.c_uint32, P],
     "rmp_scatter_add_rows": [P, P, P, I, P],
     "rmp_gemm_dw_bf16": [P, P, P, I, P],
-    "rmp_adam_step": [P, P, P, P, I64, F, F, F, F, F, I, P],
+    "rmp_adam_step": [P, P, P, P, I64, F, F, F, F, F, I, P, P],
+    "rmp_gemm_rows_bf16": [P, P, P, P, P, P, P, P, P, P, I, I, I, F, U64, P, C.c_uint32, P],
 }
 STRING_GETTERS = ("rmp_version", "rmp_last_error_string")
 

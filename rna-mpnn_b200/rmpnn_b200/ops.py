@@ -436,23 +436,24 @@ __all__ = ["collate", "tc_eligible", "ResGraph", "res_graph", "res_edge_rows", "
 
 
 # --------------------------------------------------------------------------- training path
-def act_fwd(z16: torch.Tensor, p_drop: float, seed: int, stream_id: int) -> torch.Tensor:
+def act_fwd(z16: torch.Tensor, p_drop: float, seed: int, stream_id: int, seed_dev=None) -> torch.Tensor:
     """a = Dropout(GELU(z)) on bf16 rows (rmp_act_fwd_bf16)."""
     _need_cuda(z16)
     assert z16.dtype == torch.bfloat16 and z16.is_contiguous()
     a = torch.empty_like(z16)
-    check(lib().rmp_act_fwd_bf16(_ptr(z16), _ptr(a), z16.shape[0], z16.shape[1], float(p_drop), int(seed), int(stream_id),
-                                 _stream()), "rmp_act_fwd_bf16")
+    check(lib().rmp_act_fwd_bf16(_ptr(z16), _ptr(a), z16.shape[0], z16.shape[1], float(p_drop), int(seed), _ptr(seed_dev),
+                                 int(stream_id), _stream()), "rmp_act_fwd_bf16")
     return a
 
 
-def act_bwd(z16, p_drop: float, seed: int, stream_id: int, da16=None, dagg=None, ctr=None, alpha: float = 1.0, db=None):
+def act_bwd(z16, p_drop: float, seed: int, stream_id: int, da16=None, dagg=None, ctr=None, alpha: float = 1.0, db=None,
+            seed_dev=None):
     """dz = da * mask/(1-p) * GELU'(z); da bf16, or gathered from dagg[ctr] * alpha; db [128] += column sums."""
     _need_cuda(z16, da16, dagg, ctr, db)
     assert z16.dtype == torch.bfloat16 and z16.is_contiguous() and z16.shape[1] == 128
     dz = torch.empty_like(z16)
     check(lib().rmp_act_bwd_bf16(_ptr(z16), _ptr(da16), _ptr(dagg), _ptr(ctr), float(alpha), _ptr(dz), _ptr(db),
-                                 z16.shape[0], float(p_drop), int(seed), int(stream_id), _stream()), "rmp_act_bwd_bf16")
+                                 z16.shape[0], float(p_drop), int(seed), _ptr(seed_dev), int(stream_id), _stream()), "rmp_act_bwd_bf16")
     return dz
 
 
@@ -472,11 +473,30 @@ def gemm_dw(dz16, x16, dW):
     return dW
 
 
+def gemm_rows(a16, w16, bias=None, Pc=None, Pn=None, ctr=None, nbr=None, want_z=True, act=None, acc32=None,
+              w_transposed=False, seed_dev=None):
+    """Z = a16 @ w16^T (or a16 @ w16 with ``w_transposed``) (+bias) (+Pc[ctr] + Pn[nbr]) on the lean tcgen05 row GEMM.  ``act=(p_drop, seed, stream_id)``
+    also returns Dropout(GELU(Z)); ``acc32`` (fp32 [rows,128]) is incremented by Z.  Returns (z16 | None, a16 | None)."""
+    _need_cuda(a16, w16, bias, Pc, Pn, ctr, nbr, acc32)
+    assert a16.dtype == w16.dtype == torch.bfloat16 and a16.is_contiguous() and w16.stride(1) == 1
+    assert a16.shape[1] == 128 and tuple(w16.shape) == (128, 128)      # w16 may be a column block of a wider matrix
+    rows = a16.shape[0]
+    z = torch.empty_like(a16) if want_z else None
+    a = torch.empty_like(a16) if act is not None else None
+    p_drop, seed, sid = act if act is not None else (0.0, 0, 0)
+    check(lib().rmp_gemm_rows_bf16(_ptr(a16), _ptr(w16), _ptr(bias), _ptr(Pc), _ptr(Pn), _ptr(ctr), _ptr(nbr), _ptr(z), _ptr(a),
+                                   _ptr(acc32), rows, int(w16.stride(0)), int(w_transposed), float(p_drop), int(seed), _ptr(seed_dev), int(sid), _stream()),
+          "rmp_gemm_rows_bf16")
+    return z, a
+
+
 def adam_step(param, grad, exp_avg, exp_avg_sq, step: int, lr: float, grad_scale: float = 1.0, betas=(0.9, 0.999),
-              eps: float = 1e-8):
-    _need_cuda(param, grad, exp_avg, exp_avg_sq)
+              eps: float = 1e-8, step_dev=None):
+    """``step_dev`` (int32 device scalar) overrides ``step`` so that a captured graph can advance it on the device."""
+    _need_cuda(param, grad, exp_avg, exp_avg_sq, step_dev)
     check(lib().rmp_adam_step(_ptr(param), _ptr(grad), _ptr(exp_avg), _ptr(exp_avg_sq), param.numel(), float(grad_scale),
-                              float(lr), float(betas[0]), float(betas[1]), float(eps), int(step), _stream()), "rmp_adam_step")
+                              float(lr), float(betas[0]), float(betas[1]), float(eps), int(step), _ptr(step_dev), _stream()),
+          "rmp_adam_step")
 
 
 # --------------------------------------------------------------------------- device guard

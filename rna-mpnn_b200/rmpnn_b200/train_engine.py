@@ -5,8 +5,8 @@ gradient all-reduce (Lightning DDP), Adam (rdesign.py:90-93).  Here:
 
 * everything per EDGE -- the three Linear + GELU + Dropout message stages on ``[h_E | h_V[ctr] | h_V[nbr]]``, the
   ``scatter_sum / scale`` and their backward (96 % of the step's flops and bytes) -- runs on the C-ABI kernels:
-  tcgen05 row GEMMs (``rmp_row_mlp_tc``), the weight-gradient GEMM ``rmp_gemm_dw_bf16``, and the HBM-bound
-  activation / scatter passes of ``csrc/train.cu``; dropout masks are regenerated from Philox, never stored;
+  the lean tcgen05 row GEMM ``rmp_gemm_rows_bf16`` (GELU + Dropout fused into its forward epilogue), the
+  weight-gradient GEMM ``rmp_gemm_dw_bf16``, and the HBM-bound activation-backward / scatter passes of ``csrc/train.cu``; dropout masks are regenerated from Philox, never stored;
   ``d h_E`` is accumulated over the layers in one fp32 buffer by the GEMM epilogue;
 * the per-NODE remainder (LayerNorms, the dense FFN on [Nv,128] rows, readout, loss) is composed from torch-CUDA ops
   under bf16 autocast -- 4 % of the work, Nv rows instead of Ne;
@@ -25,75 +25,61 @@ import torch.nn.functional as F
 from . import ops
 
 
-def _pl(weight: torch.Tensor, bias: Optional[torch.Tensor]) -> ops.PackedLinear:
-    """bf16 nn.Linear-layout weight + fp32 bias for the tcgen05 row GEMM (the fp32 transposed copy is not needed)."""
-    n_out, k_in = weight.shape
-    b = torch.zeros(n_out, dtype=torch.float32, device=weight.device) if bias is None else bias.detach().float().contiguous()
-    return ops.PackedLinear(None, b, k_in, n_out, weight.detach().to(torch.bfloat16).contiguous(), None)
-
-
-def _gemm16(segments, weight, bias, rows, resid_acc=None):
-    """bf16 rows x W^T (+ bias) on tcgen05: -> bf16 [rows, N], or accumulated into the fp32 buffer ``resid_acc``."""
-    pl = _pl(weight, bias)
-    if resid_acc is not None:
-        ops.row_mlp(segments, [(pl, False)], ops.EPI_RESID_ADD, resid_acc, rows, resid=resid_acc, tensor_core=True)
-        return resid_acc
-    out16 = torch.empty(rows, pl.n_out, dtype=torch.bfloat16, device=weight.device)
-    ops.row_mlp(segments, [(pl, False)], ops.EPI_STORE, None, rows, tensor_core=True, out_bf16=out16)
-    return out16
+def _mm16(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """Small node-level products ([Nv,128] operands) on the bf16 tensor cores, fp32 result."""
+    return (a.to(torch.bfloat16) @ b.to(torch.bfloat16)).float()
 
 
 class EdgeMessageFn(torch.autograd.Function):
     """agg[v] = sum_{e: ctr[e]=v} Dropout(GELU(W3 Dropout(GELU(W2 Dropout(GELU(W1 [h_E|h_V[ctr]|h_V[nbr]]+b1))+b2))+b3)) / scale
-    (rdesign/model/rdesign.py:85 + rdesign/model/mpnn.py:33-34).  ``token`` orders the edge-embedding backward behind
-    every layer; d h_E goes to ``ctx_state['dhE']`` (fp32, accumulated over the layers)."""
+    (rdesign/model/rdesign.py:85 + rdesign/model/mpnn.py:33-34).  W1 = [W1e | W1c | W1n]: the h_V part is applied per
+    node (Pc = h_V W1c^T + b1, Pn = h_V W1n^T) and gathered in the GEMM epilogue.  ``token`` orders the edge-embedding
+    backward behind every layer; d h_E goes to ``state['dhE']`` (fp32, accumulated over the layers by the GEMM).
+    ``state['w16'](param)`` is the parameter's view in the step's bf16 copy of the flat parameter buffer."""
 
     @staticmethod
     def forward(ctx, h_V, token, W1, b1, W2, b2, W3, b3, state):
-        g, hE16 = state["graph"], state["hE16"]
-        p, seed, sid, scale = state["p_drop"], state["seed"], state["stream_id"], state["scale"]
-        Ne, Nv = g.Ne, g.Nv
-        hV16 = h_V.detach().to(torch.bfloat16).contiguous()
-        z0 = _gemm16([(hE16, None), (hV16, g.ctr), (hV16, g.nbr)], W1, b1, Ne)
-        a0 = ops.act_fwd(z0, p, seed, sid)
-        z1 = _gemm16([(a0, None)], W2, b2, Ne)
-        a1 = ops.act_fwd(z1, p, seed, sid + 1)
-        z2 = _gemm16([(a1, None)], W3, b3, Ne)
-        a2 = ops.act_fwd(z2, p, seed, sid + 2)
-        agg = torch.zeros(Nv, 128, dtype=torch.float32, device=h_V.device)
+        g, hE16, w16 = state["graph"], state["hE16"], state["w16"]
+        p, seed, sid, scale, sd = state["p_drop"], state["seed"], state["stream_id"], state["scale"], state["seed_dev"]
+        hV16 = h_V.detach().to(torch.bfloat16)
+        W1h = w16(W1)                                              # [128,384] bf16 view, columns e | c | n
+        Pc = ((hV16 @ W1h[:, 128:256].t()).float() + b1.detach()).contiguous()
+        Pn = (hV16 @ W1h[:, 256:].t()).float().contiguous()
+        z0, a0 = ops.gemm_rows(hE16, W1h[:, :128], Pc=Pc, Pn=Pn, ctr=g.ctr, nbr=g.nbr, act=(p, seed, sid), seed_dev=sd)
+        z1, a1 = ops.gemm_rows(a0, w16(W2), bias=b2.detach(), act=(p, seed, sid + 1), seed_dev=sd)
+        z2, a2 = ops.gemm_rows(a1, w16(W3), bias=b3.detach(), act=(p, seed, sid + 2), seed_dev=sd)
+        agg = torch.zeros(g.Nv, 128, dtype=torch.float32, device=h_V.device)
         ops.scatter_add_rows(a2, g.ctr, agg)
-        ctx.save_for_backward(h_V, W1, W2, W3, z0, z1, z2, a0, a1)
+        ctx.save_for_backward(hV16, W1, W2, W3, z0, z1, z2, a0, a1)
         ctx.state = (state, p, seed, sid, scale)
         return agg * (1.0 / scale)
 
     @staticmethod
     def backward(ctx, dagg):
-        h_V, W1, W2, W3, z0, z1, z2, a0, a1 = ctx.saved_tensors
+        hV16, W1, W2, W3, z0, z1, z2, a0, a1 = ctx.saved_tensors
         state, p, seed, sid, scale = ctx.state
-        g, hE16 = state["graph"], state["hE16"]
-        Ne, dev = g.Ne, h_V.device
+        g, hE16, w16, sd = state["graph"], state["hE16"], state["w16"], state["seed_dev"]
+        dev = hV16.device
         dagg = dagg.detach().float().contiguous()
-        f32 = dict(dtype=torch.float32, device=dev)
-        db1, db2, db3 = (torch.zeros(128, **f32) for _ in range(3))
-        dW2, dW3, dW1e = (torch.zeros(128, 128, **f32) for _ in range(3))
-        dz2 = ops.act_bwd(z2, p, seed, sid + 2, dagg=dagg, ctr=g.ctr, alpha=1.0 / scale, db=db3)
-        ops.gemm_dw(dz2, a1, dW3)
-        da1 = _gemm16([(dz2, None)], W3.detach().t().contiguous(), None, Ne)
-        dz1 = ops.act_bwd(z1, p, seed, sid + 1, da16=da1, db=db2)
-        ops.gemm_dw(dz1, a0, dW2)
-        da0 = _gemm16([(dz1, None)], W2.detach().t().contiguous(), None, Ne)
-        dz0 = ops.act_bwd(z0, p, seed, sid, da16=da0, db=db1)
-        ops.gemm_dw(dz0, hE16, dW1e)
-        W1f = W1.detach().float()
-        _gemm16([(dz0, None)], W1f[:, :128].t().contiguous(), None, Ne, resid_acc=state["dhE"])     # d h_E += dz0 W1e
-        dPc = torch.zeros(g.Nv, 128, **f32)
-        dPn = torch.zeros(g.Nv, 128, **f32)
-        ops.scatter_add_rows(dz0, g.ctr, dPc)
-        ops.scatter_add_rows(dz0, g.nbr, dPn)
-        hV = h_V.detach().float()
-        dW1 = torch.cat([dW1e, dPc.t() @ hV, dPn.t() @ hV], dim=1)
-        dhV = dPc @ W1f[:, 128:256] + dPn @ W1f[:, 256:]
-        return dhV, torch.zeros_like(state["token"]), dW1, db1, dW2, db2, dW3, db3, None
+        db = torch.zeros(3, 128, dtype=torch.float32, device=dev)
+        dW = torch.zeros(3, 128, 128, dtype=torch.float32, device=dev)           # dW3, dW2, dW1e
+        dP = torch.zeros(2, g.Nv, 128, dtype=torch.float32, device=dev)           # d Pc, d Pn
+        W1h = w16(W1)
+        dz2 = ops.act_bwd(z2, p, seed, sid + 2, dagg=dagg, ctr=g.ctr, alpha=1.0 / scale, db=db[2], seed_dev=sd)
+        ops.gemm_dw(dz2, a1, dW[0])
+        da1, _ = ops.gemm_rows(dz2, w16(W3), w_transposed=True)                  # da1 = dz2 W3
+        dz1 = ops.act_bwd(z1, p, seed, sid + 1, da16=da1, db=db[1], seed_dev=sd)
+        ops.gemm_dw(dz1, a0, dW[1])
+        da0, _ = ops.gemm_rows(dz1, w16(W2), w_transposed=True)
+        dz0 = ops.act_bwd(z0, p, seed, sid, da16=da0, db=db[0], seed_dev=sd)
+        ops.gemm_dw(dz0, hE16, dW[2])
+        ops.gemm_rows(dz0, W1h[:, :128], want_z=False, acc32=state["dhE"], w_transposed=True)      # d h_E += dz0 W1e
+        ops.scatter_add_rows(dz0, g.ctr, dP[0])
+        ops.scatter_add_rows(dz0, g.nbr, dP[1])
+        dP16 = dP.to(torch.bfloat16)
+        dW1 = torch.cat([dW[2], (dP16[0].t() @ hV16).float(), (dP16[1].t() @ hV16).float()], dim=1)
+        dhV = (dP16[0] @ W1h[:, 128:256] + dP16[1] @ W1h[:, 256:]).float()
+        return dhV, torch.zeros(1, device=dev), dW1, db[0], dW[1], db[1], dW[0], db[2], None
 
 
 class EdgeEmbedFn(torch.autograd.Function):
@@ -103,9 +89,9 @@ class EdgeEmbedFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, W, b, gain, beta, state):
         raw16 = state["edge_raw16"]                                # [Ne,128] bf16, columns >= 115 zero
-        Wp = F.pad(W.detach(), (0, 128 - W.shape[1]))
-        z = torch.empty(raw16.shape[0], 128, dtype=torch.float32, device=W.device)
-        ops.row_mlp([(raw16, None)], [(_pl(Wp, b), False)], ops.EPI_STORE, z, raw16.shape[0], tensor_core=True)
+        Wp = F.pad(state["w16"](W), (0, 128 - W.shape[1]))
+        z = torch.zeros(raw16.shape[0], 128, dtype=torch.float32, device=W.device)       # fp32 result through the += output
+        ops.gemm_rows(raw16, Wp, bias=b.detach(), want_z=False, acc32=z)
         ctx.save_for_backward(z, W, gain, beta)
         ctx.state = state
         with torch.no_grad():
@@ -159,29 +145,49 @@ class RDesignTrainer:
             p.data = self.flat_p[at:at + k].view_as(p)
             p.grad = self.flat_g[at:at + k].view_as(p)
             at += k
+        self._slot = {}
+        at = 0
+        for p in self.params:
+            self._slot[id(p)] = (at, tuple(p.shape))
+            at += p.numel()
+        self.flat_p16 = torch.zeros(n_pad, dtype=torch.bfloat16, device=dev)     # the step's bf16 copy of every parameter
         self.step_no = 0
+        # device-side step number and dropout seed offset: a captured CUDA graph advances them itself
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.seed_dev = torch.zeros(1, dtype=torch.int64, device=dev)
         self.comm_stream = torch.cuda.Stream(device=dev) if world > 1 else None
+        self._graph = None
+
+    def _w16(self, param: torch.Tensor) -> torch.Tensor:
+        at, shape = self._slot[id(param)]
+        n = 1
+        for d in shape:
+            n *= d
+        return self.flat_p16[at:at + n].view(shape)
 
     # ------------------------------------------------------------------ forward + backward
-    def loss_and_grads(self, X, S, mask, seed: int = 0):
+    def loss_and_grads(self, X, S, mask, seed: int = 0, sizes=None):
         m = self.model
         f = m.features
         B, N = X.shape[:2]
-        g = ops.build_graph(X, mask, f.top_k)
+        self.flat_p16.copy_(self.flat_p)                           # one cast for all weights of the step
+        g = ops.build_graph(X, mask, f.top_k, sizes)
         node_raw, edge_raw = ops.raw_features(X, g)
-        state: Dict = {"graph": g, "p_drop": self.p_drop, "seed": seed, "scale": float(m.mpnn_layers[0].scale)}
+        state: Dict = {"graph": g, "p_drop": self.p_drop, "seed": seed, "scale": float(m.mpnn_layers[0].scale),
+                       "w16": self._w16, "seed_dev": self.seed_dev}
         state["edge_raw16"] = F.pad(edge_raw, (0, 128 - edge_raw.shape[1])).to(torch.bfloat16).contiguous()
         state["dhE"] = torch.zeros(g.Ne, 128, dtype=torch.float32, device=X.device)
         del edge_raw
         S_valid = S.reshape(B * N)[g.node_src[:g.Nv].long()]
-        self.flat_g.zero_()
         token = EdgeEmbedFn.apply(f.edge_embedding.weight, f.edge_embedding.bias, f.norm_edges.gain, f.norm_edges.bias, state)
-        state["token"] = token
+        # (the token is passed to the layers as an argument and never stored in ``state``: state is referenced by the
+        # autograd contexts, and a reference cycle would keep this step's graph -- and its AccumulateGrad nodes with
+        # the stream they were created on -- alive into the next step, which breaks CUDA-graph capture)
         h_V = f.norm_nodes(f.node_embedding(node_raw))             # [Nv,128] fp32, torch (node level)
         for l, layer in enumerate(m.mpnn_layers):
             lin = [x for x in layer.message_layers if isinstance(x, torch.nn.Linear)]
             st = dict(state, stream_id=16 * l)
-            st["dhE"], st["token"] = state["dhE"], token
+            st["dhE"] = state["dhE"]
             agg = EdgeMessageFn.apply(h_V, token, lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight,
                                       lin[2].bias, st)
             with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.autocast):
@@ -190,7 +196,10 @@ class RDesignTrainer:
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.autocast):
             logits = m.readout(h_V)
         loss = F.cross_entropy(logits.float(), S_valid)
-        loss.backward()
+        # torch.autograd.grad instead of backward(): no AccumulateGrad nodes, whose stream (the one the parameters were
+        # created on) would have to be synchronised with the capturing stream and invalidates a CUDA-graph capture
+        grads = torch.autograd.grad(loss, self.params)
+        torch.cat([g.reshape(-1) for g in grads], out=self.flat_g[:self.n_params])
         return loss.detach()
 
     # ------------------------------------------------------------------ all-reduce + Adam
@@ -198,6 +207,8 @@ class RDesignTrainer:
         """ONE all-reduce of the flat gradient buffer (the only data-path collective of training), then fused Adam."""
         import torch.distributed as dist
         self.step_no += 1
+        self.step_dev += 1
+        self.seed_dev += 0x5851F42D4C957F2D
         if self.world > 1:
             cur = torch.cuda.current_stream()
             self.comm_stream.wait_stream(cur)
@@ -205,9 +216,34 @@ class RDesignTrainer:
                 dist.all_reduce(self.flat_g)
             cur.wait_stream(self.comm_stream)
         ops.adam_step(self.flat_p, self.flat_g, self.exp_avg, self.exp_avg_sq, self.step_no, self.lr,
-                      grad_scale=1.0 / self.world)
+                      grad_scale=1.0 / self.world, step_dev=self.step_dev)
 
-    def step(self, X, S, mask, seed: Optional[int] = None):
-        loss = self.loss_and_grads(X, S, mask, self.step_no if seed is None else seed)
+    def step(self, X, S, mask, seed: int = 0, sizes=None):
+        """One eager training step (the dropout seed is ``seed`` plus the device-side offset that advances every step)."""
+        loss = self.loss_and_grads(X, S, mask, seed, sizes)
         self.apply_gradients()
         return loss
+
+    def capture(self, X, S, mask, sizes):
+        """Capture one whole training step (forward, backward, all-reduce, Adam) for fixed shapes into a CUDA graph.
+        Returns ``(replay, static)``: overwrite ``static['X'|'S'|'mask']`` and call ``replay()`` -> loss tensor.
+        ``sizes = (Nv, Ne)`` must be given (a captured step cannot read the two counters back to the host)."""
+        static = {"X": X.clone(), "S": S.clone(), "mask": mask.clone()}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side), torch.autograd.set_multithreading_enabled(False):   # warm-up outside the capture
+            for _ in range(3):
+                self.step(static["X"], static["S"], static["mask"], sizes=sizes)
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        # the backward must run on the capturing thread / stream: the ctypes launches take torch's current stream, and a
+        # launch from an autograd worker thread that sees the legacy stream invalidates the capture
+        with torch.autograd.set_multithreading_enabled(False), torch.cuda.graph(graph, capture_error_mode="thread_local"):
+            loss = self.step(static["X"], static["S"], static["mask"], sizes=sizes)
+        self._graph = graph
+
+        def replay():
+            graph.replay()
+            return loss
+        return replay, static

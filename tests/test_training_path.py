@@ -139,3 +139,26 @@ def test_training_loss_decreases_with_dropout_on():
     tr = RDesignTrainer(model)
     losses = [tr.step(X, S, mask).item() for _ in range(25)]
     assert np.isfinite(losses).all() and np.mean(losses[-5:]) < np.mean(losses[:5]) - 0.05, losses
+
+
+@pytest.mark.parametrize("rows", [1, 130, 5000])
+def test_gemm_rows_outputs(rows):
+    """Lean row GEMM: z, fused Dropout(GELU(z)) with the same mask as rmp_act_fwd_bf16, fp32 accumulation, gathers."""
+    from rmpnn_b200 import ops
+    g = torch.Generator().manual_seed(rows)
+    A = torch.randn(rows, 128, generator=g).cuda().to(torch.bfloat16)
+    W = (torch.randn(128, 128, generator=g) / 11.3).cuda().to(torch.bfloat16)
+    b = 0.1 * torch.randn(128, generator=g).cuda()
+    Nv = 37
+    Pc, Pn = torch.randn(Nv, 128, generator=g).cuda(), torch.randn(Nv, 128, generator=g).cuda()
+    ctr = torch.randint(0, Nv, (rows,), generator=g, dtype=torch.int32).cuda()
+    nbr = torch.randint(0, Nv, (rows,), generator=g, dtype=torch.int32).cuda()
+    acc = torch.full((rows, 128), 2.0, device="cuda")
+    z, a = ops.gemm_rows(A, W, bias=b, Pc=Pc, Pn=Pn, ctr=ctr, nbr=nbr, act=(0.1, 5, 9), acc32=acc)
+    ref = A.float() @ W.float().t() + b + Pc[ctr.long()] + Pn[nbr.long()]
+    np.testing.assert_allclose(z.float().cpu().numpy(), _bf(ref).cpu().numpy(), atol=3e-2, rtol=1e-2)
+    np.testing.assert_allclose(acc.cpu().numpy(), (ref + 2.0).cpu().numpy(), atol=2e-3, rtol=1e-4)
+    assert torch.equal(a, ops.act_fwd(z, 0.1, 5, 9))                   # the fused activation IS the stand-alone pass
+    z2, a2 = ops.gemm_rows(A, W)
+    assert a2 is None
+    np.testing.assert_allclose(z2.float().cpu().numpy(), _bf(A.float() @ W.float().t()).cpu().numpy(), atol=3e-2, rtol=1e-2)
