@@ -321,8 +321,9 @@ int rmp_gemm_dw_bf16(const void* dZ_bf16, const void* X_bf16, float* dW, int row
 /* One 128 -> 128 Linear stage over bf16 rows as a lean HBM-bound tcgen05 GEMM with fused epilogues:
  *   Z = A W^T (+ bias) (+ Pc[ctr[r]] + Pn[nbr[r]]);   A bf16 [rows,128], W bf16 [128,128] (nn.Linear layout)
  *   z_bf16 <- Z;  a_bf16 <- Dropout_p(GELU(Z)) (same mask as rmp_act_fwd/bwd_bf16 for (seed, stream_id));
- *   acc32 += Z (fp32, gradient accumulation).  Any subset of the three outputs; Pc/Pn fp32 [Nv,128] optional. */
-int rmp_gemm_rows_bf16(const void* A_bf16, const void* W_bf16, const float* bias, const float* Pc, const float* Pn,
+ *   acc32 += Z (fp32, gradient accumulation).  Any subset of the three outputs; Pc/Pn bf16 [Nv,128] optional.
+ * The dropout probability is quantised to round(256 p)/256 (one 64-bit hash per 8 elements, 8-bit lanes). */
+int rmp_gemm_rows_bf16(const void* A_bf16, const void* W_bf16, const float* bias, const void* Pc_bf16, const void* Pn_bf16,
                        const int32_t* ctr, const int32_t* nbr, void* z_bf16, void* a_bf16, float* acc32, int rows,
                        int w_ld /* elements per row of the matrix W is a 128x128 window of; 0 = 128 */,
                        int w_transposed /* Z = A W instead of A W^T: backward-data without a transposed copy */,

@@ -25,16 +25,18 @@ __device__ __forceinline__ uint64_t mix64(uint64_t x) {
     x ^= x >> 33;
     return x;
 }
-// keep-mask of the 8 elements of group g (16-bit lanes): bit j set = element j survives
-__device__ __forceinline__ uint32_t keep_mask8(uint64_t seed, uint64_t g, uint32_t stream, uint32_t thresh16) {
-    if (thresh16 == 0) return 0xffu;
-    const uint64_t k = seed + 0x9E3779B97F4A7C15ull * (g + 1) + ((uint64_t)stream << 40);
-    const uint64_t h0 = mix64(k), h1 = mix64(k ^ 0xD6E8FEB86659FD93ull);
+// keep-mask of the 8 elements of group g: one hash, eight 8-bit lanes; bit j set = element j survives.
+// The drop probability is quantised to thresh8 / 256 and the survivors are scaled by 256 / (256 - thresh8), so the
+// expectation is exact for the quantised p (0.1 -> 26/256 = 0.1016).
+__device__ __forceinline__ uint32_t keep_mask8(uint64_t seed, uint64_t g, uint32_t stream, uint32_t thresh8) {
+    if (thresh8 == 0) return 0xffu;
+    const uint64_t h = mix64(seed + 0x9E3779B97F4A7C15ull * (g + 1) + ((uint64_t)stream << 40));
+    const uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
     uint32_t m = 0;
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
-        m |= (uint32_t)(((h0 >> (16 * j)) & 0xffffu) >= thresh16) << j;
-        m |= (uint32_t)(((h1 >> (16 * j)) & 0xffffu) >= thresh16) << (4 + j);
+        m |= (uint32_t)(((lo >> (8 * j)) & 0xffu) >= thresh8) << j;
+        m |= (uint32_t)(((hi >> (8 * j)) & 0xffu) >= thresh8) << (4 + j);
     }
     return m;
 }
@@ -263,13 +265,22 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant_
 //   a16   bf16 [rows,128]   Dropout(GELU(z16)): the activation pass fused in (forward)
 //   acc32 fp32 [rows,128]   += Z: gradient accumulation over the layers (d h_E)
 // ------------------------------------------------------------------------------------------------------------------
-constexpr int kGrStages = 4;
-constexpr int kGrEpiWarps = 8;
-constexpr int kGrThreads = 64 + 32 * kGrEpiWarps;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kGrStages = 3;
+constexpr int kGrEpiWarps = 16;
+constexpr int kGrThreads = 128 + 32 * kGrEpiWarps;         // warp 0 TMA, warp 1 MMA, warps 2..3 idle, warps 4..19 epilogue
 struct alignas(8) GrBarriers { uint64_t w_full, full[kGrStages], empty[kGrStages], acc_full[2], acc_empty[2]; };
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map),
+                 "r"(tc::smem_u32(src)), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void gr_epi_bar() { asm volatile("bar.sync 1, %0;" ::"n"(512) : "memory"); }
+
 struct GrParams {
     const float* bias;
-    const float* Pc; const float* Pn; const int32_t* ctr; const int32_t* nbr;
+    const uint16_t* Pc; const uint16_t* Pn; const int32_t* ctr; const int32_t* nbr;      // bf16 [Nv,128] per-node projections
     uint16_t* z16; uint16_t* a16; float* acc32;
     int rows;
     uint32_t thresh16; float keep_scale; uint64_t seed; const uint64_t* seed_dev; uint32_t stream;
@@ -277,13 +288,16 @@ struct GrParams {
 };
 
 __global__ void __launch_bounds__(kGrThreads, 1)
-gemm_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w, const GrParams p) {
+gemm_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant__ CUtensorMap tm_w,
+                 const __grid_constant__ CUtensorMap tm_z, const __grid_constant__ CUtensorMap tm_act, const GrParams p) {
     using namespace tc;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
     uint8_t* sW = smem;                                    // [2][128][64] bf16
     uint8_t* sA = sW + kTileBytes;                         // [stages][2][128][64]
-    GrBarriers* bars = reinterpret_cast<GrBarriers*>(sA + kGrStages * kTileBytes);
+    uint8_t* sZ = sA + kGrStages * kTileBytes;             // [2][128][64] bf16 staging of the z16 tile (TMA store source)
+    uint8_t* sAct = sZ + kTileBytes;                       // the same for the a16 tile
+    GrBarriers* bars = reinterpret_cast<GrBarriers*>(sAct + kTileBytes);
     uint32_t* s_tmem = reinterpret_cast<uint32_t*>(bars + 1);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n_tiles = (p.rows + kTileM - 1) / kTileM;
@@ -338,84 +352,103 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
             }
         }
         __syncwarp();
-    } else {
-        const int ew = warp - 2;
+    } else if (warp >= 4) {
+        const int ew = warp - 4;
         const int lane_grp = warp & 3;
         const int row = lane_grp * 32 + lane;
-        const int cb = (ew >> 2) * 64;                     // this thread's 64 columns
+        const int col0 = (ew >> 2) * 32;                   // this thread's 32 columns
         const uint64_t seed = p.seed + (p.seed_dev ? __ldg(p.seed_dev) : 0ull);
         const uint32_t t_row = tmem_base + ((uint32_t)(lane_grp * 32) << 16);
+        float bias[32];
+#pragma unroll
+        for (int q = 0; q < 32; ++q) bias[q] = p.bias ? __ldg(p.bias + col0 + q) : 0.f;
         for (int i = 0; i < my_tiles; ++i) {
             const int ab = i & 1;
             const int tile = blockIdx.x + i * gridDim.x;
             const int r = tile * kTileM + row;
             const bool valid = r < p.rows;
-            int c = 0, nb = 0;
-            if (p.Pc && valid) { c = __ldg(p.ctr + r); nb = __ldg(p.nbr + r); }
+            // gathered per-node projections (the h_V[E_idx] part of W1): requested before the accumulator wait
+            float add[32];
+#pragma unroll
+            for (int q = 0; q < 32; ++q) add[q] = bias[q];
+            if (p.Pc && valid) {
+                uint32_t pc[16], pn[16];
+                const uint16_t* pcr = p.Pc + (size_t)__ldg(p.ctr + r) * 128 + col0;
+                const uint16_t* pnr = p.Pn + (size_t)__ldg(p.nbr + r) * 128 + col0;
+                ldg256(pcr, reinterpret_cast<uint32_t(&)[8]>(pc[0])); ldg256(pcr + 16, reinterpret_cast<uint32_t(&)[8]>(pc[8]));
+                ldg256(pnr, reinterpret_cast<uint32_t(&)[8]>(pn[0])); ldg256(pnr + 16, reinterpret_cast<uint32_t(&)[8]>(pn[8]));
+#pragma unroll
+                for (int q = 0; q < 16; ++q) {
+                    add[2 * q] += bf_lo(pc[q]) + bf_lo(pn[q]);
+                    add[2 * q + 1] += bf_hi(pc[q]) + bf_hi(pn[q]);
+                }
+            }
             mbar_wait(&bars->acc_full[ab], (i >> 1) & 1);
             tc_fence_after();
+            float v[32];
+            tmem_ld32(t_row + (uint32_t)(ab * 128 + col0), v);
+            tc_fence_before();
+            mbar_arrive(&bars->acc_empty[ab]);             // the accumulator is in registers: free for the next GEMM
 #pragma unroll
-            for (int ch = 0; ch < 2; ++ch) {
-                const int col0 = cb + ch * 32;
-                float v[32];
-                tmem_ld32(t_row + (uint32_t)(ab * 128 + col0), v);
-                if (ch == 1) {                             // both chunks are in registers: the accumulator is free again
-                    tc_fence_before();
-                    mbar_arrive(&bars->acc_empty[ab]);
+            for (int q = 0; q < 32; ++q) v[q] += add[q];
+            if (p.acc32 && valid) {
+                float* dst = p.acc32 + (size_t)r * 128 + col0;
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    float t[8];
+                    ldg256f(dst + 8 * q, t);
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) t[k] += v[8 * q + k];
+                    stg256f(dst + 8 * q, t);
                 }
-                if (!valid) continue;
-                if (p.bias) {
+            }
+            // bf16 outputs: staged in shared memory in the 128-byte-swizzled tile layout and written with TMA stores
+            // (a thread-per-row 32-byte store pattern touches 32 lines per instruction and was LSU-bound)
+            uint32_t zp[16];
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + col0) + q);
-                        v[4 * q] += b.x; v[4 * q + 1] += b.y; v[4 * q + 2] += b.z; v[4 * q + 3] += b.w;
+            for (int q = 0; q < 16; ++q) zp[q] = pack_bf16(v[2 * q], v[2 * q + 1]);
+            if (i > 0) {                                   // the previous tile's TMA stores have read the staging buffers
+                if (threadIdx.x == 128) tma_store_wait_read();
+                gr_epi_bar();
+            }
+            const int kb = col0 >> 6, j0 = (col0 & 63) >> 3;
+            if (p.z16) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4*>(sZ + kb * kKBlockBytes + sw128_chunk(row, j0 + j)) =
+                        make_uint4(zp[4 * j], zp[4 * j + 1], zp[4 * j + 2], zp[4 * j + 3]);
+            }
+            if (p.a16) {                                   // a = Dropout(GELU(bf16(z))): what rmp_act_fwd_bf16 would write
+                uint32_t ap[16];
+#pragma unroll
+                for (int g8 = 0; g8 < 4; ++g8) {
+                    const uint32_t keep = keep_mask8(seed, (uint64_t)r * 16 + (uint64_t)(col0 / 8 + g8), p.stream, p.thresh16);
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const uint32_t w = zp[4 * g8 + j];
+                        const float lo = (keep >> (2 * j)) & 1u ? gelu_tanh_y(bf_lo(w)) * p.keep_scale : 0.f;
+                        const float hi = (keep >> (2 * j + 1)) & 1u ? gelu_tanh_y(bf_hi(w)) * p.keep_scale : 0.f;
+                        ap[4 * g8 + j] = pack_bf16(lo, hi);
                     }
                 }
-                if (p.Pc) {                                // gathered per-node projections (the h_V[E_idx] part of W1)
-                    const float4* pc = reinterpret_cast<const float4*>(p.Pc + (size_t)c * 128 + col0);
-                    const float4* pn = reinterpret_cast<const float4*>(p.Pn + (size_t)nb * 128 + col0);
 #pragma unroll
-                    for (int q = 0; q < 8; ++q) {
-                        const float4 x = __ldg(pc + q), y = __ldg(pn + q);
-                        v[4 * q] += x.x + y.x; v[4 * q + 1] += x.y + y.y; v[4 * q + 2] += x.z + y.z; v[4 * q + 3] += x.w + y.w;
+                for (int j = 0; j < 4; ++j)
+                    *reinterpret_cast<uint4*>(sAct + kb * kKBlockBytes + sw128_chunk(row, j0 + j)) =
+                        make_uint4(ap[4 * j], ap[4 * j + 1], ap[4 * j + 2], ap[4 * j + 3]);
+            }
+            if (p.z16 || p.a16) {
+                fence_proxy_async();                       // staging bytes -> visible to the TMA engine
+                gr_epi_bar();
+                if (threadIdx.x == 128) {                  // rows past the end of the tensor are clipped by the TMA unit
+                    for (int b2 = 0; b2 < 2; ++b2) {
+                        if (p.z16) tma_store_2d(&tm_z, sZ + b2 * kKBlockBytes, b2 * 64, tile * kTileM);
+                        if (p.a16) tma_store_2d(&tm_act, sAct + b2 * kKBlockBytes, b2 * 64, tile * kTileM);
                     }
-                }
-                if (p.acc32) {
-                    float* dst = p.acc32 + (size_t)r * 128 + col0;
-#pragma unroll
-                    for (int q = 0; q < 4; ++q) {
-                        float t[8];
-                        ldg256f(dst + 8 * q, t);
-#pragma unroll
-                        for (int k = 0; k < 8; ++k) t[k] += v[8 * q + k];
-                        stg256f(dst + 8 * q, t);
-                    }
-                }
-                uint32_t zp[16];
-#pragma unroll
-                for (int q = 0; q < 16; ++q) zp[q] = pack_bf16(v[2 * q], v[2 * q + 1]);
-                if (p.z16) {
-                    stg256u(p.z16 + (size_t)r * 128 + col0, &zp[0]);
-                    stg256u(p.z16 + (size_t)r * 128 + col0 + 16, &zp[8]);
-                }
-                if (p.a16) {                               // a = Dropout(GELU(bf16(z))): what rmp_act_fwd_bf16 would write
-                    uint32_t ap[16];
-#pragma unroll
-                    for (int g8 = 0; g8 < 4; ++g8) {
-                        const uint32_t keep = keep_mask8(seed, (uint64_t)r * 16 + (uint64_t)(col0 / 8 + g8), p.stream, p.thresh16);
-#pragma unroll
-                        for (int j = 0; j < 4; ++j) {
-                            const uint32_t w = zp[4 * g8 + j];
-                            const float lo = (keep >> (2 * j)) & 1u ? gelu_tanh_y(bf_lo(w)) * p.keep_scale : 0.f;
-                            const float hi = (keep >> (2 * j + 1)) & 1u ? gelu_tanh_y(bf_hi(w)) * p.keep_scale : 0.f;
-                            ap[4 * g8 + j] = pack_bf16(lo, hi);
-                        }
-                    }
-                    stg256u(p.a16 + (size_t)r * 128 + col0, &ap[0]);
-                    stg256u(p.a16 + (size_t)r * 128 + col0 + 16, &ap[8]);
+                    tma_store_commit();
                 }
             }
         }
+        if (threadIdx.x == 128 && my_tiles > 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     tc_fence_before();
     __syncthreads();
@@ -427,7 +460,8 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 
 using namespace rmp;
 
-static uint32_t drop_threshold(float p) { return p <= 0.f ? 0u : (uint32_t)(p * 65536.0f + 0.5f); }
+static uint32_t drop_threshold(float p) { return p <= 0.f ? 0u : (uint32_t)(p * 256.0f + 0.5f); }
+static float keep_scale_of(float p) { return 256.0f / (256.0f - (float)drop_threshold(p)); }
 
 extern "C" int rmp_act_fwd_bf16(const void* z_bf16, void* a_bf16, int64_t rows, int width, float p_drop, uint64_t seed,
                                 const uint64_t* seed_dev, uint32_t stream_id, void* stream) {
@@ -438,7 +472,7 @@ extern "C" int rmp_act_fwd_bf16(const void* z_bf16, void* a_bf16, int64_t rows, 
     if (groups == 0) return RMP_OK;
     train::act_fwd_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const uint4*>(z_bf16), reinterpret_cast<uint4*>(a_bf16), groups, drop_threshold(p_drop),
-        1.0f / (1.0f - p_drop), seed, seed_dev, stream_id);
+        keep_scale_of(p_drop), seed, seed_dev, stream_id);
     return check_launch("rmp_act_fwd_bf16");
 }
 
@@ -454,7 +488,7 @@ extern "C" int rmp_act_bwd_bf16(const void* z_bf16, const void* da_bf16, const f
     const int rows_per_block = 128;
     train::act_bwd_kernel<<<ceil_div(rows, rows_per_block), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const uint4*>(z_bf16), reinterpret_cast<const uint4*>(da_bf16), dagg, ctr, alpha,
-        reinterpret_cast<uint4*>(dz_bf16), db, rows, rows_per_block, drop_threshold(p_drop), 1.0f / (1.0f - p_drop), seed,
+        reinterpret_cast<uint4*>(dz_bf16), db, rows, rows_per_block, drop_threshold(p_drop), keep_scale_of(p_drop), seed,
         seed_dev, stream_id);
     return check_launch("rmp_act_bwd_bf16");
 }
@@ -500,13 +534,13 @@ extern "C" int rmp_gemm_dw_bf16(const void* dZ_bf16, const void* X_bf16, float* 
     return check_launch("rmp_gemm_dw_bf16");
 }
 
-extern "C" int rmp_gemm_rows_bf16(const void* A_bf16, const void* W_bf16, const float* bias, const float* Pc, const float* Pn,
+extern "C" int rmp_gemm_rows_bf16(const void* A_bf16, const void* W_bf16, const float* bias, const void* Pc, const void* Pn,
                                   const int32_t* ctr, const int32_t* nbr, void* z_bf16, void* a_bf16, float* acc32, int rows,
                                   int w_ld, int w_transposed, float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t stream_id,
                                   void* stream) {
     RMP_REQUIRE(A_bf16 && W_bf16 && rows >= 0 && (z_bf16 || a_bf16 || acc32), RMP_E_ARG, "rmp_gemm_rows_bf16: null pointer / no output");
     RMP_REQUIRE((Pc == nullptr) == (Pn == nullptr) && (!Pc || (ctr && nbr)), RMP_E_ARG, "rmp_gemm_rows_bf16: Pc, Pn, ctr, nbr go together");
-    RMP_REQUIRE(aligned16(A_bf16) && aligned16(W_bf16) && (!bias || aligned16(bias)) && (!Pc || (aligned16(Pc) && aligned16(Pn))) &&
+    RMP_REQUIRE(aligned16(A_bf16) && aligned16(W_bf16) && (!bias || aligned16(bias)) && (!Pc || (aligned32(Pc) && aligned32(Pn))) &&
                 (!z_bf16 || aligned32(z_bf16)) && (!a_bf16 || aligned32(a_bf16)) && (!acc32 || aligned32(acc32)), RMP_E_ALIGN,
                 "rmp_gemm_rows_bf16: inputs 16-byte, outputs 32-byte aligned");
     RMP_REQUIRE(p_drop >= 0.f && p_drop < 1.f, RMP_E_ARG, "rmp_gemm_rows_bf16: dropout probability in [0,1)");
@@ -529,14 +563,18 @@ extern "C" int rmp_gemm_rows_bf16(const void* A_bf16, const void* W_bf16, const 
         RMP_REQUIRE(r == CUDA_SUCCESS, RMP_E_ARG, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     }
     train::GrParams p{};
-    p.bias = bias; p.Pc = Pc; p.Pn = Pn; p.ctr = ctr; p.nbr = nbr;
+    p.bias = bias; p.Pc = reinterpret_cast<const uint16_t*>(Pc); p.Pn = reinterpret_cast<const uint16_t*>(Pn); p.ctr = ctr; p.nbr = nbr;
     p.z16 = reinterpret_cast<uint16_t*>(z_bf16); p.a16 = reinterpret_cast<uint16_t*>(a_bf16); p.acc32 = acc32; p.rows = rows;
-    p.thresh16 = drop_threshold(p_drop); p.keep_scale = 1.0f / (1.0f - p_drop); p.seed = seed; p.seed_dev = seed_dev;
+    p.thresh16 = drop_threshold(p_drop); p.keep_scale = keep_scale_of(p_drop); p.seed = seed; p.seed_dev = seed_dev;
     p.stream = stream_id; p.w_mn_major = w_transposed ? 1 : 0;
-    const size_t smem = 1024 + (size_t)(1 + train::kGrStages) * tc::kTileBytes + sizeof(train::GrBarriers) + 16;
+    CUtensorMap tm_z, tm_act;
+    memset(&tm_z, 0, sizeof(tm_z)); memset(&tm_act, 0, sizeof(tm_act));
+    if (z_bf16) { rc = tc::make_map_bf16_rows128(&tm_z, z_bf16, (uint64_t)rows); if (rc) return rc; }
+    if (a_bf16) { rc = tc::make_map_bf16_rows128(&tm_act, a_bf16, (uint64_t)rows); if (rc) return rc; }
+    const size_t smem = 1024 + (size_t)(3 + train::kGrStages) * tc::kTileBytes + sizeof(train::GrBarriers) + 16;
     cudaFuncSetAttribute(train::gemm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     const int n_tiles = ceil_div(rows, tc::kTileM);
     const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
-    train::gemm_rows_kernel<<<grid, train::kGrThreads, smem, (cudaStream_t)stream>>>(tm_a, tm_w, p);
+    train::gemm_rows_kernel<<<grid, train::kGrThreads, smem, (cudaStream_t)stream>>>(tm_a, tm_w, tm_z, tm_act, p);
     return check_launch("rmp_gemm_rows_bf16");
 }

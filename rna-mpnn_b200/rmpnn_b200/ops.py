@@ -480,6 +480,7 @@ def gemm_rows(a16, w16, bias=None, Pc=None, Pn=None, ctr=None, nbr=None, want_z=
     _need_cuda(a16, w16, bias, Pc, Pn, ctr, nbr, acc32)
     assert a16.dtype == w16.dtype == torch.bfloat16 and a16.is_contiguous() and w16.stride(1) == 1
     assert a16.shape[1] == 128 and tuple(w16.shape) == (128, 128)      # w16 may be a column block of a wider matrix
+    assert Pc is None or (Pc.dtype == Pn.dtype == torch.bfloat16 and Pc.is_contiguous() and Pn.is_contiguous())
     rows = a16.shape[0]
     z = torch.empty_like(a16) if want_z else None
     a = torch.empty_like(a16) if act is not None else None

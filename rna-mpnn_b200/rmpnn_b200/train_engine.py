@@ -43,8 +43,8 @@ class EdgeMessageFn(torch.autograd.Function):
         p, seed, sid, scale, sd = state["p_drop"], state["seed"], state["stream_id"], state["scale"], state["seed_dev"]
         hV16 = h_V.detach().to(torch.bfloat16)
         W1h = w16(W1)                                              # [128,384] bf16 view, columns e | c | n
-        Pc = ((hV16 @ W1h[:, 128:256].t()).float() + b1.detach()).contiguous()
-        Pn = (hV16 @ W1h[:, 256:].t()).float().contiguous()
+        Pc = torch.addmm(b1.detach().to(torch.bfloat16), hV16, W1h[:, 128:256].t())      # [Nv,128] bf16
+        Pn = hV16 @ W1h[:, 256:].t()
         z0, a0 = ops.gemm_rows(hE16, W1h[:, :128], Pc=Pc, Pn=Pn, ctr=g.ctr, nbr=g.nbr, act=(p, seed, sid), seed_dev=sd)
         z1, a1 = ops.gemm_rows(a0, w16(W2), bias=b2.detach(), act=(p, seed, sid + 1), seed_dev=sd)
         z2, a2 = ops.gemm_rows(a1, w16(W3), bias=b3.detach(), act=(p, seed, sid + 2), seed_dev=sd)

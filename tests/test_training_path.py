@@ -47,9 +47,10 @@ def test_dropout_mask_is_regenerated_identically_and_has_the_right_rate():
     z = torch.ones(20000, 128, device="cuda", dtype=torch.bfloat16)
     a = ops.act_fwd(z, 0.1, 11, 5)
     keep = a != 0
-    assert abs(keep.float().mean().item() - 0.9) < 2e-3
+    p_eff = 26 / 256                                                   # 0.1 quantised to 8 bits
+    assert abs(keep.float().mean().item() - (1 - p_eff)) < 2e-3
     kept_val = a[keep].float().unique()
-    assert kept_val.numel() == 1 and abs(kept_val.item() - F.gelu(torch.tensor(1.0)).item() / 0.9) < 1e-2
+    assert kept_val.numel() == 1 and abs(kept_val.item() - F.gelu(torch.tensor(1.0)).item() / (1 - p_eff)) < 1e-2
     dz = ops.act_bwd(z, 0.1, 11, 5, da16=torch.ones_like(z))
     assert torch.equal(dz != 0, keep)                                   # same mask in both directions
     assert not torch.equal(ops.act_fwd(z, 0.1, 11, 6) != 0, keep)       # another stream id, another mask
@@ -154,8 +155,9 @@ def test_gemm_rows_outputs(rows):
     ctr = torch.randint(0, Nv, (rows,), generator=g, dtype=torch.int32).cuda()
     nbr = torch.randint(0, Nv, (rows,), generator=g, dtype=torch.int32).cuda()
     acc = torch.full((rows, 128), 2.0, device="cuda")
+    Pc, Pn = Pc.to(torch.bfloat16), Pn.to(torch.bfloat16)
     z, a = ops.gemm_rows(A, W, bias=b, Pc=Pc, Pn=Pn, ctr=ctr, nbr=nbr, act=(0.1, 5, 9), acc32=acc)
-    ref = A.float() @ W.float().t() + b + Pc[ctr.long()] + Pn[nbr.long()]
+    ref = A.float() @ W.float().t() + b + Pc.float()[ctr.long()] + Pn.float()[nbr.long()]
     np.testing.assert_allclose(z.float().cpu().numpy(), _bf(ref).cpu().numpy(), atol=3e-2, rtol=1e-2)
     np.testing.assert_allclose(acc.cpu().numpy(), (ref + 2.0).cpu().numpy(), atol=2e-3, rtol=1e-4)
     assert torch.equal(a, ops.act_fwd(z, 0.1, 5, 9))                   # the fused activation IS the stand-alone pass
