@@ -341,7 +341,7 @@ def run_c4(args):
                                "csrc/train.cu), per-node remainder torch under bf16 autocast",
                        "collective": f"one NCCL all-reduce of a flat fp32 gradient buffer, {tr.n_params * 4 / 1e6:.1f} MB, "
                                      "side stream, then rmp_adam_step",
-                       "launch": "CUDA graph replay of the whole step" if replay else "eager"},
+                       "launch": "CUDA graph replay of forward + backward, then one NCCL all-reduce and the Adam kernel" if replay else "eager"},
             "e2e": {"value": Nv * world / (ms_e2e * 1e-3), "unit": UNIT,
                     "h2d_bytes_per_step": Xp.numel() * 4 + Sp.numel() * 8 + mp.numel() * 4, "d2h_bytes_per_step": 4},
             "gpu_launches": int(launches), "clocks": clocks.summary()}), flush=True)
