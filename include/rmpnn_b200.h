@@ -328,6 +328,12 @@ int rmp_gemm_rows_bf16(const void* A_bf16, const void* W_bf16, const float* bias
                        int w_ld /* elements per row of the matrix W is a 128x128 window of; 0 = 128 */,
                        int w_transposed /* Z = A W instead of A W^T: backward-data without a transposed copy */,
                        float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t stream_id, void* stream);
+/* Reference Normalize (rdesign/model/functional.py:79-96) over 128 channels for the training path:
+ *   forward   y_bf16 = gain * (x - mu) / (sqrt(var_unbiased + eps) + eps) + bias            x fp32 [rows,128]
+ *   backward  dx_bf16 from dy fp32; dgain[128] += sum dy * xhat, dbias[128] += sum dy, dbsum[128] += sum dx */
+int rmp_normalize_fwd_bf16(const float* x, const float* gain, const float* bias, void* y_bf16, int rows, float eps, void* stream);
+int rmp_normalize_bwd_bf16(const float* x, const float* dy, const float* gain, void* dx_bf16, float* dgain, float* dbias,
+                           float* dbsum, int rows, float eps, void* stream);
 /* torch.optim.Adam step (no weight decay, no amsgrad) over flat fp32 buffers of n elements (n % 4 == 0);
  * grad is multiplied by grad_scale first (1 / world size after the all-reduce; rdesign.py:90-93) */
 int rmp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float grad_scale,

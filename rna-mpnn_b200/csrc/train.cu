@@ -166,6 +166,69 @@ __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const
     p[i] = pi; m[i] = mi; v[i] = vi;
 }
 
+// Reference Normalize (rdesign/model/functional.py:79-96) over 128 channels, forward and backward, one warp per row:
+//   y = gain * (x - mu) / (sqrt(var_unbiased + eps) + eps) + bias
+// forward : x fp32 -> y bf16 (the layers' h_E operand)
+// backward: dy fp32 (d h_E accumulated over the layers) -> dx bf16 (operand of the weight-gradient GEMM), and the
+//           column sums d gain = sum dy * xhat, d bias = sum dy, d b = sum dx (bias gradient of the Linear in front)
+__global__ void __launch_bounds__(256) normalize_fwd_kernel(const float4* __restrict__ x, const float4* __restrict__ gain,
+                                                            const float4* __restrict__ bias, uint2* __restrict__ y16, int rows,
+                                                            float eps) {
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    const float4 v = x[(size_t)r * 32 + lane];
+    const float mu = warp_sum((v.x + v.y) + (v.z + v.w)) * (1.f / 128.f);
+    const float a = v.x - mu, b = v.y - mu, c = v.z - mu, d = v.w - mu;
+    const float var = warp_sum((a * a + b * b) + (c * c + d * d)) * (1.f / 127.f);
+    const float inv = 1.f / (sqrtf(var + eps) + eps);
+    const float4 g = __ldg(gain + lane), be = __ldg(bias + lane);
+    y16[(size_t)r * 32 + lane] = make_uint2(tc::pack_bf16(fmaf(g.x, a * inv, be.x), fmaf(g.y, b * inv, be.y)),
+                                            tc::pack_bf16(fmaf(g.z, c * inv, be.z), fmaf(g.w, d * inv, be.w)));
+}
+
+__global__ void __launch_bounds__(256) normalize_bwd_kernel(const float4* __restrict__ x, const float4* __restrict__ dy,
+                                                            const float4* __restrict__ gain, uint2* __restrict__ dx16,
+                                                            float* __restrict__ dgain, float* __restrict__ dbias,
+                                                            float* __restrict__ dbsum, int rows, int rows_per_block, float eps) {
+    __shared__ float s_acc[3][8][128];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float4 g = __ldg(gain + lane);
+    float ag[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f}, ax[4] = {0.f, 0.f, 0.f, 0.f};
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    for (int r = r0 + w; r < r1; r += 8) {
+        const float4 v = x[(size_t)r * 32 + lane], d = dy[(size_t)r * 32 + lane];
+        const float mu = warp_sum((v.x + v.y) + (v.z + v.w)) * (1.f / 128.f);
+        const float xc[4] = {v.x - mu, v.y - mu, v.z - mu, v.w - mu};
+        const float var = warp_sum((xc[0] * xc[0] + xc[1] * xc[1]) + (xc[2] * xc[2] + xc[3] * xc[3])) * (1.f / 127.f);
+        const float sigma = sqrtf(var + eps), s = sigma + eps, inv = 1.f / s;
+        const float dd[4] = {d.x, d.y, d.z, d.w}, gg[4] = {g.x, g.y, g.z, g.w};
+        float dxh[4], t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { dxh[j] = dd[j] * gg[j]; t1 += dxh[j] * xc[j]; t2 += dxh[j]; }
+        t1 = warp_sum(t1); t2 = warp_sum(t2);
+        // d s = -sum(dxh * xc) / s^2;  d xc_i = dxh_i / s + d s * xc_i / (sigma (n - 1));  d x_i = d xc_i - mean(d xc)
+        const float cvar = -t1 * inv * inv / (sigma * 127.f), mean_dxc = t2 * inv * (1.f / 128.f);
+        float dx[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            dx[j] = dxh[j] * inv + cvar * xc[j] - mean_dxc;
+            ag[j] += dd[j] * xc[j] * inv; ab[j] += dd[j];
+        }
+        const uint2 o = make_uint2(tc::pack_bf16(dx[0], dx[1]), tc::pack_bf16(dx[2], dx[3]));
+        dx16[(size_t)r * 32 + lane] = o;
+        ax[0] += bf_lo(o.x); ax[1] += bf_hi(o.x); ax[2] += bf_lo(o.y); ax[3] += bf_hi(o.y);
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { s_acc[0][w][4 * lane + j] = ag[j]; s_acc[1][w][4 * lane + j] = ab[j]; s_acc[2][w][4 * lane + j] = ax[j]; }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { t0 += s_acc[0][k][threadIdx.x]; t1 += s_acc[1][k][threadIdx.x]; t2 += s_acc[2][k][threadIdx.x]; }
+        atomicAdd(dgain + threadIdx.x, t0); atomicAdd(dbias + threadIdx.x, t1); atomicAdd(dbsum + threadIdx.x, t2);
+    }
+}
+
 // ------------------------------------------------------------------------------------------------------------------
 // dW[n][k] += sum_r dZ[r][n] X[r][k]   (dZ, X bf16 [rows,128]; dW fp32 [128,128])
 // The contraction runs over the rows, so both operand tiles are read MN-major from their natural row-major
@@ -577,4 +640,27 @@ extern "C" int rmp_gemm_rows_bf16(const void* A_bf16, const void* W_bf16, const 
     const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
     train::gemm_rows_kernel<<<grid, train::kGrThreads, smem, (cudaStream_t)stream>>>(tm_a, tm_w, tm_z, tm_act, p);
     return check_launch("rmp_gemm_rows_bf16");
+}
+
+extern "C" int rmp_normalize_fwd_bf16(const float* x, const float* gain, const float* bias, void* y_bf16, int rows, float eps,
+                                      void* stream) {
+    RMP_REQUIRE(x && gain && bias && y_bf16 && rows >= 0, RMP_E_ARG, "rmp_normalize_fwd_bf16: null pointer");
+    RMP_REQUIRE(aligned16(x) && aligned16(gain) && aligned16(bias) && aligned16(y_bf16), RMP_E_ALIGN, "rmp_normalize_fwd_bf16: 16-byte alignment");
+    if (rows == 0) return RMP_OK;
+    train::normalize_fwd_kernel<<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(gain), reinterpret_cast<const float4*>(bias),
+        reinterpret_cast<uint2*>(y_bf16), rows, eps);
+    return check_launch("rmp_normalize_fwd_bf16");
+}
+
+extern "C" int rmp_normalize_bwd_bf16(const float* x, const float* dy, const float* gain, void* dx_bf16, float* dgain, float* dbias,
+                                      float* dbsum, int rows, float eps, void* stream) {
+    RMP_REQUIRE(x && dy && gain && dx_bf16 && dgain && dbias && dbsum && rows >= 0, RMP_E_ARG, "rmp_normalize_bwd_bf16: null pointer");
+    RMP_REQUIRE(aligned16(x) && aligned16(dy) && aligned16(gain) && aligned16(dx_bf16), RMP_E_ALIGN, "rmp_normalize_bwd_bf16: 16-byte alignment");
+    if (rows == 0) return RMP_OK;
+    const int rows_per_block = 256;
+    train::normalize_bwd_kernel<<<ceil_div(rows, rows_per_block), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(x), reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(gain),
+        reinterpret_cast<uint2*>(dx_bf16), dgain, dbias, dbsum, rows, rows_per_block, eps);
+    return check_launch("rmp_normalize_bwd_bf16");
 }

@@ -80,6 +80,8 @@ SIGNATURES = {
     "rmp_scatter_add_rows": [P, P, P, I, P],
     "rmp_gemm_dw_bf16": [P, P, P, I, P],
     "rmp_adam_step": [P, P, P, P, I64, F, F, F, F, F, I, P, P],
+    "rmp_normalize_fwd_bf16": [P, P, P, P, I, F, P],
+    "rmp_normalize_bwd_bf16": [P, P, P, P, P, P, P, I, F, P],
     "rmp_gemm_rows_bf16": [P, P, P, P, P, P, P, P, P, P, I, I, I, F, U64, P, C.c_uint32, P],
 }
 STRING_GETTERS = ("rmp_version", "rmp_last_error_string")

@@ -491,6 +491,27 @@ def gemm_rows(a16, w16, bias=None, Pc=None, Pn=None, ctr=None, nbr=None, want_z=
     return z, a
 
 
+def normalize_fwd(x, gain, bias, eps: float = 1e-6):
+    """Reference Normalize over 128 channels -> bf16 rows (rmp_normalize_fwd_bf16)."""
+    _need_cuda(x, gain, bias)
+    assert x.dtype == torch.float32 and x.is_contiguous() and x.shape[1] == 128
+    y = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    check(lib().rmp_normalize_fwd_bf16(_ptr(x), _ptr(gain), _ptr(bias), _ptr(y), x.shape[0], float(eps), _stream()),
+          "rmp_normalize_fwd_bf16")
+    return y
+
+
+def normalize_bwd(x, dy, gain, eps: float = 1e-6):
+    """-> (dx bf16 [rows,128], dgain [128], dbias [128], column sums of dx [128])."""
+    _need_cuda(x, dy, gain)
+    assert x.dtype == dy.dtype == torch.float32 and x.is_contiguous() and dy.is_contiguous() and x.shape == dy.shape
+    dx = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device)
+    sums = torch.zeros(3, 128, dtype=torch.float32, device=x.device)
+    check(lib().rmp_normalize_bwd_bf16(_ptr(x), _ptr(dy), _ptr(gain), _ptr(dx), _ptr(sums[0]), _ptr(sums[1]), _ptr(sums[2]),
+                                       x.shape[0], float(eps), _stream()), "rmp_normalize_bwd_bf16")
+    return dx, sums[0], sums[1], sums[2]
+
+
 def adam_step(param, grad, exp_avg, exp_avg_sq, step: int, lr: float, grad_scale: float = 1.0, betas=(0.9, 0.999),
               eps: float = 1e-8, step_dev=None):
     """``step_dev`` (int32 device scalar) overrides ``step`` so that a captured graph can advance it on the device."""

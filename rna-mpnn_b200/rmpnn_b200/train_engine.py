@@ -94,22 +94,17 @@ class EdgeEmbedFn(torch.autograd.Function):
         ops.gemm_rows(raw16, Wp, bias=b.detach(), want_z=False, acc32=z)
         ctx.save_for_backward(z, W, gain, beta)
         ctx.state = state
-        with torch.no_grad():
-            state["hE16"] = _normalize(z, gain, beta).to(torch.bfloat16)
+        state["hE16"] = ops.normalize_fwd(z, gain.detach(), beta.detach())
         return torch.zeros(1, device=W.device)                     # the ordering token
 
     @staticmethod
     def backward(ctx, _dtoken):
         z, W, gain, beta = ctx.saved_tensors
         state = ctx.state
-        with torch.enable_grad():
-            zz = z.detach().requires_grad_(True)
-            gg, bb = gain.detach().requires_grad_(True), beta.detach().requires_grad_(True)
-            h = _normalize(zz, gg, bb)
-            dz, dgain, dbeta = torch.autograd.grad(h, (zz, gg, bb), state["dhE"])
+        dz16, dgain, dbeta, db = ops.normalize_bwd(z, state["dhE"], gain.detach())
         dW = torch.zeros(128, 128, dtype=torch.float32, device=W.device)
-        ops.gemm_dw(dz.to(torch.bfloat16).contiguous(), state["edge_raw16"], dW)
-        return dW[:, :W.shape[1]].contiguous(), dz.sum(0), dgain, dbeta, None
+        ops.gemm_dw(dz16, state["edge_raw16"], dW)
+        return dW[:, :W.shape[1]].contiguous(), db, dgain, dbeta, None
 
 
 def _normalize(x, gain, bias, eps=1e-6):

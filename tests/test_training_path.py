@@ -164,3 +164,23 @@ def test_gemm_rows_outputs(rows):
     z2, a2 = ops.gemm_rows(A, W)
     assert a2 is None
     np.testing.assert_allclose(z2.float().cpu().numpy(), _bf(A.float() @ W.float().t()).cpu().numpy(), atol=3e-2, rtol=1e-2)
+
+
+def test_normalize_fwd_bwd_match_autograd():
+    from rmpnn_b200 import ops
+    from rmpnn_b200.train_engine import _normalize
+    g = torch.Generator().manual_seed(4)
+    x = (3 * torch.randn(2000, 128, generator=g) + 0.5).cuda()
+    dy = torch.randn(2000, 128, generator=g).cuda()
+    gain = (1 + 0.1 * torch.randn(128, generator=g)).cuda()
+    bias = (0.1 * torch.randn(128, generator=g)).cuda()
+    y = ops.normalize_fwd(x, gain, bias)
+    xr, gr, br = x.clone().requires_grad_(True), gain.clone().requires_grad_(True), bias.clone().requires_grad_(True)
+    ref = _normalize(xr, gr, br)
+    np.testing.assert_allclose(y.float().cpu().numpy(), _bf(ref.detach()).cpu().numpy(), atol=2e-2, rtol=1e-2)
+    ref.backward(dy)
+    dx, dgain, dbias, dbsum = ops.normalize_bwd(x, dy, gain)
+    np.testing.assert_allclose(dx.float().cpu().numpy(), _bf(xr.grad).cpu().numpy(), atol=2e-3, rtol=2e-2)
+    np.testing.assert_allclose(dgain.cpu().numpy(), gr.grad.cpu().numpy(), atol=2e-2, rtol=1e-3)
+    np.testing.assert_allclose(dbias.cpu().numpy(), br.grad.cpu().numpy(), atol=2e-2, rtol=1e-3)
+    np.testing.assert_allclose(dbsum.cpu().numpy(), dx.float().sum(0).cpu().numpy(), atol=2e-2, rtol=1e-3)
