@@ -2,7 +2,7 @@
 """bench.py -- RNA nucleotides/s of the structure-to-sequence forward path on B200.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                    [--precision fp32|bf16] [--workload c2|c3|c4|c5]
+                    [--precision fp32|fp32x3|bf16] [--workload c2|c3|c4|c5]
 
 One "step" = one pass of the hot path (kNN + featurizer -> 9 message-passing layers ->
 readout head with softmax/argmax) over one synthetic padded batch.  The N=1 workload is
@@ -392,7 +392,7 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     L_ = _lib.lib()
-    prec = _lib.PREC_BF16 if args.precision == "bf16" else _lib.PREC_FP32
+    prec = {"bf16": _lib.PREC_BF16, "fp32x3": _lib.PREC_FP32X3}.get(args.precision, _lib.PREC_FP32)
 
     cfg, params, X, S, mask = model_and_inputs(args.workload, rank)
     B, L, K, _ = WORKLOADS[args.workload]
@@ -542,7 +542,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--precision", default=os.environ.get("RMPNN_PRECISION", "bf16"), choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default=os.environ.get("RMPNN_PRECISION", "bf16"), choices=["fp32", "fp32x3", "bf16"])
     ap.add_argument("--workload", default="c2", choices=sorted(WORKLOADS) + ["c4", "c5"])
     ap.add_argument("--structures", type=int, default=0, help="c5: number of structures (default 100000)")
     ap.add_argument("--no-cpu-baseline", action="store_true")

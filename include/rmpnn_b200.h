@@ -50,6 +50,7 @@ extern "C" {
 /* precision of the fused layer path */
 #define RMP_PREC_FP32     0   /* fp32 CUDA-core kernels: 1e-4 logit parity with the reference's CPU path */
 #define RMP_PREC_BF16     1   /* bf16 operands on tcgen05 tensor cores, fp32 accumulate: 2e-2 budget */
+#define RMP_PREC_FP32X3   2   /* fp32 parity on tcgen05: split bf16 operands, 3 MMAs per product (rmp_row_mlp_x3) */
 
 const char* rmp_version(void);
 const char* rmp_last_error_string(void);
@@ -266,9 +267,21 @@ int rmp_row_mlp_bf16(const rmp_mlp_desc* desc, const void* const* W_bf16, void* 
 #define RMP_OPERAND_BF16 0
 #define RMP_OPERAND_FP16 1
 int rmp_row_mlp_tc(const rmp_mlp_desc* desc, const void* const* W_16, int operand_format, void* stream);
+/* fp32-parity arm of rmp_row_mlp on tcgen05: fp32 inputs / weights / activations carried as two bf16 terms
+ * (x = x_hi + x_lo, |error| <= 2^-18 |x|), three MMAs per product (hi*hi + lo*hi + hi*lo), fp32 accumulate in TMEM,
+ * bias / exact erf GELU / epilogues in fp32: keeps RMP_PREC_FP32's 1e-4 logit parity (measured 1.5e-5 at the C2 shapes).
+ * W_split[s] = bf16 [2][n_out[s]][k_in[s]] (high terms, then low terms of the nn.Linear weight; desc->Wt is ignored).
+ * add0 / add1 (optional, n_out[0] = 128): fp32 rows of 128 values, add_stride floats apart, gathered by add*_idx (or row r when NULL), added to stage 0's
+ * pre-activation -- the per-node projections of W_0's centre / neighbour column blocks, which replace the
+ * [h_V[ctr] | h_V[nbr]] input columns of the message MLP (rdesign/model/mpnn.py:31-33).
+ * Restrictions: fp32 segments, widths multiples of 128; k_in % 64 == 0 up to 384; n_out 128 or 256; bias required;
+ * epilogues RMP_EPI_STORE / RMP_EPI_SEGSUM / RMP_EPI_RESID_ADD; rows given on the host. */
+int rmp_row_mlp_x3(const rmp_mlp_desc* desc, const void* const* W_split, const float* add0, const int32_t* add0_idx,
+                   const float* add1, const int32_t* add1_idx, int add_stride, void* stream);
 /* tuning aid: int64 [500] device buffer receiving (tag, clock64) pairs of CTA 0's first epilogue thread of every
  * following rmp_row_mlp_tc launch (scripts/rowmlp_tc_timeline.py); NULL disables it */
 void rmp_set_row_tc_timeline(void* buf);
+void rmp_set_row_x3_timeline(void* buf);    /* the same for rmp_row_mlp_x3 */
 
 /* ------------------------------------------------------------------ bf16 tensor-core layer path
  * (tcgen05 / TMEM / TMA).  Declared here, implemented in layer_tc.cu.

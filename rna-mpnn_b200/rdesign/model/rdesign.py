@@ -126,7 +126,7 @@ class RNAModel(_Base):
         params = list(self.parameters())
         key = (tuple((p.data_ptr(), p._version) for p in params), self.precision_mode)
         if self._engine is None or key != self._engine_key:
-            prec = _lib.PREC_BF16 if self.precision_mode == "bf16" else _lib.PREC_FP32
+            prec = {"bf16": _lib.PREC_BF16, "fp32x3": _lib.PREC_FP32X3}.get(self.precision_mode, _lib.PREC_FP32)
             self._engine = RDesignEngine(self.state_dict(), self.k_neighbors, float(self.mpnn_layers[0].scale)
                                          if len(self.mpnn_layers) else 30.0, device=params[0].device,
                                          precision=prec)

@@ -10,7 +10,7 @@ _LIB = None
 MAX_STAGES = 6
 MAX_SEGS = 3
 EPI_STORE, EPI_NORMALIZE, EPI_RESID_LN, EPI_SEGSUM, EPI_RESID_ADD = 0, 1, 2, 3, 4
-PREC_FP32, PREC_BF16 = 0, 1
+PREC_FP32, PREC_BF16, PREC_FP32X3 = 0, 1, 2
 OPERAND_BF16, OPERAND_FP16 = 0, 1
 
 
@@ -60,6 +60,7 @@ SIGNATURES = {
     "rmp_row_mlp": [C.POINTER(MlpDesc), P],
     "rmp_row_mlp_bf16": [C.POINTER(MlpDesc), P, P],
     "rmp_row_mlp_tc": [C.POINTER(MlpDesc), P, I, P],
+    "rmp_row_mlp_x3": [C.POINTER(MlpDesc), P, P, P, P, P, I, P],
     "rmp_add_layernorm": [P, P, P, P, F, P, I, I, I, I, P, P],
     "rmp_readout_head": [P, I, P, P, F, U64, P, I, I, P, P, P, P],
     "rmp_cast_bf16": [P, P, I64, P],

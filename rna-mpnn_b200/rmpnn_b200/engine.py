@@ -16,7 +16,7 @@ from typing import Dict, List, Mapping, Optional
 import torch
 
 from . import ops
-from ._lib import PREC_BF16, PREC_FP32
+from ._lib import PREC_BF16, PREC_FP32, PREC_FP32X3
 
 
 @dataclass
@@ -33,6 +33,7 @@ class LayerWeights:
     proj: Optional[ops.PackedLinear] = None       # h_V -> [Pc | Pn]  (128 -> 256, bias [b_0 | 0])
     proj16: Optional[tuple] = None                # (W bf16 [256,128], bias fp32 [256]) for the tcgen05 node kernel
     dense16: Optional[list] = None                # [(W bf16 [N,K], bias fp32 [N])] dense stages, or None if unsupported
+    msg_x3: Optional[list] = None                 # message stages of the fp32-parity tensor-core arm (W_0e alone, no b_0)
 
 
 def _indexed(params: Mapping[str, torch.Tensor], prefix: str):
@@ -75,6 +76,8 @@ class RDesignWeights:
                 bp = torch.cat([b0, torch.zeros_like(b0)], 0).contiguous()
                 lw.proj = ops.pack_linear(Wp, bp)
                 lw.proj16 = (Wp.to(torch.bfloat16).contiguous(), bp)
+                # fp32-parity tensor-core arm: W_0's edge columns alone (its bias rides on the centre projection)
+                lw.msg_x3 = [ops.pack_linear(W0[:, :H].contiguous(), torch.zeros_like(b0))] + msg[1:]
             dw = _indexed(p, pre + "dense.")
             widths_ok = all(w.shape[0] in (128, 256) and w.shape[1] in (128, 256) for w, _ in dw)
             if widths_ok and dw[0][0].shape[1] == H and dw[-1][0].shape[0] == H and len(dw) <= 4:
@@ -97,12 +100,14 @@ class RDesignEngine:
         self.scale = float(scale)
         self.precision = precision
         self.kernel_timer = None      # bench.py: list collecting (start, end) events of the message kernel
-        if precision not in (PREC_FP32, PREC_BF16):
-            raise ValueError("precision must be RMP_PREC_FP32 or RMP_PREC_BF16")
+        if precision not in (PREC_FP32, PREC_BF16, PREC_FP32X3):
+            raise ValueError("precision must be RMP_PREC_FP32, RMP_PREC_BF16 or RMP_PREC_FP32X3")
 
     def dominant_kernel_name(self) -> str:
         if self.precision == PREC_BF16:
             return "edge_mlp_tc_kernel (edge message MLP + neighbour sum, bf16 tcgen05/TMEM/TMA)"
+        if self.precision == PREC_FP32X3:
+            return "row_mlp_x3_kernel (edge message MLP + segmented sum, split-bf16 fp32 parity on tcgen05)"
         return "row_mlp_kernel<64> (edge message MLP + segmented sum, fp32 CUDA cores)"
 
     # ---- stages -----------------------------------------------------------------
@@ -151,6 +156,16 @@ class RDesignEngine:
             if self.kernel_timer is not None:
                 ev[0].record(torch.cuda.current_stream())
             ops.edge_mlp_bf16(h_E, lw.msg_w16, lw.msg_bias, P[0], P[1], g.ctr, g.nbr, g.row_ptr, agg, 1.0 / self.scale)
+        elif self.precision == PREC_FP32X3 and lw.msg_x3 is not None:
+            # [Pc + b_0 | Pn] = h_V [W_0c | W_0n]^T per node, then the message MLP over h_E alone with the two
+            # projections gathered into stage 0's pre-activation
+            P = torch.empty(g.Nv, 2 * ops.HIDDEN, dtype=torch.float32, device=h_V.device)
+            ops.row_mlp([(h_V, None)], [(lw.proj, False)], ops.EPI_STORE, P, g.Nv, split=True)
+            if self.kernel_timer is not None:
+                ev[0].record(torch.cuda.current_stream())
+            ops.row_mlp([(h_E, None)], [(m, True) for m in lw.msg_x3], ops.EPI_SEGSUM, agg, g.Ne, seg_id=g.ctr,
+                        alpha=1.0 / self.scale, split=True, adds=[(P, g.ctr), (P[:, ops.HIDDEN:], g.nbr)],
+                        add_stride=2 * ops.HIDDEN)
         else:
             ops.row_mlp([(h_E, None), (h_V, g.ctr), (h_V, g.nbr)], [(m, True) for m in lw.message],
                         ops.EPI_SEGSUM, agg, g.Ne, seg_id=g.ctr, alpha=1.0 / self.scale)
@@ -162,6 +177,10 @@ class RDesignEngine:
         x1 = ops.add_layernorm(h_V, agg, lw.norm1_w, lw.norm1_b, 1e-5, zero_b=True)
         out = torch.empty_like(h_V)
         stages = [(d, True) for d in lw.dense[:-1]] + [(lw.dense[-1], False)]
+        if self.precision == PREC_FP32X3 and ops.x3_eligible([(x1, None)], stages):
+            y = torch.empty_like(h_V)
+            ops.row_mlp([(x1, None)], stages, ops.EPI_STORE, y, g.Nv, split=True)
+            return ops.add_layernorm(x1, y, lw.norm2_w, lw.norm2_b, 1e-5, out=out)
         ops.row_mlp([(x1, None)], stages, ops.EPI_RESID_LN, out, g.Nv, gain=lw.norm2_w, beta=lw.norm2_b, resid=x1)
         return out
 
@@ -203,7 +222,8 @@ class RDesignEngine:
         x = h_V
         for pl in self.w.readout_hidden:
             y = torch.empty(x.shape[0], pl.n_out, dtype=torch.float32, device=x.device)
-            ops.row_mlp([(x, None)], [(pl, True)], ops.EPI_STORE, y, x.shape[0])
+            ops.row_mlp([(x, None)], [(pl, True)], ops.EPI_STORE, y, x.shape[0],
+                        split=self.precision == PREC_FP32X3 and ops.x3_eligible([(x, None)], [(pl, True)]))
             x = y
         return ops.readout_head(x, self.w.readout_w, self.w.readout_b, temperature, seed)
 

@@ -160,6 +160,7 @@ class PackedLinear:
     n_out: int
     W16: Optional[torch.Tensor] = None      # bf16 [n_out, k_in] (nn.Linear layout) for the tensor-core arm
     W16h: Optional[torch.Tensor] = None     # the same as IEEE fp16 (RMP_OPERAND_FP16)
+    W16x2: Optional[torch.Tensor] = None    # bf16 [2, n_out, k_in]: high and low terms of the fp32 weight (rmp_row_mlp_x3)
 
 
 def pack_linear(weight: torch.Tensor, bias: Optional[torch.Tensor]) -> PackedLinear:
@@ -175,6 +176,23 @@ def pack_linear(weight: torch.Tensor, bias: Optional[torch.Tensor]) -> PackedLin
                         weight.detach().to(torch.float32).clamp(-65504.0, 65504.0).to(torch.float16).contiguous())
 
 
+def split_weight(pl: PackedLinear) -> torch.Tensor:
+    """W = W_hi + W_lo with both terms bf16 (|W - W_hi - W_lo| <= 2^-18 |W|), cached on the PackedLinear."""
+    if pl.W16x2 is None:
+        W = pl.Wt[:pl.k_in].t().contiguous()
+        hi = W.to(torch.bfloat16)
+        lo = (W - hi.float()).to(torch.bfloat16)
+        pl.W16x2 = torch.stack([hi, lo]).contiguous()
+    return pl.W16x2
+
+
+def x3_eligible(segments: Sequence, stages: Sequence) -> bool:
+    """Shapes the split-operand tcgen05 row MLP (rmp_row_mlp_x3) takes."""
+    return (all(src.shape[-1] % 128 == 0 and src.dtype == torch.float32 for src, _ in segments)
+            and all(pl.k_in % 64 == 0 and pl.k_in <= 384 and pl.n_out in (128, 256) and pl.bias is not None
+                    for pl, _ in stages))
+
+
 def tc_eligible(segments: Sequence, stages: Sequence) -> bool:
     """Shapes the tcgen05 row-MLP kernel (rmp_row_mlp_bf16) takes."""
     return (all(src.shape[-1] % 128 == 0 for src, _ in segments) and len({src.dtype for src, _ in segments}) <= 1
@@ -184,7 +202,8 @@ def tc_eligible(segments: Sequence, stages: Sequence) -> bool:
 
 def row_mlp(segments: Sequence, stages: Sequence, epilogue: int, out: torch.Tensor, rows: int,
             gain=None, beta=None, resid=None, seg_id=None, alpha: float = 1.0,
-            rows_dev: Optional[torch.Tensor] = None, rows_slot: int = 0, row_scale=None, tensor_core: bool = False, fp16: bool = False, out_bf16=None):
+            rows_dev: Optional[torch.Tensor] = None, rows_slot: int = 0, row_scale=None, tensor_core: bool = False, fp16: bool = False, out_bf16=None,
+            split: bool = False, adds: Sequence = (), add_stride: int = 0):
     """One fused launch: concat(gathered segments) -> chained Linear(+GELU) -> epilogue.
 
     segments: [(src [*, width] fp32, idx int32 [rows] or None), ...]
@@ -216,7 +235,14 @@ def row_mlp(segments: Sequence, stages: Sequence, epilogue: int, out: torch.Tens
     d.out_bf16 = _ptr(out_bf16)
     d.out = _ptr(out)
     d.rows_dev, d.rows_slot, d.rows_cap = _ptr(rows_dev), rows_slot, int(rows)
-    if tensor_core:
+    if split:
+        # fp32-parity arm on tcgen05 (split bf16 operands); adds = [(fp32 [*, n_out0], idx or None), ...] (<= 2)
+        w2 = (C.c_void_p * len(stages))(*[_ptr(split_weight(pl)) for pl, _ in stages])
+        a = list(adds) + [(None, None)] * (2 - len(adds))
+        _need_cuda(*[t for pair in a for t in pair])
+        check(lib().rmp_row_mlp_x3(C.byref(d), C.cast(w2, C.c_void_p), _ptr(a[0][0]), _ptr(a[0][1]), _ptr(a[1][0]),
+                                   _ptr(a[1][1]), int(add_stride), _stream()), "rmp_row_mlp_x3")
+    elif tensor_core:
         w16 = (C.c_void_p * len(stages))(*[_ptr(pl.W16h if fp16 else pl.W16) for pl, _ in stages])
         check(lib().rmp_row_mlp_tc(C.byref(d), C.cast(w16, C.c_void_p), int(fp16), _stream()), "rmp_row_mlp_tc")
     else:

@@ -37,7 +37,7 @@ def parse_args(argv=None):
     ap.add_argument("--temperature", type=float, default=0.5)
     ap.add_argument("--token-budget", type=int, default=32768)
     ap.add_argument("--k", type=int, default=30)
-    ap.add_argument("--precision", default="bf16", choices=["fp32", "bf16"])
+    ap.add_argument("--precision", default="bf16", choices=["fp32", "fp32x3", "bf16"])
     ap.add_argument("--check", action="store_true", help="T=0 argmax of ~200 structures against the CPU oracle")
     ap.add_argument("--check-structures", type=int, default=200)
     ap.add_argument("--total-nt", type=int, default=0,
@@ -86,7 +86,7 @@ def run(args, init_dist=True):
     packed_host = packed.cpu().pin_memory()
 
     cfg = RDesignConfig(k_neighbors=args.k)
-    prec = _lib.PREC_BF16 if args.precision == "bf16" else _lib.PREC_FP32
+    prec = {"bf16": _lib.PREC_BF16, "fp32x3": _lib.PREC_FP32X3}.get(args.precision, _lib.PREC_FP32)
     eng = RDesignEngine(make_state_dict(cfg, 42), args.k, cfg.scale, device=dev, precision=prec)
 
     # per batch: host-side sizes (no device read-back), device-side row_start / lengths

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 600 python -u -m pytest tests/test_x3_kernels.py -x -q -s > gpurun_out/r2c16_x3.log 2>&1; tail -8 gpurun_out/r2c16_x3.log
+for v in noadds nogelu ffn; do timeout 60 python scripts/x3_launch.py 5 30 16384 $v; done 2>&1 | tee gpurun_out/r2c16_variants.log
+X3_TIMELINE=1 timeout 60 python scripts/x3_launch.py 5 30 16384 edge 2>&1 | head -24 | tee gpurun_out/r2c16_tl_edge.log
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --precision fp32x3 > gpurun_out/r2c16_bench_x3.json 2> gpurun_out/r2c16_bench_x3.err; tail -3 gpurun_out/r2c16_bench_x3.err
+python -c "
+import json; d=json.load(open('gpurun_out/r2c16_bench_x3.json')); print(d['ms_per_step'], d['value'], d['e2e']['value'], d['gpu_launches'], d['roofline']['kernel_ms'], d['roofline']['kernel_share_of_step'])"
