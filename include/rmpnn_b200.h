@@ -112,6 +112,12 @@ int rmp_rdesign_raw_features(const float* X, int B, int N,
                              const int32_t* counts, int nv_cap, int ne_cap,
                              const float* rbf_mu, float* frames,
                              float* node_raw, float* edge_raw, void* stream);
+/* The same with edge rows 128 floats apart (columns 115..127 zero): the K = 128 input of the tensor-core row MLPs */
+int rmp_rdesign_raw_features_k128(const float* X, int B, int N,
+                                  const int32_t* node_src, const int32_t* ctr, const int32_t* nbr,
+                                  const int32_t* counts, int nv_cap, int ne_cap,
+                                  const float* rbf_mu, float* frames,
+                                  float* node_raw, float* edge_raw128, void* stream);
 
 /* ------------------------------------------------------------------ fused row MLP (a-6, a-8, a-9)
  * One launch = up to RMP_MAX_STAGES chained Linear(+exact GELU) stages over row
@@ -275,7 +281,8 @@ int rmp_row_mlp_tc(const rmp_mlp_desc* desc, const void* const* W_16, int operan
  * pre-activation -- the per-node projections of W_0's centre / neighbour column blocks, which replace the
  * [h_V[ctr] | h_V[nbr]] input columns of the message MLP (rdesign/model/mpnn.py:31-33).
  * Restrictions: fp32 segments, widths multiples of 128; k_in % 64 == 0 up to 384; n_out 128 or 256; bias required;
- * epilogues RMP_EPI_STORE / RMP_EPI_SEGSUM / RMP_EPI_RESID_ADD; rows given on the host. */
+ * every epilogue of rmp_row_mlp (NORMALIZE / RESID_LN / SEGSUM stage whole 128-wide rows in shared memory: coalesced
+ * rows out, one red per segment and column); rows given on the host. */
 int rmp_row_mlp_x3(const rmp_mlp_desc* desc, const void* const* W_split, const float* add0, const int32_t* add0_idx,
                    const float* add1, const int32_t* add1_idx, int add_stride, void* stream);
 /* tuning aid: int64 [500] device buffer receiving (tag, clock64) pairs of CTA 0's first epilogue thread of every

@@ -116,6 +116,7 @@ __global__ void __launch_bounds__(kNodeTile * kNodeParts) node_raw_kernel(const 
 // --------------------------------------------------------------------------------
 constexpr int kEdgeTile = 128;
 
+template <int STRIDE>   // floats per output row: 115 (packed) or 128 (columns 115.. zero: the tensor-core arms' K)
 __global__ void __launch_bounds__(kEdgeTile) edge_raw_kernel(const float* __restrict__ X, int N,
                                                             const int32_t* __restrict__ node_src,
                                                             const int32_t* __restrict__ ctr,
@@ -123,13 +124,15 @@ __global__ void __launch_bounds__(kEdgeTile) edge_raw_kernel(const float* __rest
                                                             const int32_t* __restrict__ counts, int ne_cap,
                                                             RbfMu mu, const float* __restrict__ frames,
                                                             float* __restrict__ edge_raw) {
-    extern __shared__ float etile[];                       // [kEdgeTile][115]
+    extern __shared__ float etile[];                       // [kEdgeTile][STRIDE]
     const int ne = min(counts[1], ne_cap);
     const int e0 = blockIdx.x * kEdgeTile;
     if (e0 >= ne) return;
     const int t = threadIdx.x, e = e0 + t;
     if (e < ne) {
-        float* f = etile + t * RMP_EDGE_RAW;
+        float* f = etile + t * STRIDE;
+#pragma unroll
+        for (int c = RMP_EDGE_RAW; c < STRIDE; ++c) f[c] = 0.f;
         const int si = node_src[ctr[e]], sj = node_src[nbr[e]];
         const float* xi = X + (size_t)si * 18;
         const float* xj = X + (size_t)sj * 18;
@@ -160,18 +163,18 @@ __global__ void __launch_bounds__(kEdgeTile) edge_raw_kernel(const float* __rest
     }
     __syncthreads();
     const int rows = min(kEdgeTile, ne - e0);
-    float* out = edge_raw + (size_t)e0 * RMP_EDGE_RAW;
-    for (int o = t; o < rows * RMP_EDGE_RAW; o += kEdgeTile) out[o] = etile[o];
+    float* out = edge_raw + (size_t)e0 * STRIDE;
+    for (int o = t; o < rows * STRIDE; o += kEdgeTile) out[o] = etile[o];
 }
 
 }  // namespace rmp
 
 using namespace rmp;
 
-extern "C" int rmp_rdesign_raw_features(const float* X, int B, int N, const int32_t* node_src, const int32_t* ctr,
-                                        const int32_t* nbr, const int32_t* counts, int nv_cap, int ne_cap,
-                                        const float* rbf_mu_host, float* frames, float* node_raw, float* edge_raw,
-                                        void* stream) {
+static int raw_features_impl(const float* X, int B, int N, const int32_t* node_src, const int32_t* ctr,
+                             const int32_t* nbr, const int32_t* counts, int nv_cap, int ne_cap,
+                             const float* rbf_mu_host, float* frames, float* node_raw, float* edge_raw, bool padded,
+                             void* stream) {
     RMP_REQUIRE(X && node_src && ctr && nbr && counts && rbf_mu_host && frames, RMP_E_ARG,
                 "rmp_rdesign_raw_features: null pointer");
     RMP_REQUIRE(B > 0 && N > 0 && nv_cap >= 0 && ne_cap >= 0, RMP_E_ARG, "rmp_rdesign_raw_features: bad sizes");
@@ -184,14 +187,28 @@ extern "C" int rmp_rdesign_raw_features(const float* X, int B, int N, const int3
         node_raw_kernel<<<ceil_div(nv_cap, kNodeTile), kNodeTile * kNodeParts, 0, st>>>(X, N, node_src, counts, nv_cap, mu, frames,
                                                                            node_raw);
     if (edge_raw && ne_cap > 0) {
-        const int smem = kEdgeTile * RMP_EDGE_RAW * (int)sizeof(float);
-        static bool attr_done = false;
-        if (!attr_done) {
-            cudaFuncSetAttribute(edge_raw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-            attr_done = true;
-        }
-        edge_raw_kernel<<<ceil_div(ne_cap, kEdgeTile), kEdgeTile, smem, st>>>(X, N, node_src, ctr, nbr, counts, ne_cap,
-                                                                              mu, frames, edge_raw);
+        const int smem = kEdgeTile * (padded ? 128 : RMP_EDGE_RAW) * (int)sizeof(float);
+        auto kern = padded ? edge_raw_kernel<128> : edge_raw_kernel<RMP_EDGE_RAW>;
+        // per device and not cached: the opt-in is a per-device function attribute
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+        kern<<<ceil_div(ne_cap, kEdgeTile), kEdgeTile, smem, st>>>(X, N, node_src, ctr, nbr, counts, ne_cap, mu, frames, edge_raw);
     }
     return check_launch("rmp_rdesign_raw_features", 1 + (node_raw && nv_cap > 0) + (edge_raw && ne_cap > 0));
+}
+
+extern "C" int rmp_rdesign_raw_features(const float* X, int B, int N, const int32_t* node_src, const int32_t* ctr,
+                                        const int32_t* nbr, const int32_t* counts, int nv_cap, int ne_cap,
+                                        const float* rbf_mu_host, float* frames, float* node_raw, float* edge_raw,
+                                        void* stream) {
+    return raw_features_impl(X, B, N, node_src, ctr, nbr, counts, nv_cap, ne_cap, rbf_mu_host, frames, node_raw, edge_raw,
+                             false, stream);
+}
+
+extern "C" int rmp_rdesign_raw_features_k128(const float* X, int B, int N, const int32_t* node_src, const int32_t* ctr,
+                                             const int32_t* nbr, const int32_t* counts, int nv_cap, int ne_cap,
+                                             const float* rbf_mu_host, float* frames, float* node_raw, float* edge_raw128,
+                                             void* stream) {
+    RMP_REQUIRE(!edge_raw128 || aligned16(edge_raw128), RMP_E_ALIGN, "rmp_rdesign_raw_features_k128: edge rows not 16-byte aligned");
+    return raw_features_impl(X, B, N, node_src, ctr, nbr, counts, nv_cap, ne_cap, rbf_mu_host, frames, node_raw, edge_raw128,
+                             true, stream);
 }

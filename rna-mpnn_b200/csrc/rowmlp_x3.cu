@@ -39,6 +39,8 @@ struct X3Params {
     const float* resid;
     const int32_t* seg_id;
     const float* row_scale;
+    const float* gain;
+    const float* beta;
     float alpha;
     float* out;
     int n_rows;
@@ -309,6 +311,7 @@ row_mlp_x3_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
                 const int cb = half * ncols;
                 const bool last = s + 1 == S;
                 const bool seg_staged = last && p.epilogue == RMP_EPI_SEGSUM && stg.N == 128;
+                const bool norm_staged = last && (p.epilogue == RMP_EPI_NORMALIZE || p.epilogue == RMP_EPI_RESID_LN);
                 float rs = 1.f;
                 int dst_row = r;
                 if (last && valid) {
@@ -343,6 +346,15 @@ row_mlp_x3_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
                             const uint32_t off = kb_off + sw128_chunk(row, j0 + j);
                             *reinterpret_cast<uint4*>(sAhi + off) = make_uint4(h[0], h[1], h[2], h[3]);
                             *reinterpret_cast<uint4*>(sAlo + off) = make_uint4(l[0], l[1], l[2], l[3]);
+                        }
+                        continue;
+                    }
+                    if (norm_staged) {                             // whole rows are needed: staged like the segment sums
+#pragma unroll
+                        for (int q = 0; q < 8; ++q) {
+                            const int j = (col0 >> 2) + q;
+                            *reinterpret_cast<float4*>(sAhi + row * 512 + ((j ^ (row & 31)) << 4)) =
+                                make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
                         }
                         continue;
                     }
@@ -415,6 +427,32 @@ row_mlp_x3_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
                     if (cur >= 0) atomicAdd(p.out + (size_t)cur * 128 + col, acc);
                     epi_bar_sync();                                // the next tile's prologue overwrites the staging rows
                 }
+                if (norm_staged) {
+                    // reference Normalize (unbiased variance, eps inside and outside the root; rdesign/model/functional.py:79-96)
+                    // or nn.LayerNorm of resid + y (rdesign/model/mpnn.py:38), one warp per row, coalesced 512-byte rows
+                    epi_bar_sync();
+                    const float4 g4 = __ldg(reinterpret_cast<const float4*>(p.gain) + lane);
+                    const float4 b4 = __ldg(reinterpret_cast<const float4*>(p.beta) + lane);
+                    for (int rr = 0; rr < 16; ++rr) {
+                        const int rl = ew * 16 + rr;
+                        const int rg = tile * kTileM + rl;
+                        if (rg >= p.n_rows) break;
+                        float4 x = *reinterpret_cast<const float4*>(sAhi + rl * 512 + ((lane ^ (rl & 31)) << 4));
+                        if (p.epilogue == RMP_EPI_RESID_LN) {
+                            const float4 t = __ldg(reinterpret_cast<const float4*>(p.resid + (size_t)rg * 128) + lane);
+                            x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
+                        }
+                        const float mu = warp_sum((x.x + x.y) + (x.z + x.w)) * (1.f / 128.f);
+                        x.x -= mu; x.y -= mu; x.z -= mu; x.w -= mu;
+                        const float ss = warp_sum((x.x * x.x + x.y * x.y) + (x.z * x.z + x.w * x.w));
+                        const float inv = p.epilogue == RMP_EPI_NORMALIZE ? 1.f / (sqrtf(ss * (1.f / 127.f) + 1e-6f) + 1e-6f)
+                                                                          : 1.f / sqrtf(ss * (1.f / 128.f) + 1e-5f);
+                        reinterpret_cast<float4*>(p.out + (size_t)rg * 128)[lane] =
+                            make_float4(g4.x * (x.x * inv) + b4.x, g4.y * (x.y * inv) + b4.y, g4.z * (x.z * inv) + b4.z,
+                                        g4.w * (x.w * inv) + b4.w);
+                    }
+                    epi_bar_sync();                                // the next tile's prologue overwrites the staging rows
+                }
                 tc_fence_before();
                 stamp(20 + s);
                 if (!last) {
@@ -447,8 +485,11 @@ extern "C" int rmp_row_mlp_x3(const rmp_mlp_desc* dp, const void* const* W_split
     RMP_REQUIRE(d.num_stages >= 1 && d.num_stages <= RMP_MAX_STAGES, RMP_E_ARG, "rmp_row_mlp_x3: num_stages=%d", d.num_stages);
     RMP_REQUIRE(d.out && d.rows_cap >= 0 && !d.rows_dev && !d.out_bf16, RMP_E_ARG,
                 "rmp_row_mlp_x3: fp32 output and a host row count only");
-    RMP_REQUIRE(d.epilogue == RMP_EPI_STORE || d.epilogue == RMP_EPI_SEGSUM || d.epilogue == RMP_EPI_RESID_ADD, RMP_E_SHAPE,
-                "rmp_row_mlp_x3: epilogue %d not supported on the tensor-core arm", d.epilogue);
+    RMP_REQUIRE(d.epilogue >= RMP_EPI_STORE && d.epilogue <= RMP_EPI_RESID_ADD, RMP_E_SHAPE, "rmp_row_mlp_x3: epilogue %d",
+                d.epilogue);
+    if (d.epilogue == RMP_EPI_NORMALIZE || d.epilogue == RMP_EPI_RESID_LN)
+        RMP_REQUIRE(d.gain && d.beta && aligned16(d.gain) && aligned16(d.beta) && d.n_out[d.num_stages - 1] == 128 && !d.row_scale,
+                    RMP_E_ARG, "rmp_row_mlp_x3: Normalize / LayerNorm epilogues need gain, beta and 128 output channels");
     RMP_REQUIRE(add0 || !add1, RMP_E_ARG, "rmp_row_mlp_x3: add1 without add0");
     RMP_REQUIRE(!add0 || (add_stride >= d.n_out[0] && add_stride % 4 == 0 && d.n_out[0] == 128), RMP_E_ARG,
                 "rmp_row_mlp_x3: add rows need n_out[0] = 128 and a stride that is a multiple of 4 (got %d)", add_stride);
@@ -487,11 +528,13 @@ extern "C" int rmp_row_mlp_x3(const rmp_mlp_desc* dp, const void* const* W_split
     for (int s = 0; s + 1 < d.num_stages; ++s) kmax = d.n_out[s] > kmax ? d.n_out[s] : kmax;
     p.S = d.num_stages;
     p.epilogue = d.epilogue;
-    if (d.epilogue == RMP_EPI_RESID_ADD) RMP_REQUIRE(d.resid && aligned32(d.resid), RMP_E_ARG, "rmp_row_mlp_x3: resid missing or not 32-byte aligned");
+    if (d.epilogue == RMP_EPI_RESID_ADD || d.epilogue == RMP_EPI_RESID_LN)
+        RMP_REQUIRE(d.resid && aligned32(d.resid), RMP_E_ARG, "rmp_row_mlp_x3: resid missing or not 32-byte aligned");
     if (d.epilogue == RMP_EPI_SEGSUM) RMP_REQUIRE(d.seg_id, RMP_E_ARG, "rmp_row_mlp_x3: seg_id missing");
     RMP_REQUIRE(aligned32(d.out), RMP_E_ALIGN, "rmp_row_mlp_x3: out not 32-byte aligned (256-bit stores)");
     RMP_REQUIRE((!add0 || aligned16(add0)) && (!add1 || aligned16(add1)), RMP_E_ALIGN, "rmp_row_mlp_x3: add rows not 16-byte aligned");
     p.resid = d.resid; p.seg_id = d.seg_id; p.row_scale = d.row_scale; p.alpha = d.alpha; p.out = d.out;
+    p.gain = d.gain; p.beta = d.beta;
     p.n_rows = d.rows_cap;
     p.timeline = reinterpret_cast<long long*>(g_row_x3_timeline);
     p.add_src[0] = add0; p.add_idx[0] = add0_idx; p.add_src[1] = add1; p.add_idx[1] = add1_idx; p.add_stride = add_stride;

@@ -57,6 +57,7 @@ SIGNATURES = {
     "rmp_knn": [P, P, I, I, I, I, I, P, P, P],
     "rmp_edge_list": [P, P, P, P, P, P, I, I, I, I, P, P, P, P],
     "rmp_rdesign_raw_features": [P, I, I, P, P, P, P, I, I, P, P, P, P, P],
+    "rmp_rdesign_raw_features_k128": [P, I, I, P, P, P, P, I, I, P, P, P, P, P],
     "rmp_row_mlp": [C.POINTER(MlpDesc), P],
     "rmp_row_mlp_bf16": [C.POINTER(MlpDesc), P, P],
     "rmp_row_mlp_tc": [C.POINTER(MlpDesc), P, I, P],

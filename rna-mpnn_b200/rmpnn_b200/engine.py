@@ -55,6 +55,9 @@ class RDesignWeights:
         self.norm_nodes = (p["features.norm_nodes.gain"], p["features.norm_nodes.bias"])
         self.norm_edges = (p["features.norm_edges.gain"], p["features.norm_edges.bias"])
         self.edge_emb16 = ops.pack_edge_embedding(p["features.edge_embedding.weight"])
+        self.edge_emb128 = ops.pack_linear(torch.nn.functional.pad(p["features.edge_embedding.weight"],
+                                                                   (0, 128 - ops.EDGE_RAW)),
+                                           p["features.edge_embedding.bias"])
         self.edge_emb_bias = p["features.edge_embedding.bias"]
         n_layers = 1 + max(int(k.split(".")[1]) for k in p if k.startswith("mpnn_layers."))
         self.layers: List[LayerWeights] = []
@@ -117,7 +120,8 @@ class RDesignEngine:
     def embed(self, X, g: ops.Graph):
         """h_V [Nv,128], h_E [Ne,128]   (rdesign/model/feature.py:179-224)."""
         bf16 = self.precision == PREC_BF16
-        node_raw, edge_raw, frames = ops.raw_features(X, g, want_edges=not bf16, return_frames=True)
+        x3 = self.precision == PREC_FP32X3
+        node_raw, edge_raw, frames = ops.raw_features(X, g, want_edges=not bf16, return_frames=True, pad_edges=x3)
         dev = node_raw.device
         h_V = torch.empty(g.Nv, ops.HIDDEN, dtype=torch.float32, device=dev)
         ops.row_mlp([(node_raw, None)], [(self.w.node_emb, False)], ops.EPI_NORMALIZE, h_V, g.Nv,
@@ -128,8 +132,9 @@ class RDesignEngine:
                                       self.w.norm_edges[0], self.w.norm_edges[1])
         else:
             h_E = torch.empty(g.Ne, ops.HIDDEN, dtype=torch.float32, device=dev)
-            ops.row_mlp([(edge_raw, None)], [(self.w.edge_emb, False)], ops.EPI_NORMALIZE, h_E, g.Ne,
-                        gain=self.w.norm_edges[0], beta=self.w.norm_edges[1])
+            # fp32x3: the 115 features zero-padded to K = 128, Linear + Normalize in one split-operand tcgen05 launch
+            ops.row_mlp([(edge_raw, None)], [(self.w.edge_emb128 if x3 else self.w.edge_emb, False)], ops.EPI_NORMALIZE, h_E,
+                        g.Ne, gain=self.w.norm_edges[0], beta=self.w.norm_edges[1], split=x3)
         return h_V, h_E
 
     def layer(self, l: int, h_V, h_E, g: ops.Graph, agg: Optional[torch.Tensor] = None):
@@ -177,11 +182,8 @@ class RDesignEngine:
         x1 = ops.add_layernorm(h_V, agg, lw.norm1_w, lw.norm1_b, 1e-5, zero_b=True)
         out = torch.empty_like(h_V)
         stages = [(d, True) for d in lw.dense[:-1]] + [(lw.dense[-1], False)]
-        if self.precision == PREC_FP32X3 and ops.x3_eligible([(x1, None)], stages):
-            y = torch.empty_like(h_V)
-            ops.row_mlp([(x1, None)], stages, ops.EPI_STORE, y, g.Nv, split=True)
-            return ops.add_layernorm(x1, y, lw.norm2_w, lw.norm2_b, 1e-5, out=out)
-        ops.row_mlp([(x1, None)], stages, ops.EPI_RESID_LN, out, g.Nv, gain=lw.norm2_w, beta=lw.norm2_b, resid=x1)
+        ops.row_mlp([(x1, None)], stages, ops.EPI_RESID_LN, out, g.Nv, gain=lw.norm2_w, beta=lw.norm2_b, resid=x1,
+                    split=self.precision == PREC_FP32X3 and ops.x3_eligible([(x1, None)], stages))
         return out
 
     def _node_update_tc(self, l, h_V, agg, g):

@@ -109,17 +109,19 @@ def build_graph(X: torch.Tensor, mask: torch.Tensor, top_k: int, sizes=None) -> 
     return Graph(B, N, K, Nv, Ne, node_map, node_src, sinfo, row_ptr, counts, E, D, ctr, nbr, E_flat)
 
 
-def raw_features(X: torch.Tensor, g: Graph, want_edges: bool = True, return_frames: bool = False):
-    """node_raw [Nv,101], edge_raw [Ne,115] (rdesign/model/feature.py:179-220)."""
+def raw_features(X: torch.Tensor, g: Graph, want_edges: bool = True, return_frames: bool = False, pad_edges: bool = False):
+    """node_raw [Nv,101], edge_raw [Ne,115] (rdesign/model/feature.py:179-220); ``pad_edges`` -> edge_raw [Ne,128]
+    with zero columns 115.. (rmp_rdesign_raw_features_k128)."""
     _need_cuda(X)
     X = _f32c(X[:, :, :6, :])
     dev = X.device
     frames = torch.empty(g.B * g.N, 9, dtype=torch.float32, device=dev)
     node_raw = torch.empty(g.Nv, NODE_RAW, dtype=torch.float32, device=dev)
-    edge_raw = torch.empty(g.Ne, EDGE_RAW, dtype=torch.float32, device=dev) if want_edges else None
-    check(lib().rmp_rdesign_raw_features(_ptr(X), g.B, g.N, _ptr(g.node_src), _ptr(g.ctr), _ptr(g.nbr),
-                                         _ptr(g.counts), g.Nv, g.Ne, C.cast(_RBF_MU, C.c_void_p),
-                                         _ptr(frames), _ptr(node_raw), _ptr(edge_raw), _stream()),
+    edge_raw = torch.empty(g.Ne, 128 if pad_edges else EDGE_RAW, dtype=torch.float32, device=dev) if want_edges else None
+    fn = lib().rmp_rdesign_raw_features_k128 if pad_edges else lib().rmp_rdesign_raw_features
+    check(fn(_ptr(X), g.B, g.N, _ptr(g.node_src), _ptr(g.ctr), _ptr(g.nbr),
+             _ptr(g.counts), g.Nv, g.Ne, C.cast(_RBF_MU, C.c_void_p),
+             _ptr(frames), _ptr(node_raw), _ptr(edge_raw), _stream()),
           "rmp_rdesign_raw_features")
     if return_frames:
         return node_raw, edge_raw, frames

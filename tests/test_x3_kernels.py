@@ -84,6 +84,42 @@ def test_x3_gathered_segments_adds_and_segsum():
     assert (out.cpu().double() - ref2).abs().max().item() < 3e-5
 
 
+@pytest.mark.parametrize("rows", [5, 128, 1000, 20001])
+def test_x3_normalize_and_residual_layernorm_epilogues(rows):
+    """Linear + reference Normalize (the edge embedding, rdesign/model/feature.py:224) and FFN + LayerNorm(resid + y)
+    (rdesign/model/mpnn.py:37-38) with the row statistics computed from the rows staged in shared memory."""
+    from rmpnn_b200 import ops
+    g = torch.Generator().manual_seed(rows)
+    x = torch.randn(rows, 128, generator=g)
+    x[:, 115:] = 0
+    Ws, bs, packed = _linears([128, 128], g)
+    gain, beta = 1 + 0.1 * torch.randn(128, generator=g), 0.1 * torch.randn(128, generator=g)
+    y = _ref_mlp(x, Ws, bs, [False])
+    mu = y.mean(-1, keepdim=True)
+    sigma = torch.sqrt(y.var(-1, keepdim=True, unbiased=True) + 1e-6)
+    ref = gain.double() * (y - mu) / (sigma + 1e-6) + beta.double()
+    out = torch.empty(rows, 128, device="cuda")
+    ops.row_mlp([(x.cuda(), None)], [(packed[0], False)], ops.EPI_NORMALIZE, out, rows, gain=gain.cuda(), beta=beta.cuda(),
+                split=True)
+    assert (out.cpu().double() - ref).abs().max().item() < 5e-5     # one split-operand stage, then / sigma (O(1) outputs)
+    Ws, bs, packed = _linears([128, 256, 256, 256, 128], g)
+    gelu = [True, True, True, False]
+    resid = torch.randn(rows, 128, generator=g)
+    ref = F.layer_norm(resid.double() + _ref_mlp(resid, Ws, bs, gelu), (128,), gain.double(), beta.double(), 1e-5)
+    ops.row_mlp([(resid.cuda(), None)], list(zip(packed, gelu)), ops.EPI_RESID_LN, out, rows, gain=gain.cuda(),
+                beta=beta.cuda(), resid=resid.cuda(), split=True)
+    assert (out.cpu().double() - ref).abs().max().item() < 6e-5     # four split-operand stages, then / sigma
+
+
+def test_padded_edge_features_equal_packed():
+    from rmpnn_b200 import ops
+    X, S, mask = synthetic_backbones(3, 90, 9, lengths=[90, 40, 7])
+    g = ops.build_graph(X.cuda(), mask.cuda(), 30)
+    _, e115 = ops.raw_features(X.cuda(), g)
+    _, e128 = ops.raw_features(X.cuda(), g, pad_edges=True)
+    assert torch.equal(e128[:, :115], e115) and float(e128[:, 115:].abs().max()) == 0.0
+
+
 def test_x3_rejects_unsupported_shapes():
     from rmpnn_b200 import ops
     g = torch.Generator().manual_seed(3)
