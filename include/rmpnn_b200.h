@@ -202,6 +202,19 @@ int rmp_readout_head(const float* h, int k_in, const float* W, const float* b,
 int rmp_collate(const void* packed, int packed_is_f64, const int64_t* row_start, const int32_t* lengths,
                 int B, int N, int A_in, int A_out, float* X, float* mask, void* stream);
 
+/* ------------------------------------------------------------------ tree-ensemble readout head (section 8f rank 4)
+ * Replaces `self.xgb_readout.predict(h_V.to('cpu').detach().numpy())` (rdesign/model/rdesign.py:153,
+ * rnampnn/model/rnampnn.py:298): xgboost gbtree inference over the node embeddings, multi:softmax -> class.
+ *   X [rows, ld] fp32 (first n_feat columns used; NaN = missing)
+ *   nodes [n_nodes] 16-byte records {fp32 threshold (leaf: value), feature | default_left << 31, left, right}
+ *         (children are global node ids, left < 0 marks a leaf);  tree_root [n_trees]
+ *   class_ptr [n_class+1], class_trees [n_trees]: the trees of every output group in tree order (CSR)
+ *   margins [rows, n_class] fp32 (optional) = base_score + the group's leaves summed in tree order in fp32;
+ *   pred [rows] int64 (optional) = first maximal margin. */
+int rmp_forest_predict(const float* X, int rows, int ld, int n_feat, const void* nodes, int n_nodes,
+                       const int32_t* tree_root, int n_trees, const int32_t* class_ptr, const int32_t* class_trees,
+                       int n_class, float base_score, float* margins, int64_t* pred, void* stream);
+
 /* ================================================================== secondary path: rnampnn (a-10 .. a-16)
  * The reference keeps the padded layout end to end: rows are dense residues b*N+i, edges are (row, slot k),
  * edge_index [B,N,K] int64 holds the neighbour's index INSIDE its structure or -1.  The Linear stacks of this

@@ -197,7 +197,9 @@ class RNAModel(_Base):
         with torch.no_grad():
             h_V, _ = self(X, S, mask)
             samples = None
-            if self.xgb_readout is not None:
+            if hasattr(self.xgb_readout, 'predict_device'):        # GPU forest: h_V never leaves the device
+                samples = self.xgb_readout.predict_device(h_V)
+            elif self.xgb_readout is not None:
                 try:
                     samples = torch.as_tensor(self.xgb_readout.predict(h_V.cpu().numpy()))
                 except Exception as e:                        # NotFittedError: fall back to the MLP head
@@ -216,6 +218,19 @@ class RNAModel(_Base):
                 f.write(f"{pdb_id},{''.join('AUCG'[i] for i in flat[start:start + n])}\n")
                 start += n
 
+    def load_xgb_readout(self, path: str) -> None:
+        """The fitted tree-ensemble head (``XGBTrainer``'s pickle) as a GPU forest: ``predict`` then keeps the embeddings
+        on the device (``rmp_forest_predict``) instead of the reference's device -> host -> CPU-trees hop.  Falls back to
+        unpickling with xgboost itself only for models the flattening does not support."""
+        from rmpnn_b200.host.xgb_model import load_readout_head
+        try:
+            self.xgb_readout = load_readout_head(path)
+        except ValueError:
+            if xgb is None:
+                raise
+            with open(path, 'rb') as f:
+                self.xgb_readout = pickle.load(f)
+
     # ------------------------------------------------------------------ checkpoint hooks
     def on_save_checkpoint(self, checkpoint: dict) -> None:
         checkpoint['name'], checkpoint['version'] = self.name, self.version
@@ -226,8 +241,7 @@ class RNAModel(_Base):
         self.version = checkpoint.get('version', 0)
         self.xgb_readout = _make_xgb(self.hparams)
         try:
-            with open(f"{OUTPUT_PATH}/checkpoints/{self.name}/XGB-V{self.version}.pkl", 'rb') as f:
-                self.xgb_readout = pickle.load(f)
+            self.load_xgb_readout(f"{OUTPUT_PATH}/checkpoints/{self.name}/XGB-V{self.version}.pkl")
         except FileNotFoundError:
             print("=========  XGBoost model not found. Please train the model first.  =========")
         print("=========  Model loaded successfully from checkpoint.  =========")

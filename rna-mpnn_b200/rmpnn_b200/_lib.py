@@ -66,6 +66,7 @@ SIGNATURES = {
     "rmp_readout_head": [P, I, P, P, F, U64, P, I, I, P, P, P, P],
     "rmp_cast_bf16": [P, P, I64, P],
     "rmp_collate": [P, I, P, P, I, I, I, I, P, P, P],
+    "rmp_forest_predict": [P, I, I, I, P, I, P, I, P, P, I, F, P, P, P],
     "rmp_res_graph": [P, P, I, I, I, I, P, P, P],
     "rmp_res_edge_rows": [P, P, I, I, I, P, P, P, P, P],
     "rmp_res_raw_features": [P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P],

@@ -346,6 +346,49 @@ def collate(packed: torch.Tensor, row_start: torch.Tensor, lengths: torch.Tensor
     return X, mask
 
 
+# =========================================================================== tree-ensemble readout head
+@dataclass
+class DeviceForest:
+    """A flattened gradient-boosted forest on the device (``rmpnn_b200.host.xgb_model.Forest`` packed for
+    ``rmp_forest_predict``)."""
+    nodes: torch.Tensor        # [n_nodes, 4] int32: threshold bits, feature | default_left << 31, left, right
+    tree_root: torch.Tensor    # [n_trees] int32
+    class_ptr: torch.Tensor    # [n_class+1] int32
+    class_trees: torch.Tensor  # [n_trees] int32, the trees of every output group in tree order
+    n_class: int
+    n_feat: int
+    base_score: float
+
+
+def pack_forest(forest, device) -> DeviceForest:
+    import numpy as np
+    thr = np.ascontiguousarray(forest.threshold, dtype=np.float32).view(np.int32)
+    feat = forest.feature.astype(np.int64) | (forest.default_left.astype(np.int64) << 31)
+    feat = (feat & 0xFFFFFFFF).astype(np.uint32).view(np.int32)
+    nodes = np.stack([thr, feat, forest.left.astype(np.int32), forest.right.astype(np.int32)], axis=1)
+    order = np.argsort(forest.tree_class, kind="stable").astype(np.int32)
+    counts = np.bincount(forest.tree_class, minlength=forest.n_class)
+    ptr = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    t = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)
+    return DeviceForest(t(nodes), t(forest.tree_root.astype(np.int32)), t(ptr), t(order), int(forest.n_class),
+                        int(forest.n_feat), float(forest.base_score))
+
+
+def forest_predict(f: DeviceForest, X: torch.Tensor, want_margins: bool = True):
+    """(margins [rows, n_class] fp32 | None, classes [rows] int64) of the tree-ensemble head on ``X [rows, >= n_feat]``
+    (rdesign/model/rdesign.py:153; semantics of xgboost's gbtree predictor, see oracle/forest_oracle.py)."""
+    _need_cuda(X, f.nodes)
+    assert X.dim() == 2 and X.dtype == torch.float32 and X.shape[1] >= f.n_feat
+    rows = X.shape[0]
+    assert rows == 0 or X.stride(1) == 1
+    margins = torch.empty(rows, f.n_class, dtype=torch.float32, device=X.device) if want_margins else None
+    pred = torch.empty(rows, dtype=torch.int64, device=X.device)
+    check(lib().rmp_forest_predict(_ptr(X), rows, int(X.stride(0)), f.n_feat, _ptr(f.nodes), f.nodes.shape[0],
+                                   _ptr(f.tree_root), f.tree_root.shape[0], _ptr(f.class_ptr), _ptr(f.class_trees),
+                                   f.n_class, f.base_score, _ptr(margins), _ptr(pred), _stream()), "rmp_forest_predict")
+    return margins, pred
+
+
 # =========================================================================== rnampnn (secondary path)
 @dataclass
 class ResGraph:
@@ -556,7 +599,7 @@ def _cuda_device_of(objs, depth=0):
         if torch.is_tensor(o):
             if o.is_cuda:
                 return o.device
-        elif isinstance(o, (Graph, ResGraph, PackedLinear)):
+        elif isinstance(o, (Graph, ResGraph, PackedLinear, DeviceForest)):
             d = _cuda_device_of(vars(o).values(), depth + 1)
             if d is not None:
                 return d

@@ -234,7 +234,10 @@ class RNAMPNN(_Base):
         coords, mask = coords.to(self.device), mask.to(self.device)
         with torch.no_grad():
             predictions = None
-            if self.xgb_readout is not None:
+            if hasattr(self.xgb_readout, 'predict_device'):        # GPU forest: the embedding never leaves the device
+                emb = self.embedding(coords, mask).reshape(mask.numel(), -1)
+                predictions = self.xgb_readout.predict_device(emb).reshape(mask.shape).cpu()
+            elif self.xgb_readout is not None:
                 try:
                     emb = self.embedding(coords, mask).reshape(mask.numel(), -1).cpu().numpy()
                     predictions = torch.as_tensor(self.xgb_readout.predict(emb)).reshape(mask.shape)
@@ -252,6 +255,19 @@ class RNAMPNN(_Base):
                 keep = (mask[i] == 1).cpu()
                 writer.writerow([pdb, "".join(REVERSE_VOCAB[int(v)] for v in predictions[i][keep].tolist())])
 
+    def load_xgb_readout(self, path: str) -> None:
+        """The fitted tree-ensemble head (``XGBTrainer``'s pickle) as a GPU forest: ``predict`` then keeps the embeddings
+        on the device (``rmp_forest_predict``) instead of the reference's device -> host -> CPU-trees hop.  Falls back to
+        unpickling with xgboost itself only for models the flattening does not support."""
+        from rmpnn_b200.host.xgb_model import load_readout_head
+        try:
+            self.xgb_readout = load_readout_head(path)
+        except ValueError:
+            if xgb is None:
+                raise
+            with open(path, 'rb') as f:
+                self.xgb_readout = pickle.load(f)
+
     # ------------------------------------------------------------------ checkpoint hooks
     def on_save_checkpoint(self, checkpoint: dict) -> None:
         checkpoint['name'], checkpoint['version'] = self.name, self.version
@@ -262,7 +278,6 @@ class RNAMPNN(_Base):
         self.version = checkpoint.get('version', 0)
         self.xgb_readout = _make_xgb(self.hparams)
         try:
-            with open(f"{OUTPUT_PATH}/checkpoints/{self.name}/XGB-V{self.version}.pkl", 'rb') as f:
-                self.xgb_readout = pickle.load(f)
+            self.load_xgb_readout(f"{OUTPUT_PATH}/checkpoints/{self.name}/XGB-V{self.version}.pkl")
         except FileNotFoundError:
             print("=========  XGBoost model not found. Please train the model first.  =========")
