@@ -164,11 +164,17 @@ __global__ void __launch_bounds__(kEdgeTile) res_cross_kernel(const float* __res
 }
 
 // --------------------------------------------------------------------------------
-// GraphNormalization (a-13), two launches:
-//   stats : per (graph, channel) sum and sum of squares of x = (a + b) over VALID rows, fp64 accumulation
-//   apply : mean = S1/n, var = (S2 - n mean^2 + n_pad mean^2)/n  [padded rows add mean^2 each, functional.py:33-38],
-//           out = ((x - mean)/sqrt(var + 1e-6) * scale + shift) * mask
+// GraphNormalization (a-13), ONE launch: a thread-block cluster per structure.
+//   pass 1: every CTA of the cluster sums x = (a + b) and x^2 over its share of the structure's VALID rows per channel
+//           (fp64, fixed order); the partials are exchanged through distributed shared memory (cluster.map_shared_rank)
+//           and every CTA adds them in rank order, so the statistics are deterministic (the two-launch version of
+//           round 1 used fp64 atomics into a global workspace: 3 graph nodes per norm, 31 % of the rnampnn step);
+//   pass 2: mean = S1/n, var = (S2 - n mean^2 + n_pad mean^2)/n  [padded rows add mean^2 each, functional.py:33-38],
+//           out = ((x - mean)/sqrt(var + 1e-6) * scale + shift) * mask over the same rows (re-read from L2; short
+//           shares stay in registers).
 // x = a + b fuses the residual adds that precede every GraphNorm in the reference (mpnn.py:222, functional.py:165).
+// The two-launch kernels below remain for structures longer than one cluster covers well and as the checked fallback
+// when the cluster launch is refused.
 // --------------------------------------------------------------------------------
 constexpr int kGnRows = 32;       // rows per block (both kernels)
 
@@ -275,6 +281,157 @@ __global__ void __launch_bounds__(256) graph_norm_apply_kernel(const float* __re
             out16[row * 32 + lane] = make_uint2(*reinterpret_cast<const unsigned*>(&lo), *reinterpret_cast<const unsigned*>(&hi));
         }
         if (b && zero_b) reinterpret_cast<float4*>(b + row * 128)[lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+}
+
+// Fused GraphNorm: grid (CL, B), cluster (CL, 1, 1); CTA `rank` owns rows [rank * share, (rank + 1) * share) of structure g.
+// 256 threads, thread = channel c = tid & 127 x row phase tid >> 7 (rows of a thread are 2 apart).  KEEP: share <= 32, the
+// thread's 16 rows are loaded once, all loads in flight, and stay in registers for the normalisation (one memory round
+// trip per norm); otherwise the rows are streamed twice (L2-resident the second time).
+template <bool KEEP>
+__global__ void __launch_bounds__(256) graph_norm_fused_kernel(const float* __restrict__ a, float* __restrict__ b,
+                                                              const float* __restrict__ mask, int N, int n_total, int share,
+                                                              const float* __restrict__ scale,
+                                                              const float* __restrict__ shift, int zero_b,
+                                                              float* __restrict__ out, uint16_t* __restrict__ out16) {
+    __shared__ double s_sum[2][128];           // this CTA's partial sums: read by the whole cluster
+    __shared__ double s_half[2][128];
+    __shared__ int s_n, s_nh;
+    __shared__ float s_mean[128], s_sd[128];
+    unsigned rank, cl;
+    asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(rank));
+    asm("mov.u32 %0, %%cluster_nctarank;" : "=r"(cl));
+    const int g = blockIdx.y, c = threadIdx.x & 127, rh = threadIdx.x >> 7;
+    const size_t base = (size_t)g * N;
+    const int r_begin = (int)rank * share, r_end = min(N, r_begin + share);
+
+    // ---- pass 1: per-channel sums over this CTA's valid rows (fp64, row order)
+    double s1 = 0.0, s2 = 0.0;
+    int n = 0;
+    float keep[KEEP ? 16 : 1];
+    unsigned keep_ok = 0;
+    if constexpr (KEEP) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int r = r_begin + rh + 2 * q;
+            keep[q] = 0.f;
+            if (r < r_end && mask[base + r] != 0.0f) {
+                keep_ok |= 1u << q;
+                keep[q] = a[(base + r) * 128 + c];
+            }
+        }
+        if (b) {
+#pragma unroll
+            for (int q = 0; q < 16; ++q)
+                if (keep_ok >> q & 1) keep[q] += b[(base + r_begin + rh + 2 * q) * 128 + c];
+        }
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            s1 += (double)keep[q];                               // masked rows hold exact zeros
+            s2 += (double)keep[q] * (double)keep[q];
+        }
+        n = __popc(keep_ok);
+    } else {
+        for (int r0 = r_begin + rh; r0 < r_end; r0 += 16) {     // eight rows in flight per thread
+            float x[8];
+            bool ok[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int r = r0 + 2 * q;
+                ok[q] = r < r_end && mask[base + r] != 0.0f;
+                x[q] = ok[q] ? a[(base + r) * 128 + c] : 0.f;
+            }
+            if (b) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (ok[q]) x[q] += b[(base + r0 + 2 * q) * 128 + c];
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                s1 += (double)x[q];
+                s2 += (double)x[q] * (double)x[q];
+                n += ok[q] ? 1 : 0;
+            }
+        }
+    }
+    if (rh == 1) { s_half[0][c] = s1; s_half[1][c] = s2; }
+    if (threadIdx.x == 128) s_nh = n;
+    __syncthreads();
+    if (rh == 0) {
+        s_sum[0][c] = s1 + s_half[0][c];
+        s_sum[1][c] = s2 + s_half[1][c];
+        if (c == 0) s_n = n + s_nh;
+    }
+    // ---- exchange: all partials of the cluster, added in rank order by every CTA
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (rh == 0) {
+        double t1 = 0.0, t2 = 0.0;
+        int cnt_i = 0;
+        for (unsigned k = 0; k < cl; ++k) {
+            uint32_t p1, p2, pn;
+            asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(p1) : "r"((uint32_t)__cvta_generic_to_shared(&s_sum[0][c])), "r"(k));
+            asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(p2) : "r"((uint32_t)__cvta_generic_to_shared(&s_sum[1][c])), "r"(k));
+            asm("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(pn) : "r"((uint32_t)__cvta_generic_to_shared(&s_n)), "r"(k));
+            double v1, v2;
+            int vn;
+            asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v1) : "r"(p1));
+            asm volatile("ld.shared::cluster.f64 %0, [%1];" : "=d"(v2) : "r"(p2));
+            asm volatile("ld.shared::cluster.s32 %0, [%1];" : "=r"(vn) : "r"(pn));
+            t1 += v1; t2 += v2; cnt_i += vn;
+        }
+        const double cnt = (double)cnt_i;
+        const double nn = cnt > 0.0 ? cnt : 1.0;
+        const double mean = t1 / nn;
+        double var = (t2 - nn * mean * mean + ((double)n_total - cnt) * mean * mean) / nn;
+        var = var > 0.0 ? var : 0.0;
+        s_mean[c] = (float)mean;
+        s_sd[c] = sqrtf((float)var + 1e-6f);
+    }
+    // nobody may leave (and release its shared memory) before every CTA has read the partials
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+    __syncthreads();
+
+    // ---- pass 2: normalise this CTA's rows; (x - mean) / sd * scale + shift, the division as in the reference
+    // (functional.py:42-43).  A row is written by 128 consecutive threads (coalesced 512 bytes).
+    const float mu = s_mean[c], sd = s_sd[c], sc = __ldg(scale + c), sh = __ldg(shift + c);
+    auto emit = [&](int r, bool live, float x) {
+        const size_t row = base + r;
+        const float o = live ? (x - mu) / sd * sc + sh : 0.f;
+        out[row * 128 + c] = o;
+        if (out16) {
+            const float o_hi = __shfl_down_sync(0xffffffffu, o, 1);
+            if ((c & 1) == 0) {
+                const __nv_bfloat162 pk = __floats2bfloat162_rn(o, o_hi);
+                reinterpret_cast<uint32_t*>(out16)[(row * 128 + c) >> 1] = *reinterpret_cast<const uint32_t*>(&pk);
+            }
+        }
+        if (b && zero_b) b[row * 128 + c] = 0.f;
+    };
+    if constexpr (KEEP) {
+#pragma unroll
+        for (int q = 0; q < 16; ++q) {
+            const int r = r_begin + rh + 2 * q;
+            if (r < r_end) emit(r, (keep_ok >> q & 1) != 0, keep[q]);      // uniform per warp (one row per 128 threads)
+        }
+    } else {
+        for (int r0 = r_begin + rh; r0 < r_end; r0 += 16) {
+            float x[8];
+            bool ok[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const int r = r0 + 2 * q;
+                ok[q] = r < r_end && mask[base + r] != 0.0f;
+                x[q] = ok[q] ? a[(base + r) * 128 + c] : 0.f;
+            }
+            if (b) {
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    if (ok[q]) x[q] += b[(base + r0 + 2 * q) * 128 + c];
+            }
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if (r0 + 2 * q < r_end) emit(r0 + 2 * q, ok[q], x[q]);
+        }
     }
 }
 
@@ -474,6 +631,29 @@ extern "C" int rmp_graph_norm(const float* a, float* b, const float* mask, int B
     RMP_REQUIRE(aligned16(a) && aligned16(out) && (!b || aligned16(b)), RMP_E_ALIGN, "rmp_graph_norm: 16-byte alignment");
     RMP_REQUIRE(B <= 65535, RMP_E_SHAPE, "rmp_graph_norm: B=%d exceeds 65535 structures per call", B);
     cudaStream_t st = (cudaStream_t)stream;
+    // one cluster of up to 8 CTAs per structure (32 rows or more per CTA); out may alias a (the passes of a CTA touch its
+    // own rows only, and pass 2 starts after every CTA of the cluster has finished pass 1)
+    static const bool two_launch = getenv("RMP_GRAPH_NORM_TWO_LAUNCH") != nullptr;
+    if (!two_launch) {
+        int cl = 1;
+        while (cl < 8 && cl * kGnRows < N) cl <<= 1;
+        const int share = ceil_div(N, cl);
+        cudaLaunchConfig_t cfg{};
+        cfg.gridDim = dim3(cl, B);
+        cfg.blockDim = dim3(256);
+        cfg.dynamicSmemBytes = 0;
+        cfg.stream = st;
+        cudaLaunchAttribute attr[1];
+        attr[0].id = cudaLaunchAttributeClusterDimension;
+        attr[0].val.clusterDim.x = cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+        cfg.attrs = attr;
+        cfg.numAttrs = 1;
+        cudaError_t le = cudaLaunchKernelEx(&cfg, share <= 32 ? graph_norm_fused_kernel<true> : graph_norm_fused_kernel<false>, a, b,
+                                            mask, N, n_total, share, scale, shift, zero_b, out,
+                                            reinterpret_cast<uint16_t*>(out_bf16));
+        if (le == cudaSuccess) return check_launch("rmp_graph_norm");
+        cudaGetLastError();          // cluster launch refused: fall through to the two-launch version
+    }
     cudaError_t e = cudaMemsetAsync(stats_ws, 0, (size_t)B * 257 * sizeof(double), st);
     if (e != cudaSuccess) { set_error("rmp_graph_norm: memset: %s", cudaGetErrorString(e)); return (int)e; }
     graph_norm_stats_kernel<<<dim3(ceil_div(N, kGnRows), B), 256, 0, st>>>(a, b, mask, N, stats_ws);

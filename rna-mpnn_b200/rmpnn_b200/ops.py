@@ -383,6 +383,8 @@ def forest_predict(f: DeviceForest, X: torch.Tensor, want_margins: bool = True):
     assert rows == 0 or X.stride(1) == 1
     margins = torch.empty(rows, f.n_class, dtype=torch.float32, device=X.device) if want_margins else None
     pred = torch.empty(rows, dtype=torch.int64, device=X.device)
+    if rows == 0:
+        return margins, pred
     check(lib().rmp_forest_predict(_ptr(X), rows, int(X.stride(0)), f.n_feat, _ptr(f.nodes), f.nodes.shape[0],
                                    _ptr(f.tree_root), f.tree_root.shape[0], _ptr(f.class_ptr), _ptr(f.class_trees),
                                    f.n_class, f.base_score, _ptr(margins), _ptr(pred), _stream()), "rmp_forest_predict")
