@@ -261,6 +261,11 @@ int rmp_graph_norm(const float* a, float* b, const float* mask, int B, int N, in
  *   qkv [B*N, 3E] = x in_proj_weight^T + in_proj_bias (q | k | v), E % heads == 0, head dim in {8,16,32}
  *   out [B*N, E] = softmax(q k^T / sqrt(hd)) v per head over the VALID keys of the structure; padded query rows 0. */
 int rmp_res_attention(const float* qkv, const float* mask, int B, int N, int E, int heads, float* out, void* stream);
+/* The same on the tcgen05 tensor cores (bf16 arm): qkv is the in-projection's bf16 side copy [B*N, 3E], E = 128, head dim 16
+ * or 32, an even number of heads.  S = Q K^T and P V per head as UMMA tiles over the valid key tiles, softmax between TMEM
+ * and registers (P goes back to tensor memory as the A operand of P V); out fp32 [B*N, E], padded query rows -> 0. */
+int rmp_res_attention_tc(const void* qkv_bf16, const float* mask, int B, int N, int E, int heads, float* out, void* stream);
+
 
 /* x[r,:] *= w[r]  (row masks) */
 int rmp_scale_rows(float* x, const float* w, int64_t rows, int width, void* stream);

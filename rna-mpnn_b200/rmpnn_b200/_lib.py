@@ -72,6 +72,7 @@ SIGNATURES = {
     "rmp_res_raw_features": [P, P, P, I, I, I, I, I, I, I, I, I, I, P, P, P],
     "rmp_graph_norm": [P, P, P, I, I, I, P, P, I, P, P, P, P],
     "rmp_res_attention": [P, P, I, I, I, I, P, P],
+    "rmp_res_attention_tc": [P, P, I, I, I, I, P, P],
     "rmp_scale_rows": [P, P, I64, I, P],
     "rmp_readout_head_masked": [P, I, P, P, P, F, U64, I, P, P, P, P],
     "rmp_edge_embed_bf16": [P, P, P, P, P, I, P, P, P, P, P, P, P],

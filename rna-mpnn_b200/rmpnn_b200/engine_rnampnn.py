@@ -163,8 +163,15 @@ class RNAMPNNEngine:
         if len(bw.attn) and self.padding_len < N:
             raise ValueError(f"padding_len={self.padding_len} is shorter than the batch (N={N})")
         for (in_proj, out_proj), (scale, shift) in zip(bw.attn, bw.norms):
-            qkv = self._mlp([(x, None)], [(in_proj, False)], rows, tensor_core=tc, fp16=fp16)
-            att = ops.res_attention(qkv, mask_flat, B, N, heads)
+            seg, st = [(x, None)], [(in_proj, False)]
+            if tc and not fp16 and ops.attention_tc_eligible(x.shape[1], heads) and ops.tc_eligible(seg, st):
+                # bf16 arm: the in-projection writes only its bf16 side copy, attention runs on tcgen05 (QK^T / PV tiles)
+                qkv16 = torch.empty(rows, 3 * x.shape[1], dtype=torch.bfloat16, device=x.device)
+                ops.row_mlp(seg, st, ops.EPI_STORE, None, rows, tensor_core=True, out_bf16=qkv16)
+                att = ops.res_attention_tc(qkv16, mask_flat, B, N, heads)
+            else:
+                qkv = self._mlp(seg, st, rows, tensor_core=tc, fp16=fp16)
+                att = ops.res_attention(qkv, mask_flat, B, N, heads)
             y = self._mlp([(att, None)], [(out_proj, False)], rows, tensor_core=tc, fp16=fp16)
             x = ops.graph_norm(x, y, mask_flat, B, N, scale, shift, n_total=self.padding_len)
         return self._mlp([(x, None)], stages, rows, row_scale=mask_flat, tensor_core=tc, fp16=fp16)

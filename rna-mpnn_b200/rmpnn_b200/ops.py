@@ -479,6 +479,23 @@ def res_attention(qkv, mask, B: int, N: int, heads: int, out=None):
     return out
 
 
+def attention_tc_eligible(E: int, heads: int) -> bool:
+    """Shapes ``rmp_res_attention_tc`` takes: 128 channels, head dim 16 or 32, an even number of heads."""
+    return E == 128 and heads > 0 and heads % 2 == 0 and E % heads == 0 and E // heads in (16, 32)
+
+
+def res_attention_tc(qkv16, mask, B: int, N: int, heads: int, out=None):
+    """``res_attention`` on the tcgen05 tensor cores: qkv16 [B*N, 384] bf16 (the in-projection's bf16 side copy)."""
+    _need_cuda(qkv16, mask, out)
+    E = qkv16.shape[-1] // 3
+    assert qkv16.dtype == torch.bfloat16 and qkv16.is_contiguous() and qkv16.shape[0] == B * N
+    if out is None:
+        out = torch.empty(B * N, E, dtype=torch.float32, device=qkv16.device)
+    check(lib().rmp_res_attention_tc(_ptr(qkv16), _ptr(mask), B, N, E, int(heads), _ptr(out), _stream()),
+          "rmp_res_attention_tc")
+    return out
+
+
 def scale_rows(x, w):
     """x[r,:] *= w[r] in place."""
     _need_cuda(x, w)

@@ -138,6 +138,47 @@ def test_attention_matches_oracle(ops, heads):
     np.testing.assert_allclose(got.cpu().numpy(), want.reshape(B * N, E).numpy(), atol=2e-5, rtol=1e-5)
 
 
+@pytest.mark.parametrize("heads,B,N", [(8, 3, 200), (8, 2, 256), (4, 2, 130), (8, 1, 1000), (8, 5, 37)])
+def test_attention_tc_matches_oracle(ops, heads, B, N):
+    """tcgen05 attention (bf16 arm) against the oracle on the SAME bf16-rounded q | k | v: what is left is the bf16
+    rounding of the softmax weights (2^-9 relative per weight) and the fp32 accumulation order."""
+    g = torch.Generator().manual_seed(77 + heads + N)
+    E = 128
+    x = torch.randn(B, N, E, generator=g)
+    mask = torch.ones(B, N)
+    if B > 1:
+        mask[1, (2 * N) // 3:] = 0
+    if B > 2:
+        mask[2, 1:] = 0                                   # a single valid residue
+    if B > 3:
+        mask[3, ::3] = 0                                  # holes
+        mask[4, :] = 0                                    # an empty structure
+    in_w = torch.randn(3 * E, E, generator=g) / E ** 0.5 * 2
+    in_b = torch.randn(3 * E, generator=g) * 0.1
+    qkv16 = torch.nn.functional.linear(x, in_w, in_b).reshape(B * N, 3 * E).to(torch.bfloat16)
+    q, k, v = qkv16.float().reshape(B, N, 3, heads, E // heads).unbind(2)
+    sc = torch.einsum("bqhd,bkhd->bhqk", q.double(), k.double()) / (E // heads) ** 0.5
+    sc = sc.masked_fill(mask[:, None, None, :] == 0, float("-inf"))
+    w = torch.softmax(sc, -1).nan_to_num(0.0)
+    want = torch.einsum("bhqk,bkhd->bqhd", w, v.double()).reshape(B, N, E) * mask[..., None]
+    got = ops.res_attention_tc(qkv16.contiguous().cuda(), mask.reshape(-1).cuda(), B, N, heads)
+    torch.cuda.synchronize()
+    err = (got.cpu().double() - want.reshape(B * N, E)).abs().max().item()
+    assert err < 1.5e-2 * max(1.0, v.abs().max().item()), err           # bf16 weights: <= 2^-8 relative per term
+    assert float(got.cpu()[mask.reshape(-1) == 0].abs().max() if (mask == 0).any() else 0.0) == 0.0
+    # and against the SIMT kernel on the same rounded inputs
+    simt = ops.res_attention(qkv16.float().contiguous().cuda(), mask.reshape(-1).cuda(), B, N, heads)
+    assert (got - simt).abs().max().item() < 1.5e-2 * max(1.0, v.abs().max().item())
+
+
+def test_attention_tc_rejects_unsupported_shapes(ops):
+    qkv16 = torch.zeros(64, 384, dtype=torch.bfloat16, device="cuda")
+    mask = torch.ones(64, device="cuda")
+    with pytest.raises(RuntimeError, match="head dim"):
+        ops.res_attention_tc(qkv16, mask, 1, 64, 16)          # head dim 8
+    assert not ops.attention_tc_eligible(128, 16) and ops.attention_tc_eligible(128, 8) and ops.attention_tc_eligible(128, 4)
+
+
 # --------------------------------------------------------------------------- whole path
 def test_forward_matches_oracle_and_reference(rgolden):
     """Engine on the reference's own graph: every stage against the oracle, logits against the reference."""
