@@ -65,3 +65,22 @@ for i in range(min(m, 60)):
     tag, ts = t[25600 + 2 * i], t[25601 + 2 * i]
     print(tag, ts - t0, (ts - prev) if prev is not None else 0)
     prev = ts
+# staggered schedule: for tiles 6..11 of CTA 0 and every stage -- when the 16 epilogue warps arrived (first / last), when the
+# MMA thread issued the next stage's GEMM, and when the warps saw that accumulator (first / last)
+if os.environ.get("RMP_EDGE_SCHEDULE", "s")[0] == "s":
+    mma = {t[25600 + 2 * i]: t[25601 + 2 * i] - t0 for i in range(m)}
+    print("--- hand-off chain per (tile, stage): arrive first/last -> MMA issue of the next stage -> accumulator seen first/last")
+    for tile in range(6, 12):
+        nth = tile // 2                      # occurrence index within the tile's parity stream
+        par = tile & 1
+        for s in range(3):
+            arr = [[ts for tag, ts in warps[w] if tag == 700 + 10 * s + par][nth] - t0 for w in range(16)]
+            wait0 = [[ts for tag, ts in warps[w] if tag == 100 + 10 * s + par][nth] - t0 for w in range(16)]
+            line = f"tile {tile} stage {s}: wait starts {min(wait0)}..{max(wait0)}  arrive {min(arr)}..{max(arr)} (spread {max(arr) - min(arr)})"
+            if s < 2:
+                issue = mma.get((tile + 1) * 1000 + s + 1)
+                seen = [[ts for tag, ts in warps[w] if tag == 200 + 10 * (s + 1) + par][nth] - t0 for w in range(16)]
+                nwait = [[ts for tag, ts in warps[w] if tag == 100 + 10 * (s + 1) + par][nth] - t0 for w in range(16)]
+                line += (f"  | next GEMM issued {issue} (+{issue - max(arr)} after the last arrive)  next wait starts {min(nwait)}..{max(nwait)}"
+                         f"  accumulator seen {min(seen)}..{max(seen)} (+{min(seen) - issue} after the issue)")
+            print(line)
