@@ -107,6 +107,52 @@ class EdgeEmbedFn(torch.autograd.Function):
         return dW[:, :W.shape[1]].contiguous(), db, dgain, dbeta, None
 
 
+class LayerNormFn(torch.autograd.Function):
+    """``nn.LayerNorm`` over the last dimension (rdesign/model/mpnn.py:11-12, :35, :37) with the weight / bias gradients as two
+    ``[1,Nv] x [Nv,128]`` products: torch's ``GammaBetaBackward`` kernel takes 75 us per call on [16384,128] (1.35 ms of the
+    C4 step), the products 10 us."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        x = x.float().contiguous()
+        y, mean, rstd = torch.native_layer_norm(x, (x.shape[-1],), weight, bias, eps)
+        ctx.save_for_backward(x, mean, rstd, weight)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, rstd, weight = ctx.saved_tensors
+        dy = dy.float().contiguous()
+        with torch.autocast("cuda", enabled=False):
+            dx = torch.ops.aten.native_layer_norm_backward(dy, x, [x.shape[-1]], mean, rstd, weight, None,
+                                                           [True, False, False])[0]
+            ones = dy.new_ones(1, dy.shape[0])
+            dw = (ones @ (dy * ((x - mean) * rstd))).reshape(-1)
+            db = (ones @ dy).reshape(-1)
+        return dx, dw, db, None
+
+
+class LinearFn(torch.autograd.Function):
+    """``nn.Linear`` of the per-node FFN on the bf16 tensor cores (what bf16 autocast computes), the bias gradient as a
+    ``[1,Nv] x [Nv,N]`` product instead of a column reduction kernel (25 us per call, 37 calls per step)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, w16):
+        x16 = x.to(torch.bfloat16)
+        ctx.save_for_backward(x16, w16)
+        return torch.addmm(bias.to(torch.bfloat16), x16, w16.t())
+
+    @staticmethod
+    def backward(ctx, dy):
+        x16, w16 = ctx.saved_tensors
+        dy = dy.to(torch.bfloat16).contiguous()
+        with torch.autocast("cuda", enabled=False):
+            dx = dy @ w16
+            dw = (dy.t() @ x16).float()
+            db = (dy.new_ones(1, dy.shape[0]) @ dy).float().reshape(-1)
+        return dx, dw, db, None
+
+
 def _normalize(x, gain, bias, eps=1e-6):
     """Reference Normalize (rdesign/model/functional.py:79-96): unbiased variance, eps inside and outside the sqrt."""
     mu = x.mean(-1, keepdim=True)
@@ -185,7 +231,18 @@ class RDesignTrainer:
             st["dhE"] = state["dhE"]
             agg = EdgeMessageFn.apply(h_V, token, lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight,
                                       lin[2].bias, st)
-            with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.autocast):
+            if self.autocast:
+                # per-node remainder: LayerNorm and Linear through the two functions above (same math as the modules under
+                # bf16 autocast), GELU / Dropout / residual adds as torch ops
+                x1 = LayerNormFn.apply(h_V + agg, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps)
+                d = x1
+                for mod in layer.dense:
+                    if isinstance(mod, torch.nn.Linear):
+                        d = LinearFn.apply(d, mod.weight, mod.bias, self._w16(mod.weight))
+                    else:
+                        d = mod(d)
+                h_V = LayerNormFn.apply(x1 + d, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps)
+            else:
                 x1 = layer.norm1(h_V + agg)
                 h_V = layer.norm2(x1 + layer.dense(x1)).float()
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.autocast):

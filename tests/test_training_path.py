@@ -184,3 +184,46 @@ def test_normalize_fwd_bwd_match_autograd():
     np.testing.assert_allclose(dgain.cpu().numpy(), gr.grad.cpu().numpy(), atol=2e-2, rtol=1e-3)
     np.testing.assert_allclose(dbias.cpu().numpy(), br.grad.cpu().numpy(), atol=2e-2, rtol=1e-3)
     np.testing.assert_allclose(dbsum.cpu().numpy(), dx.float().sum(0).cpu().numpy(), atol=2e-2, rtol=1e-3)
+
+
+def test_node_side_functions_match_the_modules():
+    """LayerNormFn / LinearFn (weight and bias gradients as small products) against nn.LayerNorm / nn.Linear."""
+    from rmpnn_b200.train_engine import LayerNormFn, LinearFn
+    torch.manual_seed(0)
+    x = torch.randn(3000, 128, device="cuda", requires_grad=True)
+    ln = torch.nn.LayerNorm(128).cuda()
+    ln.weight.data.normal_(); ln.bias.data.normal_()
+    g = torch.randn(3000, 128, device="cuda")
+    got = torch.autograd.grad(LayerNormFn.apply(x, ln.weight, ln.bias, ln.eps), (x, ln.weight, ln.bias), g)
+    want = torch.autograd.grad(ln(x), (x, ln.weight, ln.bias), g)
+    for a, b in zip(got, want):
+        assert (a - b).abs().max().item() <= 2e-4 * max(1.0, b.abs().max().item())
+    lin = torch.nn.Linear(128, 256).cuda()
+    g = torch.randn(3000, 256, device="cuda")
+    y = LinearFn.apply(x, lin.weight, lin.bias, lin.weight.detach().to(torch.bfloat16))
+    assert y.dtype == torch.bfloat16 and (y.float() - lin(x)).abs().max().item() < 3e-2
+    got = torch.autograd.grad(y, (x, lin.weight, lin.bias), g.to(torch.bfloat16))
+    want = torch.autograd.grad(lin(x), (x, lin.weight, lin.bias), g)
+    for a, b in zip(got, want):
+        assert (a.float() - b).abs().max().item() <= 2e-2 * b.abs().max().item()
+
+
+def test_autocast_step_gradients_are_close_to_the_fp32_step():
+    """The bf16 node-side path (LayerNormFn / LinearFn) against the same step with the fp32 modules, dropout off."""
+    from oracle.weights import RDesignConfig, make_state_dict, synthetic_backbones
+    from rdesign.model.rdesign import RNAModel
+    from rmpnn_b200.train_engine import RDesignTrainer
+    cfg = RDesignConfig(k_neighbors=12, num_mpnn_layers=3)
+    X, S, mask = (t.cuda() for t in synthetic_backbones(3, 60, 9, lengths=[60, 41, 23]))
+    grads = []
+    for autocast in (False, True):
+        model = RNAModel(**cfg.as_kwargs(), dropout=0.0).cuda().train()
+        model.load_state_dict(make_state_dict(cfg, 42), strict=True)
+        tr = RDesignTrainer(model, autocast=autocast)
+        loss = tr.loss_and_grads(X, S, mask, seed=1)
+        grads.append((loss.item(), {n: p.grad.clone().float() for n, p in model.named_parameters()}))
+    assert abs(grads[0][0] - grads[1][0]) < 2e-2
+    for n, b in grads[0][1].items():
+        a = grads[1][1][n]
+        rel = ((a - b).norm() / (b.norm() + 1e-12)).item()
+        assert rel < 8e-2 or (a - b).abs().max().item() < 1e-5, (n, rel)
