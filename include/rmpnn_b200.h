@@ -353,6 +353,10 @@ int rmp_act_bwd_bf16(const void* z_bf16, const void* da_bf16, const float* dagg,
                      uint32_t stream_id, void* stream);
 /* out[idx[r],:] += x[r,:]   x bf16 [rows,128], out fp32: backward of the h_V[E_idx] gathers (rdesign.py:85) */
 int rmp_scatter_add_rows(const void* x_bf16, const int32_t* idx, float* out, int rows, void* stream);
+/* out[v,:] = sum of rows row_ptr[v] .. row_ptr[v+1]-1 of x (bf16 [rows,128]) in row order, fp32 [n_seg,128], OVERWRITTEN: the
+ * scatter_sum by centre node (functional.scatter_sum with src_idx = E_idx[0], rdesign/model/mpnn.py:34) and its transposes
+ * in the backward, without atomics (the edges of a node are contiguous). */
+int rmp_segment_sum_rows(const void* x_bf16, const int32_t* row_ptr, float* out, int n_seg, void* stream);
 /* dW[n,k] += sum_r dZ[r,n] X[r,k]   dZ, X bf16 [rows,128], dW fp32 [128,128]: weight gradient of a 128->128 Linear
  * (tcgen05, both operands read MN-major from their row-major tiles, per-CTA TMEM accumulator, one red.global pass) */
 int rmp_gemm_dw_bf16(const void* dZ_bf16, const void* X_bf16, float* dW, int rows, void* stream);

@@ -141,6 +141,38 @@ __global__ void __launch_bounds__(256) scatter_add_kernel(const uint4* __restric
     tc::red_add_v4(dst + 4, bf_lo(xi.z), bf_hi(xi.z), bf_lo(xi.w), bf_hi(xi.w));
 }
 
+// out[v, :] = sum of the rows row_ptr[v] .. row_ptr[v+1]-1 of x (bf16 [rows,128]; the edges of a node are contiguous,
+// SURVEY section 8a a-2): the scatter_sum by CENTRE node without atomics.  Half a warp per node: lane = 8 columns (one
+// 16-byte load per row), rows summed in order in fp32 -> deterministic; one pass over x at HBM rate where the red.global
+// version moved every row through the L2 atomic units (70 -> ~25 us on [409,600 x 128]).
+__global__ void __launch_bounds__(256) segment_sum_kernel(const uint4* __restrict__ x, const int32_t* __restrict__ row_ptr,
+                                                          float* __restrict__ out, int n_seg) {
+    const int v = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4);
+    const int cg = threadIdx.x & 15;
+    if (v >= n_seg) return;
+    const int r0 = __ldg(row_ptr + v), r1 = __ldg(row_ptr + v + 1);
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int r = r0;
+    for (; r + 4 <= r1; r += 4) {                    // four independent 16-byte loads in flight
+        uint4 xi[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) xi[q] = x[(size_t)(r + q) * 16 + cg];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            acc[0] += bf_lo(xi[q].x); acc[1] += bf_hi(xi[q].x); acc[2] += bf_lo(xi[q].y); acc[3] += bf_hi(xi[q].y);
+            acc[4] += bf_lo(xi[q].z); acc[5] += bf_hi(xi[q].z); acc[6] += bf_lo(xi[q].w); acc[7] += bf_hi(xi[q].w);
+        }
+    }
+    for (; r < r1; ++r) {
+        const uint4 xi = x[(size_t)r * 16 + cg];
+        acc[0] += bf_lo(xi.x); acc[1] += bf_hi(xi.x); acc[2] += bf_lo(xi.y); acc[3] += bf_hi(xi.y);
+        acc[4] += bf_lo(xi.z); acc[5] += bf_hi(xi.z); acc[6] += bf_lo(xi.w); acc[7] += bf_hi(xi.w);
+    }
+    float4* dst = reinterpret_cast<float4*>(out + (size_t)v * 128 + cg * 8);
+    dst[0] = make_float4(acc[0], acc[1], acc[2], acc[3]);
+    dst[1] = make_float4(acc[4], acc[5], acc[6], acc[7]);
+}
+
 // Adam (torch.optim.Adam semantics, no weight decay / amsgrad): p -= lr * m_hat / (sqrt(v_hat) + eps)
 __global__ void __launch_bounds__(256) adam_kernel(float4* __restrict__ p, const float4* __restrict__ g, float4* __restrict__ m,
                                                    float4* __restrict__ v, size_t n4, float grad_scale, float lr, float b1,
@@ -564,6 +596,16 @@ extern "C" int rmp_scatter_add_rows(const void* x_bf16, const int32_t* idx, floa
     train::scatter_add_kernel<<<(unsigned)((groups + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const uint4*>(x_bf16), idx, out, rows);
     return check_launch("rmp_scatter_add_rows");
+}
+
+extern "C" int rmp_segment_sum_rows(const void* x_bf16, const int32_t* row_ptr, float* out, int n_seg, void* stream) {
+    RMP_REQUIRE(x_bf16 && row_ptr && out && n_seg >= 0, RMP_E_ARG, "rmp_segment_sum_rows: null pointer");
+    RMP_REQUIRE(aligned16(x_bf16) && aligned16(out), RMP_E_ALIGN, "rmp_segment_sum_rows: 16-byte alignment");
+    if (n_seg == 0) return RMP_OK;
+    const size_t threads = (size_t)n_seg * 16;
+    train::segment_sum_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(x_bf16), row_ptr, out, n_seg);
+    return check_launch("rmp_segment_sum_rows");
 }
 
 extern "C" int rmp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float grad_scale,

@@ -554,6 +554,18 @@ def scatter_add_rows(x16, idx, out):
     return out
 
 
+def segment_sum_rows(x16, row_ptr, out=None):
+    """out[v] = sum of rows row_ptr[v]..row_ptr[v+1]-1 of x16 (bf16 [rows,128]) -> fp32 [n_seg,128] (overwritten, no atomics)."""
+    _need_cuda(x16, row_ptr, out)
+    assert x16.dtype == torch.bfloat16 and x16.is_contiguous() and x16.shape[1] == 128 and row_ptr.dtype == torch.int32
+    n_seg = row_ptr.shape[0] - 1
+    if out is None:
+        out = torch.empty(n_seg, 128, dtype=torch.float32, device=x16.device)
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.shape[0] >= n_seg
+    check(lib().rmp_segment_sum_rows(_ptr(x16), _ptr(row_ptr), _ptr(out), n_seg, _stream()), "rmp_segment_sum_rows")
+    return out
+
+
 def gemm_dw(dz16, x16, dW):
     """dW [128,128] fp32 += dz16^T @ x16 (both bf16 [rows,128])."""
     _need_cuda(dz16, x16, dW)

@@ -48,8 +48,7 @@ class EdgeMessageFn(torch.autograd.Function):
         z0, a0 = ops.gemm_rows(hE16, W1h[:, :128], Pc=Pc, Pn=Pn, ctr=g.ctr, nbr=g.nbr, act=(p, seed, sid), seed_dev=sd)
         z1, a1 = ops.gemm_rows(a0, w16(W2), bias=b2.detach(), act=(p, seed, sid + 1), seed_dev=sd)
         z2, a2 = ops.gemm_rows(a1, w16(W3), bias=b3.detach(), act=(p, seed, sid + 2), seed_dev=sd)
-        agg = torch.zeros(g.Nv, 128, dtype=torch.float32, device=h_V.device)
-        ops.scatter_add_rows(a2, g.ctr, agg)
+        agg = ops.segment_sum_rows(a2, g.row_ptr[:g.Nv + 1])        # edges of a node are contiguous: no atomics
         ctx.save_for_backward(hV16, W1, W2, W3, z0, z1, z2, a0, a1)
         ctx.state = (state, p, seed, sid, scale)
         return agg * (1.0 / scale)
@@ -74,7 +73,7 @@ class EdgeMessageFn(torch.autograd.Function):
         dz0 = ops.act_bwd(z0, p, seed, sid, da16=da0, db=db[0], seed_dev=sd)
         ops.gemm_dw(dz0, hE16, dW[2])
         ops.gemm_rows(dz0, W1h[:, :128], want_z=False, acc32=state["dhE"], w_transposed=True)      # d h_E += dz0 W1e
-        ops.scatter_add_rows(dz0, g.ctr, dP[0])
+        ops.segment_sum_rows(dz0, g.row_ptr[:g.Nv + 1], dP[0])
         ops.scatter_add_rows(dz0, g.nbr, dP[1])
         dP16 = dP.to(torch.bfloat16)
         dW1 = torch.cat([dW[2], (dP16[0].t() @ hV16).float(), (dP16[1].t() @ hV16).float()], dim=1)

@@ -227,3 +227,22 @@ def test_autocast_step_gradients_are_close_to_the_fp32_step():
         a = grads[1][1][n]
         rel = ((a - b).norm() / (b.norm() + 1e-12)).item()
         assert rel < 8e-2 or (a - b).abs().max().item() < 1e-5, (n, rel)
+
+
+def test_segment_sum_equals_scatter_add_by_centre():
+    """rmp_segment_sum_rows (no atomics; a node's edges are contiguous) against rmp_scatter_add_rows and torch, on a real
+    ragged graph (degrees min(K, L_b)) and with empty segments."""
+    from rmpnn_b200 import ops
+    from rmpnn_b200.synthetic import synthetic_backbones
+    X, S, mask = synthetic_backbones(4, 70, 3, lengths=[70, 33, 9, 1])
+    g = ops.build_graph(X.cuda(), mask.cuda(), 25)
+    x = torch.randn(g.Ne, 128, device="cuda").to(torch.bfloat16)
+    got = ops.segment_sum_rows(x, g.row_ptr[:g.Nv + 1])
+    ref = torch.zeros(g.Nv, 128, device="cuda")
+    ops.scatter_add_rows(x, g.ctr, ref)
+    want = torch.zeros(g.Nv, 128, device="cuda").index_add_(0, g.ctr[:g.Ne].long(), x.float())
+    assert (got - want).abs().max().item() < 1e-4 and (got - ref).abs().max().item() < 1e-4
+    rp = torch.tensor([0, 0, 3, 3, 10, 10], dtype=torch.int32, device="cuda")          # empty segments -> zeros
+    got = ops.segment_sum_rows(x[:10].contiguous(), rp)
+    assert float(got[0].abs().max()) == 0.0 and float(got[2].abs().max()) == 0.0 and float(got[4].abs().max()) == 0.0
+    assert (got[1] - x[:3].float().sum(0)).abs().max().item() < 1e-5 and (got[3] - x[3:10].float().sum(0)).abs().max().item() < 1e-5
