@@ -90,7 +90,7 @@ res_attention_tc_kernel(const __grid_constant__ CUtensorMap tm_qkv, const AttnPa
 
     if (warp == 0) {
         // ===================== TMA producer: Q once, then the key tiles of pass 1 (K) and pass 2 (K and V) =====
-        if (lane == 0) {
+        if (elect_one()) {
             tma_prefetch_desc(&tm_qkv);
             mbar_expect_tx(&bars->q_full, kTileBytes);
             tma_load_2d(sQ, &tm_qkv, &bars->q_full, 0, row0 + qt * kTileM);

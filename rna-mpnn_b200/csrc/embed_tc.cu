@@ -85,7 +85,7 @@ edge_embed_tc_kernel(const __grid_constant__ CUtensorMap tm_w, const EmbedParams
 
     if (warp == 1) {
         // ===================== weight load + MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             mbar_expect_tx(&bars->w_full, kTileBytes);
             for (int kb = 0; kb < 2; ++kb) tma_load_2d(sW + kb * kKBlockBytes, &tm_w, &bars->w_full, kb * 64, 0);
             mbar_wait(&bars->w_full, 0);

@@ -14,6 +14,9 @@
 // drain (accumulator pre-initialisation, selector matrix, neighbour sums), warps 8..23 = epilogue.
 #include "tc_common.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+
 namespace rmp {
 namespace tc {
 
@@ -29,6 +32,7 @@ struct EdgeParams {
     float alpha;
     float* agg;                      // [Nv,128] fp32, pre-zeroed
     int n_edges;
+    int flags;                       // 1 = first edge tile requested before W2.., 2 = run-ahead GEMMs behind hand-offs
     float* debug;                    // optional [num_stages][n_edges][128] post-activation dump
     long long* timeline;             // optional int64[32768] clock64 trace of CTA 0 (per epilogue warp + MMA thread; tuning)
 };
@@ -59,7 +63,7 @@ constexpr uint32_t kEdgeTmemCols = 512;                        // X[s] at 128*s;
 constexpr uint32_t kYCol = 384;
 
 struct alignas(8) Barriers {
-    uint64_t w_full, a_full[kSlots], a_empty[kSlots];
+    uint64_t w_full[kMaxStages], a_full[kSlots], a_empty[kSlots];
     uint64_t init_done[kSlots], acc_full[kSlots], act_ready[kSlots], agg_full[kSlots];
 };
 
@@ -107,6 +111,18 @@ __device__ __forceinline__ void tmem_ld32_wait(uint32_t (&r)[32]) {
                  : "memory");
 }
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// 2 * GELU(x), packed (the epilogue's form): y = x + x * tanh(..) saves the 0.5 x multiply of gelu_bf16x2 on the co-limiting
+// FMA pipe.  The factor 2 is exact in bf16 and is taken back where the next GEMM's result is read (one packed
+// fma(acc, 0.5, bias) instead of the bias add; the neighbour sums with alpha / 2): bit-identical results.
+__device__ __forceinline__ uint32_t gelu2x_bf16x2(float a, float b) {
+    const __nv_bfloat162 x = __floats2bfloat162_rn(a, b);
+    const __nv_bfloat162 c1 = __float2bfloat162_rn(0.0356774081f), c0 = __float2bfloat162_rn(0.7978845608f);
+    const __nv_bfloat162 inner = __hmul2(x, __hfma2(__hmul2(x, x), c1, c0));
+    uint32_t t;
+    asm("tanh.approx.bf16x2 %0, %1;" : "=r"(t) : "r"(*reinterpret_cast<const uint32_t*>(&inner)));
+    const __nv_bfloat162 y = __hfma2(x, *reinterpret_cast<const __nv_bfloat162*>(&t), x);
+    return *reinterpret_cast<const uint32_t*>(&y);
+}
 
 // D[tmem] (+)= A[tmem] . B[smem]^T: the A operand (128 rows x 16 bf16 = 8 columns) is read from tensor memory
 __device__ __forceinline__ void umma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc,
@@ -139,6 +155,19 @@ __device__ __forceinline__ void add2(float& a, float& b, float x, float y) {
         : "+f"(a), "+f"(b)
         : "f"(x), "f"(y));
 }
+// (a, b) = (a, b) * 0.5 + (x, y): one packed fp32x2 fma
+__device__ __forceinline__ void fma2_half(float& a, float& b, float x, float y) {
+    asm("{\n\t"
+        ".reg .b64 va, vx, vh;\n\t"
+        "mov.b64 va, {%0, %1};\n\t"
+        "mov.b64 vx, {%2, %3};\n\t"
+        "mov.b64 vh, {0f3F000000, 0f3F000000};\n\t"
+        "fma.rn.f32x2 va, va, vh, vx;\n\t"
+        "mov.b64 {%0, %1}, va;\n\t"
+        "}"
+        : "+f"(a), "+f"(b)
+        : "f"(x), "f"(y));
+}
 template <int N>
 __device__ __forceinline__ void set_max_regs_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" ::"n"(N)); }
 template <int N>
@@ -151,7 +180,7 @@ __device__ __forceinline__ void gelu_pack32(const float (&v)[32], uint32_t (&o)[
     for (int q = 0; q < 16; ++q) o[q] = gelu_bf16x2(v[2 * q], v[2 * q + 1]);
 }
 
-template <bool TRACE, bool DECOUPLED>
+template <bool TRACE, bool DECOUPLED, int V = 0>
 __global__ void __launch_bounds__(kEdgeThreads, 1)
 edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_constant__ CUtensorMap tm_w,
                    const EdgeParams p) {
@@ -174,9 +203,10 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
     const int n_tiles = (p.n_edges + kTileM - 1) / kTileM;
     const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int S = p.num_stages;
+    constexpr bool kFold = (V & 1) != 0;            // activations held as 2 * GELU (gelu2x_bf16x2)
 
     if (threadIdx.x == 0) {
-        mbar_init(&bars->w_full, 1);
+        for (int s = 0; s < kMaxStages; ++s) mbar_init(&bars->w_full[s], 1);
         for (int b = 0; b < kSlots; ++b) {
             mbar_init(&bars->a_full[b], 1); mbar_init(&bars->a_empty[b], 1);
             mbar_init(&bars->init_done[b], kGatherThreads);
@@ -202,13 +232,18 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
         set_max_regs_dec<40>();
         if (warp == 0) {
             // ===================== TMA producer =====================
-            if (lane == 0) {
+            if (elect_one()) {
                 tma_prefetch_desc(&tm_e);
                 tma_prefetch_desc(&tm_w);
-                mbar_expect_tx(&bars->w_full, (uint32_t)(S * kTileBytes));
-                for (int s = 0; s < S; ++s)
+                // one barrier per stage's weights; with flag 1 the first edge tile is requested right behind W1e, so
+                // that the first GEMM does not queue behind the 64 KB of later-stage weights of all 148 CTAs
+                auto load_w = [&](int s) {
+                    mbar_expect_tx(&bars->w_full[s], (uint32_t)kTileBytes);
                     for (int kb = 0; kb < 2; ++kb)
-                        tma_load_2d(sW + (size_t)s * kTileBytes + kb * kKBlockBytes, &tm_w, &bars->w_full, kb * 64, s * 128);
+                        tma_load_2d(sW + (size_t)s * kTileBytes + kb * kKBlockBytes, &tm_w, &bars->w_full[s], kb * 64, s * 128);
+                };
+                const bool w_late = (p.flags & 1) != 0;
+                for (int s = 0; s < (w_late ? 1 : S); ++s) load_w(s);
                 for (int i = 0; i < my_tiles; ++i) {
                     const int b = i % kSlots;
                     const int tile = blockIdx.x + i * gridDim.x;
@@ -217,12 +252,16 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
                     for (int kb = 0; kb < 2; ++kb)
                         tma_load_2d(sA + (size_t)b * kTileBytes + kb * kKBlockBytes, &tm_e, &bars->a_full[b], kb * 64,
                                     tile * kTileM);
+                    if (w_late && i == 0)
+                        for (int s = 1; s < S; ++s) load_w(s);
                 }
+                if (w_late && my_tiles == 0)
+                    for (int s = 1; s < S; ++s) load_w(s);
             }
             __syncwarp();
         } else if (warp == 1) {
             // ===================== MMA issuer: serves the tiles in flight as their operands become ready ====
-            if (lane == 0) {
+            if (elect_one()) {
                 constexpr uint32_t idesc_stage = instr_desc_bf16(128, 128, 0);
                 constexpr uint32_t idesc_sel = instr_desc_bf16_amn(128, kSelSlots);
                 int ti[kSlots], st[kSlots];
@@ -233,7 +272,9 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
                 const uint64_t d_am0 = smem_desc_sw128(smem_u32(sA), kKBlockBytes, 1024);   // m3 read MN-major
                 const uint64_t d_w0 = smem_desc_sw128(smem_u32(sW), 16, 1024);
                 const uint64_t d_sel0 = smem_desc_sw128(smem_u32(sSel), 16, 1024);
-                mbar_wait(&bars->w_full, 0);
+                mbar_wait(&bars->w_full[0], 0);
+                uint32_t w_seen = 1u;                   // stages whose weights have been waited for
+                const bool defer_ahead = (p.flags & 2) != 0;
                 int remaining = my_tiles;
                 int tlm = 0;
                 const bool tlm_on = TRACE && p.timeline != nullptr && blockIdx.x == 0;
@@ -248,7 +289,17 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
                     // pass 1: stage-0 GEMMs of tiles ahead (nobody waits yet) -- only when pass 0 found nothing
 #pragma unroll
                     for (int pass = 0; pass < 2; ++pass) {
-                        if (pass == 1 && progressed) break;
+                        if (!defer_ahead) {
+                            if (pass == 1 && progressed) break;
+                        } else if (pass == 1 && !progressed) {
+                            // flag 2: a run-ahead stage-0 GEMM is issued right behind a GEMM somebody waits for (the next
+                            // such hand-off is most of an epilogue phase away), or when fewer than two tiles are in their
+                            // later stages (start, tail) -- never at a random time in front of a hand-off
+                            int late = 0;
+#pragma unroll
+                            for (int b = 0; b < kSlots; ++b) late += (ti[b] < my_tiles && st[b] > 0) ? 1 : 0;
+                            if (late >= 2) break;
+                        }
 #pragma unroll
                         for (int b = 0; b < kSlots; ++b) {
                             const int i = ti[b], s = st[b];
@@ -277,10 +328,12 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
                                     umma_bf16(acc, d_a + off, d_w0 + zero + off, idesc_stage, 1u);
                                 }
                                 umma_commit(&bars->acc_full[b]);
+                                mstamp(-(1000 * (i + 1) + s));
                                 const volatile int* meta = s_meta + 2 * (kSlots * (int)par_tile + b);
                                 sel_path[b] = meta[1] <= kSelSlots;
                                 st[b] = 1;
                             } else if (s < S) {
+                                if (!(w_seen & (1u << s))) { mbar_wait(&bars->w_full[s], 0); w_seen |= 1u << s; }
                                 const uint64_t d_w = d_w0 + (uint64_t)(zero + s * (kTileBytes >> 4));
                                 const uint32_t a_tmem = tmem_base + kYCol + (uint32_t)((i & 1) * 64);
 #pragma unroll
@@ -289,6 +342,7 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
                                     umma_bf16_ts(acc, a_tmem + (uint32_t)(k * 8), d_w + off, idesc_stage, (uint32_t)(k > 0));
                                 }
                                 umma_commit(&bars->acc_full[b]);
+                                mstamp(-(1000 * (i + 1) + s));
                                 st[b] = s + 1;
                             } else {
                                 // neighbour sums, transposed: aggT[ch][slot] = sum_r m3[r][ch] * Sel[slot][r], written
@@ -306,6 +360,7 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
                                 }
                                 umma_commit(&bars->agg_full[b]);
                                 umma_commit(&bars->a_empty[b]);
+                                mstamp(-(1000 * (i + 1) + s));
                                 st[b] = 0;
                                 ti[b] = i + kSlots;
                                 --remaining;
@@ -331,6 +386,7 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
             tc_fence_after();
             const volatile int* meta = s_meta + 2 * (kSlots * ((j_prev / kSlots) & 1) + b);
             const int fn = meta[0], nslots = meta[1];
+            const float alpha_sum = kFold ? 0.5f * p.alpha : p.alpha;      // m3 is held as 2 * GELU
             if (nslots <= kSelSlots) {
                 float v[16];
                 tmem_ld16(t_row + (uint32_t)(b * 128), v);
@@ -338,7 +394,7 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
 #pragma unroll
                 for (int n = 0; n < 16; ++n)
                     if (n < nslots)
-                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + n * 128), "f"(v[n] * p.alpha) : "memory");
+                        asm volatile("red.global.add.f32 [%0], %1;" ::"l"(dst + n * 128), "f"(v[n] * alpha_sum) : "memory");
             }
             tc_fence_before();
         };
@@ -494,8 +550,13 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const float4 x = bs[q];
-                        add2(v[4 * q + 0], v[4 * q + 1], x.x, x.y);
-                        add2(v[4 * q + 2], v[4 * q + 3], x.z, x.w);
+                        if constexpr (kFold) {                 // the previous stage wrote 2 * GELU: v = acc / 2 + bias
+                            fma2_half(v[4 * q + 0], v[4 * q + 1], x.x, x.y);
+                            fma2_half(v[4 * q + 2], v[4 * q + 3], x.z, x.w);
+                        } else {
+                            add2(v[4 * q + 0], v[4 * q + 1], x.x, x.y);
+                            add2(v[4 * q + 2], v[4 * q + 3], x.z, x.w);
+                        }
                     }
                 }
                 uint32_t o[16];
@@ -516,9 +577,15 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
                                        v[4 * q + 2] * p.alpha, v[4 * q + 3] * p.alpha);
                     }
 #pragma unroll
-                    for (int q = 0; q < 16; ++q) o[q] = pack_bf16(v[2 * q], v[2 * q + 1]);
+                    for (int q = 0; q < 16; ++q)
+                        o[q] = kFold ? pack_bf16(2.f * v[2 * q], 2.f * v[2 * q + 1]) : pack_bf16(v[2 * q], v[2 * q + 1]);
                 } else {
-                    gelu_pack32(v, o);                             // packed bf16x2 GELU
+                    if constexpr (kFold) {
+#pragma unroll
+                        for (int q = 0; q < 16; ++q) o[q] = gelu2x_bf16x2(v[2 * q], v[2 * q + 1]);
+                    } else {
+                        gelu_pack32(v, o);                         // packed bf16x2 GELU
+                    }
                 }
                 stamp(500 + st * 10 + (i & 1));
                 if (last) {
@@ -624,7 +691,7 @@ node_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
 
     if (warp == 0) {
         // ===================== TMA producer: weight slabs [N rows][64 k] through the ring =====================
-        if (lane == 0) {
+        if (elect_one()) {
             for (int s = 0; s < S; ++s) tma_prefetch_desc(maps[s]);
             uint32_t n = 0;
             for (int i = 0; i < my_tiles; ++i)
@@ -639,7 +706,7 @@ node_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constan
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t n = 0, ph_act = 0;
             const uint32_t a_addr = smem_u32(sA);
             for (int i = 0; i < my_tiles; ++i)
@@ -879,6 +946,13 @@ extern "C" int rmp_edge_mlp_bf16_traced(const void* h_E_bf16, const void* W_bf16
                                         const int32_t* ctr, const int32_t* nbr, const int32_t* row_ptr, int n_edges,
                                         float alpha, float* agg, float* debug, long long* timeline, void* stream);
 
+// tuning hooks (scripts/edge_variants.py): epilogue variant (template) and producer / issuer flags of the edge kernel
+static int g_edge_variant = 1, g_edge_flags = 3;
+static bool g_edge_tuning_set = false;
+extern "C" void rmp_set_edge_tuning(int variant, int flags) {
+    g_edge_variant = variant; g_edge_flags = flags; g_edge_tuning_set = true;
+}
+
 extern "C" int rmp_edge_mlp_bf16(const void* h_E_bf16, const void* W_bf16, int num_stages, const float* const* bias,
                                  const float* Pc, const void* Pn_bf16, const int32_t* ctr, const int32_t* nbr,
                                  const int32_t* row_ptr, int n_edges, float alpha, float* agg, float* debug,
@@ -924,8 +998,21 @@ extern "C" int rmp_edge_mlp_bf16_traced(const void* h_E_bf16, const void* W_bf16
         cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         kernel<<<grid, tc::kEdgeThreads, smem, (cudaStream_t)stream>>>(tm_e, tm_w, p);
     };
-    if (timeline) { if (decoupled) launch(tc::edge_mlp_tc_kernel<true, true>); else launch(tc::edge_mlp_tc_kernel<true, false>); }
-    else { if (decoupled) launch(tc::edge_mlp_tc_kernel<false, true>); else launch(tc::edge_mlp_tc_kernel<false, false>); }
+    if (!g_edge_tuning_set) {                        // RMP_EDGE_TUNING="<variant>,<flags>" (tuning aid)
+        g_edge_tuning_set = true;
+        if (const char* e = getenv("RMP_EDGE_TUNING")) sscanf(e, "%d,%d", &g_edge_variant, &g_edge_flags);
+    }
+    p.flags = g_edge_flags;
+    const int v = g_edge_variant & 1;
+    if (timeline) {
+        if (decoupled) launch(tc::edge_mlp_tc_kernel<true, true>);
+        else if (v == 1) launch(tc::edge_mlp_tc_kernel<true, false, 1>);
+        else launch(tc::edge_mlp_tc_kernel<true, false>);
+    } else {
+        if (decoupled) launch(tc::edge_mlp_tc_kernel<false, true>);
+        else if (v == 1) launch(tc::edge_mlp_tc_kernel<false, false, 1>);
+        else launch(tc::edge_mlp_tc_kernel<false, false>);
+    }
     return check_launch("rmp_edge_mlp_bf16");
 }
 

@@ -117,7 +117,7 @@ row_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
 
     if (warp == 0) {
         // ===================== TMA producer: weight slabs [128 rows][64 k] through the ring =====================
-        if (lane == 0) {
+        if (elect_one()) {
             for (int s = 0; s < S; ++s) tma_prefetch_desc(maps[s]);
             uint32_t n = 0;
             for (int i = 0; i < my_tiles; ++i)
@@ -133,7 +133,7 @@ row_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t n = 0, ph_act = 0;
             const uint32_t a_addr = smem_u32(sA);
             const uint32_t idesc = F16 ? instr_desc_f16(128, 128) : instr_desc_bf16(128, 128, 0);

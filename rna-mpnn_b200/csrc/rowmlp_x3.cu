@@ -140,7 +140,7 @@ row_mlp_x3_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
 
     if (warp == 0) {
         // ===================== TMA producer: per (k-block, column chunk) the hi slab, then the lo slab =====================
-        if (lane == 0) {
+        if (elect_one()) {
             for (int s = 0; s < S; ++s) tma_prefetch_desc(maps[s]);
             uint32_t n = 0;
             for (int i = 0; i < my_tiles; ++i)
@@ -158,7 +158,7 @@ row_mlp_x3_kernel(const __grid_constant__ CUtensorMap tm0, const __grid_constant
         __syncwarp();
     } else if (warp == 1) {
         // ===================== MMA issuer =====================
-        if (lane == 0) {
+        if (elect_one()) {
             uint32_t n = 0, ph_act = 0;
             const uint32_t hi_addr = smem_u32(sAhi), lo_addr = smem_u32(sAlo);
             const uint32_t idesc = instr_desc_bf16(128, 128, 0);

@@ -44,6 +44,21 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         "r"(parity)
         : "memory");
 }
+// One thread of a CONVERGED warp (elect.sync).  With `if (lane == 0)` ptxas cannot tell that a single thread is active and
+// wraps every warp-level instruction (UTCHMMA, UTMALDG, UTCBAR) in an ELECT / BRA.U.ANY loop over the active lanes: ~80
+// cycles per tcgen05.mma in the issuing thread (700-1,100 per 8-step GEMM, profiles/r2_edge_issue_cost.txt); with the
+// elect.sync predicate the instructions are emitted back to back.
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }

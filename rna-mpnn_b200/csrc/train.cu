@@ -296,7 +296,7 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant_
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             tma_prefetch_desc(&tm_dz); tma_prefetch_desc(&tm_x);
             for (int i = 0; i < my_tiles; ++i) {
                 const int st = i % kDwStages;
@@ -311,7 +311,7 @@ gemm_dw_kernel(const __grid_constant__ CUtensorMap tm_dz, const __grid_constant_
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             constexpr uint32_t idesc = instr_desc_bf16(128, 128, 1) | (1u << 15);     // A and B MN-major
             for (int i = 0; i < my_tiles; ++i) {
                 const int st = i % kDwStages;
@@ -409,7 +409,7 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     tc_fence_after();
     const uint32_t tmem_base = *s_tmem;
     if (warp == 0) {
-        if (lane == 0) {
+        if (elect_one()) {
             tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_w);
             mbar_expect_tx(&bars->w_full, kTileBytes);
             for (int kb = 0; kb < 2; ++kb) tma_load_2d(sW + kb * kKBlockBytes, &tm_w, &bars->w_full, kb * 64, 0);
@@ -424,7 +424,7 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
         }
         __syncwarp();
     } else if (warp == 1) {
-        if (lane == 0) {
+        if (elect_one()) {
             const uint32_t idesc = instr_desc_bf16(128, 128, p.w_mn_major);
             mbar_wait(&bars->w_full, 0);
             for (int i = 0; i < my_tiles; ++i) {

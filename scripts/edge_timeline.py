@@ -61,7 +61,7 @@ for g in range(2):
 m = t[32016]
 print("MMA thread issues (tile+1)*1000+stage, cycle, delta:")
 prev = None
-for i in range(min(m, 60)):
+for i in range(min(m, 120)):
     tag, ts = t[25600 + 2 * i], t[25601 + 2 * i]
     print(tag, ts - t0, (ts - prev) if prev is not None else 0)
     prev = ts
