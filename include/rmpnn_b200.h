@@ -370,6 +370,12 @@ int rmp_gemm_rows_bf16(const void* A_bf16, const void* W_bf16, const float* bias
                        int w_ld /* elements per row of the matrix W is a 128x128 window of; 0 = 128 */,
                        int w_transposed /* Z = A W instead of A W^T: backward-data without a transposed copy */,
                        float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t stream_id, void* stream);
+/* out32 = sum_l A_l W_l^T (or A_l W_l with w_transposed), l < k_blocks:   A bf16 [k_blocks][rows][128], W bf16 [k_blocks][128][128],
+ * out32 fp32 [rows,128], OVERWRITTEN.  One pass over the K-concatenated operands (W_l streamed with A_l through the TMA ring):
+ * the backward of the edge embedding needs d h_E = sum over the layers of dZ0_l W1e_l (rdesign/model/rdesign.py:85 feeds the
+ * same h_E to every layer); accumulating it layer by layer re-reads and re-writes the fp32 [Ne,128] buffer nine times. */
+int rmp_gemm_rows_kcat_bf16(const void* A_bf16, const void* W_bf16, int k_blocks, float* out32, int rows, int w_transposed,
+                            void* stream);
 /* Reference Normalize (rdesign/model/functional.py:79-96) over 128 channels for the training path:
  *   forward   y_bf16 = gain * (x - mu) / (sqrt(var_unbiased + eps) + eps) + bias            x fp32 [rows,128]
  *   backward  dx_bf16 from dy fp32; dgain[128] += sum dy * xhat, dbias[128] += sum dy, dbsum[128] += sum dx */

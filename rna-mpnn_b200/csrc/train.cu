@@ -380,6 +380,11 @@ struct GrParams {
     int rows;
     uint32_t thresh16; float keep_scale; uint64_t seed; const uint64_t* seed_dev; uint32_t stream;
     int w_mn_major;                 // 1: W is used transposed (Z = A W): read MN-major, no transposed copy needed
+    // K-concatenated mode (k_blocks > 1): Z = sum_l A_l W_l with A = [k_blocks][a_block_rows][128] and W = [k_blocks][128][128];
+    // W_l travels through the ring with A_l (the slots are the resident-W buffer and the two staging buffers, which the
+    // mode does not use: its only output is acc32)
+    int k_blocks, a_block_rows;
+    int acc32_store;                // 1: acc32 = Z (no read-modify-write)
 };
 
 __global__ void __launch_bounds__(kGrThreads, 1)
@@ -410,7 +415,27 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
     const uint32_t tmem_base = *s_tmem;
     if (warp == 0) {
         if (elect_one()) {
+            bool my_tiles_done = false;
             tma_prefetch_desc(&tm_a); tma_prefetch_desc(&tm_w);
+            if (p.k_blocks > 1) {
+                uint32_t n = 0;
+                for (int i = 0; i < my_tiles; ++i) {
+                    const int tile = blockIdx.x + i * gridDim.x;
+                    for (int l = 0; l < p.k_blocks; ++l, ++n) {
+                        const int st = (int)(n % kGrStages);
+                        uint8_t* w_slot = st == 0 ? sW : (st == 1 ? sZ : sAct);
+                        mbar_wait(&bars->empty[st], ((n / kGrStages) & 1) ^ 1);
+                        mbar_expect_tx(&bars->full[st], 2 * kTileBytes);
+                        for (int kb = 0; kb < 2; ++kb) {
+                            tma_load_2d(sA + (size_t)st * kTileBytes + kb * kKBlockBytes, &tm_a, &bars->full[st], kb * 64,
+                                        l * p.a_block_rows + tile * kTileM);
+                            tma_load_2d(w_slot + kb * kKBlockBytes, &tm_w, &bars->full[st], kb * 64, l * 128);
+                        }
+                    }
+                }
+                my_tiles_done = true;
+            }
+            if (!my_tiles_done) {
             mbar_expect_tx(&bars->w_full, kTileBytes);
             for (int kb = 0; kb < 2; ++kb) tma_load_2d(sW + kb * kKBlockBytes, &tm_w, &bars->w_full, kb * 64, 0);
             for (int i = 0; i < my_tiles; ++i) {
@@ -421,11 +446,36 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 for (int kb = 0; kb < 2; ++kb)
                     tma_load_2d(sA + (size_t)st * kTileBytes + kb * kKBlockBytes, &tm_a, &bars->full[st], kb * 64, tile * kTileM);
             }
+            }
         }
         __syncwarp();
     } else if (warp == 1) {
         if (elect_one()) {
             const uint32_t idesc = instr_desc_bf16(128, 128, p.w_mn_major);
+            if (p.k_blocks > 1) {
+                uint32_t n = 0;
+                for (int i = 0; i < my_tiles; ++i) {
+                    const int ab = i & 1;
+                    mbar_wait(&bars->acc_empty[ab], ((i >> 1) & 1) ^ 1);
+                    for (int l = 0; l < p.k_blocks; ++l, ++n) {
+                        const int st = (int)(n % kGrStages);
+                        mbar_wait(&bars->full[st], (n / kGrStages) & 1);
+                        tc_fence_after();
+                        const uint32_t a_addr = smem_u32(sA + (size_t)st * kTileBytes);
+                        const uint32_t w_addr = smem_u32(st == 0 ? sW : (st == 1 ? sZ : sAct));
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            const uint32_t off = (uint32_t)((k >> 2) * kKBlockBytes + (k & 3) * 32);
+                            const uint64_t d_w = p.w_mn_major ? smem_desc_sw128(w_addr + (uint32_t)(k * 2048), kKBlockBytes, 1024)
+                                                              : smem_desc_sw128(w_addr + off, 16, 1024);
+                            umma_bf16(tmem_base + (uint32_t)(ab * 128), smem_desc_sw128(a_addr + off, 16, 1024), d_w, idesc,
+                                      (uint32_t)((l | k) > 0));
+                        }
+                        umma_commit(&bars->empty[st]);
+                    }
+                    umma_commit(&bars->acc_full[ab]);
+                }
+            } else {
             mbar_wait(&bars->w_full, 0);
             for (int i = 0; i < my_tiles; ++i) {
                 const int st = i % kGrStages, ab = i & 1;
@@ -444,6 +494,7 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
                 }
                 umma_commit(&bars->empty[st]);
                 umma_commit(&bars->acc_full[ab]);
+            }
             }
         }
         __syncwarp();
@@ -491,9 +542,14 @@ gemm_rows_kernel(const __grid_constant__ CUtensorMap tm_a, const __grid_constant
 #pragma unroll
                 for (int q = 0; q < 4; ++q) {
                     float t[8];
-                    ldg256f(dst + 8 * q, t);
+                    if (p.acc32_store) {
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) t[k] += v[8 * q + k];
+                        for (int k = 0; k < 8; ++k) t[k] = v[8 * q + k];
+                    } else {
+                        ldg256f(dst + 8 * q, t);
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) t[k] += v[8 * q + k];
+                    }
                     stg256f(dst + 8 * q, t);
                 }
             }
@@ -671,7 +727,7 @@ extern "C" int rmp_gemm_rows_bf16(const void* A_bf16, const void* W_bf16, const 
     p.bias = bias; p.Pc = reinterpret_cast<const uint16_t*>(Pc); p.Pn = reinterpret_cast<const uint16_t*>(Pn); p.ctr = ctr; p.nbr = nbr;
     p.z16 = reinterpret_cast<uint16_t*>(z_bf16); p.a16 = reinterpret_cast<uint16_t*>(a_bf16); p.acc32 = acc32; p.rows = rows;
     p.thresh16 = drop_threshold(p_drop); p.keep_scale = keep_scale_of(p_drop); p.seed = seed; p.seed_dev = seed_dev;
-    p.stream = stream_id; p.w_mn_major = w_transposed ? 1 : 0;
+    p.stream = stream_id; p.w_mn_major = w_transposed ? 1 : 0; p.k_blocks = 1;
     CUtensorMap tm_z, tm_act;
     memset(&tm_z, 0, sizeof(tm_z)); memset(&tm_act, 0, sizeof(tm_act));
     if (z_bf16) { rc = tc::make_map_bf16_rows128(&tm_z, z_bf16, (uint64_t)rows); if (rc) return rc; }
@@ -682,6 +738,31 @@ extern "C" int rmp_gemm_rows_bf16(const void* A_bf16, const void* W_bf16, const 
     const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
     train::gemm_rows_kernel<<<grid, train::kGrThreads, smem, (cudaStream_t)stream>>>(tm_a, tm_w, tm_z, tm_act, p);
     return check_launch("rmp_gemm_rows_bf16");
+}
+
+extern "C" int rmp_gemm_rows_kcat_bf16(const void* A_bf16, const void* W_bf16, int k_blocks, float* out32, int rows,
+                                       int w_transposed, void* stream) {
+    RMP_REQUIRE(A_bf16 && W_bf16 && out32 && rows >= 0, RMP_E_ARG, "rmp_gemm_rows_kcat_bf16: null pointer");
+    RMP_REQUIRE(k_blocks >= 2 && k_blocks <= 64, RMP_E_SHAPE, "rmp_gemm_rows_kcat_bf16: 2..64 K blocks");
+    RMP_REQUIRE((int64_t)k_blocks * rows < (int64_t)1 << 31, RMP_E_SHAPE, "rmp_gemm_rows_kcat_bf16: k_blocks * rows exceeds int32");
+    RMP_REQUIRE(aligned16(A_bf16) && aligned16(W_bf16) && aligned32(out32), RMP_E_ALIGN,
+                "rmp_gemm_rows_kcat_bf16: inputs 16-byte, output 32-byte aligned");
+    if (rows == 0) return RMP_OK;
+    CUtensorMap tm_a, tm_w, tm_z, tm_act;
+    int rc = tc::make_map_bf16_rows128(&tm_a, A_bf16, (uint64_t)k_blocks * (uint64_t)rows);
+    if (rc) return rc;
+    rc = tc::make_map_bf16_rows128(&tm_w, W_bf16, (uint64_t)k_blocks * 128);
+    if (rc) return rc;
+    memset(&tm_z, 0, sizeof(tm_z)); memset(&tm_act, 0, sizeof(tm_act));
+    train::GrParams p{};
+    p.acc32 = out32; p.acc32_store = 1; p.rows = rows; p.w_mn_major = w_transposed ? 1 : 0;
+    p.k_blocks = k_blocks; p.a_block_rows = rows; p.keep_scale = 1.f;
+    const size_t smem = 1024 + (size_t)(3 + train::kGrStages) * tc::kTileBytes + sizeof(train::GrBarriers) + 16;
+    cudaFuncSetAttribute(train::gemm_rows_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    const int n_tiles = ceil_div(rows, tc::kTileM);
+    const int grid = n_tiles < kNumSMs ? n_tiles : kNumSMs;
+    train::gemm_rows_kernel<<<grid, train::kGrThreads, smem, (cudaStream_t)stream>>>(tm_a, tm_w, tm_z, tm_act, p);
+    return check_launch("rmp_gemm_rows_kcat_bf16");
 }
 
 extern "C" int rmp_normalize_fwd_bf16(const float* x, const float* gain, const float* bias, void* y_bf16, int rows, float eps,

@@ -537,11 +537,12 @@ def act_fwd(z16: torch.Tensor, p_drop: float, seed: int, stream_id: int, seed_de
 
 
 def act_bwd(z16, p_drop: float, seed: int, stream_id: int, da16=None, dagg=None, ctr=None, alpha: float = 1.0, db=None,
-            seed_dev=None):
+            seed_dev=None, out=None):
     """dz = da * mask/(1-p) * GELU'(z); da bf16, or gathered from dagg[ctr] * alpha; db [128] += column sums."""
-    _need_cuda(z16, da16, dagg, ctr, db)
+    _need_cuda(z16, da16, dagg, ctr, db, out)
     assert z16.dtype == torch.bfloat16 and z16.is_contiguous() and z16.shape[1] == 128
-    dz = torch.empty_like(z16)
+    dz = torch.empty_like(z16) if out is None else out
+    assert dz.dtype == torch.bfloat16 and dz.is_contiguous() and dz.shape == z16.shape
     check(lib().rmp_act_bwd_bf16(_ptr(z16), _ptr(da16), _ptr(dagg), _ptr(ctr), float(alpha), _ptr(dz), _ptr(db),
                                  z16.shape[0], float(p_drop), int(seed), _ptr(seed_dev), int(stream_id), _stream()), "rmp_act_bwd_bf16")
     return dz
@@ -591,6 +592,21 @@ def gemm_rows(a16, w16, bias=None, Pc=None, Pn=None, ctr=None, nbr=None, want_z=
                                    _ptr(acc32), rows, int(w16.stride(0)), int(w_transposed), float(p_drop), int(seed), _ptr(seed_dev), int(sid), _stream()),
           "rmp_gemm_rows_bf16")
     return z, a
+
+
+def gemm_rows_kcat(a16, w16, w_transposed=False, out=None):
+    """out = sum_l a16[l] @ w16[l]^T (or a16[l] @ w16[l] with ``w_transposed``): a16 bf16 [L,rows,128], w16 bf16 [L,128,128]
+    -> fp32 [rows,128] in one pass (rmp_gemm_rows_kcat_bf16)."""
+    _need_cuda(a16, w16, out)
+    assert a16.dtype == w16.dtype == torch.bfloat16 and a16.is_contiguous() and w16.is_contiguous()
+    L, rows = a16.shape[0], a16.shape[1]
+    assert a16.shape[2] == 128 and tuple(w16.shape) == (L, 128, 128) and L >= 2
+    if out is None:
+        out = torch.empty(rows, 128, dtype=torch.float32, device=a16.device)
+    assert out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (rows, 128)
+    check(lib().rmp_gemm_rows_kcat_bf16(_ptr(a16), _ptr(w16), L, _ptr(out), rows, int(w_transposed), _stream()),
+          "rmp_gemm_rows_kcat_bf16")
+    return out
 
 
 def normalize_fwd(x, gain, bias, eps: float = 1e-6):

@@ -7,7 +7,7 @@ gradient all-reduce (Lightning DDP), Adam (rdesign.py:90-93).  Here:
   ``scatter_sum / scale`` and their backward (96 % of the step's flops and bytes) -- runs on the C-ABI kernels:
   the lean tcgen05 row GEMM ``rmp_gemm_rows_bf16`` (GELU + Dropout fused into its forward epilogue), the
   weight-gradient GEMM ``rmp_gemm_dw_bf16``, and the HBM-bound activation-backward / scatter passes of ``csrc/train.cu``; dropout masks are regenerated from Philox, never stored;
-  ``d h_E`` is accumulated over the layers in one fp32 buffer by the GEMM epilogue;
+  ``d h_E`` = sum over the layers of ``dz0_l W1e_l`` is ONE K-concatenated GEMM (``rmp_gemm_rows_kcat_bf16``) over the saved ``dz0_l``;
 * the per-NODE remainder (LayerNorms, the dense FFN on [Nv,128] rows, readout, loss) is composed from torch-CUDA ops
   under bf16 autocast -- 4 % of the work, Nv rows instead of Ne;
 * gradients live in ONE flat fp32 buffer; ``step`` all-reduces it with a single NCCL call on a side stream and applies
@@ -34,7 +34,7 @@ class EdgeMessageFn(torch.autograd.Function):
     """agg[v] = sum_{e: ctr[e]=v} Dropout(GELU(W3 Dropout(GELU(W2 Dropout(GELU(W1 [h_E|h_V[ctr]|h_V[nbr]]+b1))+b2))+b3)) / scale
     (rdesign/model/rdesign.py:85 + rdesign/model/mpnn.py:33-34).  W1 = [W1e | W1c | W1n]: the h_V part is applied per
     node (Pc = h_V W1c^T + b1, Pn = h_V W1n^T) and gathered in the GEMM epilogue.  ``token`` orders the edge-embedding
-    backward behind every layer; d h_E goes to ``state['dhE']`` (fp32, accumulated over the layers by the GEMM).
+    backward behind every layer; the layer's ``dz0`` goes to ``state['dz0_all'][layer]`` (d h_E is formed from them, once).
     ``state['w16'](param)`` is the parameter's view in the step's bf16 copy of the flat parameter buffer."""
 
     @staticmethod
@@ -70,9 +70,9 @@ class EdgeMessageFn(torch.autograd.Function):
         dz1 = ops.act_bwd(z1, p, seed, sid + 1, da16=da1, db=db[1], seed_dev=sd)
         ops.gemm_dw(dz1, a0, dW[1])
         da0, _ = ops.gemm_rows(dz1, w16(W2), w_transposed=True)
-        dz0 = ops.act_bwd(z0, p, seed, sid, da16=da0, db=db[0], seed_dev=sd)
+        # dz0 of every layer is kept: d h_E = sum_l dz0_l W1e_l is ONE K-concatenated GEMM in the edge embedding's backward
+        dz0 = ops.act_bwd(z0, p, seed, sid, da16=da0, db=db[0], seed_dev=sd, out=state["dz0_all"][state["layer"]])
         ops.gemm_dw(dz0, hE16, dW[2])
-        ops.gemm_rows(dz0, W1h[:, :128], want_z=False, acc32=state["dhE"], w_transposed=True)      # d h_E += dz0 W1e
         ops.segment_sum_rows(dz0, g.row_ptr[:g.Nv + 1], dP[0])
         ops.scatter_add_rows(dz0, g.nbr, dP[1])
         dP16 = dP.to(torch.bfloat16)
@@ -83,7 +83,7 @@ class EdgeMessageFn(torch.autograd.Function):
 
 class EdgeEmbedFn(torch.autograd.Function):
     """h_E = Normalize(edge_raw W^T + b) (rdesign/model/feature.py:224) -> bf16 rows for the layers; its backward
-    consumes the d h_E accumulated by the layers (not a tensor gradient: the bf16 copy is never differentiated)."""
+    forms d h_E from the layers' saved ``dz0`` (not a tensor gradient: the bf16 copy is never differentiated)."""
 
     @staticmethod
     def forward(ctx, W, b, gain, beta, state):
@@ -100,7 +100,13 @@ class EdgeEmbedFn(torch.autograd.Function):
     def backward(ctx, _dtoken):
         z, W, gain, beta = ctx.saved_tensors
         state = ctx.state
-        dz16, dgain, dbeta, db = ops.normalize_bwd(z, state["dhE"], gain.detach())
+        dz0_all, w1e_all = state["dz0_all"], state["w1e_all"]
+        if dz0_all.shape[0] >= 2:                                  # d h_E = sum_l dz0_l W1e_l: one pass, K = 128 L
+            dhE = ops.gemm_rows_kcat(dz0_all, w1e_all, w_transposed=True)
+        else:
+            dhE = torch.zeros(dz0_all.shape[1], 128, dtype=torch.float32, device=W.device)
+            ops.gemm_rows(dz0_all[0], w1e_all[0], want_z=False, acc32=dhE, w_transposed=True)
+        dz16, dgain, dbeta, db = ops.normalize_bwd(z, dhE, gain.detach())
         dW = torch.zeros(128, 128, dtype=torch.float32, device=W.device)
         ops.gemm_dw(dz16, state["edge_raw16"], dW)
         return dW[:, :W.shape[1]].contiguous(), db, dgain, dbeta, None
@@ -216,7 +222,10 @@ class RDesignTrainer:
         state: Dict = {"graph": g, "p_drop": self.p_drop, "seed": seed, "scale": float(m.mpnn_layers[0].scale),
                        "w16": self._w16, "seed_dev": self.seed_dev}
         state["edge_raw16"] = F.pad(edge_raw, (0, 128 - edge_raw.shape[1])).to(torch.bfloat16).contiguous()
-        state["dhE"] = torch.zeros(g.Ne, 128, dtype=torch.float32, device=X.device)
+        n_layers = len(m.mpnn_layers)
+        state["dz0_all"] = torch.empty(n_layers, g.Ne, 128, dtype=torch.bfloat16, device=X.device)
+        state["w1e_all"] = torch.stack([self._w16([x for x in layer.message_layers if isinstance(x, torch.nn.Linear)][0].weight)[:, :128]
+                                        for layer in m.mpnn_layers]).contiguous()
         del edge_raw
         S_valid = S.reshape(B * N)[g.node_src[:g.Nv].long()]
         token = EdgeEmbedFn.apply(f.edge_embedding.weight, f.edge_embedding.bias, f.norm_edges.gain, f.norm_edges.bias, state)
@@ -226,8 +235,7 @@ class RDesignTrainer:
         h_V = f.norm_nodes(f.node_embedding(node_raw))             # [Nv,128] fp32, torch (node level)
         for l, layer in enumerate(m.mpnn_layers):
             lin = [x for x in layer.message_layers if isinstance(x, torch.nn.Linear)]
-            st = dict(state, stream_id=16 * l)
-            st["dhE"] = state["dhE"]
+            st = dict(state, stream_id=16 * l, layer=l)
             agg = EdgeMessageFn.apply(h_V, token, lin[0].weight, lin[0].bias, lin[1].weight, lin[1].bias, lin[2].weight,
                                       lin[2].bias, st)
             if self.autocast:

@@ -166,6 +166,21 @@ def test_gemm_rows_outputs(rows):
     np.testing.assert_allclose(z2.float().cpu().numpy(), _bf(A.float() @ W.float().t()).cpu().numpy(), atol=3e-2, rtol=1e-2)
 
 
+@pytest.mark.parametrize("rows,L,transposed", [(1, 2, True), (130, 3, False), (5000, 9, True), (20000, 9, True)])
+def test_gemm_rows_kcat_matches_sum_of_products(rows, L, transposed):
+    """K-concatenated row GEMM (d h_E = sum over the layers of dz0_l W1e_l): one pass, fp32 output overwritten; a tile of
+    block l that runs past its rows reads block l + 1's first rows, which must only reach output rows that are not stored."""
+    from rmpnn_b200 import ops
+    g = torch.Generator().manual_seed(rows + L)
+    A = torch.randn(L, rows, 128, generator=g).cuda().to(torch.bfloat16)
+    W = (torch.randn(L, 128, 128, generator=g) / 11.3).cuda().to(torch.bfloat16)
+    out = torch.full((rows, 128), 7.0, device="cuda")
+    got = ops.gemm_rows_kcat(A, W, w_transposed=transposed, out=out)
+    assert got is out
+    ref = sum(A[l].float() @ (W[l].float() if transposed else W[l].float().t()) for l in range(L))
+    np.testing.assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), atol=2e-3 * L ** 0.5, rtol=1e-4)
+
+
 def test_normalize_fwd_bwd_match_autograd():
     from rmpnn_b200 import ops
     from rmpnn_b200.train_engine import _normalize
