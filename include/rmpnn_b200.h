@@ -370,6 +370,11 @@ int rmp_gemm_rows_bf16(const void* A_bf16, const void* W_bf16, const float* bias
                        int w_ld /* elements per row of the matrix W is a 128x128 window of; 0 = 128 */,
                        int w_transposed /* Z = A W instead of A W^T: backward-data without a transposed copy */,
                        float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t stream_id, void* stream);
+/* Column sums over the rows of a [rows,width] matrix, ADDED to the outputs (bias / LayerNorm parameter gradients of the per-node
+ * modules, rdesign/model/mpnn.py:11-12,20-28):  s0[c] += sum_r a[r][c];  with x (fp32), mean, rstd [rows]:
+ * s1[c] += sum_r a[r][c] (x[r][c] - mean[r]) rstd[r].   a fp32 or bf16; width = 4 * (a divisor of 256). */
+int rmp_colsum(const void* a, int a_is_bf16, const float* x, const float* mean, const float* rstd, int rows, int width, float* s0,
+               float* s1, void* stream);
 /* out32 = sum_l A_l W_l^T (or A_l W_l with w_transposed), l < k_blocks:   A bf16 [k_blocks][rows][128], W bf16 [k_blocks][128][128],
  * out32 fp32 [rows,128], OVERWRITTEN.  One pass over the K-concatenated operands (W_l streamed with A_l through the TMA ring):
  * the backward of the edge embedding needs d h_E = sum over the layers of dZ0_l W1e_l (rdesign/model/rdesign.py:85 feeds the

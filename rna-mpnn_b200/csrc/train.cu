@@ -141,6 +141,50 @@ __global__ void __launch_bounds__(256) scatter_add_kernel(const uint4* __restric
     tc::red_add_v4(dst + 4, bf_lo(xi.z), bf_hi(xi.z), bf_lo(xi.w), bf_hi(xi.w));
 }
 
+// Column sums over the rows of a [rows, width] matrix (bias gradients of the per-node Linear / LayerNorm modules):
+//   s0[c] += sum_r a[r][c]                                     a fp32 or bf16
+//   s1[c] += sum_r a[r][c] * (x[r][c] - mean[r]) * rstd[r]     (x fp32, optional: the LayerNorm weight gradient)
+// Thread = 4 consecutive columns x a row lane; per-block partial sums through shared memory, one red per column and block.
+template <bool A_BF16>
+__global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ a_, const float* __restrict__ x,
+                                                     const float* __restrict__ mean, const float* __restrict__ rstd, int rows,
+                                                     int width, int rows_per_block, float* __restrict__ s0,
+                                                     float* __restrict__ s1) {
+    __shared__ float4 sh[2][256];
+    const int ncg = width >> 2;                                  // column groups of 4: 32 (width 128) .. 64 (width 256)
+    const int cg = threadIdx.x % ncg, rl = threadIdx.x / ncg, nrl = 256 / ncg;
+    float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0;
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    for (int r = r0 + rl; r < r1; r += nrl) {
+        float4 v;
+        if constexpr (A_BF16) {
+            const uint2 w = reinterpret_cast<const uint2*>(a_)[(size_t)r * ncg + cg];
+            v = make_float4(bf_lo(w.x), bf_hi(w.x), bf_lo(w.y), bf_hi(w.y));
+        } else {
+            v = reinterpret_cast<const float4*>(a_)[(size_t)r * ncg + cg];
+        }
+        t0.x += v.x; t0.y += v.y; t0.z += v.z; t0.w += v.w;
+        if (x) {
+            const float4 xv = reinterpret_cast<const float4*>(x)[(size_t)r * ncg + cg];
+            const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
+            t1.x += v.x * ((xv.x - mu) * rs); t1.y += v.y * ((xv.y - mu) * rs);
+            t1.z += v.z * ((xv.z - mu) * rs); t1.w += v.w * ((xv.w - mu) * rs);
+        }
+    }
+    sh[0][threadIdx.x] = t0; sh[1][threadIdx.x] = t1;
+    __syncthreads();
+    if (threadIdx.x < ncg) {
+        float4 u0 = make_float4(0.f, 0.f, 0.f, 0.f), u1 = u0;
+        for (int k = 0; k < nrl; ++k) {
+            const float4 p0 = sh[0][k * ncg + threadIdx.x], p1 = sh[1][k * ncg + threadIdx.x];
+            u0.x += p0.x; u0.y += p0.y; u0.z += p0.z; u0.w += p0.w;
+            u1.x += p1.x; u1.y += p1.y; u1.z += p1.z; u1.w += p1.w;
+        }
+        tc::red_add_v4(s0 + 4 * threadIdx.x, u0.x, u0.y, u0.z, u0.w);
+        if (x) tc::red_add_v4(s1 + 4 * threadIdx.x, u1.x, u1.y, u1.z, u1.w);
+    }
+}
+
 // out[v, :] = sum of the rows row_ptr[v] .. row_ptr[v+1]-1 of x (bf16 [rows,128]; the edges of a node are contiguous,
 // SURVEY section 8a a-2): the scatter_sum by CENTRE node without atomics.  Half a warp per node: lane = 8 columns (one
 // 16-byte load per row), rows summed in order in fp32 -> deterministic; one pass over x at HBM rate where the red.global
@@ -662,6 +706,23 @@ extern "C" int rmp_segment_sum_rows(const void* x_bf16, const int32_t* row_ptr, 
     train::segment_sum_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const uint4*>(x_bf16), row_ptr, out, n_seg);
     return check_launch("rmp_segment_sum_rows");
+}
+
+extern "C" int rmp_colsum(const void* a, int a_is_bf16, const float* x, const float* mean, const float* rstd, int rows, int width,
+                          float* s0, float* s1, void* stream) {
+    RMP_REQUIRE(a && s0 && rows >= 0, RMP_E_ARG, "rmp_colsum: null pointer");
+    RMP_REQUIRE((x == nullptr) == (s1 == nullptr) && (!x || (mean && rstd)), RMP_E_ARG, "rmp_colsum: x, mean, rstd, s1 go together");
+    RMP_REQUIRE(width >= 4 && width <= 1024 && width % 4 == 0 && 256 % (width / 4) == 0, RMP_E_SHAPE,
+                "rmp_colsum: width must be 4 * (a divisor of 256), got %d", width);
+    RMP_REQUIRE(aligned16(a) && aligned16(s0) && (!x || (aligned16(x) && aligned16(s1))), RMP_E_ALIGN, "rmp_colsum: 16-byte alignment");
+    if (rows == 0) return RMP_OK;
+    const int rows_per_block = 64;
+    const unsigned grid = (unsigned)ceil_div(rows, rows_per_block);
+    if (a_is_bf16)
+        train::colsum_kernel<true><<<grid, 256, 0, (cudaStream_t)stream>>>(a, x, mean, rstd, rows, width, rows_per_block, s0, s1);
+    else
+        train::colsum_kernel<false><<<grid, 256, 0, (cudaStream_t)stream>>>(a, x, mean, rstd, rows, width, rows_per_block, s0, s1);
+    return check_launch("rmp_colsum");
 }
 
 extern "C" int rmp_adam_step(float* param, const float* grad, float* exp_avg, float* exp_avg_sq, int64_t n, float grad_scale,

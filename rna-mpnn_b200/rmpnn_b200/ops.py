@@ -594,6 +594,22 @@ def gemm_rows(a16, w16, bias=None, Pc=None, Pn=None, ctr=None, nbr=None, want_z=
     return z, a
 
 
+def colsum(a, x=None, mean=None, rstd=None):
+    """Column sums of ``a`` [rows,width] (fp32 or bf16) -> fp32 [width]; with ``x`` (fp32), ``mean``, ``rstd`` [rows] also the
+    sums of ``a * (x - mean) * rstd`` (LayerNorm weight gradient).  Returns (s0, s1 | None).  rmp_colsum."""
+    _need_cuda(a, x, mean, rstd)
+    assert a.dim() == 2 and a.is_contiguous() and a.dtype in (torch.float32, torch.bfloat16)
+    rows, width = a.shape
+    out = torch.zeros(2 if x is not None else 1, width, dtype=torch.float32, device=a.device)
+    if x is not None:
+        assert x.dtype == torch.float32 and x.is_contiguous() and x.shape == a.shape
+        mean, rstd = mean.reshape(-1), rstd.reshape(-1)
+        assert mean.dtype == rstd.dtype == torch.float32 and mean.is_contiguous() and rstd.is_contiguous() and mean.numel() == rows
+    check(lib().rmp_colsum(_ptr(a), int(a.dtype == torch.bfloat16), _ptr(x), _ptr(mean), _ptr(rstd), rows, width, _ptr(out[0]),
+                           _ptr(out[1]) if x is not None else None, _stream()), "rmp_colsum")
+    return out[0], (out[1] if x is not None else None)
+
+
 def gemm_rows_kcat(a16, w16, w_transposed=False, out=None):
     """out = sum_l a16[l] @ w16[l]^T (or a16[l] @ w16[l] with ``w_transposed``): a16 bf16 [L,rows,128], w16 bf16 [L,128,128]
     -> fp32 [rows,128] in one pass (rmp_gemm_rows_kcat_bf16)."""

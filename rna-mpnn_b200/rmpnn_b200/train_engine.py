@@ -113,9 +113,9 @@ class EdgeEmbedFn(torch.autograd.Function):
 
 
 class LayerNormFn(torch.autograd.Function):
-    """``nn.LayerNorm`` over the last dimension (rdesign/model/mpnn.py:11-12, :35, :37) with the weight / bias gradients as two
-    ``[1,Nv] x [Nv,128]`` products: torch's ``GammaBetaBackward`` kernel takes 75 us per call on [16384,128] (1.35 ms of the
-    C4 step), the products 10 us."""
+    """``nn.LayerNorm`` over the last dimension (rdesign/model/mpnn.py:11-12, :35, :37) with the weight / bias gradients as one
+    column-sum pass (``rmp_colsum``): torch's ``GammaBetaBackward`` kernel takes 75 us per call on [16384,128] (1.35 ms of the
+    C4 step), two ``[1,Nv] x [Nv,128]`` split-K products plus the ``xhat`` elementwise kernels 40 us, the pass 4 us."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, eps):
@@ -131,15 +131,13 @@ class LayerNormFn(torch.autograd.Function):
         with torch.autocast("cuda", enabled=False):
             dx = torch.ops.aten.native_layer_norm_backward(dy, x, [x.shape[-1]], mean, rstd, weight, None,
                                                            [True, False, False])[0]
-            ones = dy.new_ones(1, dy.shape[0])
-            dw = (ones @ (dy * ((x - mean) * rstd))).reshape(-1)
-            db = (ones @ dy).reshape(-1)
+            db, dw = ops.colsum(dy, x, mean, rstd)                 # one pass: sum dy, sum dy * xhat
         return dx, dw, db, None
 
 
 class LinearFn(torch.autograd.Function):
-    """``nn.Linear`` of the per-node FFN on the bf16 tensor cores (what bf16 autocast computes), the bias gradient as a
-    ``[1,Nv] x [Nv,N]`` product instead of a column reduction kernel (25 us per call, 37 calls per step)."""
+    """``nn.Linear`` of the per-node FFN on the bf16 tensor cores (what bf16 autocast computes), the bias gradient as one
+    ``rmp_colsum`` pass (torch's column reduction kernel: 25 us per call, a split-K ``[1,Nv] x [Nv,N]`` product: 14 us)."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, w16):
@@ -154,7 +152,7 @@ class LinearFn(torch.autograd.Function):
         with torch.autocast("cuda", enabled=False):
             dx = dy @ w16
             dw = (dy.t() @ x16).float()
-            db = (dy.new_ones(1, dy.shape[0]) @ dy).float().reshape(-1)
+            db = ops.colsum(dy)[0]
         return dx, dw, db, None
 
 

@@ -181,6 +181,26 @@ def test_gemm_rows_kcat_matches_sum_of_products(rows, L, transposed):
     np.testing.assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), atol=2e-3 * L ** 0.5, rtol=1e-4)
 
 
+@pytest.mark.parametrize("rows,width,bf16", [(1, 128, False), (1000, 128, True), (16384, 256, True), (777, 256, False)])
+def test_colsum_matches_torch(rows, width, bf16):
+    """Column sums (bias gradients) and the LayerNorm weight-gradient sums of the per-node modules in one pass."""
+    from rmpnn_b200 import ops
+    g = torch.Generator().manual_seed(rows + width)
+    a = torch.randn(rows, width, generator=g).cuda()
+    if bf16:
+        a = a.to(torch.bfloat16)
+    s0, s1 = ops.colsum(a)
+    assert s1 is None
+    np.testing.assert_allclose(s0.cpu().numpy(), a.double().sum(0).cpu().numpy(), atol=2e-3 * max(1.0, rows ** 0.5), rtol=1e-4)
+    if not bf16:
+        x = (2 * torch.randn(rows, width, generator=g) + 1).cuda()
+        y, mean, rstd = torch.native_layer_norm(x, (width,), None, None, 1e-5)
+        s0, s1 = ops.colsum(a, x, mean, rstd)
+        ref = (a.double() * ((x.double() - mean.double()) * rstd.double())).sum(0)
+        np.testing.assert_allclose(s1.cpu().numpy(), ref.cpu().numpy(), atol=2e-3 * max(1.0, rows ** 0.5), rtol=1e-4)
+        np.testing.assert_allclose(s0.cpu().numpy(), a.double().sum(0).cpu().numpy(), atol=2e-3 * max(1.0, rows ** 0.5), rtol=1e-4)
+
+
 def test_normalize_fwd_bwd_match_autograd():
     from rmpnn_b200 import ops
     from rmpnn_b200.train_engine import _normalize
