@@ -370,6 +370,14 @@ int rmp_gemm_rows_bf16(const void* A_bf16, const void* W_bf16, const float* bias
                        int w_ld /* elements per row of the matrix W is a 128x128 window of; 0 = 128 */,
                        int w_transposed /* Z = A W instead of A W^T: backward-data without a transposed copy */,
                        float p_drop, uint64_t seed, const uint64_t* seed_dev, uint32_t stream_id, void* stream);
+/* nn.LayerNorm over 128 channels with the residual add in front of it (rdesign/model/mpnn.py:35 norm1(h_V + dh), :37
+ * norm2(h_V + dh)), training path:
+ *   forward   x = a + b (b fp32 or bf16, may be NULL: x = a, x_out untouched);  y = gamma (x - mean) rstd + beta;  mean, rstd [rows]
+ *   backward  dx (fp32, and optionally a bf16 copy) from dy;  dgamma[128] += sum dy xhat;  dbeta[128] += sum dy */
+int rmp_add_layernorm_fwd(const float* a, const void* b, int b_is_bf16, const float* gamma, const float* beta, float eps, int rows,
+                          float* x_out, float* y, float* mean, float* rstd, void* stream);
+int rmp_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, int rows, float* dx,
+                      void* dx_bf16, float* dgamma, float* dbeta, void* stream);
 /* Column sums over the rows of a [rows,width] matrix, ADDED to the outputs (bias / LayerNorm parameter gradients of the per-node
  * modules, rdesign/model/mpnn.py:11-12,20-28):  s0[c] += sum_r a[r][c];  with x (fp32), mean, rstd [rows]:
  * s1[c] += sum_r a[r][c] (x[r][c] - mean[r]) rstd[r].   a fp32 or bf16; width = 4 * (a divisor of 256). */

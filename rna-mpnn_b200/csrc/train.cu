@@ -141,6 +141,80 @@ __global__ void __launch_bounds__(256) scatter_add_kernel(const uint4* __restric
     tc::red_add_v4(dst + 4, bf_lo(xi.z), bf_hi(xi.z), bf_lo(xi.w), bf_hi(xi.w));
 }
 
+// nn.LayerNorm over 128 channels with the residual add in front of it (rdesign/model/mpnn.py:35,37), training forward:
+//   x = a + b (b fp32 or bf16, optional) -> x_out (kept for the backward), y = gamma * (x - mean) * rstd + beta, mean, rstd.
+// One warp per row, one float4 per lane.
+template <bool B_BF16>
+__global__ void __launch_bounds__(256) add_ln_fwd_kernel(const float4* __restrict__ a, const void* __restrict__ b_,
+                                                         const float4* __restrict__ gamma, const float4* __restrict__ beta,
+                                                         float eps, int rows, float4* __restrict__ x_out, float4* __restrict__ y,
+                                                         float* __restrict__ mean, float* __restrict__ rstd) {
+    const int r = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+    if (r >= rows) return;
+    float4 v = a[(size_t)r * 32 + lane];
+    if (b_) {
+        if constexpr (B_BF16) {
+            const uint2 w = reinterpret_cast<const uint2*>(b_)[(size_t)r * 32 + lane];
+            v.x += bf_lo(w.x); v.y += bf_hi(w.x); v.z += bf_lo(w.y); v.w += bf_hi(w.y);
+        } else {
+            const float4 w = reinterpret_cast<const float4*>(b_)[(size_t)r * 32 + lane];
+            v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+        }
+        x_out[(size_t)r * 32 + lane] = v;
+    }
+    const float mu = warp_sum((v.x + v.y) + (v.z + v.w)) * (1.f / 128.f);
+    const float c0 = v.x - mu, c1 = v.y - mu, c2 = v.z - mu, c3 = v.w - mu;
+    const float var = warp_sum((c0 * c0 + c1 * c1) + (c2 * c2 + c3 * c3)) * (1.f / 128.f);
+    const float rs = 1.f / sqrtf(var + eps);
+    const float4 g = __ldg(gamma + lane), be = __ldg(beta + lane);
+    y[(size_t)r * 32 + lane] = make_float4(fmaf(g.x, c0 * rs, be.x), fmaf(g.y, c1 * rs, be.y), fmaf(g.z, c2 * rs, be.z),
+                                           fmaf(g.w, c3 * rs, be.w));
+    if (lane == 0) { mean[r] = mu; rstd[r] = rs; }
+}
+
+// LayerNorm backward in one pass: dx = rstd * (g - mean(g) - xhat * mean(g * xhat)) with g = dy * gamma, plus the parameter
+// gradients dgamma += sum dy * xhat, dbeta += sum dy (per-warp registers -> shared -> one red per column and block); dx16 is
+// an optional bf16 copy of dx (the gradient of a bf16 residual branch).
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float4* __restrict__ dy, const float4* __restrict__ x,
+                                                     const float* __restrict__ mean, const float* __restrict__ rstd,
+                                                     const float4* __restrict__ gamma, int rows, int rows_per_block,
+                                                     float4* __restrict__ dx, uint2* __restrict__ dx16,
+                                                     float* __restrict__ dgamma, float* __restrict__ dbeta) {
+    __shared__ float s_acc[2][8][128];
+    const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const float4 gm = __ldg(gamma + lane);
+    float ag[4] = {0.f, 0.f, 0.f, 0.f}, ab[4] = {0.f, 0.f, 0.f, 0.f};
+    const int r0 = blockIdx.x * rows_per_block, r1 = min(rows, r0 + rows_per_block);
+    for (int r = r0 + w; r < r1; r += 8) {
+        const float4 d = dy[(size_t)r * 32 + lane], v = x[(size_t)r * 32 + lane];
+        const float mu = __ldg(mean + r), rs = __ldg(rstd + r);
+        const float xh[4] = {(v.x - mu) * rs, (v.y - mu) * rs, (v.z - mu) * rs, (v.w - mu) * rs};
+        const float dd[4] = {d.x, d.y, d.z, d.w}, gg[4] = {gm.x, gm.y, gm.z, gm.w};
+        float g[4], t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            g[j] = dd[j] * gg[j]; t1 += g[j]; t2 += g[j] * xh[j];
+            ag[j] += dd[j] * xh[j]; ab[j] += dd[j];
+        }
+        t1 = warp_sum(t1) * (1.f / 128.f); t2 = warp_sum(t2) * (1.f / 128.f);
+        float o[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) o[j] = rs * (g[j] - t1 - xh[j] * t2);
+        dx[(size_t)r * 32 + lane] = make_float4(o[0], o[1], o[2], o[3]);
+        if (dx16) dx16[(size_t)r * 32 + lane] = make_uint2(tc::pack_bf16(o[0], o[1]), tc::pack_bf16(o[2], o[3]));
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { s_acc[0][w][lane * 4 + j] = ag[j]; s_acc[1][w][lane * 4 + j] = ab[j]; }
+    __syncthreads();
+    if (threadIdx.x < 128) {
+        float t = 0.f, u = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) { t += s_acc[0][k][threadIdx.x]; u += s_acc[1][k][threadIdx.x]; }
+        atomicAdd(dgamma + threadIdx.x, t);
+        atomicAdd(dbeta + threadIdx.x, u);
+    }
+}
+
 // Column sums over the rows of a [rows, width] matrix (bias gradients of the per-node Linear / LayerNorm modules):
 //   s0[c] += sum_r a[r][c]                                     a fp32 or bf16
 //   s1[c] += sum_r a[r][c] * (x[r][c] - mean[r]) * rstd[r]     (x fp32, optional: the LayerNorm weight gradient)
@@ -706,6 +780,34 @@ extern "C" int rmp_segment_sum_rows(const void* x_bf16, const int32_t* row_ptr, 
     train::segment_sum_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
         reinterpret_cast<const uint4*>(x_bf16), row_ptr, out, n_seg);
     return check_launch("rmp_segment_sum_rows");
+}
+
+extern "C" int rmp_add_layernorm_fwd(const float* a, const void* b, int b_is_bf16, const float* gamma, const float* beta, float eps,
+                                     int rows, float* x_out, float* y, float* mean, float* rstd, void* stream) {
+    RMP_REQUIRE(a && gamma && beta && y && mean && rstd && rows >= 0 && (!b || x_out), RMP_E_ARG, "rmp_add_layernorm_fwd: null pointer");
+    RMP_REQUIRE(aligned16(a) && aligned16(gamma) && aligned16(beta) && aligned16(y) && (!b || (aligned16(b) && aligned16(x_out))),
+                RMP_E_ALIGN, "rmp_add_layernorm_fwd: 16-byte alignment");
+    if (rows == 0) return RMP_OK;
+    auto launch = [&](auto kernel) {
+        kernel<<<ceil_div(rows, 8), 256, 0, (cudaStream_t)stream>>>(
+            reinterpret_cast<const float4*>(a), b, reinterpret_cast<const float4*>(gamma), reinterpret_cast<const float4*>(beta), eps,
+            rows, reinterpret_cast<float4*>(x_out), reinterpret_cast<float4*>(y), mean, rstd);
+    };
+    if (b && b_is_bf16) launch(train::add_ln_fwd_kernel<true>); else launch(train::add_ln_fwd_kernel<false>);
+    return check_launch("rmp_add_layernorm_fwd");
+}
+
+extern "C" int rmp_layernorm_bwd(const float* dy, const float* x, const float* mean, const float* rstd, const float* gamma, int rows,
+                                 float* dx, void* dx_bf16, float* dgamma, float* dbeta, void* stream) {
+    RMP_REQUIRE(dy && x && mean && rstd && gamma && dx && dgamma && dbeta && rows >= 0, RMP_E_ARG, "rmp_layernorm_bwd: null pointer");
+    RMP_REQUIRE(aligned16(dy) && aligned16(x) && aligned16(gamma) && aligned16(dx) && (!dx_bf16 || aligned16(dx_bf16)), RMP_E_ALIGN,
+                "rmp_layernorm_bwd: 16-byte alignment");
+    if (rows == 0) return RMP_OK;
+    const int rows_per_block = 64;
+    train::ln_bwd_kernel<<<ceil_div(rows, rows_per_block), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const float4*>(dy), reinterpret_cast<const float4*>(x), mean, rstd, reinterpret_cast<const float4*>(gamma),
+        rows, rows_per_block, reinterpret_cast<float4*>(dx), reinterpret_cast<uint2*>(dx_bf16), dgamma, dbeta);
+    return check_launch("rmp_layernorm_bwd");
 }
 
 extern "C" int rmp_colsum(const void* a, int a_is_bf16, const float* x, const float* mean, const float* rstd, int rows, int width,

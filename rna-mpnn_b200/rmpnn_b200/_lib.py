@@ -90,6 +90,8 @@ SIGNATURES = {
     "rmp_gemm_rows_bf16": [P, P, P, P, P, P, P, P, P, P, I, I, I, F, U64, P, C.c_uint32, P],
     "rmp_gemm_rows_kcat_bf16": [P, P, I, P, I, I, P],
     "rmp_colsum": [P, I, P, P, P, I, I, P, P, P],
+    "rmp_add_layernorm_fwd": [P, P, I, P, P, F, I, P, P, P, P, P],
+    "rmp_layernorm_bwd": [P, P, P, P, P, I, P, P, P, P, P],
 }
 STRING_GETTERS = ("rmp_version", "rmp_last_error_string")
 

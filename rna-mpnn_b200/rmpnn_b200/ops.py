@@ -594,6 +594,33 @@ def gemm_rows(a16, w16, bias=None, Pc=None, Pn=None, ctr=None, nbr=None, want_z=
     return z, a
 
 
+def add_layernorm_fwd(a, b, gamma, beta, eps: float):
+    """x = a + b (b fp32 / bf16 / None), y = LayerNorm(x) over 128 channels -> (x, y, mean, rstd)   (rmp_add_layernorm_fwd)."""
+    _need_cuda(a, b, gamma, beta)
+    assert a.dtype == torch.float32 and a.is_contiguous() and a.dim() == 2 and a.shape[1] == 128
+    assert b is None or (b.shape == a.shape and b.is_contiguous() and b.dtype in (torch.float32, torch.bfloat16))
+    rows = a.shape[0]
+    x = torch.empty_like(a) if b is not None else a
+    y = torch.empty_like(a)
+    stats = torch.empty(2, rows, dtype=torch.float32, device=a.device)
+    check(lib().rmp_add_layernorm_fwd(_ptr(a), _ptr(b), int(b is not None and b.dtype == torch.bfloat16), _ptr(_f32c(gamma)),
+                                      _ptr(_f32c(beta)), float(eps), rows, _ptr(x) if b is not None else None, _ptr(y),
+                                      _ptr(stats[0]), _ptr(stats[1]), _stream()), "rmp_add_layernorm_fwd")
+    return x, y, stats[0], stats[1]
+
+
+def layernorm_bwd(dy, x, mean, rstd, gamma, want_bf16: bool = False):
+    """-> (dx fp32, dx bf16 | None, dgamma [128], dbeta [128])   (rmp_layernorm_bwd)."""
+    _need_cuda(dy, x, mean, rstd, gamma)
+    assert dy.dtype == x.dtype == torch.float32 and dy.is_contiguous() and x.is_contiguous() and dy.shape == x.shape and x.shape[1] == 128
+    dx = torch.empty_like(x)
+    dx16 = torch.empty(x.shape, dtype=torch.bfloat16, device=x.device) if want_bf16 else None
+    sums = torch.zeros(2, 128, dtype=torch.float32, device=x.device)
+    check(lib().rmp_layernorm_bwd(_ptr(dy), _ptr(x), _ptr(mean), _ptr(rstd), _ptr(_f32c(gamma)), x.shape[0], _ptr(dx), _ptr(dx16),
+                                  _ptr(sums[0]), _ptr(sums[1]), _stream()), "rmp_layernorm_bwd")
+    return dx, dx16, sums[0], sums[1]
+
+
 def colsum(a, x=None, mean=None, rstd=None):
     """Column sums of ``a`` [rows,width] (fp32 or bf16) -> fp32 [width]; with ``x`` (fp32), ``mean``, ``rstd`` [rows] also the
     sums of ``a * (x - mean) * rstd`` (LayerNorm weight gradient).  Returns (s0, s1 | None).  rmp_colsum."""

@@ -135,6 +135,47 @@ class LayerNormFn(torch.autograd.Function):
         return dx, dw, db, None
 
 
+class AddLayerNormFn(torch.autograd.Function):
+    """``norm(a + b)`` (rdesign/model/mpnn.py:35, :37) as one forward and one backward kernel (``rmp_add_layernorm_fwd`` /
+    ``rmp_layernorm_bwd``): the residual add, the statistics, ``dx`` and the weight / bias gradients; ``b`` fp32 or bf16."""
+
+    @staticmethod
+    def forward(ctx, a, b, weight, bias, eps):
+        x, y, mean, rstd = ops.add_layernorm_fwd(a.detach().float().contiguous(), b.detach().contiguous(), weight.detach(),
+                                                 bias.detach(), eps)
+        ctx.save_for_backward(x, mean, rstd, weight)
+        ctx.b_bf16 = b.dtype == torch.bfloat16
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mean, rstd, weight = ctx.saved_tensors
+        dx, dx16, dw, db = ops.layernorm_bwd(dy.detach().float().contiguous(), x, mean, rstd, weight.detach(), want_bf16=ctx.b_bf16)
+        return dx, (dx16 if ctx.b_bf16 else dx), dw, db, None
+
+
+class NodeActFn(torch.autograd.Function):
+    """``Dropout(GELU(z))`` on the per-node FFN rows (rdesign/model/mpnn.py:20-28) with the edge path's kernels: tanh-form GELU
+    and its exact derivative, the keep mask regenerated from (seed, stream id, element) in the backward -- one kernel per
+    direction instead of GELU + Dropout (+ their two backward kernels).  ``z`` bf16 [rows, 128 k]."""
+
+    @staticmethod
+    def forward(ctx, z, p, seed, stream_id, seed_dev):
+        z = z.detach().contiguous()
+        ctx.save_for_backward(z)
+        ctx.args = (p, seed, stream_id, seed_dev)
+        return ops.act_fwd(z, p, seed, stream_id, seed_dev=seed_dev)
+
+    @staticmethod
+    def backward(ctx, da):
+        (z,) = ctx.saved_tensors
+        p, seed, stream_id, seed_dev = ctx.args
+        da = da.detach().to(torch.bfloat16).contiguous()
+        # the kernel indexes groups of 8 elements globally, so a [rows, 256] matrix is its own [2 rows, 128] view
+        dz = ops.act_bwd(z.view(-1, 128), p, seed, stream_id, da16=da.view(-1, 128), seed_dev=seed_dev)
+        return dz.view(z.shape), None, None, None, None
+
+
 class LinearFn(torch.autograd.Function):
     """``nn.Linear`` of the per-node FFN on the bf16 tensor cores (what bf16 autocast computes), the bias gradient as one
     ``rmp_colsum`` pass (torch's column reduction kernel: 25 us per call, a split-K ``[1,Nv] x [Nv,N]`` product: 14 us)."""
@@ -239,14 +280,23 @@ class RDesignTrainer:
             if self.autocast:
                 # per-node remainder: LayerNorm and Linear through the two functions above (same math as the modules under
                 # bf16 autocast), GELU / Dropout / residual adds as torch ops
-                x1 = LayerNormFn.apply(h_V + agg, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps)
+                x1 = AddLayerNormFn.apply(h_V, agg, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps)
                 d = x1
-                for mod in layer.dense:
+                mods = list(layer.dense)
+                k = 0
+                while k < len(mods):
+                    mod = mods[k]
                     if isinstance(mod, torch.nn.Linear):
                         d = LinearFn.apply(d, mod.weight, mod.bias, self._w16(mod.weight))
+                    elif (isinstance(mod, torch.nn.GELU) and k + 1 < len(mods) and isinstance(mods[k + 1], torch.nn.Dropout)
+                          and d.dtype == torch.bfloat16 and d.shape[1] % 128 == 0):
+                        # GELU + Dropout in one kernel per direction (stream ids 8.. of the layer: the edge stages use 0..2)
+                        d = NodeActFn.apply(d, self.p_drop, seed, 16 * l + 8 + k, self.seed_dev)
+                        k += 1
                     else:
                         d = mod(d)
-                h_V = LayerNormFn.apply(x1 + d, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps)
+                    k += 1
+                h_V = AddLayerNormFn.apply(x1, d, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps)
             else:
                 x1 = layer.norm1(h_V + agg)
                 h_V = layer.norm2(x1 + layer.dense(x1)).float()

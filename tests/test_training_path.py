@@ -201,6 +201,83 @@ def test_colsum_matches_torch(rows, width, bf16):
         np.testing.assert_allclose(s0.cpu().numpy(), a.double().sum(0).cpu().numpy(), atol=2e-3 * max(1.0, rows ** 0.5), rtol=1e-4)
 
 
+@pytest.mark.parametrize("rows,b_kind", [(1, "none"), (1000, "fp32"), (16384, "bf16"), (77, "bf16")])
+def test_add_layernorm_fwd_bwd_match_autograd(rows, b_kind):
+    """norm(a + b) of the MPNN layer (rdesign/model/mpnn.py:35,37): fused forward (sum, statistics) and one-pass backward
+    (dx, bf16 copy for a bf16 residual branch, weight / bias gradients) against torch autograd."""
+    from rmpnn_b200 import ops
+    g = torch.Generator().manual_seed(rows)
+    a = (2 * torch.randn(rows, 128, generator=g) + 0.3).cuda()
+    b = None if b_kind == "none" else torch.randn(rows, 128, generator=g).cuda().to(torch.bfloat16 if b_kind == "bf16" else torch.float32)
+    gamma = (1 + 0.1 * torch.randn(128, generator=g)).cuda()
+    beta = (0.1 * torch.randn(128, generator=g)).cuda()
+    dy = torch.randn(rows, 128, generator=g).cuda()
+    x, y, mean, rstd = ops.add_layernorm_fwd(a, b, gamma, beta, 1e-5)
+    xr = (a if b is None else a + b.float()).clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    ref = F.layer_norm(xr, (128,), gr, br, 1e-5)
+    np.testing.assert_allclose(x.cpu().numpy(), xr.detach().cpu().numpy(), atol=1e-6, rtol=0)
+    np.testing.assert_allclose(y.cpu().numpy(), ref.detach().cpu().numpy(), atol=2e-5, rtol=1e-5)
+    ref.backward(dy)
+    dx, dx16, dgamma, dbeta = ops.layernorm_bwd(dy, x, mean, rstd, gamma, want_bf16=b_kind == "bf16")
+    np.testing.assert_allclose(dx.cpu().numpy(), xr.grad.cpu().numpy(), atol=2e-5, rtol=1e-4)
+    if b_kind == "bf16":
+        assert torch.equal(dx16, dx.to(torch.bfloat16))
+    else:
+        assert dx16 is None
+    np.testing.assert_allclose(dgamma.cpu().numpy(), gr.grad.cpu().numpy(), atol=2e-3 * max(1.0, rows ** 0.5), rtol=1e-4)
+    np.testing.assert_allclose(dbeta.cpu().numpy(), br.grad.cpu().numpy(), atol=2e-3 * max(1.0, rows ** 0.5), rtol=1e-4)
+
+
+def test_node_act_fn_is_gelu_dropout_with_regenerated_mask():
+    """Dropout(GELU(z)) of the per-node FFN rows through the edge path's kernels: [rows,256] rows as their own [2 rows,128] view."""
+    from rmpnn_b200.train_engine import NodeActFn
+    g = torch.Generator().manual_seed(1)
+    z = (2 * torch.randn(500, 256, generator=g)).cuda().to(torch.bfloat16).requires_grad_(True)
+    a = NodeActFn.apply(z, 0.0, 3, 40, None)
+    zf = z.detach().float().requires_grad_(True)
+    ref = F.gelu(zf)
+    np.testing.assert_allclose(a.detach().float().cpu().numpy(), _bf(ref.detach()).cpu().numpy(), atol=1e-2, rtol=1e-2)
+    da = torch.randn(500, 256, generator=g).cuda().to(torch.bfloat16)
+    a.backward(da)
+    (ref * da.float()).sum().backward()
+    np.testing.assert_allclose(z.grad.float().cpu().numpy(), _bf(zf.grad).cpu().numpy(), atol=2e-2, rtol=2e-2)
+    z2 = torch.ones(4000, 256, device="cuda", dtype=torch.bfloat16, requires_grad=True)
+    a2 = NodeActFn.apply(z2, 0.1, 3, 41, None)
+    a2.backward(torch.ones_like(a2))
+    assert torch.equal(z2.grad != 0, a2.detach() != 0)                      # the backward regenerates the forward's mask
+    assert abs((a2.detach() != 0).float().mean().item() - (1 - 26 / 256)) < 3e-3
+
+
+def test_native_training_step_autocast_gradients_match_autograd():
+    """The bench path (bf16 node FFN, fused add + LayerNorm, fused GELU + Dropout, column-sum bias gradients) with dropout
+    off against fp32 autograd through the drop-in's composition: looser than the fp32 node path (bf16 activations)."""
+    from oracle.weights import RDesignConfig, make_state_dict, synthetic_backbones
+    from rdesign.model.rdesign import RNAModel
+    from rmpnn_b200.train_engine import RDesignTrainer
+    cfg = RDesignConfig(k_neighbors=12, num_mpnn_layers=3)
+    X, S, mask = synthetic_backbones(3, 60, 9, lengths=[60, 41, 23])
+    X, S, mask = X.cuda(), S.cuda(), mask.cuda()
+    ref = RNAModel(**cfg.as_kwargs(), dropout=0.0).cuda().train()
+    ref.load_state_dict(make_state_dict(cfg, 42), strict=True)
+    h_V, S_v = ref(X, S, mask)
+    loss_ref = F.cross_entropy(ref.readout(h_V), S_v)
+    loss_ref.backward()
+    ref_grads = {n: p.grad.clone() for n, p in ref.named_parameters()}
+    model = RNAModel(**cfg.as_kwargs(), dropout=0.0).cuda().train()
+    model.load_state_dict(make_state_dict(cfg, 42), strict=True)
+    tr = RDesignTrainer(model, autocast=True)
+    loss = tr.loss_and_grads(X, S, mask, seed=1)
+    assert abs(loss.item() - loss_ref.item()) < 3e-2, (loss.item(), loss_ref.item())
+    worst = 0.0
+    for n, p in model.named_parameters():
+        a, b = p.grad.float(), ref_grads[n].float()
+        rel = ((a - b).norm() / (b.norm() + 1e-12)).item()
+        worst = max(worst, rel)
+        assert rel < 1e-1 or (a - b).abs().max().item() < 1e-5, (n, rel, b.norm().item())
+    print(f"native training step (autocast): loss {loss.item():.5f} vs {loss_ref.item():.5f}, worst relative gradient error {worst:.3e}")
+
+
 def test_normalize_fwd_bwd_match_autograd():
     from rmpnn_b200 import ops
     from rmpnn_b200.train_engine import _normalize
