@@ -334,6 +334,17 @@ int rmp_edge_mlp_bf16_traced(const void* h_E_bf16, const void* W_bf16, int num_s
                              const float* Pc, const void* Pn_bf16, const int32_t* ctr, const int32_t* nbr,
                              const int32_t* row_ptr, int n_edges, float alpha, float* agg, float* debug,
                              long long* timeline, void* stream);
+/* Training forward of the same kernel (rdesign/model/mpnn.py:15-19,33-34 with Dropout after every GELU): the three message
+ * stages and the neighbour sums in ONE pass over h_E, with what the backward needs written out on the way:
+ *   z_save[s]   bf16 [n_edges,128]  pre-activation of stage s (s < num_stages)
+ *   a_save[s]   bf16 [n_edges,128]  activation of stage s < num_stages-1 in OPERAND FORM 2 GELU(z) mask: the true
+ *                                    Dropout(GELU(z)) is a_save * keep_scale / 2, keep_scale = 256 / (256 - round(256 p))
+ *   agg         += alpha * sum over the node's edges of Dropout(GELU(z_last))
+ * The keep mask of stage s is that of rmp_act_fwd_bf16 / rmp_act_bwd_bf16 for (seed [+ *seed_dev], stream_id0 + s). */
+int rmp_edge_mlp_train_fwd_bf16(const void* h_E_bf16, const void* W_bf16, int num_stages, const float* const* bias, const float* Pc,
+                                const void* Pn_bf16, const int32_t* ctr, const int32_t* nbr, const int32_t* row_ptr, int n_edges,
+                                float alpha, float* agg, void* const* z_save, void* const* a_save, float p_drop, uint64_t seed,
+                                const uint64_t* seed_dev, uint32_t stream_id0, void* stream);
 
 /* ------------------------------------------------------------------ training path (section 8f rank 1, configs[3])
  * Per-edge backward of MPNNLayer's message MLP (rdesign/model/mpnn.py:15-19, :33-34), decomposed into HBM-bound passes

@@ -13,6 +13,7 @@
 // Roles (768 threads): warp 0 = TMA producer, warp 1 = MMA issuer + TMEM owner, warps 4..7 = gather /
 // drain (accumulator pre-initialisation, selector matrix, neighbour sums), warps 8..23 = epilogue.
 #include "tc_common.cuh"
+#include "dropout.cuh"
 
 #include <cstdio>
 #include <cstdlib>
@@ -33,6 +34,11 @@ struct EdgeParams {
     float* agg;                      // [Nv,128] fp32, pre-zeroed
     int n_edges;
     int flags;                       // 1 = first edge tile requested before W2.., 2 = run-ahead GEMMs behind hand-offs
+    // training forward (template variant bit 2; rmp_edge_mlp_train_fwd_bf16): Dropout after every GELU with the training
+    // path's regenerable mask, and what the backward needs written out: z_s = bf16 pre-activations of every stage, a_s =
+    // the activations of the non-final stages IN OPERAND FORM 2 * GELU(z) * mask (the caller scales by keep_scale / 2)
+    uint16_t* zsave[kMaxStages]; uint16_t* asave[kMaxStages];
+    uint32_t thresh8; float keep_scale; uint64_t seed; const uint64_t* seed_dev; uint32_t stream0;
     float* debug;                    // optional [num_stages][n_edges][128] post-activation dump
     long long* timeline;             // optional int64[32768] clock64 trace of CTA 0 (per epilogue warp + MMA thread; tuning)
 };
@@ -155,6 +161,29 @@ __device__ __forceinline__ void add2(float& a, float& b, float x, float y) {
         : "+f"(a), "+f"(b)
         : "f"(x), "f"(y));
 }
+// 2 * GELU of a packed bf16x2 pre-activation (the training forward also stores that bf16 z)
+__device__ __forceinline__ uint32_t gelu2x_of_bf16x2(uint32_t xz) {
+    const __nv_bfloat162 x = *reinterpret_cast<const __nv_bfloat162*>(&xz);
+    const __nv_bfloat162 c1 = __float2bfloat162_rn(0.0356774081f), c0 = __float2bfloat162_rn(0.7978845608f);
+    const __nv_bfloat162 inner = __hmul2(x, __hfma2(__hmul2(x, x), c1, c0));
+    uint32_t t;
+    asm("tanh.approx.bf16x2 %0, %1;" : "=r"(t) : "r"(*reinterpret_cast<const uint32_t*>(&inner)));
+    const __nv_bfloat162 y = __hfma2(x, *reinterpret_cast<const __nv_bfloat162*>(&t), x);
+    return *reinterpret_cast<const uint32_t*>(&y);
+}
+// (a, b) = (a, b) * s + (x, y) with the same scale s in both lanes
+__device__ __forceinline__ void fma2_scale(float& a, float& b, float s, float x, float y) {
+    asm("{\n\t"
+        ".reg .b64 va, vx, vs;\n\t"
+        "mov.b64 va, {%0, %1};\n\t"
+        "mov.b64 vx, {%2, %3};\n\t"
+        "mov.b64 vs, {%4, %4};\n\t"
+        "fma.rn.f32x2 va, va, vs, vx;\n\t"
+        "mov.b64 {%0, %1}, va;\n\t"
+        "}"
+        : "+f"(a), "+f"(b)
+        : "f"(x), "f"(y), "f"(s));
+}
 // (a, b) = (a, b) * 0.5 + (x, y): one packed fp32x2 fma
 __device__ __forceinline__ void fma2_half(float& a, float& b, float x, float y) {
     asm("{\n\t"
@@ -204,6 +233,8 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
     const int my_tiles = ((int)blockIdx.x < n_tiles) ? (n_tiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int S = p.num_stages;
     constexpr bool kFold = (V & 1) != 0;            // activations held as 2 * GELU (gelu2x_bf16x2)
+    constexpr bool kTrain = (V & 4) != 0;           // training forward: dropout + saved z / a (needs kFold)
+    static_assert(!kTrain || (kFold && !DECOUPLED), "the training forward builds on the folded, staggered variant");
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kMaxStages; ++s) mbar_init(&bars->w_full[s], 1);
@@ -386,7 +417,8 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
             tc_fence_after();
             const volatile int* meta = s_meta + 2 * (kSlots * ((j_prev / kSlots) & 1) + b);
             const int fn = meta[0], nslots = meta[1];
-            const float alpha_sum = kFold ? 0.5f * p.alpha : p.alpha;      // m3 is held as 2 * GELU
+            // m3 is held as 2 * GELU (training: 2 * GELU * mask, survivors scaled here)
+            const float alpha_sum = (kFold ? 0.5f : 1.f) * p.alpha * (kTrain ? p.keep_scale : 1.f);
             if (nslots <= kSelSlots) {
                 float v[16];
                 tmem_ld16(t_row + (uint32_t)(b * 128), v);
@@ -504,6 +536,8 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
             }
         };
 
+        [[maybe_unused]] const float half_ks = kTrain ? 0.5f * p.keep_scale : 0.5f;
+        [[maybe_unused]] const uint64_t seed_tr = kTrain ? p.seed + (p.seed_dev ? __ldg(p.seed_dev) : 0ull) : 0ull;
         // phase sequence: the even-tile stream at (pair k, stage sa), then the odd-tile stream S/2 stages behind it
         const int off = S >> 1;
         int seq_k = 0, seq_s = 0, seq_half = 0;
@@ -539,6 +573,7 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
             tc_fence_after();
             stamp(200 + st * 10 + (i & 1));                    // accumulator ready
             const bool bypass = last && reinterpret_cast<const volatile int*>(s_meta)[2 * (kSlots * ((i / kSlots) & 1) + b) + 1] > kSelSlots;
+            [[maybe_unused]] uint32_t o_keep[16], xz_keep[16];       // training forward: this phase's z and activation, stored below
 #pragma unroll
             for (int ch = 0; ch < kChunks; ++ch) {
                 const int col0 = colb + ch * 32;
@@ -550,7 +585,10 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
 #pragma unroll
                     for (int q = 0; q < 8; ++q) {
                         const float4 x = bs[q];
-                        if constexpr (kFold) {                 // the previous stage wrote 2 * GELU: v = acc / 2 + bias
+                        if constexpr (kTrain) {                // operand was 2 * GELU * mask: v = acc * keep_scale / 2 + bias
+                            fma2_scale(v[4 * q + 0], v[4 * q + 1], half_ks, x.x, x.y);
+                            fma2_scale(v[4 * q + 2], v[4 * q + 3], half_ks, x.z, x.w);
+                        } else if constexpr (kFold) {          // the previous stage wrote 2 * GELU: v = acc / 2 + bias
                             fma2_half(v[4 * q + 0], v[4 * q + 1], x.x, x.y);
                             fma2_half(v[4 * q + 2], v[4 * q + 3], x.z, x.w);
                         } else {
@@ -560,7 +598,32 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
                     }
                 }
                 uint32_t o[16];
-                if (p.debug != nullptr || bypass) {
+                [[maybe_unused]] uint32_t xz[16];
+                if constexpr (kTrain) {
+                    // z (bf16) is what the backward sees; the activation is evaluated at exactly that value
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) { xz[q] = pack_bf16(v[2 * q], v[2 * q + 1]); o[q] = gelu2x_of_bf16x2(xz[q]); }
+                    if (p.thresh8 != 0) {
+#pragma unroll
+                        for (int g8 = 0; g8 < 4; ++g8) {
+                            const uint32_t keep = keep_mask8(seed_tr, (uint64_t)(e_base + row) * 16 + (uint64_t)(col0 / 8 + g8),
+                                                             p.stream0 + (uint32_t)st, p.thresh8);
+#pragma unroll
+                            for (int j = 0; j < 4; ++j) {
+                                const uint32_t m = (((keep >> (2 * j)) & 1u) ? 0x0000ffffu : 0u) | (((keep >> (2 * j + 1)) & 1u) ? 0xffff0000u : 0u);
+                                o[4 * g8 + j] &= m;
+                            }
+                        }
+                    }
+                    if (bypass && valid) {                     // > 16 nodes in the tile: vector reductions instead of the selector
+                        float* dst = p.agg + (size_t)__ldg(p.ctr + e_base + row) * 128 + col0;
+                        const float sc = 0.5f * p.alpha * p.keep_scale;
+#pragma unroll
+                        for (int q = 0; q < 8; ++q)
+                            red_add_v4(dst + 4 * q, __uint_as_float(o[2 * q] << 16) * sc, __uint_as_float(o[2 * q] & 0xffff0000u) * sc,
+                                       __uint_as_float(o[2 * q + 1] << 16) * sc, __uint_as_float(o[2 * q + 1] & 0xffff0000u) * sc);
+                    }
+                } else if (p.debug != nullptr || bypass) {
                     // fp32 GELU: debug dump (tests) and the tiny-degree bypass that sums with vector reductions
 #pragma unroll
                     for (int q = 0; q < 32; ++q) v[q] = gelu_tanh_fast(v[q]);
@@ -599,12 +662,29 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
                 } else {
                     tmem_st16(t_row + kYCol + (uint32_t)((i & 1) * 64 + col0 / 2), o);     // next stage's A operand, in TMEM
                 }
+                if constexpr (kTrain) {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q) { o_keep[q] = o[q]; xz_keep[q] = xz[q]; }
+                }
             }
             if (last) fence_proxy_async();
             else tmem_st_wait();
             tc_fence_before();
             mbar_arrive(&bars->act_ready[b]);
             stamp(700 + st * 10 + (i & 1));
+            if constexpr (kTrain) {
+                // saved tensors, written AFTER the hand-off (an mbarrier arrive has release semantics and would wait for
+                // these stores): this row's 32 columns = 64 contiguous bytes per tensor, two full sectors
+                if (valid) {
+                    const size_t at = (size_t)(e_base + row) * 128 + colb;
+                    uint16_t* zs = st == 0 ? p.zsave[0] : (st == 1 ? p.zsave[1] : (st == 2 ? p.zsave[2] : p.zsave[3]));
+                    stg256u(zs + at, &xz_keep[0]); stg256u(zs + at + 16, &xz_keep[8]);
+                    if (!last) {
+                        uint16_t* as = st == 0 ? p.asave[0] : (st == 1 ? p.asave[1] : p.asave[2]);
+                        stg256u(as + at, &o_keep[0]); stg256u(as + at + 16, &o_keep[8]);
+                    }
+                }
+            }
         }
         if (tl_on) p.timeline[32000 + ew] = tl_n;
     }
@@ -961,10 +1041,41 @@ extern "C" int rmp_edge_mlp_bf16(const void* h_E_bf16, const void* W_bf16, int n
                                     agg, debug, nullptr, stream);
 }
 
+struct EdgeTrainArgs {
+    void* const* z_save; void* const* a_save; float p_drop; uint64_t seed; const uint64_t* seed_dev; uint32_t stream0;
+};
+static int edge_mlp_launch(const void* h_E_bf16, const void* W_bf16, int num_stages, const float* const* bias, const float* Pc,
+                           const void* Pn_bf16, const int32_t* ctr, const int32_t* nbr, const int32_t* row_ptr, int n_edges,
+                           float alpha, float* agg, float* debug, long long* timeline, const EdgeTrainArgs* train, void* stream);
+
 extern "C" int rmp_edge_mlp_bf16_traced(const void* h_E_bf16, const void* W_bf16, int num_stages,
                                         const float* const* bias, const float* Pc, const void* Pn_bf16,
                                         const int32_t* ctr, const int32_t* nbr, const int32_t* row_ptr, int n_edges,
                                         float alpha, float* agg, float* debug, long long* timeline, void* stream) {
+    return edge_mlp_launch(h_E_bf16, W_bf16, num_stages, bias, Pc, Pn_bf16, ctr, nbr, row_ptr, n_edges, alpha, agg, debug, timeline,
+                           nullptr, stream);
+}
+
+extern "C" int rmp_edge_mlp_train_fwd_bf16(const void* h_E_bf16, const void* W_bf16, int num_stages, const float* const* bias,
+                                           const float* Pc, const void* Pn_bf16, const int32_t* ctr, const int32_t* nbr,
+                                           const int32_t* row_ptr, int n_edges, float alpha, float* agg, void* const* z_save,
+                                           void* const* a_save, float p_drop, uint64_t seed, const uint64_t* seed_dev,
+                                           uint32_t stream_id0, void* stream) {
+    RMP_REQUIRE(z_save && a_save, RMP_E_ARG, "rmp_edge_mlp_train_fwd_bf16: z_save / a_save are null");
+    RMP_REQUIRE(p_drop >= 0.f && p_drop < 1.f, RMP_E_ARG, "rmp_edge_mlp_train_fwd_bf16: dropout probability in [0,1)");
+    for (int s = 0; s < num_stages && s < tc::kMaxStages; ++s) {
+        RMP_REQUIRE(z_save[s] && aligned32(z_save[s]), RMP_E_ALIGN, "rmp_edge_mlp_train_fwd_bf16: z_save[%d] null or not 32-byte aligned", s);
+        RMP_REQUIRE(s == num_stages - 1 || (a_save[s] && aligned32(a_save[s])), RMP_E_ALIGN,
+                    "rmp_edge_mlp_train_fwd_bf16: a_save[%d] null or not 32-byte aligned", s);
+    }
+    const EdgeTrainArgs t{z_save, a_save, p_drop, seed, seed_dev, stream_id0};
+    return edge_mlp_launch(h_E_bf16, W_bf16, num_stages, bias, Pc, Pn_bf16, ctr, nbr, row_ptr, n_edges, alpha, agg, nullptr, nullptr,
+                           &t, stream);
+}
+
+static int edge_mlp_launch(const void* h_E_bf16, const void* W_bf16, int num_stages, const float* const* bias, const float* Pc,
+                           const void* Pn_bf16, const int32_t* ctr, const int32_t* nbr, const int32_t* row_ptr, int n_edges,
+                           float alpha, float* agg, float* debug, long long* timeline, const EdgeTrainArgs* train, void* stream) {
     const void* Pn = Pn_bf16;
     RMP_REQUIRE(row_ptr, RMP_E_ARG, "rmp_edge_mlp_bf16: row_ptr is null");
     RMP_REQUIRE(h_E_bf16 && W_bf16 && Pc && Pn && ctr && nbr && agg && bias, RMP_E_ARG, "rmp_edge_mlp_bf16: null pointer");
@@ -1004,7 +1115,17 @@ extern "C" int rmp_edge_mlp_bf16_traced(const void* h_E_bf16, const void* W_bf16
     }
     p.flags = g_edge_flags;
     const int v = g_edge_variant & 1;
-    if (timeline) {
+    if (train) {
+        // same 8-bit quantisation of the drop probability as the stand-alone activation kernels (train.cu)
+        const uint32_t thresh = train->p_drop <= 0.f ? 0u : (uint32_t)(train->p_drop * 256.0f + 0.5f);
+        p.thresh8 = thresh; p.keep_scale = 256.0f / (256.0f - (float)thresh);
+        p.seed = train->seed; p.seed_dev = train->seed_dev; p.stream0 = train->stream0;
+        for (int s = 0; s < num_stages; ++s) {
+            p.zsave[s] = reinterpret_cast<uint16_t*>(train->z_save[s]);
+            p.asave[s] = s < num_stages - 1 ? reinterpret_cast<uint16_t*>(train->a_save[s]) : nullptr;
+        }
+        launch(tc::edge_mlp_tc_kernel<false, false, 5>);
+    } else if (timeline) {
         if (decoupled) launch(tc::edge_mlp_tc_kernel<true, true>);
         else if (v == 1) launch(tc::edge_mlp_tc_kernel<true, false, 1>);
         else launch(tc::edge_mlp_tc_kernel<true, false>);

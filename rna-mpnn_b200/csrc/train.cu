@@ -12,34 +12,12 @@
 //             d(Pc) = segment sums of dz_0 by centre / neighbour: rmp_scatter_add_rows
 // plus rmp_adam_step, a fused Adam update over the flat parameter / gradient buffers.
 #include "tc_common.cuh"
+#include "dropout.cuh"
 
 namespace rmp {
 namespace train {
 
-// Counter-based mask generator: 128 bits per (seed, element group, stream) from two rounds of the 64-bit murmur3 /
-// splitmix finalizer (stateless, so the backward regenerates exactly the forward's mask; ~25 integer instructions per
-// 8 elements where Philox-4x32-10 needs ~80, which made the activation passes instruction-bound).
-__device__ __forceinline__ uint64_t mix64(uint64_t x) {
-    x ^= x >> 33; x *= 0xff51afd7ed558ccdull;
-    x ^= x >> 33; x *= 0xc4ceb9fe1a85ec53ull;
-    x ^= x >> 33;
-    return x;
-}
-// keep-mask of the 8 elements of group g: one hash, eight 8-bit lanes; bit j set = element j survives.
-// The drop probability is quantised to thresh8 / 256 and the survivors are scaled by 256 / (256 - thresh8), so the
-// expectation is exact for the quantised p (0.1 -> 26/256 = 0.1016).
-__device__ __forceinline__ uint32_t keep_mask8(uint64_t seed, uint64_t g, uint32_t stream, uint32_t thresh8) {
-    if (thresh8 == 0) return 0xffu;
-    const uint64_t h = mix64(seed + 0x9E3779B97F4A7C15ull * (g + 1) + ((uint64_t)stream << 40));
-    const uint32_t lo = (uint32_t)h, hi = (uint32_t)(h >> 32);
-    uint32_t m = 0;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-        m |= (uint32_t)(((lo >> (8 * j)) & 0xffu) >= thresh8) << j;
-        m |= (uint32_t)(((hi >> (8 * j)) & 0xffu) >= thresh8) << (4 + j);
-    }
-    return m;
-}
+// (the counter-based dropout mask generator lives in dropout.cuh)
 // GELU (tanh form, MUFU.TANH) and its derivative; the same pair is used in both directions, so the backward is the
 // exact derivative of what the forward computed (|tanh form - erf form| <= 5e-4, below the bf16 rounding of a)
 __device__ __forceinline__ void gelu_tanh_both(float x, float& y, float& dy) {

@@ -79,6 +79,7 @@ SIGNATURES = {
     "rmp_node_mlp_bf16": [P, P, I, P, P, I, P, P, P, P, P, P, P, P, P, P, P, I, P],
     "rmp_edge_mlp_bf16": [P, P, I, P, P, P, P, P, P, I, F, P, P, P],
     "rmp_edge_mlp_bf16_traced": [P, P, I, P, P, P, P, P, P, I, F, P, P, P, P],
+    "rmp_edge_mlp_train_fwd_bf16": [P, P, I, P, P, P, P, P, P, I, F, P, P, P, F, U64, P, C.c_uint32, P],
     "rmp_act_fwd_bf16": [P, P, I64, I, F, U64, P, C.c_uint32, P],
     "rmp_act_bwd_bf16": [P, P, P, P, F, P, P, I, F, U64, P, C.c_uint32, P],
     "rmp_scatter_add_rows": [P, P, P, I, P],

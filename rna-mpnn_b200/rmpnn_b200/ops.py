@@ -298,6 +298,34 @@ def edge_mlp_bf16(h_E16, W16, biases, Pc, Pn16, ctr, nbr, row_ptr, agg, alpha: f
     return agg
 
 
+def edge_mlp_train_fwd(h_E16, W16, biases, Pc, Pn16, ctr, nbr, row_ptr, agg, alpha: float, p_drop: float, seed: int,
+                       stream_id0: int, seed_dev=None):
+    """Training forward of the tcgen05 edge-message kernel (rmp_edge_mlp_train_fwd_bf16): agg += alpha * segment sums of the last
+    activation, Dropout after every GELU.  Returns (zs, as_): zs[s] bf16 [Ne,128] pre-activations; as_[s] (s < S-1) the
+    activations in operand form ``2 GELU(z) mask`` (true activation = as_[s] * keep_scale(p_drop) / 2)."""
+    _need_cuda(h_E16, W16, Pc, Pn16, ctr, nbr, row_ptr, agg, seed_dev, *[b for b in biases if b is not None])
+    S = W16.shape[0] // 128
+    assert h_E16.dtype == torch.bfloat16 and W16.dtype == torch.bfloat16 and h_E16.is_contiguous() and W16.is_contiguous()
+    assert Pc.dtype == torch.float32 and Pc.is_contiguous() and Pc.shape[1] == 128
+    assert Pn16.dtype == torch.bfloat16 and Pn16.is_contiguous() and Pn16.shape[1] == 128
+    zs = [torch.empty_like(h_E16) for _ in range(S)]
+    as_ = [torch.empty_like(h_E16) for _ in range(S - 1)]
+    barr = (C.c_void_p * 4)(*([_ptr(b) if b is not None else None for b in biases] + [None] * (4 - len(biases))))
+    zarr = (C.c_void_p * 4)(*([_ptr(z) for z in zs] + [None] * (4 - S)))
+    aarr = (C.c_void_p * 4)(*([_ptr(a) for a in as_] + [None] * (4 - (S - 1))))
+    check(lib().rmp_edge_mlp_train_fwd_bf16(_ptr(h_E16), _ptr(W16), S, C.cast(barr, C.c_void_p), _ptr(Pc), _ptr(Pn16), _ptr(ctr),
+                                            _ptr(nbr), _ptr(row_ptr), h_E16.shape[0], float(alpha), _ptr(agg),
+                                            C.cast(zarr, C.c_void_p), C.cast(aarr, C.c_void_p), float(p_drop), int(seed),
+                                            _ptr(seed_dev), int(stream_id0), _stream()), "rmp_edge_mlp_train_fwd_bf16")
+    return zs, as_
+
+
+def keep_scale(p_drop: float) -> float:
+    """1 / (1 - p) for the 8-bit quantised drop probability of the training kernels."""
+    t = 0 if p_drop <= 0 else int(p_drop * 256.0 + 0.5)
+    return 256.0 / (256.0 - t)
+
+
 def node_mlp_bf16(h_in, stages, n_rows, agg=None, ln1=None, ln2=None, x1=None, h_out=None, p_out=None, pn_out=None):
     """tcgen05 node-update kernel (rmp_node_mlp_bf16).
 

@@ -45,6 +45,18 @@ class EdgeMessageFn(torch.autograd.Function):
         W1h = w16(W1)                                              # [128,384] bf16 view, columns e | c | n
         Pc = torch.addmm(b1.detach().to(torch.bfloat16), hV16, W1h[:, 128:256].t())      # [Nv,128] bf16
         Pn = hV16 @ W1h[:, 256:].t()
+        ctx.fused = state.get("wmsg_all") is not None
+        if ctx.fused:
+            # ONE pass over h_E: the inference edge kernel's three chained tcgen05 stages with Dropout in the epilogue, the
+            # neighbour sums by the selector MMA, and z0..z2 / a0, a1 written out for the backward (a in operand form
+            # 2 GELU(z) mask: the weight gradients below are rescaled by keep_scale / 2)
+            agg = torch.zeros(g.Nv, 128, dtype=torch.float32, device=h_V.device)
+            (z0, z1, z2), (a0, a1) = ops.edge_mlp_train_fwd(
+                hE16, state["wmsg_all"][state["layer"]], [None, b2.detach().float(), b3.detach().float()], Pc.float(), Pn,
+                g.ctr, g.nbr, g.row_ptr, agg, 1.0 / scale, p, seed, sid, seed_dev=sd)
+            ctx.save_for_backward(hV16, W1, W2, W3, z0, z1, z2, a0, a1)
+            ctx.state = (state, p, seed, sid, scale)
+            return agg
         z0, a0 = ops.gemm_rows(hE16, W1h[:, :128], Pc=Pc, Pn=Pn, ctr=g.ctr, nbr=g.nbr, act=(p, seed, sid), seed_dev=sd)
         z1, a1 = ops.gemm_rows(a0, w16(W2), bias=b2.detach(), act=(p, seed, sid + 1), seed_dev=sd)
         z2, a2 = ops.gemm_rows(a1, w16(W3), bias=b3.detach(), act=(p, seed, sid + 2), seed_dev=sd)
@@ -73,6 +85,8 @@ class EdgeMessageFn(torch.autograd.Function):
         # dz0 of every layer is kept: d h_E = sum_l dz0_l W1e_l is ONE K-concatenated GEMM in the edge embedding's backward
         dz0 = ops.act_bwd(z0, p, seed, sid, da16=da0, db=db[0], seed_dev=sd, out=state["dz0_all"][state["layer"]])
         ops.gemm_dw(dz0, hE16, dW[2])
+        if ctx.fused:
+            dW[:2] *= 0.5 * ops.keep_scale(p)                      # a0, a1 were saved as 2 GELU(z) mask
         ops.segment_sum_rows(dz0, g.row_ptr[:g.Nv + 1], dP[0])
         ops.scatter_add_rows(dz0, g.nbr, dP[1])
         dP16 = dP.to(torch.bfloat16)
@@ -212,6 +226,10 @@ class RDesignTrainer:
         self.model = model
         self.world = world
         self.autocast = autocast
+        # forward of the per-edge message MLP: one fused launch per layer (rmp_edge_mlp_train_fwd_bf16) or, with
+        # RMP_TRAIN_FUSED_FWD=0, one row GEMM per stage + segmented sum
+        import os
+        self.fused_forward = os.environ.get("RMP_TRAIN_FUSED_FWD", "1") != "0"
         self.lr = float(model.hparams.lr if lr is None else lr)
         self.p_drop = float(model.hparams.dropout if p_drop is None else p_drop)
         self.params: List[torch.nn.Parameter] = [p for p in model.parameters() if p.requires_grad]
@@ -263,8 +281,14 @@ class RDesignTrainer:
         state["edge_raw16"] = F.pad(edge_raw, (0, 128 - edge_raw.shape[1])).to(torch.bfloat16).contiguous()
         n_layers = len(m.mpnn_layers)
         state["dz0_all"] = torch.empty(n_layers, g.Ne, 128, dtype=torch.bfloat16, device=X.device)
-        state["w1e_all"] = torch.stack([self._w16([x for x in layer.message_layers if isinstance(x, torch.nn.Linear)][0].weight)[:, :128]
-                                        for layer in m.mpnn_layers]).contiguous()
+        lins = [[x for x in layer.message_layers if isinstance(x, torch.nn.Linear)] for layer in m.mpnn_layers]
+        state["w1e_all"] = torch.stack([self._w16(ll[0].weight)[:, :128] for ll in lins]).contiguous()
+        state["wmsg_all"] = None
+        if self.fused_forward and all(len(ll) == 3 and tuple(ll[0].weight.shape) == (128, 384) and tuple(ll[1].weight.shape) ==
+                                      tuple(ll[2].weight.shape) == (128, 128) for ll in lins):
+            # per layer [W1e ; W2 ; W3] as the edge kernel's resident [3 x 128, 128] bf16 operand
+            state["wmsg_all"] = torch.stack([torch.cat([self._w16(ll[0].weight)[:, :128], self._w16(ll[1].weight),
+                                                        self._w16(ll[2].weight)]) for ll in lins]).contiguous()
         del edge_raw
         S_valid = S.reshape(B * N)[g.node_src[:g.Nv].long()]
         token = EdgeEmbedFn.apply(f.edge_embedding.weight, f.edge_embedding.bias, f.norm_edges.gain, f.norm_edges.bias, state)

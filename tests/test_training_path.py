@@ -278,6 +278,42 @@ def test_native_training_step_autocast_gradients_match_autograd():
     print(f"native training step (autocast): loss {loss.item():.5f} vs {loss_ref.item():.5f}, worst relative gradient error {worst:.3e}")
 
 
+@pytest.mark.parametrize("Nv,deg,p_drop", [(300, 7, 0.0), (2000, 25, 0.1), (64, 3, 0.1)])
+def test_edge_mlp_train_fwd_matches_the_stage_by_stage_path(Nv, deg, p_drop):
+    """Fused training forward of the edge kernel against the three row GEMMs + segmented sum it replaces: same bf16 z within
+    rounding, the SAME dropout masks (operand-form activations are zero exactly where the stand-alone pass drops), activations
+    and neighbour sums within bf16 tolerance.  deg 3 puts more than 16 nodes into a tile (vector-reduction bypass)."""
+    from rmpnn_b200 import ops
+    g = torch.Generator().manual_seed(Nv)
+    ctr = torch.repeat_interleave(torch.arange(Nv), deg).to(torch.int32).cuda()
+    Ne = ctr.numel()
+    rp = (torch.arange(Nv + 1) * deg).to(torch.int32).cuda()
+    nbr = torch.randint(0, Nv, (Ne,), generator=g, dtype=torch.int32).cuda()
+    hE = torch.randn(Ne, 128, generator=g).cuda().to(torch.bfloat16)
+    W = (torch.randn(384, 128, generator=g) / 11.3).cuda().to(torch.bfloat16)
+    b = [None, (0.1 * torch.randn(128, generator=g)).cuda(), (0.1 * torch.randn(128, generator=g)).cuda()]
+    Pc = torch.randn(Nv, 128, generator=g).cuda().to(torch.bfloat16)
+    Pn = torch.randn(Nv, 128, generator=g).cuda().to(torch.bfloat16)
+    seed, sid, alpha = 17, 32, 1 / 30
+    agg = torch.zeros(Nv, 128, device="cuda")
+    zs, as_ = ops.edge_mlp_train_fwd(hE, W, b, Pc.float(), Pn, ctr, nbr, rp, agg, alpha, p_drop, seed, sid)
+    z0, a0 = ops.gemm_rows(hE, W[:128], Pc=Pc, Pn=Pn, ctr=ctr, nbr=nbr, act=(p_drop, seed, sid))
+    z1, a1 = ops.gemm_rows(a0, W[128:256], bias=b[1], act=(p_drop, seed, sid + 1))
+    z2, a2 = ops.gemm_rows(a1, W[256:], bias=b[2], act=(p_drop, seed, sid + 2))
+    agg_ref = ops.segment_sum_rows(a2, rp) * alpha
+    ks = ops.keep_scale(p_drop)
+    tol = dict(atol=6e-2, rtol=3e-2)                       # bf16 activations through three stages, two evaluation orders
+    np.testing.assert_allclose(zs[0].float().cpu().numpy(), z0.float().cpu().numpy(), **tol)
+    assert torch.equal(as_[0] != 0, a0 != 0) or ((as_[0] != 0) != (a0 != 0)).float().mean().item() < 1e-3   # GELU(z) == 0 ties
+    np.testing.assert_allclose((as_[0].float() * (0.5 * ks)).cpu().numpy(), a0.float().cpu().numpy(), **tol)
+    np.testing.assert_allclose(zs[1].float().cpu().numpy(), z1.float().cpu().numpy(), **tol)
+    np.testing.assert_allclose((as_[1].float() * (0.5 * ks)).cpu().numpy(), a1.float().cpu().numpy(), **tol)
+    np.testing.assert_allclose(zs[2].float().cpu().numpy(), z2.float().cpu().numpy(), **tol)
+    np.testing.assert_allclose(agg.cpu().numpy(), agg_ref.cpu().numpy(), atol=2e-2, rtol=3e-2)
+    if p_drop > 0:
+        assert abs((as_[1] == 0).float().mean().item() - 26 / 256) < 2e-2
+
+
 def test_normalize_fwd_bwd_match_autograd():
     from rmpnn_b200 import ops
     from rmpnn_b200.train_engine import _normalize
