@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+timeout 300 python -u -m pytest tests/test_training_path.py -x -q > gpurun_out/r2c55_train.log 2>&1; tail -25 gpurun_out/r2c55_train.log
+timeout 300 python bench.py --workload c4 --no-cpu-baseline > gpurun_out/r2c55_bench_c4.json 2> gpurun_out/r2c55_err.log; tail -1 gpurun_out/r2c55_err.log
+python -c "
+import json
+d=json.loads([l for l in open('gpurun_out/r2c55_bench_c4.json') if l.startswith('{')][0]); print('c4', d['ms_per_step'], d['value'], d['loss'], d['gpu_launches'])"
+timeout 200 python scripts/train_profile.py > gpurun_out/r2c55_train_profile.txt 2>&1; grep "edge_mlp_tc_kernel" gpurun_out/r2c55_train_profile.txt | cut -c1-60,150-250
