@@ -368,6 +368,10 @@ int rmp_scatter_add_rows(const void* x_bf16, const int32_t* idx, float* out, int
  * scatter_sum by centre node (functional.scatter_sum with src_idx = E_idx[0], rdesign/model/mpnn.py:34) and its transposes
  * in the backward, without atomics (the edges of a node are contiguous). */
 int rmp_segment_sum_rows(const void* x_bf16, const int32_t* row_ptr, float* out, int n_seg, void* stream);
+/* The same with an indirection: out[v,:] = sum over r in [row_ptr[v], row_ptr[v+1]) of x[perm[r],:].  With perm = the edges
+ * sorted by NEIGHBOUR node and row_ptr the matching offsets (the transposed CSR of the kNN graph) this is the scatter of
+ * d Pn = sum of dZ0 rows by E_idx[1] (backward of the h_V[E_idx] gather, rdesign/model/rdesign.py:85), atomics-free. */
+int rmp_segment_sum_rows_perm(const void* x_bf16, const int32_t* perm, const int32_t* row_ptr, float* out, int n_seg, void* stream);
 /* dW[n,k] += sum_r dZ[r,n] X[r,k]   dZ, X bf16 [rows,128], dW fp32 [128,128]: weight gradient of a 128->128 Linear
  * (tcgen05, both operands read MN-major from their row-major tiles, per-CTA TMEM accumulator, one red.global pass) */
 int rmp_gemm_dw_bf16(const void* dZ_bf16, const void* X_bf16, float* dW, int rows, void* stream);

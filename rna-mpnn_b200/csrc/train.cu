@@ -241,8 +241,11 @@ __global__ void __launch_bounds__(256) colsum_kernel(const void* __restrict__ a_
 // SURVEY section 8a a-2): the scatter_sum by CENTRE node without atomics.  Half a warp per node: lane = 8 columns (one
 // 16-byte load per row), rows summed in order in fp32 -> deterministic; one pass over x at HBM rate where the red.global
 // version moved every row through the L2 atomic units (70 -> ~25 us on [409,600 x 128]).
-__global__ void __launch_bounds__(256) segment_sum_kernel(const uint4* __restrict__ x, const int32_t* __restrict__ row_ptr,
-                                                          float* __restrict__ out, int n_seg) {
+// With `perm` the segment's rows are x[perm[r]]: the scatter by NEIGHBOUR node as a gather through the edges sorted by
+// neighbour (the transposed CSR of the graph, built once per step), deterministic and without atomics as well.
+template <bool PERM>
+__global__ void __launch_bounds__(256) segment_sum_kernel(const uint4* __restrict__ x, const int32_t* __restrict__ perm,
+                                                          const int32_t* __restrict__ row_ptr, float* __restrict__ out, int n_seg) {
     const int v = (int)(((size_t)blockIdx.x * blockDim.x + threadIdx.x) >> 4);
     const int cg = threadIdx.x & 15;
     if (v >= n_seg) return;
@@ -252,7 +255,7 @@ __global__ void __launch_bounds__(256) segment_sum_kernel(const uint4* __restric
     for (; r + 4 <= r1; r += 4) {                    // four independent 16-byte loads in flight
         uint4 xi[4];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) xi[q] = x[(size_t)(r + q) * 16 + cg];
+        for (int q = 0; q < 4; ++q) xi[q] = x[(size_t)(PERM ? __ldg(perm + r + q) : r + q) * 16 + cg];
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
             acc[0] += bf_lo(xi[q].x); acc[1] += bf_hi(xi[q].x); acc[2] += bf_lo(xi[q].y); acc[3] += bf_hi(xi[q].y);
@@ -260,7 +263,7 @@ __global__ void __launch_bounds__(256) segment_sum_kernel(const uint4* __restric
         }
     }
     for (; r < r1; ++r) {
-        const uint4 xi = x[(size_t)r * 16 + cg];
+        const uint4 xi = x[(size_t)(PERM ? __ldg(perm + r) : r) * 16 + cg];
         acc[0] += bf_lo(xi.x); acc[1] += bf_hi(xi.x); acc[2] += bf_lo(xi.y); acc[3] += bf_hi(xi.y);
         acc[4] += bf_lo(xi.z); acc[5] += bf_hi(xi.z); acc[6] += bf_lo(xi.w); acc[7] += bf_hi(xi.w);
     }
@@ -755,9 +758,20 @@ extern "C" int rmp_segment_sum_rows(const void* x_bf16, const int32_t* row_ptr, 
     RMP_REQUIRE(aligned16(x_bf16) && aligned16(out), RMP_E_ALIGN, "rmp_segment_sum_rows: 16-byte alignment");
     if (n_seg == 0) return RMP_OK;
     const size_t threads = (size_t)n_seg * 16;
-    train::segment_sum_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
-        reinterpret_cast<const uint4*>(x_bf16), row_ptr, out, n_seg);
+    train::segment_sum_kernel<false><<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(x_bf16), nullptr, row_ptr, out, n_seg);
     return check_launch("rmp_segment_sum_rows");
+}
+
+extern "C" int rmp_segment_sum_rows_perm(const void* x_bf16, const int32_t* perm, const int32_t* row_ptr, float* out, int n_seg,
+                                         void* stream) {
+    RMP_REQUIRE(x_bf16 && perm && row_ptr && out && n_seg >= 0, RMP_E_ARG, "rmp_segment_sum_rows_perm: null pointer");
+    RMP_REQUIRE(aligned16(x_bf16) && aligned16(out), RMP_E_ALIGN, "rmp_segment_sum_rows_perm: 16-byte alignment");
+    if (n_seg == 0) return RMP_OK;
+    const size_t threads = (size_t)n_seg * 16;
+    train::segment_sum_kernel<true><<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)stream>>>(
+        reinterpret_cast<const uint4*>(x_bf16), perm, row_ptr, out, n_seg);
+    return check_launch("rmp_segment_sum_rows_perm");
 }
 
 extern "C" int rmp_add_layernorm_fwd(const float* a, const void* b, int b_is_bf16, const float* gamma, const float* beta, float eps,

@@ -84,6 +84,7 @@ SIGNATURES = {
     "rmp_act_bwd_bf16": [P, P, P, P, F, P, P, I, F, U64, P, C.c_uint32, P],
     "rmp_scatter_add_rows": [P, P, P, I, P],
     "rmp_segment_sum_rows": [P, P, P, I, P],
+    "rmp_segment_sum_rows_perm": [P, P, P, P, I, P],
     "rmp_gemm_dw_bf16": [P, P, P, I, P],
     "rmp_adam_step": [P, P, P, P, I64, F, F, F, F, F, I, P, P],
     "rmp_normalize_fwd_bf16": [P, P, P, P, I, F, P],

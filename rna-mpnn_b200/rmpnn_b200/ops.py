@@ -595,6 +595,31 @@ def segment_sum_rows(x16, row_ptr, out=None):
     return out
 
 
+def segment_sum_rows_perm(x16, perm, row_ptr, out=None):
+    """out[v] = sum over r in [row_ptr[v], row_ptr[v+1]) of x16[perm[r]] -> fp32 [n_seg,128] (rmp_segment_sum_rows_perm)."""
+    _need_cuda(x16, perm, row_ptr, out)
+    assert x16.dtype == torch.bfloat16 and x16.is_contiguous() and x16.shape[1] == 128
+    assert perm.dtype == row_ptr.dtype == torch.int32 and perm.is_contiguous() and row_ptr.is_contiguous()
+    n_seg = row_ptr.shape[0] - 1
+    if out is None:
+        out = torch.empty(n_seg, 128, dtype=torch.float32, device=x16.device)
+    assert out.dtype == torch.float32 and out.is_contiguous() and out.shape[0] >= n_seg
+    check(lib().rmp_segment_sum_rows_perm(_ptr(x16), _ptr(perm), _ptr(row_ptr), _ptr(out), n_seg, _stream()),
+          "rmp_segment_sum_rows_perm")
+    return out
+
+
+def transposed_csr(idx, n_seg: int):
+    """(perm, row_ptr) of the rows grouped by ``idx`` (int32 [rows], values in [0, n_seg)): perm = stable argsort,
+    row_ptr [n_seg+1] = offsets of every value's group.  torch ops only, capturable in a CUDA graph (no host sync)."""
+    _need_cuda(idx)
+    il = idx.long()
+    perm = torch.argsort(il, stable=True).to(torch.int32)
+    cnt = torch.zeros(n_seg + 1, dtype=torch.int32, device=idx.device)
+    cnt[1:].index_add_(0, il, torch.ones_like(idx))
+    return perm, torch.cumsum(cnt, 0, dtype=torch.int32)
+
+
 def gemm_dw(dz16, x16, dW):
     """dW [128,128] fp32 += dz16^T @ x16 (both bf16 [rows,128])."""
     _need_cuda(dz16, x16, dW)

@@ -74,7 +74,7 @@ class EdgeMessageFn(torch.autograd.Function):
         dagg = dagg.detach().float().contiguous()
         db = torch.zeros(3, 128, dtype=torch.float32, device=dev)
         dW = torch.zeros(3, 128, 128, dtype=torch.float32, device=dev)           # dW3, dW2, dW1e
-        dP = torch.zeros(2, g.Nv, 128, dtype=torch.float32, device=dev)           # d Pc, d Pn
+        dP = torch.empty(2, g.Nv, 128, dtype=torch.float32, device=dev)           # d Pc, d Pn (both overwritten)
         W1h = w16(W1)
         dz2 = ops.act_bwd(z2, p, seed, sid + 2, dagg=dagg, ctr=g.ctr, alpha=1.0 / scale, db=db[2], seed_dev=sd)
         ops.gemm_dw(dz2, a1, dW[0])
@@ -88,10 +88,13 @@ class EdgeMessageFn(torch.autograd.Function):
         if ctx.fused:
             dW[:2] *= 0.5 * ops.keep_scale(p)                      # a0, a1 were saved as 2 GELU(z) mask
         ops.segment_sum_rows(dz0, g.row_ptr[:g.Nv + 1], dP[0])
-        ops.scatter_add_rows(dz0, g.nbr, dP[1])
+        # d Pn: rows of dz0 summed by NEIGHBOUR node through the edges sorted by neighbour (built once per step)
+        ops.segment_sum_rows_perm(dz0, state["nbr_perm"], state["nbr_row_ptr"], dP[1])
         dP16 = dP.to(torch.bfloat16)
-        dW1 = torch.cat([dW[2], (dP16[0].t() @ hV16).float(), (dP16[1].t() @ hV16).float()], dim=1)
-        dhV = (dP16[0] @ W1h[:, 128:256] + dP16[1] @ W1h[:, 256:]).float()
+        dW1 = torch.cat([dW[2], torch.mm(dP16[0].t(), hV16, out_dtype=torch.float32),
+                         torch.mm(dP16[1].t(), hV16, out_dtype=torch.float32)], dim=1)
+        dhV = (torch.mm(dP16[0], W1h[:, 128:256], out_dtype=torch.float32) +
+               torch.mm(dP16[1], W1h[:, 256:], out_dtype=torch.float32))
         return dhV, torch.zeros(1, device=dev), dW1, db[0], dW[1], db[1], dW[0], db[2], None
 
 
@@ -197,6 +200,7 @@ class LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x, weight, bias, w16):
         x16 = x.to(torch.bfloat16)
+        ctx.x_fp32 = x.dtype == torch.float32
         ctx.save_for_backward(x16, w16)
         return torch.addmm(bias.to(torch.bfloat16), x16, w16.t())
 
@@ -205,8 +209,8 @@ class LinearFn(torch.autograd.Function):
         x16, w16 = ctx.saved_tensors
         dy = dy.to(torch.bfloat16).contiguous()
         with torch.autocast("cuda", enabled=False):
-            dx = dy @ w16
-            dw = (dy.t() @ x16).float()
+            dx = torch.mm(dy, w16, out_dtype=torch.float32) if ctx.x_fp32 else dy @ w16   # the gradient in the input's dtype
+            dw = torch.mm(dy.t(), x16, out_dtype=torch.float32)
             db = ops.colsum(dy)[0]
         return dx, dw, db, None
 
@@ -279,6 +283,7 @@ class RDesignTrainer:
         state: Dict = {"graph": g, "p_drop": self.p_drop, "seed": seed, "scale": float(m.mpnn_layers[0].scale),
                        "w16": self._w16, "seed_dev": self.seed_dev}
         state["edge_raw16"] = F.pad(edge_raw, (0, 128 - edge_raw.shape[1])).to(torch.bfloat16).contiguous()
+        state["nbr_perm"], state["nbr_row_ptr"] = ops.transposed_csr(g.nbr[:g.Ne], g.Nv)
         n_layers = len(m.mpnn_layers)
         state["dz0_all"] = torch.empty(n_layers, g.Ne, 128, dtype=torch.bfloat16, device=X.device)
         lins = [[x for x in layer.message_layers if isinstance(x, torch.nn.Linear)] for layer in m.mpnn_layers]

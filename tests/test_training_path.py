@@ -71,6 +71,21 @@ def test_act_bwd_gathers_the_scatter_sum_gradient():
     np.testing.assert_allclose(dz.float().cpu().numpy(), _bf(zf.grad).cpu().numpy(), atol=2e-3, rtol=2e-2)
 
 
+def test_segment_sum_rows_perm_is_the_scatter_by_neighbour():
+    """Transposed-CSR gather (edges sorted by neighbour) = index_add by neighbour, without atomics."""
+    from rmpnn_b200 import ops
+    g = torch.Generator().manual_seed(8)
+    rows, Nv = 9000, 211
+    x = torch.randn(rows, 128, generator=g).cuda().to(torch.bfloat16)
+    idx = torch.randint(0, Nv - 3, (rows,), generator=g, dtype=torch.int32).cuda()      # the last nodes receive nothing
+    perm, row_ptr = ops.transposed_csr(idx, Nv)
+    assert row_ptr.shape[0] == Nv + 1 and int(row_ptr[-1]) == rows
+    out = ops.segment_sum_rows_perm(x, perm, row_ptr)
+    ref = torch.zeros(Nv, 128, device="cuda").index_add_(0, idx.long(), x.float())
+    np.testing.assert_allclose(out.cpu().numpy(), ref.cpu().numpy(), atol=1e-3, rtol=1e-4)
+    assert torch.equal(out, ops.segment_sum_rows_perm(x, perm, row_ptr))               # deterministic
+
+
 def test_scatter_add_and_adam():
     from rmpnn_b200 import ops
     g = torch.Generator().manual_seed(3)
