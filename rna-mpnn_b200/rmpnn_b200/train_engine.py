@@ -43,7 +43,7 @@ class EdgeMessageFn(torch.autograd.Function):
         p, seed, sid, scale, sd = state["p_drop"], state["seed"], state["stream_id"], state["scale"], state["seed_dev"]
         hV16 = h_V.detach().to(torch.bfloat16)
         W1h = w16(W1)                                              # [128,384] bf16 view, columns e | c | n
-        Pc = torch.addmm(b1.detach().to(torch.bfloat16), hV16, W1h[:, 128:256].t())      # [Nv,128] bf16
+        Pc = torch.addmm(w16(b1), hV16, W1h[:, 128:256].t())      # [Nv,128] bf16 (bias from the step's bf16 parameter copy)
         Pn = hV16 @ W1h[:, 256:].t()
         ctx.fused = state.get("wmsg_all") is not None
         if ctx.fused:
@@ -198,11 +198,11 @@ class LinearFn(torch.autograd.Function):
     ``rmp_colsum`` pass (torch's column reduction kernel: 25 us per call, a split-K ``[1,Nv] x [Nv,N]`` product: 14 us)."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, w16):
+    def forward(ctx, x, weight, bias, w16, b16=None):
         x16 = x.to(torch.bfloat16)
         ctx.x_fp32 = x.dtype == torch.float32
         ctx.save_for_backward(x16, w16)
-        return torch.addmm(bias.to(torch.bfloat16), x16, w16.t())
+        return torch.addmm(bias.to(torch.bfloat16) if b16 is None else b16, x16, w16.t())
 
     @staticmethod
     def backward(ctx, dy):
@@ -212,7 +212,7 @@ class LinearFn(torch.autograd.Function):
             dx = torch.mm(dy, w16, out_dtype=torch.float32) if ctx.x_fp32 else dy @ w16   # the gradient in the input's dtype
             dw = torch.mm(dy.t(), x16, out_dtype=torch.float32)
             db = ops.colsum(dy)[0]
-        return dx, dw, db, None
+        return dx, dw, db, None, None
 
 
 def _normalize(x, gain, bias, eps=1e-6):
@@ -316,7 +316,7 @@ class RDesignTrainer:
                 while k < len(mods):
                     mod = mods[k]
                     if isinstance(mod, torch.nn.Linear):
-                        d = LinearFn.apply(d, mod.weight, mod.bias, self._w16(mod.weight))
+                        d = LinearFn.apply(d, mod.weight, mod.bias, self._w16(mod.weight), self._w16(mod.bias))
                     elif (isinstance(mod, torch.nn.GELU) and k + 1 < len(mods) and isinstance(mods[k + 1], torch.nn.Dropout)
                           and d.dtype == torch.bfloat16 and d.shape[1] % 128 == 0):
                         # GELU + Dropout in one kernel per direction (stream ids 8.. of the layer: the edge stages use 0..2)
