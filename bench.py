@@ -337,8 +337,9 @@ def run_c4(args):
             "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic", "loss": loss_host,
             "config": {"workload": f"c4: {B} x L={L} per GPU, K={cfg.k_neighbors}, RNAModel default (9 layers), dropout 0.1, Adam",
-                       "path": "per-edge forward/backward on the sm_100a kernels (tcgen05 row GEMMs, rmp_gemm_dw_bf16, "
-                               "csrc/train.cu), per-node remainder torch under bf16 autocast",
+                       "path": "per-edge forward as one fused tcgen05 launch per layer (rmp_edge_mlp_train_fwd_bf16), backward on the "
+                               "sm_100a kernels of csrc/train.cu (row / weight-gradient / K-concatenated GEMMs, activation backward, "
+                               "segment sums), per-node LayerNorm / activation / column-sum kernels, dense node products on cuBLAS",
                        "collective": f"one NCCL all-reduce of a flat fp32 gradient buffer, {tr.n_params * 4 / 1e6:.1f} MB, "
                                      "side stream, then rmp_adam_step",
                        "launch": "CUDA graph replay of forward + backward, then one NCCL all-reduce and the Adam kernel" if replay else "eager"},
