@@ -113,6 +113,8 @@ class RNAModel(_Base):
         self._engine = None
         self._engine_key = None
         self.precision_mode = os.environ.get("RMPNN_PRECISION", "fp32")
+        self._native = None                  # rmpnn_b200.train_engine.RDesignTrainer, built at the first training step
+        self._native_seed = 0
 
     # ------------------------------------------------------------------ fused engine
     def _full_feature_set(self):
@@ -160,10 +162,33 @@ class RNAModel(_Base):
         dev = self.device
         return X.to(dev), S.to(dev), mask.to(dev), lengths, names
 
+    def _native_training(self, X) -> bool:
+        """The training step of the reference (rdesign/model/rdesign.py:95-104) on the sm_100a kernels: default model shape
+        (hidden 128, three 384/128/128 message layers, full feature set), parameters on the GPU, autograd on.
+        ``RMPNN_NATIVE_TRAIN=0`` keeps the fp32 torch composition (bit-for-bit the reference's math)."""
+        if os.environ.get("RMPNN_NATIVE_TRAIN", "1") == "0" or not (self.training and torch.is_grad_enabled() and X.is_cuda):
+            return False
+        if not (self._full_feature_set() and self.hidden_dim == 128 and len(self.mpnn_layers) > 0):
+            return False
+        for layer in self.mpnn_layers:
+            lins = [m for m in layer.message_layers if isinstance(m, nn.Linear)]
+            if [tuple(m.weight.shape) for m in lins] != [(128, 384), (128, 128), (128, 128)]:
+                return False
+        return all(p.is_cuda for p in self.parameters())
+
     def training_step(self, batch):
         X, S, mask, _, _ = self._to_device(batch)
-        h_V, S = self(X, S, mask)
-        loss = self.loss_fn(self.readout(h_V), S)
+        if self._native_training(X):
+            # native forward; ``loss`` carries the autograd graph of the kernel-backed Functions, so the caller's
+            # ``loss.backward()`` + optimizer step (Lightning's loop, configure_optimizers above) work unchanged
+            if self._native is None:
+                from rmpnn_b200.train_engine import RDesignTrainer
+                self._native = RDesignTrainer(self)
+            loss = self._native.forward_loss(X, S, mask, seed=self._native_seed)
+            self._native_seed += 1
+        else:
+            h_V, S = self(X, S, mask)
+            loss = self.loss_fn(self.readout(h_V), S)
         self.log('train_loss', loss, prog_bar=True, sync_dist=True)
         return loss
 

@@ -274,6 +274,18 @@ class RDesignTrainer:
 
     # ------------------------------------------------------------------ forward + backward
     def loss_and_grads(self, X, S, mask, seed: int = 0, sizes=None):
+        """Forward + backward into the flat gradient buffer; returns the detached loss."""
+        loss = self.forward_loss(X, S, mask, seed, sizes)
+        # torch.autograd.grad instead of backward(): no AccumulateGrad nodes, whose stream (the one the parameters were
+        # created on) would have to be synchronised with the capturing stream and invalidates a CUDA-graph capture
+        grads = torch.autograd.grad(loss, self.params)
+        torch.cat([g.reshape(-1) for g in grads], out=self.flat_g[:self.n_params])
+        return loss.detach()
+
+    def forward_loss(self, X, S, mask, seed: int = 0, sizes=None):
+        """Cross-entropy loss of one batch with its autograd graph (the per-edge and per-node blocks are autograd Functions
+        over the C-ABI kernels): ``loss.backward()`` fills ``p.grad`` like any torch loss, which is how the drop-in
+        ``RNAModel.training_step`` hands the native path to Lightning's optimizer loop."""
         m = self.model
         f = m.features
         B, N = X.shape[:2]
@@ -331,12 +343,7 @@ class RDesignTrainer:
                 h_V = layer.norm2(x1 + layer.dense(x1)).float()
         with torch.autocast("cuda", dtype=torch.bfloat16, enabled=self.autocast):
             logits = m.readout(h_V)
-        loss = F.cross_entropy(logits.float(), S_valid)
-        # torch.autograd.grad instead of backward(): no AccumulateGrad nodes, whose stream (the one the parameters were
-        # created on) would have to be synchronised with the capturing stream and invalidates a CUDA-graph capture
-        grads = torch.autograd.grad(loss, self.params)
-        torch.cat([g.reshape(-1) for g in grads], out=self.flat_g[:self.n_params])
-        return loss.detach()
+        return F.cross_entropy(logits.float(), S_valid)
 
     # ------------------------------------------------------------------ all-reduce + Adam
     def apply_gradients(self):

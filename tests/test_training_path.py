@@ -143,6 +143,59 @@ def test_native_training_step_gradients_match_autograd():
     assert torch.isfinite(delta).all() and (delta.abs() <= model.hparams.lr * 1.001).all() and delta.abs().max() > 0
 
 
+def test_dropin_training_step_runs_on_the_native_kernels(monkeypatch):
+    """``RNAModel.training_step`` (the reference-facing API, rdesign/model/rdesign.py:95-104) + ``loss.backward()`` + the
+    optimizer of ``configure_optimizers``: the per-edge / per-node blocks run on the C-ABI kernels (launch counter), the
+    gradients match the fp32 torch composition (``RMPNN_NATIVE_TRAIN=0``) and the loss goes down."""
+    from oracle.weights import RDesignConfig, make_state_dict, synthetic_backbones
+    from rdesign.model.rdesign import RNAModel
+    from rmpnn_b200 import _lib
+    cfg = RDesignConfig(k_neighbors=12, num_mpnn_layers=3)
+    X, S, mask = synthetic_backbones(3, 60, 9, lengths=[60, 41, 23])
+    batch = (X, S, mask, mask.sum(1).long(), ["a", "b", "c"])
+
+    monkeypatch.setenv("RMPNN_NATIVE_TRAIN", "0")
+    ref = RNAModel(**cfg.as_kwargs(), dropout=0.0).cuda().train()
+    ref.load_state_dict(make_state_dict(cfg, 42), strict=True)
+    loss_ref = ref.training_step(batch)
+    loss_ref.backward()
+    ref_grads = {n: p.grad.clone() for n, p in ref.named_parameters()}
+
+    monkeypatch.setenv("RMPNN_NATIVE_TRAIN", "1")
+    model = RNAModel(**cfg.as_kwargs(), dropout=0.0).cuda().train()
+    model.load_state_dict(make_state_dict(cfg, 42), strict=True)
+    (opt,), _ = model.configure_optimizers()
+    n0 = _lib.lib().rmp_launch_count()
+    loss = model.training_step(batch)
+    opt.zero_grad()
+    loss.backward()
+    assert _lib.lib().rmp_launch_count() - n0 > 20 * len(model.mpnn_layers)          # the step ran on the library's kernels
+    assert abs(loss.item() - loss_ref.item()) < 3e-2
+    for n, p in model.named_parameters():
+        a, b = p.grad.float(), ref_grads[n].float()
+        rel = ((a - b).norm() / (b.norm() + 1e-12)).item()
+        assert rel < 1e-1 or (a - b).abs().max().item() < 1e-5, (n, rel)
+    opt.step()
+    sd = model.state_dict()                                                        # still a loadable reference state_dict
+    RNAModel(**cfg.as_kwargs(), dropout=0.0).load_state_dict(sd, strict=True)
+
+    model = RNAModel(**cfg.as_kwargs()).cuda().train()                              # dropout 0.1: the loop trains
+    model.load_state_dict(make_state_dict(cfg, 42), strict=True)
+    (opt,), _ = model.configure_optimizers()
+    losses = []
+    for _ in range(25):
+        loss = model.training_step(batch)
+        opt.zero_grad()
+        loss.backward()
+        opt.step()
+        losses.append(loss.item())
+    assert np.isfinite(losses).all() and np.mean(losses[-5:]) < np.mean(losses[:5]) - 0.05, losses
+    model.eval()                                                                   # and the eval path sees the trained weights
+    with torch.no_grad():
+        h_V, S_v = model(X.cuda(), S.cuda(), mask.cuda())
+    assert torch.isfinite(h_V).all() and h_V.shape[0] == int(mask.sum())
+
+
 def test_training_loss_decreases_with_dropout_on():
     from oracle.weights import RDesignConfig, make_state_dict, synthetic_backbones
     from rdesign.model.rdesign import RNAModel
