@@ -1,5 +1,5 @@
 """Small end-to-end invocation of every kernel family for compute-sanitizer (memcheck): rdesign fp32 / fp32x3 / bf16 forward,
-rnampnn fp32 / bf16 forward (cluster GraphNorm, tcgen05 attention), device collate, tree-ensemble head.  Kept tiny: the
+rnampnn fp32 / bf16 forward (cluster GraphNorm, tcgen05 attention), device collate, tree-ensemble head, the native training step.  Kept tiny: the
 sanitizer slows kernels down by 10-100x."""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -41,3 +41,15 @@ qkv16 = torch.randn(2 * 150, 384, device="cuda").to(torch.bfloat16)
 att = ops.res_attention_tc(qkv16, torch.ones(300, device="cuda"), 2, 150, 8)
 torch.cuda.synchronize()
 print("attention_tc", float(att.abs().max()))
+# native training step (fused edge forward with dropout and saved tensors, backward GEMMs incl. the K-concatenated one,
+# permuted segment sums, fused add + LayerNorm, column sums, Adam) on a tiny model; lengths 5 puts > 16 nodes into a tile
+from rdesign.model.rdesign import RNAModel
+from rmpnn_b200.train_engine import RDesignTrainer
+tcfg = RDesignConfig(k_neighbors=8, num_mpnn_layers=2)
+model = RNAModel(**tcfg.as_kwargs())
+model.load_state_dict(make_state_dict(tcfg, 3), strict=True)
+tr = RDesignTrainer(model.cuda().train())
+for it in range(2):
+    loss = tr.step(X.cuda(), S.cuda(), mask.cuda(), seed=it)
+torch.cuda.synchronize()
+print("training step", float(loss))
