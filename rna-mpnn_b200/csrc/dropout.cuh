@@ -29,4 +29,18 @@ __device__ __forceinline__ uint32_t keep_mask8(uint64_t seed, uint64_t g, uint32
     return m;
 }
 
+// The same mask as four 32-bit AND masks for the group's four packed bf16x2 pairs (pair j = elements 2j, 2j+1): a per-byte
+// compare of the hash against the threshold and one byte permute per pair instead of eight bit extractions and eight
+// selects.  The fused training forward of the edge kernel evaluates four of these per thread and tile-stage and is
+// instruction-bound there (94.5 M warp instructions per launch against 45 M for the inference launch,
+// profiles/r2s3_edge_trainfwd_full.txt): 64 instructions fewer per thread and tile-stage.
+__device__ __forceinline__ void keep_masks_bf16x2(uint64_t seed, uint64_t g, uint32_t stream, uint32_t thresh8, uint32_t (&m)[4]) {
+    if (thresh8 == 0) { m[0] = m[1] = m[2] = m[3] = 0xffffffffu; return; }
+    const uint64_t h = mix64(seed + 0x9E3779B97F4A7C15ull * (g + 1) + ((uint64_t)stream << 40));
+    const uint32_t t4 = thresh8 * 0x01010101u;
+    const uint32_t klo = __vcmpgeu4((uint32_t)h, t4), khi = __vcmpgeu4((uint32_t)(h >> 32), t4);      // 0xff per surviving element
+    m[0] = __byte_perm(klo, 0u, 0x1100); m[1] = __byte_perm(klo, 0u, 0x3322);
+    m[2] = __byte_perm(khi, 0u, 0x1100); m[3] = __byte_perm(khi, 0u, 0x3322);
+}
+
 }  // namespace rmp

@@ -606,13 +606,11 @@ edge_mlp_tc_kernel(const __grid_constant__ CUtensorMap tm_e, const __grid_consta
                     if (p.thresh8 != 0) {
 #pragma unroll
                         for (int g8 = 0; g8 < 4; ++g8) {
-                            const uint32_t keep = keep_mask8(seed_tr, (uint64_t)(e_base + row) * 16 + (uint64_t)(col0 / 8 + g8),
-                                                             p.stream0 + (uint32_t)st, p.thresh8);
+                            uint32_t m[4];
+                            keep_masks_bf16x2(seed_tr, (uint64_t)(e_base + row) * 16 + (uint64_t)(col0 / 8 + g8),
+                                              p.stream0 + (uint32_t)st, p.thresh8, m);
 #pragma unroll
-                            for (int j = 0; j < 4; ++j) {
-                                const uint32_t m = (((keep >> (2 * j)) & 1u) ? 0x0000ffffu : 0u) | (((keep >> (2 * j + 1)) & 1u) ? 0xffff0000u : 0u);
-                                o[4 * g8 + j] &= m;
-                            }
+                            for (int j = 0; j < 4; ++j) o[4 * g8 + j] &= m[j];
                         }
                     }
                     if (bypass && valid) {                     // > 16 nodes in the tile: vector reductions instead of the selector
