@@ -611,8 +611,8 @@ def segment_sum_rows_perm(x16, perm, row_ptr, out=None):
 
 def transposed_csr(idx, n_seg: int):
     """(perm, row_ptr) of the rows grouped by ``idx`` (int32 [rows], values in [0, n_seg)): perm = stable argsort,
-    row_ptr [n_seg+1] = offsets of every value's group.  torch ops only, capturable in a CUDA graph (no host sync)."""
-    _need_cuda(idx)
+    row_ptr [n_seg+1] = offsets of every value's group.  torch ops only (any device), capturable in a CUDA graph (no host
+    sync)."""
     il = idx.long()
     perm = torch.argsort(il, stable=True).to(torch.int32)
     cnt = torch.zeros(n_seg + 1, dtype=torch.int32, device=idx.device)

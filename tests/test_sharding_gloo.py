@@ -57,3 +57,22 @@ def test_partition_is_balanced_and_batches_respect_budget():
             assert max(lengths[i] for i in b) * len(b) <= 8192 or len(b) == 1
     worst, mean = shard.imbalance(lengths, parts)
     assert worst / mean < 1.10          # ~9 batches per rank: longest-processing-time-first granularity
+
+
+def test_transposed_csr_host_logic():
+    """Edges grouped by neighbour node (the training backward's atomics-free d Pn): stable permutation + offsets, against numpy;
+    nodes that are nobody's neighbour get an empty range.  Runs on the CPU (torch ops only)."""
+    import numpy as np
+    from rmpnn_b200 import ops
+    rng = np.random.default_rng(3)
+    n_seg, rows = 57, 1000
+    idx = rng.integers(0, n_seg - 5, size=rows).astype(np.int32)
+    perm, row_ptr = ops.transposed_csr(torch.from_numpy(idx), n_seg)
+    assert perm.dtype == row_ptr.dtype == torch.int32 and row_ptr.shape[0] == n_seg + 1
+    assert np.array_equal(perm.numpy(), np.argsort(idx, kind="stable").astype(np.int32))
+    counts = np.bincount(idx, minlength=n_seg)
+    assert np.array_equal(row_ptr.numpy(), np.concatenate([[0], np.cumsum(counts)]).astype(np.int32))
+    for v in (0, 17, n_seg - 1):
+        seg = perm.numpy()[row_ptr[v]:row_ptr[v + 1]]
+        assert (idx[seg] == v).all() and len(seg) == counts[v]
+    assert abs(ops.keep_scale(0.1) - 256.0 / 230.0) < 1e-12 and ops.keep_scale(0.0) == 1.0
