@@ -444,6 +444,11 @@ int rmp_edge_embed_bf16(const float* X, const float* frames, const int32_t* node
 /* tuning aid: int64 [800] device buffer that receives a clock64 trace of the node kernel while the environment
  * variable RMP_NODE_TIMELINE is set (scripts/node_timeline.py); NULL disables it */
 void rmp_set_node_timeline(void* buf);
+/* tuning aid (scripts/edge_variants.py): epilogue variant of rmp_edge_mlp_bf16 (0 = GELU, 1 = activations held as 2 GELU,
+ * bit-identical results; shipped default 1) and producer / issuer flags (1 = first edge tile requested right behind W1e,
+ * 2 = run-ahead stage-0 GEMMs issued only behind a GEMM the epilogue waits for; shipped default 3).  The environment variable
+ * RMP_EDGE_TUNING="<variant>,<flags>" sets the same pair before the first launch. */
+void rmp_set_edge_tuning(int variant, int flags);
 
 /* fp32 -> bf16 row conversion (h_E storage for the bf16 path), n elements */
 int rmp_cast_bf16(const float* src, void* dst_bf16, int64_t n, void* stream);
